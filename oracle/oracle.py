@@ -1,0 +1,237 @@
+"""numpy front end of the CPU oracle (oracle/libd3d_oracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may import
+this module; the product package d3d_b200/ never does (tests/test_no_oracle_in_product.py enforces it).
+
+Each function mirrors one reference entry point (file:line in the docstring) and takes/returns numpy
+arrays with the reference's layouts and dtypes.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+ALG_RC, ALG_SH, ALG_TRUTH = 1, 2, 3
+IOU_BOX, IOU_RBOX = 1, 2
+SUP_HARD, SUP_LINEAR, SUP_GAUSSIAN = 0, 1, 2
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", HERE])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        p = os.path.join(HERE, "libd3d_oracle.so")
+        if not os.path.exists(p):
+            build()
+        _LIB = C.CDLL(p)
+        _LIB.orc_nms2d_f.restype = C.c_int64
+        _LIB.orc_nms2d_d.restype = C.c_int64
+        _LIB.orc_voxelize_dense.restype = C.c_int64
+        _LIB.orc_voxelize_sparse.restype = C.c_int64
+        _LIB.orc_voxelize_filter.restype = C.c_int64
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _boxes(b, dt):
+    b = np.ascontiguousarray(b, dtype=dt)
+    assert b.ndim == 2 and b.shape[1] == 5
+    return b
+
+
+def iou2dr(b1, b2, alg=ALG_RC, return_blowups=False):
+    """Pairwise rotated IoU, dtype = b1.dtype (f32 or f64): reference d3d/box/iou.cpp:94-141."""
+    dt = np.float32 if b1.dtype == np.float32 else np.float64
+    b1, b2 = _boxes(b1, dt), _boxes(b2, dt)
+    out = np.empty((len(b1), len(b2)), dt)
+    bl = np.zeros(out.shape, np.uint8)
+    f = lib().orc_iou2dr_f32 if dt == np.float32 else lib().orc_iou2dr_f64
+    f(_p(b1), C.c_int64(len(b1)), _p(b2), C.c_int64(len(b2)), _p(out), C.c_int(alg), _p(bl))
+    return (out, bl) if return_blowups else out
+
+
+def iou2dr_truth(b1, b2):
+    """Geometric truth (long-double closed half-plane clip) from float64 inputs."""
+    b1, b2 = _boxes(b1, np.float64), _boxes(b2, np.float64)
+    out = np.empty((len(b1), len(b2)), np.float64)
+    lib().orc_iou2dr_truth(_p(b1), C.c_int64(len(b1)), _p(b2), C.c_int64(len(b2)), _p(out))
+    return out
+
+
+def iou2d(b1, b2):
+    """Pairwise IoU of the AABBs of the rotated boxes (method="box"): d3d/box/iou.cpp:11-46."""
+    dt = np.float32 if b1.dtype == np.float32 else np.float64
+    b1, b2 = _boxes(b1, dt), _boxes(b2, dt)
+    out = np.empty((len(b1), len(b2)), dt)
+    f = lib().orc_iou2d_f32 if dt == np.float32 else lib().orc_iou2d_f64
+    f(_p(b1), C.c_int64(len(b1)), _p(b2), C.c_int64(len(b2)), _p(out))
+    return out
+
+
+def box2d_iou(b1, b2, method="box", precise=True, alg=ALG_RC):
+    """Front door: d3d/box/__init__.py:180-224 (dtype policy: fp64 compute when precise)."""
+    otype = b1.dtype
+    if precise:
+        b1, b2 = b1.astype(np.float64), b2.astype(np.float64)
+    r = iou2d(b1, b2) if method == "box" else iou2dr(b1, b2, alg)
+    return r.astype(otype) if precise else r
+
+
+def nms2d(boxes, scores, iou_type=IOU_BOX, sup_type=SUP_HARD, iou_threshold=0.0, score_threshold=0.0,
+          sup_param=0.0, alg=ALG_RC, cuda_score_rule=False, return_evals=False):
+    """Suppressed mask u8[n]: d3d/box/nms.cpp:98-119 (order = stable descending argsort)."""
+    dt = np.float32 if boxes.dtype == np.float32 else np.float64
+    boxes = _boxes(boxes, dt)
+    sc = np.ascontiguousarray(scores, dtype=dt).copy()
+    order = np.argsort(-sc, kind="stable").astype(np.int64)
+    sup = np.zeros(len(boxes), np.uint8)
+    f = lib().orc_nms2d_f if dt == np.float32 else lib().orc_nms2d_d
+    ev = f(_p(boxes), _p(sc), _p(order), C.c_int64(len(boxes)), C.c_int(iou_type), C.c_int(sup_type),
+           C.c_float(iou_threshold), C.c_float(score_threshold), C.c_float(sup_param), C.c_int(alg),
+           C.c_int(1 if cuda_score_rule else 0), _p(sup))
+    return (sup.astype(bool), ev) if return_evals else sup.astype(bool)
+
+
+def box2d_nms(boxes, scores, iou_method="box", supression_method="hard", iou_threshold=0, score_threshold=0,
+              supression_param=0, precise=True, alg=ALG_RC, cuda_score_rule=False):
+    """Front door: d3d/box/__init__.py:226-276; returns the KEEP mask bool[n]."""
+    if precise:
+        boxes, scores = boxes.astype(np.float64), scores.astype(np.float64)
+    if scores.ndim == 2:
+        scores = scores.max(axis=1)
+    if boxes.size == 0:
+        return np.zeros(0, bool)
+    it = {"box": IOU_BOX, "rbox": IOU_RBOX}[iou_method]
+    st = {"hard": SUP_HARD, "linear": SUP_LINEAR, "gaussian": SUP_GAUSSIAN}[supression_method]
+    return ~nms2d(boxes, scores, it, st, iou_threshold, score_threshold, supression_param, alg, cuda_score_rule)
+
+
+# ------------------------------------------------------------------ voxelization
+def voxelize_dense(points, shape, bounds, max_points, max_voxels, reduction=0):
+    """d3d/voxel/voxelize.cpp:45-199. Returns dict like the reference (pmask False where unset)."""
+    pts = np.ascontiguousarray(points, np.float32)
+    n, c = pts.shape
+    shape = np.ascontiguousarray(shape, np.int32)
+    bounds = np.ascontiguousarray(bounds, np.float32)
+    voxels = np.zeros((max_voxels, max_points, c), np.float32)
+    coords = np.zeros((max_voxels, 3), np.int64)
+    pmask = np.zeros((max_voxels, max_points), np.uint8)
+    npts = np.zeros(max_voxels, np.int32)
+    agg = np.zeros((max_voxels, c), np.float32) if reduction else None
+    nv = lib().orc_voxelize_dense(_p(pts), C.c_int64(n), C.c_int64(c), _p(shape), _p(bounds), C.c_int32(max_points),
+                                  C.c_int32(max_voxels), C.c_int(reduction), _p(voxels), _p(coords), _p(pmask),
+                                  _p(npts), _p(agg) if agg is not None else None)
+    ret = dict(voxels=voxels[:nv], coords=coords[:nv], voxel_pmask=pmask[:nv].astype(bool), voxel_npoints=npts[:nv])
+    if reduction:
+        ret["aggregates"] = agg[:nv]
+    return ret
+
+
+def voxelize_sparse(points, voxel_size):
+    """d3d/voxel/voxelize.cpp:288-335."""
+    pts = np.ascontiguousarray(points, np.float32)
+    n, c = pts.shape
+    vs = np.ascontiguousarray(voxel_size, np.float32)
+    mapping = np.empty(n, np.int64)
+    coords = np.empty((max(n, 1), 3), np.int64)
+    npts = np.empty(max(n, 1), np.int32)
+    nv = lib().orc_voxelize_sparse(_p(pts), C.c_int64(n), C.c_int64(c), _p(vs), _p(mapping), _p(coords), _p(npts))
+    return dict(points_mapping=mapping, coords=coords[:nv].copy(), voxel_npoints=npts[:nv].copy())
+
+
+def voxelize_filter(points, mapping, coords, npoints, coords_bound, min_points, max_points, max_voxels,
+                    pfilter, vfilter):
+    """d3d/voxel/voxelize.cpp:337-484."""
+    pts = np.ascontiguousarray(points, np.float32)
+    n = len(pts)
+    nv = len(coords)
+    mapping = np.ascontiguousarray(mapping, np.int64)
+    coords = np.ascontiguousarray(coords, np.int64)
+    npoints = np.ascontiguousarray(npoints, np.int32)
+    bnd = None if coords_bound is None else np.ascontiguousarray(coords_bound, np.int64)
+    out_mask = np.empty(max(n, 1), np.int64)
+    out_map = np.empty(max(n, 1), np.int64)
+    out_np = np.empty(max(nv, 1), np.int32)
+    out_co = np.empty((max(nv, 1), 3), np.int64)
+    k = C.c_int64(0)
+    v = lib().orc_voxelize_filter(C.c_int64(n), _p(mapping), _p(coords), _p(npoints), C.c_int64(nv),
+                                  _p(bnd) if bnd is not None else None, C.c_int32(min_points), C.c_int32(max_points),
+                                  C.c_int32(max_voxels), C.c_int(pfilter), C.c_int(vfilter), _p(out_mask), _p(out_map),
+                                  _p(out_np), _p(out_co), C.byref(k))
+    k = k.value
+    return dict(points=pts[out_mask[:k]], points_mask=out_mask[:k].copy(), points_mapping=out_map[:k].copy(),
+                voxel_npoints=out_np[:v].copy(), coords=out_co[:v].copy())
+
+
+_RED = {None: 0, "none": 0, "mean": 1, "max": 2, "min": 3}
+_PF = {None: 0, "none": 0, "trim": 1}
+_VF = {None: 0, "none": 0, "trim": 1, "descending": 2}
+
+
+class VoxelGenerator:
+    """d3d/voxel/__init__.py:12-104 restated on numpy + the C oracle (fp32 derivations kept identical)."""
+
+    def __init__(self, bounds, shape, min_points=0, max_points=30, max_voxels=20000, max_points_filter=None,
+                 max_voxels_filter=None, reduction=None, dense=False):
+        self.bounds = np.asarray(bounds, np.float32)
+        self.shape = np.asarray(shape, np.int32)
+        ba = self.bounds.reshape(3, 2)
+        self.size = ((ba[:, 1] - ba[:, 0]) / self.shape.astype(np.float32)).astype(np.float32)
+        dist = (ba[:, 0] / self.size).astype(np.float32)
+        if np.any(np.abs(np.round(dist) - dist) > 1e-3):
+            raise ValueError("The voxelization grids is not aligned with the origin")
+        self.offset = np.round(dist).astype(np.int32)
+        self.vbounds = np.round((ba / self.size.reshape(3, 1)).astype(np.float32)).astype(np.int64)
+        self.min_points, self.max_points, self.max_voxels = min_points, max_points, max_voxels
+        self.pf = _PF[max_points_filter.lower() if max_points_filter else None]
+        self.vf = _VF[max_voxels_filter.lower() if max_voxels_filter else None]
+        self.red = _RED[reduction.lower() if reduction else None]
+        self.dense = dense
+
+    def __call__(self, points):
+        if self.dense:
+            return voxelize_dense(points, self.shape, self.bounds, self.max_points, self.max_voxels, self.red)
+        sp = voxelize_sparse(points, self.size)
+        ret = voxelize_filter(points, sp["points_mapping"], sp["coords"], sp["voxel_npoints"], self.vbounds,
+                              self.min_points, self.max_points, self.max_voxels, self.pf, self.vf)
+        ret["coords"] = ret["coords"] - self.offset.astype(np.int64)
+        return ret
+
+
+# ------------------------------------------------------------------ aligned scatter
+def scatter_forward(coord, image, atype):
+    """d3d/point/scatter.cpp:79-134,175-188. atype: 1 MEAN, 2 LINEAR."""
+    dt = np.float32 if image.dtype == np.float32 else np.float64
+    coord = np.ascontiguousarray(coord, dt)
+    image = np.ascontiguousarray(image, dt)
+    n, dim = coord.shape[0], coord.shape[1] - 1
+    dims = np.asarray(image.shape[2:], np.int64)
+    out = np.empty((n, image.shape[1]), dt)
+    f = lib().orc_scatter_fwd_f32 if dt == np.float32 else lib().orc_scatter_fwd_f64
+    f(_p(coord), C.c_int64(n), C.c_int(dim), _p(image), C.c_int64(image.shape[0]), C.c_int64(image.shape[1]),
+      _p(dims), C.c_int(atype), _p(out))
+    return out
+
+
+def scatter_backward(coord, grad, atype, image_shape):
+    """d3d/point/scatter.cpp:136-172,190-201 (image_grad starts at zero, d3d/point/__init__.py:32)."""
+    dt = np.float32 if grad.dtype == np.float32 else np.float64
+    coord = np.ascontiguousarray(coord, dt)
+    grad = np.ascontiguousarray(grad, dt)
+    n, dim = coord.shape[0], coord.shape[1] - 1
+    dims = np.asarray(image_shape[2:], np.int64)
+    ig = np.zeros(image_shape, dt)
+    f = lib().orc_scatter_bwd_f32 if dt == np.float32 else lib().orc_scatter_bwd_f64
+    f(_p(coord), C.c_int64(n), C.c_int(dim), _p(grad), C.c_int64(image_shape[0]), C.c_int64(image_shape[1]),
+      _p(dims), C.c_int(atype), _p(ig))
+    return ig

@@ -1,0 +1,223 @@
+"""Pin the CPU oracle (oracle/d3d_oracle.c) against the reference: its own golden vectors and
+known-answer tests, fixtures generated from its compiled CPU extensions (tests/golden/make_golden.py),
+and -- when oracle/_ref is present -- the reference extensions live.  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import golden, gen_boxes, lidar
+
+
+def _unpack(bits, n):
+    return np.unpackbits(bits)[:n].astype(bool)
+
+
+# ------------------------------------------------------------------ IoU
+def test_iou_rc_bit_exact_vs_reference_fixture(oracle):
+    g = golden("iou_c1.npz")
+    a, b = g["boxes1"], g["boxes2"]
+    assert np.array_equal(oracle.iou2dr(a, b, oracle.ALG_RC), g["rbox_f64"])
+    assert np.array_equal(oracle.iou2d(a, b), g["box_f64"])
+    a32, b32 = a.astype(np.float32), b.astype(np.float32)
+    # fp32 goes through libm sinf/cosf/atan2f: identical on the same glibc, else within tolerance
+    assert np.allclose(oracle.iou2dr(a32, b32, oracle.ALG_RC), g["rbox_f32"], atol=1e-4)
+    assert np.allclose(oracle.iou2d(a32, b32), g["box_f32"], atol=1e-5)
+
+
+def test_iou_c1_anchors(oracle):
+    """SURVEY Appendix C anchors for config C1 (1k x 1k fp64)."""
+    rng = np.random.default_rng(0)
+    A, B = gen_boxes(rng, 1000), gen_boxes(rng, 1000)
+    r = oracle.iou2dr(A, B, oracle.ALG_RC)
+    g = golden("iou_c1.npz")
+    assert abs(r.sum() - float(g["c1_rbox_sum"])) < 1e-7
+    assert (r != 0).sum() == int(g["c1_rbox_nnz"]) == 205623
+    assert abs(oracle.iou2d(A, B).sum() - float(g["c1_box_sum"])) < 1e-7
+    # the three algorithms agree in generic position (<= 1.3e-13)
+    assert np.abs(oracle.iou2dr(A, B, oracle.ALG_SH) - r).max() < 1e-10
+    assert np.abs(oracle.iou2dr_truth(A, B) - r).max() < 1e-10
+
+
+def test_iou_reference_known_answers(oracle):
+    """test/test_box.py:12-100 with the reference's own tolerances."""
+    g = golden("iou_known_answers.npz")
+    eps = 1e-3
+    for alg in (oracle.ALG_RC, oracle.ALG_TRUTH):
+        assert np.allclose(oracle.box2d_iou(g["aa_boxes1"], g["aa_boxes2"], "box"), g["aa_expected"], atol=eps)
+        assert np.allclose(oracle.box2d_iou(g["aa_boxes1"], g["aa_boxes2"], "rbox", alg=alg), g["aa_expected"], atol=4 * eps)
+        assert np.allclose(oracle.box2d_iou(g["rot_boxes1"], g["rot_boxes2"], "box"), g["rot_box_expected"], atol=2 * eps)
+        assert np.allclose(oracle.box2d_iou(g["rot_boxes1"], g["rot_boxes2"], "rbox", alg=alg), g["rot_rbox_expected"], atol=4 * eps)
+        ab = g["apart_boxes"]
+        assert np.allclose(oracle.box2d_iou(ab, ab, "box") - np.eye(4), 0, atol=1e-6)
+        rb = g["apart_rboxes"]
+        d = oracle.box2d_iou(rb, rb, "rbox", alg=alg) - np.eye(5)
+        np.fill_diagonal(d, 0)
+        assert np.allclose(d, 0, atol=1e-6)
+
+
+def test_iou_degenerate_list(oracle):
+    """RC restatement reproduces the reference's (wrong) answers bit for bit in
+    fp64; the truth clip returns the geometric values."""
+    g = golden("iou_degenerate.npz")
+    for i, name in enumerate(g["names"]):
+        a, b = g["boxes1"][i:i + 1], g["boxes2"][i:i + 1]
+        rc = oracle.iou2dr(a, b, oracle.ALG_RC)[0, 0]
+        assert rc == g["ref_f64"][i] or (np.isnan(rc) and np.isnan(g["ref_f64"][i])), name
+        assert abs(oracle.iou2dr_truth(a, b)[0, 0] - g["truth"][i]) < 1e-15, name
+    expect = dict(D1=1 / 3, D4=1 / 7, D5=1 / 3, D8=0.0, D9=0.0, D10=1.0, D11=1 / 16, D12=0.0, D13=0.0)
+    for i, name in enumerate(g["names"]):
+        if str(name) in expect:
+            assert abs(g["truth"][i] - expect[str(name)]) < 1e-12, name
+
+
+# ------------------------------------------------------------------ NMS
+def test_nms_known_answer_and_fixtures(oracle):
+    g = golden("nms.npz")
+    for m in ("box", "rbox"):
+        k = oracle.box2d_nms(g["test_boxes"], g["test_scores"], m)
+        assert np.array_equal(k, g["test_expected"])
+        assert np.array_equal(k, g[f"test_ref_{m}"])
+    A, B, s = g["c1_boxes"], g["c1_boxes_b"], g["c1_scores"]
+    k = oracle.box2d_nms(A, s, "rbox", iou_threshold=0.5)
+    assert k.sum() == 673 and np.array_equal(k, _unpack(g["c1_keep_rbox"], 1000))
+    assert np.array_equal(oracle.box2d_nms(B, s, "rbox", iou_threshold=0.5), _unpack(g["c1_keep_rbox_b"], 1000))
+    assert np.array_equal(oracle.box2d_nms(A, s, "box", iou_threshold=0.5), _unpack(g["c1_keep_box"], 1000))
+    assert np.array_equal(oracle.box2d_nms(A, s, "rbox", iou_threshold=0.3, score_threshold=0.2),
+                          _unpack(g["c1_keep_rbox_thr03_s02"], 1000))
+    P, ps = g["prop_boxes"], g["prop_scores"]
+    assert np.array_equal(oracle.box2d_nms(P, ps, "rbox", iou_threshold=0.5), _unpack(g["prop_keep_rbox"], len(P)))
+    assert np.array_equal(oracle.box2d_nms(P, ps, "box", iou_threshold=0.5), _unpack(g["prop_keep_box"], len(P)))
+    # the truth clip gives the same fp64 decisions as RC on generic clustered proposals
+    assert np.array_equal(oracle.box2d_nms(P, ps, "rbox", iou_threshold=0.5, alg=oracle.ALG_TRUTH),
+                          _unpack(g["prop_keep_rbox"], len(P)))
+
+
+def test_nms_soft_smoke(oracle):
+    """test/test_box.py:157-189: without a score threshold soft-NMS keeps everything."""
+    boxes = np.array([[1, 1, 2, 2, 0], [2, 2, 2, 2, 0.01], [3, 3, 2, 2, 0.02], [3, 1, 1, 1, 0.03], [4, 2, 1, 1, 0.04],
+                      [5, 3, 1, 1, 0.05]], np.float32)
+    scores = np.array([0.5, 0.3, 0.4, 0.4, 0.2, 0.1], np.float32)
+    for m in ("box", "rbox"):
+        for s, p in (("linear", 1.0), ("gaussian", 0.5)):
+            assert oracle.box2d_nms(boxes, scores, m, s, supression_param=p).all()
+
+
+# ------------------------------------------------------------------ voxelization
+def test_voxel_spconv_golden(oracle):
+    """test/test_voxel.py:80-88 + test/voxel_data.npz (spconv VoxelGeneratorV2 output)."""
+    d = golden("voxel_spconv.npz")
+    r = oracle.VoxelGenerator([0, 1, 0, 1, 0, 1], [10, 10, 10], max_points=5, max_points_filter="trim", dense=True)(d["cloud"])
+    assert np.array_equal(r["voxels"], d["voxels"])
+    assert np.array_equal(r["coords"], d["coords"])
+
+
+def test_voxel_fixtures(oracle):
+    g = golden("voxel_c2small.npz")
+    pts = g["points"]
+    cases = {
+        "sp_default": dict(), "sp_trim5": dict(max_points=5, max_points_filter="trim"),
+        "sp_trim2_v1000": dict(max_points=2, max_points_filter="trim", max_voxels=1000, max_voxels_filter="trim"),
+        "sp_min2": dict(min_points=2, max_points=3, max_points_filter="trim"),
+        "de_p5": dict(dense=True, max_points=5, max_voxels=20000), "de_p2_v1000": dict(dense=True, max_points=2, max_voxels=1000),
+        "de_mean": dict(dense=True, max_points=3, max_voxels=20000, reduction="mean"),
+        "de_max": dict(dense=True, max_points=3, max_voxels=20000, reduction="max"),
+        "de_min": dict(dense=True, max_points=3, max_voxels=700, reduction="min"),
+    }
+    for name, kw in cases.items():
+        r = oracle.VoxelGenerator(g["bounds"], g["shape"], **kw)(pts)
+        _check_voxel(r, g, name, kw)
+    for name, kw in {"co_trim5": dict(max_points=5, max_points_filter="trim"),
+                     "co_de_mean": dict(dense=True, max_points=4, max_voxels=300, reduction="mean")}.items():
+        r = oracle.VoxelGenerator(g["coarse_bounds"], g["coarse_shape"], **kw)(pts)
+        _check_voxel(r, g, name, kw)
+
+
+def _check_voxel(r, g, name, kw):
+    for k, v in r.items():
+        if k == "points":
+            assert np.array_equal(v, g["points"][r["points_mask"]])
+            continue
+        exp = g[f"{name}.{k}"]
+        if k == "voxel_pmask":  # reference leaves false slots uninitialised: compare the set slots only
+            P = kw["max_points"]
+            exp = np.unpackbits(exp)[:v.size].reshape(v.shape).astype(bool)
+            sl = np.arange(P)[None, :] < np.minimum(r["voxel_npoints"], P)[:, None]
+            assert np.array_equal(v[sl], exp[sl]) and v[sl].all() and not v[~sl].any(), (name, k)
+        else:
+            assert v.dtype == exp.dtype and np.array_equal(v, exp), (name, k)
+
+
+def test_voxel_reference_properties(oracle):
+    """test/test_voxel.py:11-78 semantic pins."""
+    rng = np.random.default_rng(5)
+    cloud = rng.random((2000, 4)).astype(np.float32)
+    cloud = np.concatenate([cloud, np.array([[-1, -1, -1, -100], [-2, -2, -2, 100]], np.float32)])
+    d = oracle.VoxelGenerator([0, 1, 0, 1, 0, 1], [10, 10, 10], reduction="mean", max_points=5, max_voxels=20000,
+                              max_points_filter="trim", max_voxels_filter="trim", dense=True)(cloud)
+    for i in range(len(d["voxels"])):
+        for j in range(min(d["voxel_npoints"][i], 5)):
+            assert (d["coords"][i] == (d["voxels"][i, j, :3] * np.float32(10)).astype(int)).all()
+    s = oracle.VoxelGenerator([0, 1, 0, 1, 0, 1], [10, 10, 10])(cloud)
+    assert len(s["points"]) == 2000 and len(s["coords"]) <= 1000
+    assert (s["coords"][s["points_mapping"]] == (cloud[s["points_mask"], :3] * np.float32(10)).astype(int)).all()
+    c3 = ((rng.random((2000, 3)) - 0.5) * 4).astype(np.float32)
+    assert len(oracle.VoxelGenerator([0, 1, 0, 1, 0, 1], [10, 10, 10], max_voxels=10, max_voxels_filter="trim")(c3)["coords"]) <= 10
+    assert len(oracle.VoxelGenerator([0, 1, 0, 1, 0, 1], [10, 10, 10], max_voxels=10, max_voxels_filter="descending")(c3)["coords"]) <= 10
+    n = oracle.VoxelGenerator([-2, 2, -2, 2, -2, 2], [4, 4, 4], min_points=2, max_points=4, max_points_filter="trim")(c3)["voxel_npoints"]
+    assert ((n >= 2) & (n <= 4)).all()
+
+
+# ------------------------------------------------------------------ aligned scatter
+def test_scatter_fixtures(oracle):
+    g = golden("scatter.npz")
+    for tag in ("f32", "f64"):
+        for dim in (1, 2, 3):
+            img, crd = g[f"{tag}.d{dim}.image"], g[f"{tag}.d{dim}.coord"]
+            assert np.array_equal(oracle.scatter_forward(crd, img, 1), g[f"{tag}.d{dim}.mean"])
+            assert np.array_equal(oracle.scatter_forward(crd, img, 2), g[f"{tag}.d{dim}.linear"])
+
+
+def test_scatter_reference_known_answers(oracle):
+    """test/test_point.py:10-69 (forward formulas and backward gradients)."""
+    rng = np.random.default_rng(3)
+    coord = np.array([[0, .25, .25, .25], [0, 1.25, 1.25, 1.25], [1, 2.25, 2.25, 2.25]], np.float32)
+    img = rng.random((2, 10, 3, 3, 3)).astype(np.float32)
+    m = oracle.scatter_forward(coord, img, 1)
+    assert np.allclose(m[0], img[0, :, 0:2, 0:2, 0:2].reshape(10, -1).mean(1))
+    assert np.allclose(m[1], img[0, :, 1:3, 1:3, 1:3].reshape(10, -1).mean(1))
+    assert np.allclose(m[2], img[1, :, 2, 2, 2])
+    lin = oracle.scatter_forward(coord, img, 2)
+    w = np.array([.75, .25], np.float32)
+    w3 = w[:, None, None] * w[None, :, None] * w[None, None, :]
+    assert np.allclose(lin[0], (img[0, :, 0:2, 0:2, 0:2] * w3).reshape(10, -1).sum(1))
+    assert np.allclose(lin[2], img[1, :, 2, 2, 2])
+    ones = np.ones((3, 10), np.float32)
+    gm = oracle.scatter_backward(coord, ones, 1, img.shape)
+    assert np.allclose(gm[0, :, 0, 0, 0], 1 / 8) and np.allclose(gm[0, :, 1, 1, 1], 1 / 4) and np.allclose(gm[1, :, 2, 2, 2], 1)
+    gl = oracle.scatter_backward(coord, ones, 2, img.shape)
+    assert np.allclose(gl[0, :, 0, 0, 0], .75 ** 3) and np.allclose(gl[0, :, 1, 1, 1], .75 ** 3 + .25 ** 3)
+    assert np.allclose(gl[1, :, 2, 2, 2], 1)
+    # integral-coordinate quirk: LINEAR doubles per integral in-range dim
+    img2 = np.zeros((1, 1, 3, 3), np.float32); img2[0, 0, 1, 1] = 4.0; img2[0, 0, 2, 1] = 7.0
+    assert oracle.scatter_forward(np.array([[0, 1.0, 1.0]], np.float32), img2, 2)[0, 0] == 16.0
+    assert oracle.scatter_forward(np.array([[0, 1.5, 1.0]], np.float32), img2, 2)[0, 0] == 11.0
+    assert oracle.scatter_forward(np.array([[0, 1.0, 1.0]], np.float32), img2, 1)[0, 0] == 4.0
+
+
+# ------------------------------------------------------------------ live reference (authoring container only)
+def test_oracle_vs_live_reference(oracle):
+    from oracle import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    rng = np.random.default_rng(11)
+    A, B = gen_boxes(rng, 300), gen_boxes(rng, 200)
+    assert np.array_equal(oracle.iou2dr(A, B), R.box2d_iou(A, B, "rbox"))
+    assert np.array_equal(oracle.iou2d(A, B), R.box2d_iou(A, B, "box"))
+    s = rng.random(300)
+    assert np.array_equal(oracle.box2d_nms(A, s, "rbox", iou_threshold=0.4, score_threshold=0.1),
+                          R.box2d_nms(A, s, "rbox", iou_threshold=0.4, score_threshold=0.1))
+    pts = lidar(rng, 4000)
+    kw = dict(max_points=3, max_points_filter="trim", max_voxels=900, max_voxels_filter="trim")
+    a = oracle.VoxelGenerator([0, 70.4, -40, 40, -3, 1], [352, 400, 40], **kw)(pts)
+    b = R.VoxelGenerator([0, 70.4, -40, 40, -3, 1], [352, 400, 40], **kw)(pts)
+    for k in b:
+        assert np.array_equal(a[k], b[k]), k
