@@ -1,0 +1,490 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the d3d hot path on B200 next to the reference's CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--op all|voxel|iou|nms] [--impl reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W      (N > 1)
+
+One JSON line on rank 0.  BASELINE.json's metric is a triple (rotated-IoU pairs/s, NMS boxes/s, voxelized
+points/s); the top-level `metric`/`value` of the line is voxelized points/s on config C2 (configs[1]: the
+configuration the tier names for N=1, HBM-bound like the `roofline` contract expects) and the other two
+operators are reported with the same keys under `ops` (`ops.iou`: config C4 100k x 100k fp32,
+`ops.nms`: config C3 50k proposals fp64).  `--op iou|nms` makes that operator the top-level line.
+
+  value     device-resident inputs, CUDA-event timed, K steps after W warm-ups, max over ranks
+  e2e       same metric through the public Python API with HOST tensors (H2D of the inputs and D2H of the
+            results inside the timed region)
+  roofline  algorithmic bytes (voxel: 16N + 32K + 28V' per frame) or flops (IoU: 230 per
+            candidate pair + 8 per rejected pair) over the CUDA-event time, against the measured peak
+  cpu_baseline  the reference's own CPU extension (oracle/_ref, kind "reference") or the C oracle ("port")
+            on this box's host cores, bounded sample, rank 0 at N=1 only
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+C2_BOUNDS, C2_SHAPE = [0, 70.4, -40, 40, -3, 1], [1408, 1600, 40]
+C2_KW = dict(max_points=5, max_points_filter="trim")
+C2_POINTS = 120_000
+W_CAND, W_REJ = 230.0, 8.0   # algorithmic FP ops per candidate / rejected pair
+
+
+# ------------------------------------------------------------------ synthetic inputs
+def lidar(seed, n=C2_POINTS):
+    rng = np.random.default_rng(seed)
+    rho = 80 * rng.random(n) ** 2
+    th = (rng.random(n) - .5) * 3.6
+    z = rng.normal(-1.2, 0.6, n)
+    inten = rng.random(n)
+    return np.stack([rho * np.cos(th), rho * np.sin(th), z, inten], 1).astype(np.float32)
+
+
+def gen_boxes(rng, n):
+    return np.stack([(rng.random(n) - .5) * 10, (rng.random(n) - .5) * 10, rng.random(n) * 5, rng.random(n) * 5,
+                     (rng.random(n) - .5) * 10], 1)
+
+
+def proposals(seed, n=50_000, n_obj=2000, extent=75.0):
+    rng = np.random.default_rng(seed)
+    ctr = (rng.random((n_obj, 2)) - .5) * 2 * extent
+    hd = (rng.random(n_obj) - .5) * 2 * np.pi
+    k = rng.integers(0, n_obj, n)
+    xy = ctr[k] + rng.normal(0, 0.3, (n, 2))
+    wh = np.array([4.5, 2.0]) + rng.normal(0, 1, (n, 2)) * np.array([.2, .1])
+    r = hd[k] + rng.normal(0, 0.05, n)
+    scores = rng.permutation(n).astype(np.float64) / n + rng.random(n) * 0.1 / n
+    return np.concatenate([xy, wh, r[:, None]], 1), scores
+
+
+# ------------------------------------------------------------------ CPU baseline (reference extension or C oracle)
+def _cpu_kind():
+    try:
+        from oracle import ref as R
+        if R.available():
+            R._voxel(); R._box()
+            return "reference"
+    except Exception:
+        pass
+    return "port"
+
+
+def _cpu_voxel_frame(seed):
+    import torch
+    torch.set_num_threads(1)
+    pts = lidar(seed)
+    kind = _CPU_KIND
+    t0 = time.perf_counter()
+    if kind == "reference":
+        from oracle import ref as R
+        R.VoxelGenerator(C2_BOUNDS, C2_SHAPE, **C2_KW)(pts)
+    else:
+        from oracle import oracle as O
+        O.VoxelGenerator(C2_BOUNDS, C2_SHAPE, **C2_KW)(pts)
+    return time.perf_counter() - t0
+
+
+def _cpu_iou_block(args):
+    import torch
+    torch.set_num_threads(1)
+    seed, lo, hi = args
+    rng = np.random.default_rng(seed)
+    A, B = gen_boxes(rng, hi).astype(np.float32)[lo:hi], gen_boxes(rng, 4000).astype(np.float32)
+    t0 = time.perf_counter()
+    if _CPU_KIND == "reference":
+        from oracle import ref as R
+        R.box2d_iou(A, B, "rbox", precise=False)
+    else:
+        from oracle import oracle as O
+        O.iou2dr(A, B)
+    return time.perf_counter() - t0, (hi - lo) * 4000
+
+
+def _cpu_nms(n):
+    import torch
+    torch.set_num_threads(1)
+    P, s = proposals(2, n, max(1, n // 25))
+    t0 = time.perf_counter()
+    if _CPU_KIND == "reference":
+        from oracle import ref as R
+        R.box2d_nms(P, s, "rbox", iou_threshold=0.5)
+    else:
+        from oracle import oracle as O
+        O.box2d_nms(P, s, "rbox", iou_threshold=0.5)
+    return time.perf_counter() - t0
+
+
+_CPU_KIND = "port"
+
+
+def cpu_pool(fn, items, cores):
+    """fork-based pool (must run before CUDA is initialised in this process)"""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(fn, items)
+        wall = time.perf_counter() - t0
+    return res, wall
+
+
+def cpu_baseline(op, cores, rounds=1):
+    """Aggregate throughput of the reference CPU path with one unit of work per host core."""
+    global _CPU_KIND
+    _CPU_KIND = _cpu_kind()
+    if op == "voxel":
+        res, wall = cpu_pool(_cpu_voxel_frame, [1000 + i for i in range(cores * rounds)], cores)
+        return dict(value=cores * rounds * C2_POINTS / wall, unit="points/s", cores=cores, kind=_CPU_KIND,
+                    sample=f"{cores * rounds} C2 frames of {C2_POINTS} points, one frame per process on {cores} cores "
+                           f"(single-frame latency {np.median(res) * 1e3:.0f} ms)")
+    if op == "iou":
+        rows = 256
+        res, wall = cpu_pool(_cpu_iou_block, [(3, i * rows, (i + 1) * rows) for i in range(cores * rounds)], cores)
+        pairs = sum(r[1] for r in res)
+        return dict(value=pairs / wall, unit="pairs/s", cores=cores, kind=_CPU_KIND,
+                    sample=f"{cores * rounds} row-blocks of {rows} x 4000 fp32 boxes (C4 distribution), one block per process")
+    if op == "nms":
+        n = 5000
+        res, wall = cpu_pool(_cpu_nms, [n] * cores, cores)
+        return dict(value=cores * n / wall, unit="boxes/s", cores=cores, kind=_CPU_KIND,
+                    sample=f"{cores} frames of {n} clustered proposals (C3 generator; the quadratic reference needs ~25 s for "
+                           f"one 50k frame), one frame per process; single-frame latency {np.median(res) * 1e3:.0f} ms")
+    raise ValueError(op)
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        busy = [x for x in sm if x > 0.6 * mx] or sm
+        return dict(sm_mhz=float(np.median(busy)) if busy else None, sm_max_mhz=mx or None, reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------ GPU timing helpers
+def timed(fn, steps, warmup, barrier):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    return e0.elapsed_time(e1) / steps   # ms per step
+
+
+def max_over_ranks(x, world):
+    import torch
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x, world):
+    import torch
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def fma_peak(dtype_code):
+    """measured CUDA-core FMA peak in TFLOP/s (FMA = 2 flops) with the library's probe kernel"""
+    import ctypes as C
+    import torch
+    from d3d_b200 import _cabi as c
+    sink = torch.zeros(4, device="cuda")
+    fl = C.c_double(0)
+    iters = 1 << 15 if dtype_code == 0 else 1 << 14
+    best = 0.0
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        c.check(c.fma_peak_probe(dtype_code, iters, c.ptr(sink), C.byref(fl), c.stream_ptr()), "fma probe")
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, fl.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
+# ------------------------------------------------------------------ operators
+def bench_voxel(args, rank, world, barrier):
+    import torch
+    from d3d_b200 import _cabi as c
+    from d3d_b200.voxel import VoxelGenerator
+    F = args.frames
+    frames = [lidar(100 + rank * F + i) for i in range(F)]      # weak scaling: every rank owns F distinct frames
+    host = [torch.from_numpy(f).pin_memory() for f in frames]
+    offs = torch.zeros(F + 1, dtype=torch.int64)
+    offs[1:] = torch.tensor([len(f) for f in frames]).cumsum(0)
+    dev_pts = torch.cat([h.cuda() for h in host], 0)
+    gen = VoxelGenerator(C2_BOUNDS, C2_SHAPE, **C2_KW)
+    res = gen.batch_packed(dev_pts, offs)
+    K = sum(int(r.points.shape[0]) for r in res)
+    V = sum(int(r.coords.shape[0]) for r in res)
+    N = int(dev_pts.shape[0])
+    alg_bytes = 16.0 * N + 32.0 * K + 28.0 * V
+    del res
+    l0 = c.launch_count()
+    with ClockSampler(torch.cuda.current_device()) as cs:
+        ms = timed(lambda: gen.batch_packed(dev_pts, offs), args.steps, args.warmup, barrier)
+    launches = (c.launch_count() - l0) // (args.steps + args.warmup) * args.steps
+    ms = max_over_ranks(ms, world)
+    e2e_steps = max(2, min(args.steps, 4))
+    ms_e2e = max_over_ranks(timed(lambda: gen.batch(host), e2e_steps, 1, barrier), world)
+    hbm, how = peaks()
+    ach = alg_bytes / (ms * 1e-3) / 1e9
+    return dict(metric="voxelized points/sec", unit="points/s", value=N * world / (ms * 1e-3), ms_per_step=ms, dtype="f32",
+                scaling="weak", gpu_launches=int(launches),
+                config=dict(workload=f"C2 KITTI-shaped voxelization: {F} frames/GPU x {C2_POINTS} pts/frame, voxel 0.05x0.05x0.1 m "
+                                     f"(grid 1408x1600x40), max 5 pts/voxel (trim), sparse VoxelGenerator path",
+                            frames_per_gpu=F, points_per_frame=C2_POINTS, kept_points=K, voxels=V,
+                            l2_policy=f"inputs larger than L2 ({N * 16 / 1e6:.0f} MB of points per step vs 126 MB L2)"),
+                e2e=dict(value=N * world / (ms_e2e * 1e-3), unit="points/s", h2d_bytes_per_step=int(N * 16 + offs.numel() * 8),
+                         d2h_bytes_per_step=int(32 * K + 28 * V + F * 16), ms_per_step=ms_e2e,
+                         api="VoxelGenerator.batch(list of pinned host tensors) -> host tensors"),
+                roofline=dict(bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm, traffic=None, peak_source=how,
+                              kernel="whole voxelize_sparse pass (all kernels of one step); algorithmic bytes 16N+32K+28V'",
+                              algorithmic_bytes_per_step=alg_bytes),
+                clocks=cs.summary())
+
+
+def bench_iou(args, rank, world, barrier):
+    import torch
+    from d3d_b200 import _cabi as c
+    from d3d_b200.box import box2d_iou, _pairwise
+    from d3d_b200.parallel import row_block
+    n = m = args.iou_n
+    rng = np.random.default_rng(3)
+    A, B = gen_boxes(rng, n).astype(np.float32), gen_boxes(rng, m).astype(np.float32)
+    lo, hi = row_block(n, rank, world)                 # strong scaling: row-blocks of the same N x M matrix
+    tA, tB = torch.from_numpy(A[lo:hi]).cuda(), torch.from_numpy(B).cuda()
+    out = torch.empty((hi - lo, m), dtype=torch.float32, device="cuda")
+    # candidate pairs of this rank's slab (roofline accounting only, outside the timed region)
+    cnt = torch.zeros(64, dtype=torch.int64, device="cuda")
+    ws = c.workspace(c.iou_workspace_bytes(hi - lo, m, 0), tA.device)
+    c.check(c.iou_count_candidates(c.ptr(tA), hi - lo, c.ptr(tB), m, 0, c.ptr(cnt), c.ptr(ws), ws.numel(), c.stream_ptr()), "count")
+    ncand = float(cnt.sum().item())
+    pairs = float(hi - lo) * m
+    l0 = c.launch_count()
+    with ClockSampler(torch.cuda.current_device()) as cs:
+        ms = timed(lambda: _pairwise(tA, tB, c.iou2dr, out), args.steps, args.warmup, barrier)
+    launches = (c.launch_count() - l0) // (args.steps + args.warmup) * args.steps
+    ms = max_over_ranks(ms, world)
+    tot_pairs, tot_cand = sum_over_ranks(pairs, world), sum_over_ranks(ncand, world)
+    peak32 = fma_peak(0)
+    flops = tot_cand * W_CAND + (tot_pairs - tot_cand) * W_REJ
+    ach = flops / (ms * 1e-3) / 1e12 / world
+    # e2e: host boxes in, a row-block slab of the matrix back on the host
+    er = min(hi - lo, args.iou_e2e_rows)
+    hA, hB = torch.from_numpy(A[lo:lo + er]).pin_memory(), torch.from_numpy(B).pin_memory()
+    hout = torch.empty((er, m), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        r = box2d_iou(hA.cuda(non_blocking=True), hB.cuda(non_blocking=True), "rbox", precise=False)
+        hout.copy_(r, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    ms_e2e = max_over_ranks(timed(e2e_step, 3, 1, barrier), world)
+    hbm, _ = peaks()
+    return dict(metric="rotated-IoU pairs/sec", unit="pairs/s", value=tot_pairs / (ms * 1e-3), ms_per_step=ms, dtype="f32", scaling="strong",
+                gpu_launches=int(launches),
+                config=dict(workload=f"C4 detection-eval rotated IoU {n}x{m} fp32 (precise=False), dense-overlap C1 distribution, "
+                                     f"row-block sharded over {world} GPU(s)", candidate_fraction=tot_cand / tot_pairs,
+                            l2_policy=f"output slab {pairs * 4 / 1e9:.1f} GB per GPU streams through HBM, far larger than L2"),
+                e2e=dict(value=er * m * world / (ms_e2e * 1e-3), unit="pairs/s", h2d_bytes_per_step=int((er + m) * 20),
+                         d2h_bytes_per_step=int(er * m * 4), ms_per_step=ms_e2e,
+                         api=f"box2d_iou(pinned host boxes [{er},5],[{m},5]) -> host [{er},{m}] slab"),
+                roofline=dict(bound="fp32_alu", achieved=ach, peak=peak32, unit="TFLOP/s", frac=ach / peak32, traffic=None,
+                              peak_source="measured with d3d_fma_peak_probe (8 FMA chains/thread, 2048 threads/SM) in this run",
+                              peak_nominal_tflops=148 * 128 * 2 * 1.965e9 / 1e12,
+                              algorithmic_flops=f"{W_CAND:.0f} per candidate pair + {W_REJ:.0f} per rejected pair (SURVEY.md 8(d))",
+                              store_gbs=tot_pairs * 4 / (ms * 1e-3) / 1e9 / world, store_frac_of_hbm=tot_pairs * 4 / (ms * 1e-3) / 1e9 / world / hbm),
+                clocks=cs.summary())
+
+
+def bench_nms(args, rank, world, barrier):
+    import torch
+    from d3d_b200 import _cabi as c
+    from d3d_b200.box import box2d_nms
+    n = args.nms_n
+    P, s = proposals(2 + rank, n)                      # weak scaling: one C3 frame per rank per step
+    tP, ts = torch.from_numpy(P).cuda(), torch.from_numpy(s).cuda()
+    keep = box2d_nms(tP, ts, "rbox", iou_threshold=0.5)
+    kept = int(keep.sum().item())
+    l0 = c.launch_count()
+    with ClockSampler(torch.cuda.current_device()) as cs:
+        ms = timed(lambda: box2d_nms(tP, ts, "rbox", iou_threshold=0.5), args.steps, args.warmup, barrier)
+    launches = (c.launch_count() - l0) // (args.steps + args.warmup) * args.steps
+    ms = max_over_ranks(ms, world)
+    hP, hs = torch.from_numpy(P).pin_memory(), torch.from_numpy(s).pin_memory()
+    ms_e2e = max_over_ranks(timed(lambda: box2d_nms(hP, hs, "rbox", iou_threshold=0.5), 3, 1, barrier), world)
+    peak64 = fma_peak(1)
+    return dict(metric="NMS boxes/sec", unit="boxes/s", value=n * world / (ms * 1e-3), ms_per_step=ms, dtype="f64", scaling="weak",
+                gpu_launches=int(launches),
+                config=dict(workload=f"C3 BEV rotated NMS: {n} clustered proposals/frame (2000 objects), rbox thr 0.5, precise=True (fp64), "
+                                     f"one frame per GPU per step", kept=kept, l2_policy="suppression mask 313 MB per step, larger than L2"),
+                e2e=dict(value=n * world / (ms_e2e * 1e-3), unit="boxes/s", h2d_bytes_per_step=int(n * 48), d2h_bytes_per_step=int(n),
+                         ms_per_step=ms_e2e, api="box2d_nms(pinned host boxes, scores) -> host keep mask"),
+                roofline=dict(bound="fp64_alu", achieved=None, peak=peak64, unit="TFLOP/s", frac=None, traffic=None,
+                              note="mask phase is reject-test bound (N^2/2 bounding-circle tests), resolve phase latency bound; see profiles/"),
+                clocks=cs.summary())
+
+
+# ------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    op = "voxel" if args.op == "all" else args.op
+    vals = []
+    for _ in range(args.warmup + args.steps):
+        vals.append(cpu_baseline(op, cores))
+    vals = vals[args.warmup:] or vals
+    v = float(np.median([x["value"] for x in vals]))
+    cb = dict(vals[-1]); cb["value"] = v
+    metric = {"voxel": "voxelized points/sec", "iou": "rotated-IoU pairs/sec", "nms": "NMS boxes/sec"}[op]
+    unit = cb["unit"]
+    line = dict(impl="reference", metric=metric, value=v, unit=unit, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=None, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype={"voxel": "f32", "iou": "f32", "nms": "f64"}[op], data="synthetic",
+                config=dict(workload={"voxel": "C2 KITTI-shaped voxelization 120k pts/frame, 0.05x0.05x0.1 m voxels, max 5 pts/voxel (reference CPU path)",
+                                      "iou": "C4 rotated IoU fp32, C1 distribution (reference CPU path, row-block sample)",
+                                      "nms": "C3-style rotated NMS fp64, 5000-proposal frames (reference CPU path)"}[op]),
+                cpu_baseline=cb, e2e=dict(value=v, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--op", default="all", choices=["all", "voxel", "iou", "nms"])
+    ap.add_argument("--frames", type=int, default=128, help="C2 frames per GPU per voxelization step")
+    ap.add_argument("--iou-n", type=int, default=100_000)
+    ap.add_argument("--iou-e2e-rows", type=int, default=8192)
+    ap.add_argument("--nms-n", type=int, default=50_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    ops = ["voxel", "iou", "nms"] if args.op == "all" else [args.op]
+
+    # CPU baseline first: the fork-based pool must run before this process touches CUDA
+    cpu = {}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        for op in ops:
+            try:
+                cpu[op] = cpu_baseline(op, cores)
+            except Exception as e:   # the baseline is reported, never required
+                cpu[op] = dict(value=None, unit=None, cores=cores, kind="unavailable", sample=str(e))
+
+    import torch
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        barrier = lambda: dist.barrier()
+    else:
+        barrier = lambda: None
+    import d3d_b200  # noqa: F401  (raises if the CUDA extension is missing: no fallback)
+
+    fns = dict(voxel=bench_voxel, iou=bench_iou, nms=bench_nms)
+    res = {}
+    for op in ops:
+        res[op] = fns[op](args, rank, world, barrier)
+        if op in cpu:
+            res[op]["cpu_baseline"] = cpu[op]
+        torch.cuda.empty_cache()
+    if world > 1:
+        # the only collective of the pipeline: small per-rank results are gathered at the end (outside the timed regions)
+        from d3d_b200.parallel import gather_ragged
+        gather_ragged(torch.tensor([res[ops[0]]["ms_per_step"]], device="cuda"))
+        dist.barrier()
+    if rank == 0:
+        top = dict(res[ops[0]])
+        line = dict(metric=top.pop("metric"), value=top.pop("value"), unit=top.pop("unit"), n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=top.pop("ms_per_step"), higher_is_better=True, scaling=top.pop("scaling"), vs_baseline=None,
+                    dtype=top.pop("dtype"), data="synthetic (seeded generators of SURVEY.md 8(d))")
+        line.update(top)
+        line.setdefault("cpu_baseline", None)
+        if len(ops) > 1:
+            line["ops"] = {op: res[op] for op in ops[1:]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,279 @@
+// iou.cu -- pairwise N x M IoU of rotated boxes (method "rbox") and of their AABBs (method "box").
+//
+// Replaces reference iou2dr_forward[_cuda] / iou2d_forward[_cuda] (d3d/box/iou.cpp:11-141,
+// d3d/box/iou_cuda.cu:9-151).  Design (B200, sm_100a):
+//   * a prep kernel turns every box into a 32-byte record once (1 sincos per box instead of 4 per pair);
+//   * one CTA owns a TR x TC tile of the output.  The records of its TR rows and TC columns are staged
+//     in shared memory; the output tile itself lives in shared memory and is streamed to HBM with
+//     full-line 16-byte stores (the reference stores 4-byte values column-major, iou_cuda.cu:110-111);
+//   * candidate compaction: each warp scans its 8 rows x TC columns with a 7-instruction
+//     bounding-circle test, pushes the survivors into a per-warp shared-memory queue
+//     (ballot + popc), and whenever 32 survivors are queued runs the ~150-instruction branch-free clip
+//     (geom.cuh) on a FULL warp.  Divergence is gone: with 1/3 of the pairs being candidates a naive
+//     thread-per-pair kernel would run the clip at ~1/3 lane utilisation;
+//   * 64-bit indexing throughout: 100k x 100k (1e10 pairs) does not fit the reference's int pair index
+//     (iou_cuda.cu:16,137).
+// Roofline: FP32/FP64 CUDA-core issue rate (not a contraction -> no tensor cores); HBM store-bound
+// when fewer than ~1 pair in 6 is a candidate.
+#include "geom.cuh"
+
+namespace d3d {
+
+// ------------------------------------------------------------------ prep
+template <typename T>
+__global__ void __launch_bounds__(256) box_prep_kernel(const T *__restrict__ boxes, int64_t n, int64_t npad, BoxRec<T> *__restrict__ recs)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npad) return;
+    BoxRec<T> r;
+    if (i < n) {
+        const T *b = boxes + 5 * i;
+        r = make_box_rec<T>(b[0], b[1], b[2], b[3], b[4]);
+    } else {
+        r.cx = r.cy = r.c = r.s = r.hw = r.hh = r.area = T(0);
+        r.rho = T(NAN);  // padding: fails every candidate test
+    }
+    recs[i] = r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) aabb_prep_kernel(const T *__restrict__ boxes, int64_t n, AABBRec<T> *__restrict__ recs)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const T *b = boxes + 5 * i;
+    recs[i] = make_aabb_rec<T>(b[0], b[1], b[2], b[3], b[4]);
+}
+
+// ------------------------------------------------------------------ rotated IoU tile kernel
+template <typename T> struct IouTile;
+template <> struct IouTile<float>  { static constexpr int TR = 64, TC = 128; };
+template <> struct IouTile<double> { static constexpr int TR = 64, TC = 64; };
+
+constexpr int IOU_THREADS = 256;
+constexpr int IOU_WARPS = IOU_THREADS / 32;
+constexpr int IOU_QCAP = 256;  // per-warp ring of pending candidate pairs (uint16: row_local << 8 | col)
+
+template <typename T>
+__global__ void __launch_bounds__(IOU_THREADS, 3)
+iou2dr_tile_kernel(const BoxRec<T> *__restrict__ recA, int64_t n, const BoxRec<T> *__restrict__ recB, int64_t m,
+                   T *__restrict__ out, int64_t ld, int64_t tiles_c)
+{
+    constexpr int TR = IouTile<T>::TR, TC = IouTile<T>::TC;
+    constexpr int RW = TR / IOU_WARPS;   // rows per warp
+    constexpr int KC = TC / 32;          // column chunks per lane
+    constexpr int V = 16 / sizeof(T);    // elements per 16-byte vector
+    __shared__ BoxRec<T> sA[TR];
+    __shared__ BoxRec<T> sB[TC];
+    __shared__ __align__(16) T tile[TR][TC];
+    __shared__ uint16_t queue[IOU_WARPS][IOU_QCAP];
+
+    const int64_t tr = blockIdx.x / tiles_c, tc = blockIdx.x % tiles_c;   // column tiles fastest: A rows reused, B streams through L2
+    const int64_t row0 = tr * TR, col0 = tc * TC;
+    const unsigned lane = lane_id(), w = threadIdx.x >> 5;
+
+    {   // stage records (arrays are padded to tile multiples, so no bounds checks)
+        const float4 *ga = reinterpret_cast<const float4 *>(recA + row0);
+        const float4 *gb = reinterpret_cast<const float4 *>(recB + col0);
+        float4 *da = reinterpret_cast<float4 *>(sA), *db = reinterpret_cast<float4 *>(sB);
+        constexpr int NA = TR * sizeof(BoxRec<T>) / 16, NB = TC * sizeof(BoxRec<T>) / 16;
+        for (int i = threadIdx.x; i < NA; i += IOU_THREADS) da[i] = __ldg(ga + i);
+        for (int i = threadIdx.x; i < NB; i += IOU_THREADS) db[i] = __ldg(gb + i);
+    }
+    // zero this warp's rows of the output tile (rejected pairs are exactly +0)
+#pragma unroll
+    for (int r = 0; r < RW; r++)
+#pragma unroll
+        for (int k = 0; k < KC; k++) tile[w * RW + r][k * 32 + lane] = T(0);
+    __syncthreads();
+
+    T bx[KC], by[KC], br[KC];
+#pragma unroll
+    for (int k = 0; k < KC; k++) { bx[k] = sB[k * 32 + lane].cx; by[k] = sB[k * 32 + lane].cy; br[k] = sB[k * 32 + lane].rho; }
+
+    uint16_t *q = queue[w];
+    unsigned head = 0, tail = 0;   // warp-uniform ring indices
+#pragma unroll 1
+    for (int r = 0; r <= RW; r++) {
+        if (r < RW) {
+            const BoxRec<T> &a = sA[w * RW + r];
+            const T ax = a.cx, ay = a.cy, ar = a.rho;
+#pragma unroll
+            for (int k = 0; k < KC; k++) {
+                T dx = ax - bx[k], dy = ay - by[k], rs = ar + br[k];
+                bool cand = dx * dx + dy * dy <= rs * rs;           // false for NaN padding
+                unsigned bal = __ballot_sync(0xffffffffu, cand);
+                if (cand) q[(tail + __popc(bal & lanemask_lt())) & (IOU_QCAP - 1)] = (uint16_t)((r << 8) | (k * 32 + lane));
+                tail += __popc(bal);
+            }
+        }
+        // drain full warps; on the extra last iteration drain the remainder too
+        while (tail - head >= 32u || (r == RW && tail != head)) {
+            __syncwarp();
+            unsigned cnt = min(tail - head, 32u);
+            unsigned e = q[(head + min(lane, cnt - 1)) & (IOU_QCAP - 1)];
+            const unsigned row = w * RW + (e >> 8), col = e & 255u;
+            BoxRec<T> A = sA[row], B = sB[col];
+            T v = rbox_iou<T>(A, B);
+            if (lane < cnt) tile[row][col] = v;
+            head += cnt;
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+
+    // stream this warp's rows to HBM: 16-byte stores when the row pointers are 16-byte aligned
+    const bool vec_ok = (ld % V == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll 1
+    for (int r = 0; r < RW; r++) {
+        const int64_t row = row0 + w * RW + r;
+        if (row >= n) break;
+        T *orow = out + row * ld + col0;
+        const T *trow = tile[w * RW + r];
+        if (vec_ok && col0 + TC <= m) {
+            for (int c = lane * V; c < TC; c += 32 * V)
+                __stcs(reinterpret_cast<float4 *>(orow + c), *reinterpret_cast<const float4 *>(trow + c));
+        } else {
+            for (int c = lane; c < TC; c += 32)
+                if (col0 + c < m) orow[c] = trow[c];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ AABB IoU (method "box"): cheap, one thread per 4 columns
+template <typename T>
+__global__ void __launch_bounds__(256) iou2d_kernel(const AABBRec<T> *__restrict__ recA, int64_t n, const AABBRec<T> *__restrict__ recB, int64_t m,
+                                                    T *__restrict__ out, int64_t ld)
+{
+    const int64_t row = blockIdx.y;
+    const int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (row >= n || c0 >= m) return;
+    const AABBRec<T> a = recA[row];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (c0 + k < m) out[row * ld + c0 + k] = aabb_iou<T>(a, recB[c0 + k]);
+}
+
+// ------------------------------------------------------------------ candidate counter (measurement only; SURVEY.md 8(d) accounting)
+template <typename T>
+__global__ void __launch_bounds__(256) count_candidates_kernel(const BoxRec<T> *__restrict__ recA, int64_t n, const BoxRec<T> *__restrict__ recB, int64_t m,
+                                                               unsigned long long *__restrict__ counter)
+{
+    __shared__ unsigned long long bsum;
+    if (threadIdx.x == 0) bsum = 0;
+    __syncthreads();
+    const int64_t row = blockIdx.y;
+    unsigned long long c = 0;
+    if (row < n) {
+        const T ax = recA[row].cx, ay = recA[row].cy, ar = recA[row].rho;
+        for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (int64_t)gridDim.x * blockDim.x) {
+            T dx = ax - recB[j].cx, dy = ay - recB[j].cy, rs = ar + recB[j].rho;
+            c += (dx * dx + dy * dy <= rs * rs) ? 1 : 0;
+        }
+    }
+    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if (lane_id() == 0 && c) atomicAdd(&bsum, c);
+    __syncthreads();
+    if (threadIdx.x == 0 && bsum) atomicAdd(counter + (blockIdx.y & 63), bsum);
+}
+
+// ------------------------------------------------------------------ host side
+template <typename T> static size_t iou_ws_bytes(int64_t n, int64_t m)
+{
+    constexpr int TR = IouTile<T>::TR, TC = IouTile<T>::TC;
+    return 256 + align_up((size_t)cdiv(n > 0 ? n : 1, TR) * TR * sizeof(BoxRec<T>)) + align_up((size_t)cdiv(m > 0 ? m : 1, TC) * TC * sizeof(BoxRec<T>));
+}
+
+template <typename T>
+static int prep_boxes(const T *boxes, int64_t n, int tile, BoxRec<T> *recs, cudaStream_t st)
+{
+    int64_t npad = cdiv(n, tile) * tile;
+    box_prep_kernel<T><<<(unsigned)cdiv(npad, 256), 256, 0, st>>>(boxes, n, npad, recs); D3D_LAUNCHED();
+    return D3D_OK;
+}
+
+template <typename T>
+static int iou2dr_impl(const T *b1, int64_t n, const T *b2, int64_t m, T *out, int64_t ld, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    if (n < 0 || m < 0 || ld < m) return D3D_ERR_INVALID_ARGUMENT;
+    if (n == 0 || m == 0) return D3D_OK;
+    if (!b1 || !b2 || !out) return D3D_ERR_INVALID_ARGUMENT;
+    if (ws_bytes < iou_ws_bytes<T>(n, m) || !ws) return D3D_ERR_WORKSPACE;
+    constexpr int TR = IouTile<T>::TR, TC = IouTile<T>::TC;
+    Arena a(ws, ws_bytes);
+    a.take<char>(256);
+    int64_t tiles_r = cdiv(n, TR), tiles_c = cdiv(m, TC);
+    BoxRec<T> *ra = a.take<BoxRec<T>>(tiles_r * TR), *rb = a.take<BoxRec<T>>(tiles_c * TC);
+    int rc;
+    if ((rc = prep_boxes<T>(b1, n, TR, ra, st))) return rc;
+    if ((rc = prep_boxes<T>(b2, m, TC, rb, st))) return rc;
+    int64_t nblocks = tiles_r * tiles_c;
+    if (nblocks > 0x7fffffffll) return D3D_ERR_INVALID_ARGUMENT;
+    iou2dr_tile_kernel<T><<<(unsigned)nblocks, IOU_THREADS, 0, st>>>(ra, n, rb, m, out, ld, tiles_c); D3D_LAUNCHED();
+    return D3D_OK;
+}
+
+template <typename T>
+static int iou2d_impl(const T *b1, int64_t n, const T *b2, int64_t m, T *out, int64_t ld, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    if (n < 0 || m < 0 || ld < m) return D3D_ERR_INVALID_ARGUMENT;
+    if (n == 0 || m == 0) return D3D_OK;
+    if (!b1 || !b2 || !out) return D3D_ERR_INVALID_ARGUMENT;
+    if (ws_bytes < iou_ws_bytes<T>(n, m) || !ws) return D3D_ERR_WORKSPACE;
+    if (n > 65535ll * 65535ll) return D3D_ERR_INVALID_ARGUMENT;
+    Arena a(ws, ws_bytes);
+    a.take<char>(256);
+    AABBRec<T> *ra = a.take<AABBRec<T>>(n), *rb = a.take<AABBRec<T>>(m);
+    aabb_prep_kernel<T><<<(unsigned)cdiv(n, 256), 256, 0, st>>>(b1, n, ra); D3D_LAUNCHED();
+    aabb_prep_kernel<T><<<(unsigned)cdiv(m, 256), 256, 0, st>>>(b2, m, rb); D3D_LAUNCHED();
+    // rows on grid.y in slabs of 65535
+    for (int64_t r0 = 0; r0 < n; r0 += 65535) {
+        int64_t nr = n - r0 < 65535 ? n - r0 : 65535;
+        dim3 grid((unsigned)cdiv(m, 1024), (unsigned)nr);
+        iou2d_kernel<T><<<grid, 256, 0, st>>>(ra + r0, nr, rb, m, out + r0 * ld, ld); D3D_LAUNCHED();
+    }
+    return D3D_OK;
+}
+
+template <typename T>
+static int count_cand_impl(const T *b1, int64_t n, const T *b2, int64_t m, unsigned long long *counters64, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    if (n <= 0 || m <= 0) return D3D_ERR_INVALID_ARGUMENT;
+    if (ws_bytes < iou_ws_bytes<T>(n, m) || !ws) return D3D_ERR_WORKSPACE;
+    constexpr int TR = IouTile<T>::TR, TC = IouTile<T>::TC;
+    Arena a(ws, ws_bytes);
+    a.take<char>(256);
+    BoxRec<T> *ra = a.take<BoxRec<T>>(cdiv(n, TR) * TR), *rb = a.take<BoxRec<T>>(cdiv(m, TC) * TC);
+    int rc;
+    if ((rc = prep_boxes<T>(b1, n, TR, ra, st))) return rc;
+    if ((rc = prep_boxes<T>(b2, m, TC, rb, st))) return rc;
+    D3D_CUDA_TRY(cudaMemsetAsync(counters64, 0, 64 * sizeof(unsigned long long), st));
+    for (int64_t r0 = 0; r0 < n; r0 += 65535) {
+        int64_t nr = n - r0 < 65535 ? n - r0 : 65535;
+        dim3 grid((unsigned)(cdiv(m, 256) < 64 ? cdiv(m, 256) : 64), (unsigned)nr);
+        count_candidates_kernel<T><<<grid, 256, 0, st>>>(ra + r0, nr, rb, m, counters64); D3D_LAUNCHED();
+    }
+    return D3D_OK;
+}
+
+}  // namespace d3d
+
+using namespace d3d;
+
+extern "C" size_t d3d_iou_workspace_bytes(int64_t n, int64_t m, int dtype)
+{
+    return dtype == D3D_F64 ? iou_ws_bytes<double>(n, m) : iou_ws_bytes<float>(n, m);
+}
+extern "C" int d3d_iou2dr_f32(const float *b1, int64_t n, const float *b2, int64_t m, float *ious, int64_t ld, void *ws, size_t wsb, void *stream)
+{ return iou2dr_impl<float>(b1, n, b2, m, ious, ld, ws, wsb, (cudaStream_t)stream); }
+extern "C" int d3d_iou2dr_f64(const double *b1, int64_t n, const double *b2, int64_t m, double *ious, int64_t ld, void *ws, size_t wsb, void *stream)
+{ return iou2dr_impl<double>(b1, n, b2, m, ious, ld, ws, wsb, (cudaStream_t)stream); }
+extern "C" int d3d_iou2d_f32(const float *b1, int64_t n, const float *b2, int64_t m, float *ious, int64_t ld, void *ws, size_t wsb, void *stream)
+{ return iou2d_impl<float>(b1, n, b2, m, ious, ld, ws, wsb, (cudaStream_t)stream); }
+extern "C" int d3d_iou2d_f64(const double *b1, int64_t n, const double *b2, int64_t m, double *ious, int64_t ld, void *ws, size_t wsb, void *stream)
+{ return iou2d_impl<double>(b1, n, b2, m, ious, ld, ws, wsb, (cudaStream_t)stream); }
+extern "C" int d3d_iou_count_candidates(const void *b1, int64_t n, const void *b2, int64_t m, int dtype, uint64_t *counters64, void *ws, size_t wsb, void *stream)
+{
+    return dtype == D3D_F64 ? count_cand_impl<double>((const double *)b1, n, (const double *)b2, m, (unsigned long long *)counters64, ws, wsb, (cudaStream_t)stream)
+                            : count_cand_impl<float>((const float *)b1, n, (const float *)b2, m, (unsigned long long *)counters64, ws, wsb, (cudaStream_t)stream);
+}

@@ -1,0 +1,312 @@
+// nms.cu -- greedy hard NMS on rotated boxes (or their AABBs) with 64-bit suppression words.
+//
+// Replaces reference nms2d / nms2d_cuda (d3d/box/nms.cpp:9-119, d3d/box/nms_cuda.cu:16-244).
+// Pipeline, all asynchronous on the caller's stream (the reference syncs the device three times):
+//   1. keys: score -> order-preserving integer key (descending), our stable radix sort (prims.cu)
+//      => order[]; ties keep the lower original index first (the reference's torch.argsort leaves
+//      ties unspecified, nms.cpp:103).
+//   2. gather + prep: sorted box records (geom.cuh) and the score-threshold flag (score > thr, the
+//      reference CUDA rule nms_cuda.cu:223).
+//   3. mask: one CTA per 64x64 tile of the upper triangle of the sorted IoU matrix.  Same warp-queue
+//      compaction as the IoU kernel: cheap bounding-circle reject, survivors clipped by full warps,
+//      `iou > thr` sets bit (col) of the row's 64-bit word with a shared-memory atomicOr.
+//   4. resolve: one CTA walks the 64-box blocks in score order.  The 64x64 diagonal word block is
+//      resolved by a single thread with register bit-ops; the rows of the survivors are then OR-ed
+//      into the removal bitmap by all threads in parallel (coalesced, independent loads).  The
+//      reference does this whole phase in a <<<1,1>>> kernel (nms_cuda.cu:79-106,201).
+#include "geom.cuh"
+#include "prims.cuh"
+
+namespace d3d {
+
+template <typename T> struct KeyBits;
+template <> struct KeyBits<float>  { static constexpr int bits = 32; };
+template <> struct KeyBits<double> { static constexpr int bits = 64; };
+
+// descending-order key: larger score -> smaller key.  -0.0 and +0.0 compare equal in the reference
+// (float comparison), so both map to the key of +0.0.
+__device__ __forceinline__ uint64_t desc_key(float s)
+{
+    if (s == 0.0f) s = 0.0f;
+    uint32_t u = __float_as_uint(s);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // ascending order-preserving
+    return (uint64_t)(~u);
+}
+__device__ __forceinline__ uint64_t desc_key(double s)
+{
+    if (s == 0.0) s = 0.0;
+    uint64_t u = (uint64_t)__double_as_longlong(s);
+    u = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+    return ~u;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) nms_keys_kernel(const T *__restrict__ scores, int64_t n, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = desc_key(scores[i]);
+    vals[i] = (uint32_t)i;
+}
+
+constexpr int NMS_TILE = 64;
+
+// sorted position p -> record of box order[p]; padded to a multiple of 64 with NaN-rho records
+template <typename T, bool AABB>
+__global__ void __launch_bounds__(256) nms_gather_kernel(const T *__restrict__ boxes, const T *__restrict__ scores, const uint32_t *__restrict__ order,
+                                                         int64_t n, int64_t npad, float score_thr, BoxRec<T> *__restrict__ recs,
+                                                         AABBRec<T> *__restrict__ arecs, T *__restrict__ raw, uint8_t *__restrict__ valid)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npad) return;
+    if (p < n) {
+        const uint32_t i = order[p];
+        const T *b = boxes + 5 * (int64_t)i;
+        if (AABB) arecs[p] = make_aabb_rec<T>(b[0], b[1], b[2], b[3], b[4]);
+        else {
+            recs[p] = make_box_rec<T>(b[0], b[1], b[2], b[3], b[4]);
+            if (raw) { for (int k = 0; k < 5; k++) raw[5 * p + k] = b[k]; }
+        }
+        valid[p] = scores[i] > score_thr ? 1 : 0;   // T vs float, promoted to T (nms.cpp:26, nms_cuda.cu:223)
+    } else {
+        if (AABB) { AABBRec<T> a; a.minx = a.maxx = a.miny = a.maxy = T(NAN); arecs[p] = a; }
+        else { BoxRec<T> r; r.cx = r.cy = r.c = r.s = r.hw = r.hh = r.area = T(0); r.rho = T(NAN); recs[p] = r; }
+        valid[p] = 0;
+    }
+}
+
+constexpr int NMS_THREADS = 128;
+constexpr int NMS_WARPS = NMS_THREADS / 32;
+
+// fp32 decisions within this distance of the threshold are re-evaluated in fp64 from the raw boxes,
+// so that the float path reproduces the decisions of the double path
+#define NMS_F32_RECHECK 1e-3f
+
+template <typename T>
+__device__ __forceinline__ bool over_threshold(T v, T thr, const T *raw, unsigned gi, unsigned gj)
+{
+    (void)raw; (void)gi; (void)gj;
+    return v > thr;
+}
+template <>
+__device__ __forceinline__ bool over_threshold<float>(float v, float thr, const float *raw, unsigned gi, unsigned gj)
+{
+    if (raw && fabsf(v - thr) < NMS_F32_RECHECK) {
+        const float *a = raw + 5 * (int64_t)gi, *b = raw + 5 * (int64_t)gj;
+        BoxRec<double> A = make_box_rec<double>(a[0], a[1], a[2], a[3], a[4]);
+        BoxRec<double> B = make_box_rec<double>(b[0], b[1], b[2], b[3], b[4]);
+        return rbox_iou<double>(A, B) > (double)thr;
+    }
+    return v > thr;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NMS_THREADS)
+nms_mask_rbox_kernel(const BoxRec<T> *__restrict__ recs, const T *__restrict__ raw, int64_t n, int64_t nwords, T thr, uint64_t *__restrict__ mask)
+{
+    const int64_t rb = blockIdx.y, cb = blockIdx.x;
+    if (cb < rb) return;   // strictly upper triangle (plus the diagonal tile)
+    constexpr int RW = NMS_TILE / NMS_WARPS;  // 16 rows per warp
+    constexpr int KC = NMS_TILE / 32;         // 2 column chunks
+    __shared__ BoxRec<T> sA[NMS_TILE];
+    __shared__ BoxRec<T> sB[NMS_TILE];
+    __shared__ unsigned long long smask[NMS_TILE];
+    __shared__ uint16_t queue[NMS_WARPS][128];
+    const unsigned lane = lane_id(), w = threadIdx.x >> 5;
+    {
+        const float4 *ga = reinterpret_cast<const float4 *>(recs + rb * NMS_TILE);
+        const float4 *gb = reinterpret_cast<const float4 *>(recs + cb * NMS_TILE);
+        float4 *da = reinterpret_cast<float4 *>(sA), *db = reinterpret_cast<float4 *>(sB);
+        constexpr int NV = NMS_TILE * sizeof(BoxRec<T>) / 16;
+        for (int i = threadIdx.x; i < NV; i += NMS_THREADS) { da[i] = __ldg(ga + i); db[i] = __ldg(gb + i); }
+        if (threadIdx.x < NMS_TILE) smask[threadIdx.x] = 0ull;
+    }
+    __syncthreads();
+    T bx[KC], by[KC], br[KC];
+#pragma unroll
+    for (int k = 0; k < KC; k++) { bx[k] = sB[k * 32 + lane].cx; by[k] = sB[k * 32 + lane].cy; br[k] = sB[k * 32 + lane].rho; }
+    uint16_t *q = queue[w];
+    unsigned head = 0, tail = 0;
+    const bool diag = (rb == cb);
+#pragma unroll 1
+    for (int r = 0; r <= RW; r++) {
+        if (r < RW) {
+            const unsigned rl = w * RW + r;
+            const BoxRec<T> &a = sA[rl];
+            const T ax = a.cx, ay = a.cy, ar = a.rho;
+#pragma unroll
+            for (int k = 0; k < KC; k++) {
+                T dx = ax - bx[k], dy = ay - by[k], rs = ar + br[k];
+                bool cand = (dx * dx + dy * dy <= rs * rs) && (!diag || (unsigned)(k * 32 + lane) > rl);
+                unsigned bal = __ballot_sync(0xffffffffu, cand);
+                if (cand) q[(tail + __popc(bal & lanemask_lt())) & 127] = (uint16_t)((rl << 8) | (k * 32 + lane));
+                tail += __popc(bal);
+            }
+        }
+        while (tail - head >= 32u || (r == RW && tail != head)) {
+            __syncwarp();
+            unsigned cnt = min(tail - head, 32u);
+            unsigned e = q[(head + min(lane, cnt - 1)) & 127];
+            const unsigned row = e >> 8, col = e & 255u;
+            BoxRec<T> A = sA[row], B = sB[col];
+            T v = rbox_iou<T>(A, B);   // iou(higher score box, lower score box), nms.cpp:50
+            if (lane < cnt && over_threshold<T>(v, thr, raw, (unsigned)(rb * NMS_TILE + row), (unsigned)(cb * NMS_TILE + col)))
+                atomicOr(&smask[row], 1ull << col);
+            head += cnt;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < NMS_TILE) {
+        int64_t row = rb * NMS_TILE + threadIdx.x;
+        if (row < n) mask[row * nwords + cb] = smask[threadIdx.x];
+    }
+}
+
+// AABB variant: every pair is a handful of instructions, no queue needed
+template <typename T>
+__global__ void __launch_bounds__(NMS_TILE)
+nms_mask_aabb_kernel(const AABBRec<T> *__restrict__ recs, int64_t n, int64_t nwords, T thr, uint64_t *__restrict__ mask)
+{
+    const int64_t rb = blockIdx.y, cb = blockIdx.x;
+    if (cb < rb) return;
+    __shared__ AABBRec<T> sB[NMS_TILE];
+    sB[threadIdx.x] = recs[cb * NMS_TILE + threadIdx.x];
+    __syncthreads();
+    const int64_t row = rb * NMS_TILE + threadIdx.x;
+    if (row >= n) return;
+    const AABBRec<T> a = recs[row];
+    unsigned long long bits = 0;
+    const int start = (rb == cb) ? threadIdx.x + 1 : 0;
+    for (int c = start; c < NMS_TILE; c++) {
+        if (cb * NMS_TILE + c >= n) break;
+        if (aabb_iou<T>(a, sB[c]) > thr) bits |= 1ull << c;
+    }
+    mask[row * nwords + cb] = bits;
+}
+
+constexpr int RESOLVE_THREADS = 1024;
+
+__global__ void __launch_bounds__(RESOLVE_THREADS)
+nms_resolve_kernel(const uint64_t *__restrict__ mask, int64_t n, int64_t nwords, const uint8_t *__restrict__ valid,
+                   const uint32_t *__restrict__ order, uint8_t *__restrict__ suppressed)
+{
+    extern __shared__ unsigned long long remv[];   // [nwords] removal bitmap in sorted order
+    __shared__ unsigned long long diag[64];
+    __shared__ unsigned long long keptbits;
+    const int tid = threadIdx.x;
+    // boxes at or below the score threshold (and the padding past n) start out removed
+    for (int64_t w = tid; w < nwords; w += RESOLVE_THREADS) {
+        unsigned long long b = 0;
+        for (int t = 0; t < 64; t++) {
+            int64_t p = w * 64 + t;
+            if (p >= n || !valid[p]) b |= 1ull << t;
+        }
+        remv[w] = b;
+    }
+    __syncthreads();
+    for (int64_t blk = 0; blk < nwords; blk++) {
+        if (tid < 64) {
+            int64_t row = blk * 64 + tid;
+            diag[tid] = row < n ? mask[row * nwords + blk] : 0ull;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long cur = remv[blk], kept = 0;
+#pragma unroll 8
+            for (int t = 0; t < 64; t++) {
+                if (!((cur >> t) & 1ull)) { kept |= 1ull << t; cur |= diag[t]; }
+            }
+            keptbits = kept;
+        }
+        __syncthreads();
+        const unsigned long long kept = keptbits;
+        if (tid < 64) {
+            int64_t row = blk * 64 + tid;
+            if (row < n) suppressed[order[row]] = ((kept >> tid) & 1ull) ? 0 : 1;
+        }
+        if (kept) {
+            for (int64_t w = blk + 1 + tid; w < nwords; w += RESOLVE_THREADS) {
+                unsigned long long acc = remv[w], k = kept;
+                const uint64_t *col = mask + (blk * 64) * nwords + w;
+                while (k) {   // up to 4 independent row loads in flight
+                    int t0 = __ffsll((long long)k) - 1; k &= k - 1;
+                    unsigned long long v0 = col[(int64_t)t0 * nwords], v1 = 0, v2 = 0, v3 = 0;
+                    if (k) { int t1 = __ffsll((long long)k) - 1; k &= k - 1; v1 = col[(int64_t)t1 * nwords]; }
+                    if (k) { int t2 = __ffsll((long long)k) - 1; k &= k - 1; v2 = col[(int64_t)t2 * nwords]; }
+                    if (k) { int t3 = __ffsll((long long)k) - 1; k &= k - 1; v3 = col[(int64_t)t3 * nwords]; }
+                    acc |= v0 | v1 | v2 | v3;
+                }
+                remv[w] = acc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T> static size_t nms_ws_bytes(int64_t n)
+{
+    if (n <= 0) n = 1;
+    int64_t npad = cdiv(n, NMS_TILE) * NMS_TILE, nwords = npad / 64;
+    size_t recs = sizeof(BoxRec<T>) > sizeof(AABBRec<T>) ? sizeof(BoxRec<T>) : sizeof(AABBRec<T>);
+    return align_up((size_t)n * 8) + align_up((size_t)n * 4) + radix_sort_workspace_bytes(n) + align_up((size_t)npad * recs) +
+           align_up((size_t)npad * 5 * sizeof(T)) + align_up((size_t)npad) + align_up((size_t)npad * nwords * 8) + 4096;
+}
+
+template <typename T>
+static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, int sup_type, float iou_thr, float score_thr, uint8_t *suppressed,
+                    void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    if (n < 0) return D3D_ERR_INVALID_ARGUMENT;
+    if (iou_type != D3D_IOU_BOX && iou_type != D3D_IOU_RBOX) return D3D_ERR_INVALID_ARGUMENT;  // reference: "Unsupported iou type!"
+    if (sup_type < D3D_SUP_HARD || sup_type > D3D_SUP_GAUSSIAN) return D3D_ERR_INVALID_ARGUMENT;
+    if (sup_type != D3D_SUP_HARD) return D3D_ERR_UNSUPPORTED;
+    if (n == 0) return D3D_OK;
+    if (!boxes || !scores || !suppressed) return D3D_ERR_INVALID_ARGUMENT;
+    if (n >= (1ll << 31)) return D3D_ERR_INVALID_ARGUMENT;
+    if (!ws || ws_bytes < nms_ws_bytes<T>(n)) return D3D_ERR_WORKSPACE;
+    const int64_t npad = cdiv(n, NMS_TILE) * NMS_TILE, nwords = npad / 64;
+    if ((size_t)nwords * 8 > 200 * 1024) return D3D_ERR_INVALID_ARGUMENT;  // removal bitmap must fit shared memory (n <= 1.6M)
+    Arena a(ws, ws_bytes);
+    uint64_t *keys = a.take<uint64_t>(n);
+    uint32_t *order = a.take<uint32_t>(n);
+    size_t sort_bytes = radix_sort_workspace_bytes(n);
+    void *sort_ws = a.take<char>(sort_bytes);
+    const bool aabb = iou_type == D3D_IOU_BOX;
+    void *recs = a.take<char>((size_t)npad * (sizeof(BoxRec<T>) > sizeof(AABBRec<T>) ? sizeof(BoxRec<T>) : sizeof(AABBRec<T>)));
+    T *raw = a.take<T>((size_t)npad * 5);
+    uint8_t *valid = a.take<uint8_t>(npad);
+    uint64_t *mask = a.take<uint64_t>((size_t)npad * nwords);
+    if (!a.ok()) return D3D_ERR_WORKSPACE;
+
+    nms_keys_kernel<T><<<(unsigned)cdiv(n, 256), 256, 0, st>>>(scores, n, keys, order); D3D_LAUNCHED();
+    int rc = radix_sort_pairs_u64(keys, order, n, KeyBits<T>::bits, sort_ws, sort_bytes, st);
+    if (rc) return rc;
+    const bool recheck = sizeof(T) == 4 && !aabb;
+    if (aabb)
+        nms_gather_kernel<T, true><<<(unsigned)cdiv(npad, 256), 256, 0, st>>>(boxes, scores, order, n, npad, score_thr, nullptr, (AABBRec<T> *)recs, nullptr, valid);
+    else
+        nms_gather_kernel<T, false><<<(unsigned)cdiv(npad, 256), 256, 0, st>>>(boxes, scores, order, n, npad, score_thr, (BoxRec<T> *)recs, nullptr, recheck ? raw : nullptr, valid);
+    D3D_LAUNCHED();
+    const T thr = (T)iou_thr;   // (T)(float): SURVEY.md 8(c) T2
+    if (nwords > 65535) return D3D_ERR_INVALID_ARGUMENT;
+    dim3 grid((unsigned)nwords, (unsigned)nwords);
+    if (aabb) nms_mask_aabb_kernel<T><<<grid, NMS_TILE, 0, st>>>((const AABBRec<T> *)recs, n, nwords, thr, mask);
+    else nms_mask_rbox_kernel<T><<<grid, NMS_THREADS, 0, st>>>((const BoxRec<T> *)recs, recheck ? raw : nullptr, n, nwords, thr, mask);
+    D3D_LAUNCHED();
+    size_t smem = (size_t)nwords * 8;
+    if (smem > 40 * 1024) D3D_CUDA_TRY(cudaFuncSetAttribute(nms_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_resolve_kernel<<<1, RESOLVE_THREADS, smem, st>>>(mask, n, nwords, valid, order, suppressed); D3D_LAUNCHED();
+    return D3D_OK;
+}
+
+}  // namespace d3d
+
+using namespace d3d;
+extern "C" size_t d3d_nms2d_workspace_bytes(int64_t n, int dtype) { return dtype == D3D_F64 ? nms_ws_bytes<double>(n) : nms_ws_bytes<float>(n); }
+extern "C" int d3d_nms2d_f32(const float *boxes, const float *scores, int64_t n, int iou_type, int sup_type, float iou_thr, float score_thr, float sup_param,
+                             uint8_t *suppressed, void *ws, size_t wsb, void *stream)
+{ (void)sup_param; return nms_impl<float>(boxes, scores, n, iou_type, sup_type, iou_thr, score_thr, suppressed, ws, wsb, (cudaStream_t)stream); }
+extern "C" int d3d_nms2d_f64(const double *boxes, const double *scores, int64_t n, int iou_type, int sup_type, float iou_thr, float score_thr, float sup_param,
+                             uint8_t *suppressed, void *ws, size_t wsb, void *stream)
+{ (void)sup_param; return nms_impl<double>(boxes, scores, n, iou_type, sup_type, iou_thr, score_thr, suppressed, ws, wsb, (cudaStream_t)stream); }

@@ -1,0 +1,225 @@
+// prims.cu -- device-wide primitives written for this library: exclusive scan and a stable LSD radix
+// sort of (key, value) pairs.  They serve NMS (score ordering) and voxelization (grouping points by
+// voxel key deterministically).  No CUB/Thrust: everything launched here is our own kernel.
+#include "prims.cuh"
+
+namespace d3d {
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan of u32 -> u32 (sums must fit 32 bits: callers scan flags / small counts)
+// three phases: per-tile reduce, single-block scan of tile sums, per-tile scan + add
+// ------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane_id() >= (unsigned)d) v += t;
+    }
+    return v;
+}
+
+// block-wide exclusive scan of one value per thread (blockDim = SCAN_THREADS); returns exclusive prefix, total in *tot
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *tot)
+{
+    __shared__ uint32_t wsum[SCAN_THREADS / 32];
+    __shared__ uint32_t total;
+    uint32_t inc = warp_incl_scan(v);
+    unsigned w = threadIdx.x >> 5;
+    if (lane_id() == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t s = lane_id() < SCAN_THREADS / 32 ? wsum[lane_id()] : 0;
+        uint32_t si = warp_incl_scan(s);
+        if (lane_id() < SCAN_THREADS / 32) wsum[lane_id()] = si - s;
+        if (lane_id() == SCAN_THREADS / 32 - 1) total = si;
+    }
+    __syncthreads();
+    uint32_t r = inc - v + wsum[w];
+    *tot = total;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const uint32_t *__restrict__ in, int64_t n, uint32_t *__restrict__ tile_sums)
+{
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        int64_t i = base + k * SCAN_THREADS + threadIdx.x;
+        if (i < n) s += in[i];
+    }
+    uint32_t tot;
+    block_excl_scan(s, &tot);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+// one block scans all tile sums in place (exclusive); writes the grand total to total_out (may be null)
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(uint32_t *__restrict__ tile_sums, int64_t ntiles, uint32_t *__restrict__ total_out)
+{
+    uint32_t carry = 0;
+    for (int64_t base = 0; base < ntiles; base += SCAN_THREADS) {
+        int64_t i = base + threadIdx.x;
+        uint32_t v = i < ntiles ? tile_sums[i] : 0, tot;
+        uint32_t ex = block_excl_scan(v, &tot);
+        if (i < ntiles) tile_sums[i] = ex + carry;
+        carry += tot;
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t *in, int64_t n, const uint32_t *__restrict__ tile_sums, uint32_t *out)
+{
+    // thread owns SCAN_ITEMS consecutive elements (blocked arrangement) so the scan order is index order
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? in[base + k] : 0; s += v[k]; }
+    uint32_t tot;
+    uint32_t ex = block_excl_scan(s, &tot) + tile_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+}
+
+size_t scan_workspace_bytes(int64_t n) { return align_up((size_t)(cdiv(n, SCAN_TILE) + 1) * sizeof(uint32_t)); }
+
+int exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, uint32_t *total_out, void *ws, cudaStream_t st)
+{
+    if (n <= 0) {
+        if (total_out) D3D_CUDA_TRY(cudaMemsetAsync(total_out, 0, sizeof(uint32_t), st));
+        return D3D_OK;
+    }
+    int64_t ntiles = cdiv(n, SCAN_TILE);
+    uint32_t *tiles = (uint32_t *)ws;
+    scan_reduce_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(in, n, tiles); D3D_LAUNCHED();
+    scan_tiles_kernel<<<1, SCAN_THREADS, 0, st>>>(tiles, ntiles, total_out); D3D_LAUNCHED();
+    scan_apply_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(in, n, tiles, out); D3D_LAUNCHED();
+    return D3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stable LSD radix sort, 8-bit digits, (u64 key, u32 value) pairs.
+// per pass: (1) per-tile digit histogram, (2) exclusive scan over the digit-major [256][ntiles] table,
+// (3) stable scatter: rank inside the tile by warp match-any + per-warp digit counters.
+// ------------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 8;                       // consecutive rounds of 32 keys per warp
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;    // 2048 keys per block
+constexpr int RS_BINS = 256;
+
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int shift, int64_t ntiles,
+                                                             uint32_t *__restrict__ hist /*[256][ntiles]*/)
+{
+    __shared__ uint32_t h[RS_BINS];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; k++) {
+        int64_t i = base + k * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 0xff], 1u);
+    }
+    __syncthreads();
+    hist[(int64_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, int64_t n,
+                                                                int shift, int64_t ntiles, const uint32_t *__restrict__ offs /*[256][ntiles] scanned*/,
+                                                                uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out)
+{
+    __shared__ uint32_t cnt[RS_WARPS][RS_BINS];  // running per-warp digit counters -> per-warp totals
+    __shared__ uint32_t binbase[RS_BINS];
+    for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+
+    const unsigned w = threadIdx.x >> 5, lane = lane_id();
+    // warp w owns the contiguous chunk [w*32*ITEMS, (w+1)*32*ITEMS) of the tile: index order == (round, lane)
+    const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * 32 * RS_ITEMS;
+    uint64_t key[RS_ITEMS];
+    uint32_t val[RS_ITEMS], rank[RS_ITEMS];
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; k++) {
+        int64_t i = wbase + k * 32 + lane;
+        bool ok = i < n;
+        key[k] = ok ? keys_in[i] : ~0ull;
+        val[k] = ok ? vals_in[i] : 0u;
+        unsigned d = (unsigned)(key[k] >> shift) & 0xff;
+        unsigned act = __ballot_sync(0xffffffffu, ok);
+        unsigned peers = __match_any_sync(0xffffffffu, ok ? d : 0x100u + lane) & act;  // inactive lanes match nobody
+        uint32_t before = 0;
+        if (ok) before = cnt[w][d];
+        __syncwarp();
+        if (ok) {
+            rank[k] = before + __popc(peers & lanemask_lt());
+            if ((peers & lanemask_lt()) == 0) cnt[w][d] = before + __popc(peers);  // leader of the peer group
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // thread d: exclusive scan over warps of cnt[.][d], plus the global offset of (digit d, this tile)
+        unsigned d = threadIdx.x;
+        uint32_t run = offs[(int64_t)d * ntiles + blockIdx.x];
+        binbase[d] = run;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ww++) { uint32_t c = cnt[ww][d]; cnt[ww][d] = acc; acc += c; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; k++) {
+        int64_t i = wbase + k * 32 + lane;
+        if (i < n) {
+            unsigned d = (unsigned)(key[k] >> shift) & 0xff;
+            uint32_t pos = binbase[d] + cnt[w][d] + rank[k];
+            keys_out[pos] = key[k];
+            vals_out[pos] = val[k];
+        }
+    }
+}
+
+size_t radix_sort_workspace_bytes(int64_t n)
+{
+    int64_t ntiles = cdiv(n > 0 ? n : 1, RS_TILE);
+    size_t hist = align_up((size_t)RS_BINS * ntiles * sizeof(uint32_t));
+    return align_up((size_t)n * sizeof(uint64_t)) + align_up((size_t)n * sizeof(uint32_t)) + hist + scan_workspace_bytes(RS_BINS * ntiles);
+}
+
+// Sorts in place semantically: on return keys/vals hold the sorted sequence (ping-pongs through the
+// workspace; copies back when the pass count is odd).  key_bits: number of significant low bits.
+int radix_sort_pairs_u64(uint64_t *keys, uint32_t *vals, int64_t n, int key_bits, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    if (n <= 1) return D3D_OK;
+    if (n >= (1ll << 32)) return D3D_ERR_INVALID_ARGUMENT;
+    if (ws_bytes < radix_sort_workspace_bytes(n)) return D3D_ERR_WORKSPACE;
+    Arena a(ws, ws_bytes);
+    uint64_t *k2 = a.take<uint64_t>(n);
+    uint32_t *v2 = a.take<uint32_t>(n);
+    int64_t ntiles = cdiv(n, RS_TILE);
+    uint32_t *hist = a.take<uint32_t>((size_t)RS_BINS * ntiles);
+    void *scan_ws = a.take<char>(scan_workspace_bytes(RS_BINS * ntiles));
+    int passes = (key_bits + 7) / 8;
+    if (passes < 1) passes = 1;
+    uint64_t *ki = keys, *ko = k2;
+    uint32_t *vi = vals, *vo = v2;
+    for (int p = 0; p < passes; p++) {
+        rs_hist_kernel<<<(unsigned)ntiles, RS_THREADS, 0, st>>>(ki, n, p * 8, ntiles, hist); D3D_LAUNCHED();
+        int rc = exclusive_scan_u32(hist, hist, RS_BINS * ntiles, nullptr, scan_ws, st);
+        if (rc) return rc;
+        rs_scatter_kernel<<<(unsigned)ntiles, RS_THREADS, 0, st>>>(ki, vi, n, p * 8, ntiles, hist, ko, vo); D3D_LAUNCHED();
+        uint64_t *tk = ki; ki = ko; ko = tk;
+        uint32_t *tv = vi; vi = vo; vo = tv;
+    }
+    if (ki != keys) {
+        D3D_CUDA_TRY(cudaMemcpyAsync(keys, ki, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+        D3D_CUDA_TRY(cudaMemcpyAsync(vals, vi, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    }
+    return D3D_OK;
+}
+
+}  // namespace d3d

@@ -1,0 +1,156 @@
+/* d3d_b200.h -- C ABI of the B200-native d3d hot path (libd3d_b200.so).
+ *
+ * Drop-in boundary for the three data-parallel geometry operators of cmpute/d3d.  Every entry point
+ * replaces one native function the reference's Python packages import from their pybind11 modules
+ * (cited per function as reference file:line).  Conventions:
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless the name says host;
+ *   - the library never allocates user-visible memory: outputs and scratch ("workspace") are caller
+ *     provided, `*_workspace_bytes` tells how much scratch a call needs;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, no globals;
+ *   - return value: D3D_OK or a D3D_ERR_* code (never exit(), unlike reference d3d/common.h:33-46);
+ *     d3d_error_string() names the code; d3d_last_cuda_error() returns the CUDA error text of the
+ *     calling thread's last D3D_ERR_CUDA.
+ *   - box rows are (x, y, w, h, r) contiguous, row-major, like reference d3d/box/__init__.py:184-185.
+ * Built for sm_100a only; there is no CPU fallback.
+ */
+#ifndef D3D_B200_H
+#define D3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D3D_B200_ABI_VERSION 1
+
+enum d3d_status {
+    D3D_OK = 0,
+    D3D_ERR_INVALID_ARGUMENT = 1, /* reference raises ValueError / py::value_error */
+    D3D_ERR_CUDA = 2,             /* a CUDA runtime call failed */
+    D3D_ERR_WORKSPACE = 3,        /* workspace smaller than *_workspace_bytes() */
+    D3D_ERR_UNSUPPORTED = 4,      /* e.g. FARTHEST_SAMPLING (reference throws, voxelize.cpp:468-471) */
+    D3D_ERR_RANGE = 5             /* voxel grid too large for the 63-bit voxel key */
+};
+
+/* reference d3d/box/common.h:5-10 (same integer values) */
+enum d3d_iou_type { D3D_IOU_NA = 0, D3D_IOU_BOX = 1, D3D_IOU_RBOX = 2, D3D_IOU_GBOX = 3, D3D_IOU_GRBOX = 4, D3D_IOU_DBOX = 5, D3D_IOU_DRBOX = 6 };
+enum d3d_supression_type { D3D_SUP_HARD = 0, D3D_SUP_LINEAR = 1, D3D_SUP_GAUSSIAN = 2 };
+/* reference d3d/voxel/voxelize.h:5-7 */
+enum d3d_reduction_type { D3D_RED_NONE = 0, D3D_RED_MEAN = 1, D3D_RED_MAX = 2, D3D_RED_MIN = 3 };
+enum d3d_max_points_filter { D3D_PF_NONE = 0, D3D_PF_TRIM = 1, D3D_PF_FARTHEST_SAMPLING = 2 };
+enum d3d_max_voxels_filter { D3D_VF_NONE = 0, D3D_VF_TRIM = 1, D3D_VF_DESCENDING = 2 };
+/* reference d3d/point/scatter.h:37 */
+enum d3d_align_type { D3D_ALIGN_DROP = 0, D3D_ALIGN_MEAN = 1, D3D_ALIGN_LINEAR = 2, D3D_ALIGN_MAX = 3, D3D_ALIGN_NEAREST = 4 };
+enum d3d_dtype { D3D_F32 = 0, D3D_F64 = 1 };
+
+int d3d_abi_version(void);
+const char *d3d_error_string(int status);
+const char *d3d_last_cuda_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+int64_t d3d_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pairwise IoU.  ious is [n, m] row-major with leading dimension ld (elements, ld >= m).
+ * d3d_iou2dr_*: rotated IoU, replaces iou2dr_forward[_cuda] (reference d3d/box/iou.h:14-16,
+ *   iou.cpp:94-141, iou_cuda.cu:99-151).  The backward-only outputs nx/xflags are not produced.
+ * d3d_iou2d_*: IoU of the axis-aligned bounding boxes of the rotated boxes, replaces
+ *   iou2d_forward[_cuda] (iou.h:7-9, iou.cpp:11-46, iou_cuda.cu:9-48).
+ * Row-block sharding (multi-GPU): pass a slice of boxes1 and the matching slab of ious.
+ * ---------------------------------------------------------------------------------------------- */
+size_t d3d_iou_workspace_bytes(int64_t n, int64_t m, int dtype);
+int d3d_iou2dr_f32(const float *boxes1, int64_t n, const float *boxes2, int64_t m, float *ious, int64_t ld,
+                   void *workspace, size_t workspace_bytes, void *stream);
+int d3d_iou2dr_f64(const double *boxes1, int64_t n, const double *boxes2, int64_t m, double *ious, int64_t ld,
+                   void *workspace, size_t workspace_bytes, void *stream);
+int d3d_iou2d_f32(const float *boxes1, int64_t n, const float *boxes2, int64_t m, float *ious, int64_t ld,
+                  void *workspace, size_t workspace_bytes, void *stream);
+int d3d_iou2d_f64(const double *boxes1, int64_t n, const double *boxes2, int64_t m, double *ious, int64_t ld,
+                  void *workspace, size_t workspace_bytes, void *stream);
+/* optional statistics of the last d3d_iou2dr_* call that used this workspace: counters[0] = candidate
+ * pairs (bounding circles overlap) -- what roofline accounting needs.  Device i64[2]
+ * at the start of the workspace; read it back after synchronising the stream. */
+
+/* ------------------------------------------------------------------------------------------------
+ * NMS, replaces nms2d[_cuda] (reference d3d/box/nms.h:6-10, nms.cpp:98-119, nms_cuda.cu:217-244).
+ * boxes [n,5], scores [n]; suppressed u8[n] (1 = suppressed) in ORIGINAL box order -- the Python
+ * front door returns ~suppressed (d3d/box/__init__.py:272).  Order = stable descending sort of
+ * scores (ties keep the lower original index first).  iou > (T)(float)iou_threshold, strict.
+ * Score rule: every box with score <= score_threshold is suppressed (reference CUDA rule,
+ * nms_cuda.cu:223).  iou_type: D3D_IOU_BOX or D3D_IOU_RBOX; supression_type: D3D_SUP_HARD only
+ * (LINEAR / GAUSSIAN return D3D_ERR_UNSUPPORTED in this ABI version).
+ * ---------------------------------------------------------------------------------------------- */
+size_t d3d_nms2d_workspace_bytes(int64_t n, int dtype);
+int d3d_nms2d_f32(const float *boxes, const float *scores, int64_t n, int iou_type, int supression_type,
+                  float iou_threshold, float score_threshold, float supression_param, uint8_t *suppressed,
+                  void *workspace, size_t workspace_bytes, void *stream);
+int d3d_nms2d_f64(const double *boxes, const double *scores, int64_t n, int iou_type, int supression_type,
+                  float iou_threshold, float score_threshold, float supression_param, uint8_t *suppressed,
+                  void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Voxelization of a BATCH of frames (one frame = one reference VoxelGenerator.__call__).
+ * points f32[total, nfeat] (first 3 columns xyz); frame_offsets DEVICE i64[nframes+1], ascending,
+ * frame f owns points [frame_offsets[f], frame_offsets[f+1]).  All per-point / per-voxel outputs of
+ * frame f are written starting at row frame_offsets[f] of the output arrays (a frame never has more
+ * voxels than points), its sizes to counts[f] = {kept points K_f, voxels V_f} (device i64[nframes,2]).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct d3d_voxel_params {
+    /* sparse path (reference voxelize.cpp:288-484 through d3d/voxel/__init__.py:96-103) */
+    float size[3];      /* _size: f32 (hi-lo)/shape, coordinate = floor(p/size)            */
+    int64_t vlo[3];     /* _vbounds[:,0]: keep voxels with vlo <= coord < vhi              */
+    int64_t vhi[3];     /* _vbounds[:,1]                                                   */
+    int32_t offset[3];  /* _offset: coords_out = coord - offset                            */
+    int32_t min_points; /* voxel filter: npoints >= min_points                             */
+    int32_t max_points; /* TRIM: first max_points points per voxel; dense: slots per voxel */
+    int32_t max_voxels; /* TRIM / DESCENDING cap; dense: voxel capacity per frame          */
+    int32_t max_points_filter; /* d3d_max_points_filter */
+    int32_t max_voxels_filter; /* d3d_max_voxels_filter */
+    /* dense path (reference voxelize.cpp:45-199) */
+    float bound[6];     /* xmin,xmax,ymin,ymax,zmin,zmax; idx = (int)((p-lo)/((hi-lo)/shape)) */
+    int32_t shape[3];
+    int32_t reduction;  /* d3d_reduction_type */
+} d3d_voxel_params;
+
+size_t d3d_voxelize_workspace_bytes(int64_t total_points, int64_t nframes);
+/* sparse + filter fused; replaces voxelize_3d_sparse + voxelize_3d_filter (voxelize.h:14-25).
+ * out_points f32[total,nfeat], out_mask i64[total] (index of the surviving point INSIDE its frame),
+ * out_mapping i64[total], out_npoints i32[total], out_coords i64[total,3]. */
+int d3d_voxelize_sparse_f32(const float *points, int64_t total, int32_t nfeat, const int64_t *frame_offsets,
+                            int64_t nframes, const d3d_voxel_params *params, float *out_points, int64_t *out_mask,
+                            int64_t *out_mapping, int32_t *out_npoints, int64_t *out_coords, int64_t *counts,
+                            void *workspace, size_t workspace_bytes, void *stream);
+/* dense; replaces voxelize_3d_dense (voxelize.h:9-12).  Per frame f the outputs live at
+ * voxels f32[nframes,max_voxels,max_points,nfeat], coords i64[nframes,max_voxels,3],
+ * pmask u8[nframes,max_voxels,max_points] (0 where the reference leaves memory uninitialised),
+ * npoints i32[nframes,max_voxels], aggregates f32[nframes,max_voxels,nfeat] (NULL when reduction NONE);
+ * counts[f] = {points stored, voxels V_f}.  The call zero-fills voxels/pmask/npoints itself. */
+int d3d_voxelize_dense_f32(const float *points, int64_t total, int32_t nfeat, const int64_t *frame_offsets,
+                           int64_t nframes, const d3d_voxel_params *params, float *voxels, int64_t *coords,
+                           uint8_t *pmask, int32_t *npoints, float *aggregates, int64_t *counts, void *workspace,
+                           size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * aligned_scatter, replaces aligned_scatter_forward/backward[_cuda] (reference d3d/point/scatter.h:39-45,
+ * scatter.cpp:79-201, scatter_cuda.cu:91-241).  coord T[n,1+dim] (col 0 = batch index), image
+ * T[nbatch,nchan,dims[0..dim)], out T[n,nchan]; align: D3D_ALIGN_MEAN or D3D_ALIGN_LINEAR; dim in 1..3.
+ * backward accumulates into image_grad (caller zero-fills it, d3d/point/__init__.py:32).
+ * ---------------------------------------------------------------------------------------------- */
+int d3d_aligned_scatter_forward(const void *coord, int64_t n, int32_t dim, const void *image, int64_t nbatch,
+                                int64_t nchan, const int64_t *dims_host, int align, int dtype, void *out, void *stream);
+int d3d_aligned_scatter_backward(const void *coord, int64_t n, int32_t dim, const void *grad, int64_t nbatch,
+                                 int64_t nchan, const int64_t *dims_host, int align, int dtype, void *image_grad,
+                                 void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Measurement helper: FMA-chain microbenchmark used as the measured FP32/FP64 ALU peak for the IoU
+ * roofline.  Runs `iters` dependent FMAs x 8 independent chains per thread on a full
+ * grid; writes the number of FLOPs executed to *flops_host.  Time it with CUDA events on `stream`.
+ * ---------------------------------------------------------------------------------------------- */
+int d3d_fma_peak_probe(int dtype, int64_t iters, float *sink, double *flops_host, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D3D_B200_H */

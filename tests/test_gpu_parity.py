@@ -1,0 +1,477 @@
+"""Parity tests proper: the CUDA path (through the Python front doors -> C ABI -> kernels) against the
+CPU oracle and the committed golden fixtures, plus size-independent properties at BASELINE sizes.
+Needs a B200: run with `pytest -m gpu`."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, gen_boxes, lidar, proposals
+
+pytestmark = pytest.mark.gpu
+
+FP64_TOL = 1e-5   # north_star: IoU within 1e-5 absolute in fp64
+FP32_TOL = 1e-4   # and 1e-4 in fp32
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _unpack(bits, n):
+    return np.unpackbits(bits)[:n].astype(bool)
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+# ------------------------------------------------------------------ IoU
+def test_iou_golden_reference_fixture(dev):
+    from d3d_b200.box import box2d_iou
+    g = golden("iou_c1.npz")
+    a, b = g["boxes1"], g["boxes2"]
+    r = box2d_iou(_t(a, dev), _t(b, dev), "rbox").cpu().numpy()
+    assert r.dtype == np.float64 and np.abs(r - g["rbox_f64"]).max() < FP64_TOL
+    assert np.abs(r - g["rbox_f64"]).max() < 1e-10   # in generic position we are ~1e-13 from the reference
+    r = box2d_iou(_t(a, dev), _t(b, dev), "box").cpu().numpy()
+    assert np.abs(r - g["box_f64"]).max() < 1e-12
+    a32, b32 = a.astype(np.float32), b.astype(np.float32)
+    r32 = box2d_iou(_t(a32, dev), _t(b32, dev), "rbox", precise=False).cpu().numpy()
+    assert r32.dtype == np.float32 and np.abs(r32 - g["rbox_f32"]).max() < FP32_TOL
+    assert np.abs(box2d_iou(_t(a32, dev), _t(b32, dev), "box", precise=False).cpu().numpy() - g["box_f32"]).max() < 1e-5
+    # precise=True on float input: fp64 compute, float result (d3d/box/__init__.py:197-221)
+    rp = box2d_iou(_t(a32, dev), _t(b32, dev), "rbox")
+    assert rp.dtype == torch.float32
+
+
+def test_iou_c1_full_vs_oracle(dev, oracle):
+    """config C1: 1k x 1k fp64 + fp32 against the oracle (reference RC restatement) and truth."""
+    from d3d_b200.box import box2d_iou
+    rng = np.random.default_rng(0)
+    A, B = gen_boxes(rng, 1000), gen_boxes(rng, 1000)
+    r = box2d_iou(_t(A, dev), _t(B, dev), "rbox").cpu().numpy()
+    ref = oracle.iou2dr(A, B)
+    assert np.abs(r - ref).max() < 1e-10
+    assert abs(r.sum() - 20745.014676358896) < 1e-6 and (r != 0).sum() == 205623   # SURVEY Appendix C anchors
+    A32, B32 = A.astype(np.float32), B.astype(np.float32)
+    r32 = box2d_iou(_t(A32, dev), _t(B32, dev), "rbox", precise=False).cpu().numpy()
+    truth = oracle.iou2dr_truth(A32.astype(np.float64), B32.astype(np.float64))
+    assert np.abs(r32 - truth).max() < 2e-6
+    assert np.abs(r32 - oracle.iou2dr(A32, B32)).max() < FP32_TOL
+    rb = box2d_iou(_t(A, dev), _t(B, dev), "box").cpu().numpy()
+    assert np.abs(rb - oracle.iou2d(A, B)).max() < 1e-12
+
+
+def test_iou_reference_known_answers(dev):
+    """test/test_box.py:12-100 with the reference's tolerances, CUDA and host inputs, numpy round trip."""
+    from d3d_b200.box import box2d_iou
+    g = golden("iou_known_answers.npz")
+    eps = 1e-3
+    for mv in (lambda x: _t(x, dev), lambda x: torch.from_numpy(x), lambda x: x):
+        def run(a, b, m):
+            r = box2d_iou(mv(a), mv(b), method=m)
+            return r if isinstance(r, np.ndarray) else r.cpu().numpy()
+        assert np.allclose(run(g["aa_boxes1"], g["aa_boxes2"], "box"), g["aa_expected"], atol=eps)
+        assert np.allclose(run(g["aa_boxes1"], g["aa_boxes2"], "rbox"), g["aa_expected"], atol=4 * eps)
+        assert np.allclose(run(g["rot_boxes1"], g["rot_boxes2"], "box"), g["rot_box_expected"], atol=2 * eps)
+        assert np.allclose(run(g["rot_boxes1"], g["rot_boxes2"], "rbox"), g["rot_rbox_expected"], atol=4 * eps)
+        ab = g["apart_boxes"]
+        assert np.allclose(run(ab, ab, "box") - np.eye(4), 0, atol=1e-6)
+        rb = g["apart_rboxes"]
+        assert np.allclose(run(rb, rb, "rbox") - np.eye(5), 0, atol=1e-6)
+
+
+def test_iou_degenerate_list(dev):
+    """the build returns geometric truth where the reference's RC returns 1.0/0.5."""
+    from d3d_b200.box import box2d_iou
+    g = golden("iou_degenerate.npz")
+    for i, name in enumerate(g["names"]):
+        a, b = g["boxes1"][i:i + 1], g["boxes2"][i:i + 1]
+        v64 = box2d_iou(_t(a, dev), _t(b, dev), "rbox").item()
+        v32 = box2d_iou(_t(a.astype(np.float32), dev), _t(b.astype(np.float32), dev), "rbox", precise=False).item()
+        assert abs(v64 - g["truth"][i]) < FP64_TOL, (name, v64)
+        assert abs(v32 - g["truth"][i]) < FP32_TOL, (name, v32)
+        if str(name) == "D13":
+            assert v64 == 0.0 and v32 == 0.0 and not np.signbit(v64)   # early reject yields exactly +0
+    z = np.array([[0, 0, 0, 2, .2]]); z2 = np.array([[5, 5, 0, 0, .1]])
+    assert box2d_iou(_t(z, dev), _t(z2, dev), "rbox").item() == 0.0   # two zero-area boxes: 0, not NaN (documented)
+
+
+def test_iou_shapes_edges_and_errors(dev, oracle):
+    from d3d_b200.box import box2d_iou
+    rng = np.random.default_rng(3)
+    for n, m in ((1, 1), (1, 257), (63, 129), (65, 127), (200, 3), (130, 1001)):   # ragged tiles, unaligned ld
+        A, B = gen_boxes(rng, n), gen_boxes(rng, m)
+        for dt, tol in ((np.float64, 1e-10), (np.float32, FP32_TOL)):
+            r = box2d_iou(_t(A.astype(dt), dev), _t(B.astype(dt), dev), "rbox", precise=False).cpu().numpy()
+            assert r.shape == (n, m) and np.abs(r - oracle.iou2dr(A.astype(dt), B.astype(dt))).max() < tol
+            rb = box2d_iou(_t(A.astype(dt), dev), _t(B.astype(dt), dev), "box", precise=False).cpu().numpy()
+            assert np.abs(rb - oracle.iou2d(A.astype(dt), B.astype(dt))).max() < (1e-12 if dt == np.float64 else 1e-5)
+    e = box2d_iou(torch.zeros((0, 5), device=dev), torch.zeros((7, 5), device=dev), "rbox")
+    assert e.shape == (0, 7)
+    with pytest.raises(ValueError):
+        box2d_iou(torch.zeros((3, 4), device=dev), torch.zeros((3, 5), device=dev), "rbox")
+    with pytest.raises(ValueError):
+        box2d_iou(torch.zeros(5, device=dev), torch.zeros((3, 5), device=dev))
+    with pytest.raises(AttributeError):
+        box2d_iou(torch.zeros((3, 5), device=dev), torch.zeros((3, 5), device=dev), "nonsense")
+    # non-contiguous inputs are accepted like the reference's strided accessors
+    big = _t(gen_boxes(rng, 40), dev)
+    assert torch.equal(box2d_iou(big[::2], big[1::2], "rbox"), box2d_iou(big[::2].contiguous(), big[1::2].contiguous(), "rbox"))
+
+
+def test_iou_large_properties(dev, oracle):
+    """20k x 20k fp32 (4e8 pairs): range, symmetry, diagonal, sampled rows vs truth; test_box.py:125-138."""
+    from d3d_b200.box import box2d_iou
+    rng = np.random.default_rng(9)
+    n = 20000
+    A = gen_boxes(rng, n, spread=60.0).astype(np.float32)
+    tA = _t(A, dev)
+    r = box2d_iou(tA, tA, "rbox", precise=False)
+    assert r.shape == (n, n) and bool(((r >= -1e-3) & (r <= 1 + 1e-3)).all())
+    assert float((r - r.t()).abs().max()) < FP32_TOL
+    assert float((torch.diagonal(r) - 1).abs().max()) < FP32_TOL
+    rows = rng.integers(0, n, 24)
+    truth = oracle.iou2dr_truth(A[rows].astype(np.float64), A.astype(np.float64))
+    assert np.abs(r[torch.from_numpy(rows).to(dev)].cpu().numpy() - truth).max() < FP32_TOL
+    x = torch.rand(500) * 200; y = torch.rand(500) * 400
+    b = torch.stack((x, y, torch.rand(500) * 20 + 10, torch.rand(500) * 30 + 5, torch.rand(500) * 2 - 1), dim=1).to(dev)
+    for m in ("box", "rbox"):
+        res = box2d_iou(b, b, method=m)
+        assert bool(torch.all(res >= -1e-3)) and bool(torch.all(res <= 1 + 1e-3))
+
+
+# ------------------------------------------------------------------ NMS
+def test_nms_known_answer_and_golden(dev):
+    from d3d_b200.box import box2d_nms
+    g = golden("nms.npz")
+    for m in ("box", "rbox"):
+        k = box2d_nms(_t(g["test_boxes"], dev), _t(g["test_scores"], dev), iou_method=m)
+        assert k.dtype == torch.bool and np.array_equal(k.cpu().numpy(), g["test_expected"])
+    A, B, s = g["c1_boxes"], g["c1_boxes_b"], g["c1_scores"]
+    k = box2d_nms(_t(A, dev), _t(s, dev), "rbox", iou_threshold=0.5).cpu().numpy()
+    assert k.sum() == 673 and np.array_equal(k, _unpack(g["c1_keep_rbox"], 1000))
+    assert np.array_equal(box2d_nms(_t(B, dev), _t(s, dev), "rbox", iou_threshold=0.5).cpu().numpy(), _unpack(g["c1_keep_rbox_b"], 1000))
+    assert np.array_equal(box2d_nms(_t(A, dev), _t(s, dev), "box", iou_threshold=0.5).cpu().numpy(), _unpack(g["c1_keep_box"], 1000))
+    assert np.array_equal(box2d_nms(_t(A, dev), _t(s, dev), "rbox", iou_threshold=0.3, score_threshold=0.2).cpu().numpy(),
+                          _unpack(g["c1_keep_rbox_thr03_s02"], 1000))
+    P, ps = g["prop_boxes"], g["prop_scores"]
+    assert np.array_equal(box2d_nms(_t(P, dev), _t(ps, dev), "rbox", iou_threshold=0.5).cpu().numpy(), _unpack(g["prop_keep_rbox"], len(P)))
+    assert np.array_equal(box2d_nms(_t(P, dev), _t(ps, dev), "box", iou_threshold=0.5).cpu().numpy(), _unpack(g["prop_keep_box"], len(P)))
+    # numpy in -> numpy out; host tensors in -> host tensors out
+    kn = box2d_nms(A, s, "rbox", iou_threshold=0.5)
+    assert isinstance(kn, np.ndarray) and np.array_equal(kn, _unpack(g["c1_keep_rbox"], 1000))
+    # fp32 path (precise=False): near-threshold pairs are re-evaluated in fp64, so the float32 keep mask of
+    # float32-rounded boxes equals the reference's fp64 decisions on those same boxes
+    P32, ps32 = P.astype(np.float32), ps.astype(np.float32)
+    if len(np.unique(ps32)) == len(ps32):
+        k32 = box2d_nms(_t(P32, dev), _t(ps32, dev), "rbox", iou_threshold=0.5, precise=False).cpu().numpy()
+        assert np.array_equal(k32, box2d_nms(_t(P32, dev), _t(ps32, dev), "rbox", iou_threshold=0.5, precise=True).cpu().numpy())
+
+
+def test_nms_vs_oracle_sizes_and_thresholds(dev, oracle):
+    from d3d_b200.box import box2d_nms
+    rng = np.random.default_rng(21)
+    for n in (1, 2, 63, 64, 65, 130, 1000, 4097):
+        P, s = proposals(rng, n, max(1, n // 25), extent=20.0)
+        for m in ("rbox", "box"):
+            for thr, sthr in ((0.5, 0.0), (0.3, 0.35), (0.0, 0.0), (0.7, 0.999)):
+                k = box2d_nms(_t(P, dev), _t(s, dev), m, iou_threshold=thr, score_threshold=sthr).cpu().numpy()
+                o = oracle.box2d_nms(P, s, m, iou_threshold=thr, score_threshold=sthr, cuda_score_rule=True)
+                assert np.array_equal(k, o), (n, m, thr, sthr, int((k != o).sum()))
+                assert not k[s <= sthr].any()          # test_box.py:140-155
+                if s.max() > sthr:                      # the CPU rule only differs when every score is <= thr (T4)
+                    assert np.array_equal(k, oracle.box2d_nms(P, s, m, iou_threshold=thr, score_threshold=sthr))
+    assert box2d_nms(torch.zeros((0, 5), device=dev), torch.zeros(0, device=dev)).numel() == 0
+    with pytest.raises(ValueError):
+        box2d_nms(torch.zeros((3, 5), device=dev), torch.zeros(2, device=dev))
+    with pytest.raises(NotImplementedError):
+        box2d_nms(torch.rand((3, 5), device=dev), torch.rand(3, device=dev), supression_method="linear")
+    # 2-D scores: max over classes (d3d/box/__init__.py:253-254)
+    P, s = proposals(rng, 300, 12, extent=10.0)
+    s2 = np.stack([s * 0.5, s, s * 0.1], 1)
+    assert np.array_equal(box2d_nms(_t(P, dev), _t(s2, dev), "rbox", iou_threshold=0.4).cpu().numpy(),
+                          oracle.box2d_nms(P, s, "rbox", iou_threshold=0.4, cuda_score_rule=True))
+
+
+def test_nms_c3_scale_properties(dev, oracle):
+    """config C3: 50k clustered proposals, rbox thr 0.5, fp64.  The oracle needs ~25 s for this, so the
+    full mask is checked through NMS invariants plus an oracle run on a prefix in score order."""
+    from d3d_b200.box import box2d_nms, box2d_iou
+    rng = np.random.default_rng(2)
+    P, s = proposals(rng, 50000, 2000)
+    tP, ts = _t(P, dev), _t(s, dev)
+    keep = box2d_nms(tP, ts, "rbox", iou_threshold=0.5)
+    k = keep.cpu().numpy()
+    assert 3000 < k.sum() < 8000
+    # invariant 1: kept boxes do not suppress each other
+    kb = tP[keep]
+    iou = box2d_iou(kb, kb, "rbox")
+    iou.fill_diagonal_(0)
+    assert float(iou.max()) <= 0.5
+    # invariant 2: every suppressed box overlaps (> thr) a kept box with a higher score
+    sb, ss = tP[~keep], ts[~keep]
+    cross = box2d_iou(sb, kb, "rbox")
+    higher = ts[keep][None, :] > ss[:, None]
+    assert bool(((cross > 0.5) & higher).any(dim=1).all())
+    # idempotence: NMS of the kept set keeps everything
+    assert bool(box2d_nms(kb, ts[keep], "rbox", iou_threshold=0.5).all())
+    # oracle on the 6000 best-scoring proposals (greedy NMS on a score prefix equals the prefix of the full run)
+    top = np.argsort(-s, kind="stable")[:6000]
+    assert np.array_equal(k[top], oracle.box2d_nms(P[top], s[top], "rbox", iou_threshold=0.5))
+
+
+# ------------------------------------------------------------------ voxelization
+VOX_CASES = {
+    "sp_default": dict(), "sp_trim5": dict(max_points=5, max_points_filter="trim"),
+    "sp_trim2_v1000": dict(max_points=2, max_points_filter="trim", max_voxels=1000, max_voxels_filter="trim"),
+    "sp_min2": dict(min_points=2, max_points=3, max_points_filter="trim"),
+    "de_p5": dict(dense=True, max_points=5, max_voxels=20000), "de_p2_v1000": dict(dense=True, max_points=2, max_voxels=1000),
+    "de_mean": dict(dense=True, max_points=3, max_voxels=20000, reduction="mean"),
+    "de_max": dict(dense=True, max_points=3, max_voxels=20000, reduction="max"),
+    "de_min": dict(dense=True, max_points=3, max_voxels=700, reduction="min"),
+}
+EXPECT_DTYPES = dict(points=torch.float32, points_mask=torch.int64, points_mapping=torch.int64, voxel_npoints=torch.int32,
+                     coords=torch.int64, voxels=torch.float32, voxel_pmask=torch.bool, aggregates=torch.float32)
+
+
+def _cmp_vox(r, exp, kw, tag):
+    assert set(r.keys()) == set(exp.keys()), (tag, r.keys(), exp.keys())
+    for k, v in exp.items():
+        got = r[k]
+        assert got.dtype == EXPECT_DTYPES[k], (tag, k, got.dtype)
+        got = got.cpu().numpy()
+        if k == "voxel_pmask":
+            P = kw["max_points"]
+            sl = np.arange(P)[None, :] < np.minimum(exp["voxel_npoints"], P)[:, None]
+            assert got.shape == v.shape and np.array_equal(got[sl], v[sl]) and not got[~sl].any(), (tag, k)
+        else:
+            assert got.shape == v.shape and np.array_equal(got, v), (tag, k)
+
+
+def test_voxel_spconv_golden(dev):
+    """test/test_voxel.py:80-88 with test/voxel_data.npz (spconv VoxelGeneratorV2)."""
+    from d3d_b200.voxel import VoxelGenerator
+    d = golden("voxel_spconv.npz")
+    gen = VoxelGenerator([0, 1, 0, 1, 0, 1], [10, 10, 10], max_points=5, max_points_filter="trim", dense=True)
+    for cloud in (_t(d["cloud"], dev), torch.from_numpy(d["cloud"])):   # CUDA and host input
+        ret = gen(cloud)
+        assert np.array_equal(ret.voxels.cpu().numpy(), d["voxels"])
+        assert np.array_equal(ret.coords.cpu().numpy(), d["coords"])
+
+
+def test_voxel_golden_fixtures(dev):
+    from d3d_b200.voxel import VoxelGenerator
+    g = golden("voxel_c2small.npz")
+    pts = g["points"]
+    for name, kw in VOX_CASES.items():
+        r = VoxelGenerator(g["bounds"].tolist(), g["shape"].tolist(), **kw)(_t(pts, dev))
+        exp = {}
+        for key in g.files:
+            if key.startswith(name + "."):
+                k = key.split(".", 1)[1]
+                v = g[key]
+                if k == "voxel_pmask":
+                    shp = (len(g[f"{name}.voxel_npoints"]), kw["max_points"])
+                    v = np.unpackbits(v)[:shp[0] * shp[1]].reshape(shp).astype(bool)
+                exp[k] = v
+        if not kw.get("dense"):
+            exp["points"] = pts[exp["points_mask"]]
+        _cmp_vox(r, exp, kw, name)
+    for name, kw in {"co_trim5": dict(max_points=5, max_points_filter="trim"),
+                     "co_de_mean": dict(dense=True, max_points=4, max_voxels=300, reduction="mean")}.items():
+        r = VoxelGenerator(g["coarse_bounds"].tolist(), g["coarse_shape"].tolist(), **kw)(_t(pts, dev))
+        exp = {}
+        for key in g.files:
+            if key.startswith(name + "."):
+                k = key.split(".", 1)[1]
+                v = g[key]
+                if k == "voxel_pmask":
+                    shp = (len(g[f"{name}.voxel_npoints"]), kw["max_points"])
+                    v = np.unpackbits(v)[:shp[0] * shp[1]].reshape(shp).astype(bool)
+                exp[k] = v
+        if not kw.get("dense"):
+            exp["points"] = pts[exp["points_mask"]]
+        _cmp_vox(r, exp, kw, name)
+
+
+def test_voxel_c2_full_vs_oracle(dev, oracle):
+    """config C2 (120k points, KITTI grid) and C3 cloud (180k, 3008^2 x 60 grid), every mode, bit-exact."""
+    from d3d_b200.voxel import VoxelGenerator
+    pts = lidar(np.random.default_rng(1), 120000)
+    bounds, shape = [0, 70.4, -40, 40, -3, 1], [1408, 1600, 40]
+    cases = [dict(max_points=5, max_points_filter="trim"),
+             dict(max_points=5, max_points_filter="trim", max_voxels=20000, max_voxels_filter="trim"), dict(),
+             dict(min_points=2, max_points=3, max_points_filter="trim"),
+             dict(dense=True, max_points=5, max_voxels=20000), dict(dense=True, max_points=5, max_voxels=200000),
+             dict(dense=True, max_points=5, max_voxels=20000, reduction="mean"),
+             dict(dense=True, max_points=3, max_voxels=20000, reduction="max")]
+    for kw in cases:
+        r = VoxelGenerator(bounds, shape, **kw)(_t(pts, dev))
+        _cmp_vox(r, oracle.VoxelGenerator(bounds, shape, **kw)(pts), kw, str(kw))
+    r = VoxelGenerator(bounds, shape, max_points=5, max_points_filter="trim")(_t(pts, dev))
+    assert len(r.coords) == 81559 and len(r.points) == 85387        # SURVEY Appendix C anchors
+    rng = np.random.default_rng(2)
+    n = 180000
+    rho = 75 * rng.random(n) ** 2; th = (rng.random(n) - .5) * 2 * np.pi
+    p3 = np.stack([rho * np.cos(th), rho * np.sin(th), rng.normal(-1.2, .6, n), rng.random(n)], 1).astype(np.float32)
+    b3, s3 = [-75.2, 75.2, -75.2, 75.2, -2, 4], [3008, 3008, 60]
+    for kw in (dict(max_points=5, max_points_filter="trim"), dict(dense=True, max_points=5, max_voxels=40000)):
+        _cmp_vox(VoxelGenerator(b3, s3, **kw)(_t(p3, dev)), oracle.VoxelGenerator(b3, s3, **kw)(p3), kw, "c3 " + str(kw))
+
+
+def test_voxel_descending_and_crowded(dev, oracle):
+    """coarse grid: many points per voxel (trim, ordered MEAN sums), DESCENDING with tie rule = ascending id"""
+    from d3d_b200.voxel import VoxelGenerator
+    pts = lidar(np.random.default_rng(8), 30000)
+    b, s = [0, 70.4, -40, 40, -3, 1], [44, 50, 4]
+    for kw in (dict(max_points=5, max_points_filter="trim"), dict(max_points=7, max_points_filter="trim", max_voxels=60, max_voxels_filter="trim"),
+               dict(max_voxels=50, max_voxels_filter="descending", min_points=3),
+               dict(max_voxels=5000, max_voxels_filter="descending", max_points=4, max_points_filter="trim"),
+               dict(dense=True, max_points=4, max_voxels=300, reduction="mean"), dict(dense=True, max_points=9, max_voxels=9000, reduction="min")):
+        _cmp_vox(VoxelGenerator(b, s, **kw)(_t(pts, dev)), oracle.VoxelGenerator(b, s, **kw)(pts), kw, "crowded " + str(kw))
+    # every point in ONE voxel (worst case for per-voxel work) and an empty / all-outside cloud
+    one = np.tile(np.array([[10.01, 0.01, -1.01, 0.5]], np.float32), (5000, 1)); one[:, 3] = np.arange(5000)
+    for kw in (dict(max_points=5, max_points_filter="trim"), dict(dense=True, max_points=5, max_voxels=10, reduction="mean")):
+        _cmp_vox(VoxelGenerator(b, s, **kw)(_t(one, dev)), oracle.VoxelGenerator(b, s, **kw)(one), kw, "one-voxel")
+    out = np.full((100, 4), 500.0, np.float32)
+    r = VoxelGenerator(b, s)(_t(out, dev))
+    assert len(r.points) == 0 and len(r.coords) == 0 and r.coords.shape == (0, 3)
+    r = VoxelGenerator(b, s)(torch.zeros((0, 4), device=dev))
+    assert len(r.points) == 0 and len(r.voxel_npoints) == 0
+    nan = lidar(np.random.default_rng(3), 1000); nan[::7, 1] = np.nan; nan[5::11, 0] = np.inf
+    for kw in (dict(), dict(dense=True, max_points=3, max_voxels=500)):
+        _cmp_vox(VoxelGenerator(b, s, **kw)(_t(nan, dev)), oracle.VoxelGenerator(b, s, **kw)(nan), kw, "nan")
+
+
+def test_voxel_reference_tests(dev):
+    """test/test_voxel.py:11-78 ported verbatim in spirit (dense + sparse semantic pins, filters)."""
+    from d3d_b200.voxel import VoxelGenerator
+    cloud = torch.rand((2000, 4), dtype=torch.float32)
+    cloud = torch.cat((cloud, torch.tensor([[-1, -1, -1, -100], [-2, -2, -2, 100]], dtype=torch.float32)), axis=0)
+    gen = VoxelGenerator([0, 1, 0, 1, 0, 1], [10, 10, 10], reduction="mean", max_points=5, max_voxels=20000,
+                         max_points_filter="trim", max_voxels_filter="trim", dense=True)
+    data = gen(cloud.to(dev))
+    assert len(data.voxels) == len(data.coords) and len(data.voxels) <= 1000
+    assert torch.all((data.voxels >= 0) & (data.voxels <= 1)) and torch.all((data.coords >= 0) & (data.coords <= 10))
+    v, c, n = data.voxels.cpu(), data.coords.cpu(), data.voxel_npoints.cpu()
+    for i in range(len(v)):
+        for j in range(min(int(n[i]), 5)):
+            for k in range(3):
+                assert c[i, k] == int(v[i, j, k] * 10)
+    gen = VoxelGenerator([0, 1, 0, 1, 0, 1], [10, 10, 10], reduction="none", max_points=5, max_voxels=20000,
+                         max_points_filter="trim", max_voxels_filter="trim", dense=True)
+    data = gen(cloud.to(dev))
+    assert 'aggregates' not in data and len(data.voxels) == len(data.coords)
+    data = VoxelGenerator([0, 1, 0, 1, 0, 1], [10, 10, 10])(cloud)       # host tensor in, host tensors out
+    assert len(data.points) == 2000 and len(data.coords) <= 1000 and not data.points.is_cuda
+    assert torch.equal(data.coords[data.points_mapping], (cloud[:2000, :3] * 10).long())
+    cloud3 = (torch.rand((2000, 3), dtype=torch.float32) - 0.5) * 4
+    data = VoxelGenerator([-1, 1, -1, 1, -1, 1], [20, 20, 20])(cloud3.to(dev))
+    assert torch.all((data.points >= -1) & (data.points <= 1)) and torch.all((data.coords >= 0) & (data.coords <= 20))
+    assert torch.equal(data.coords[data.points_mapping], ((data.points + 1) * 10).long())
+    assert len(VoxelGenerator([0, 1, 0, 1, 0, 1], [10, 10, 10], max_voxels=10, max_voxels_filter="trim")(cloud3.to(dev)).coords) <= 10
+    assert len(VoxelGenerator([0, 1, 0, 1, 0, 1], [10, 10, 10], max_voxels=10, max_voxels_filter="descending")(cloud3.to(dev)).coords) <= 10
+    data = VoxelGenerator([0, 1, 0, 1, 0, 1], [10, 10, 10], min_points=2, max_points=4, max_points_filter="trim")(cloud3.to(dev))
+    assert torch.all((data.voxel_npoints >= 2) & (data.voxel_npoints <= 4))
+    with pytest.raises(ValueError):
+        VoxelGenerator([0.013, 1, 0, 1, 0, 1], [10, 10, 10])
+    with pytest.raises(ValueError):
+        VoxelGenerator([0, 1, 0, 1, 0, 1], [10, 10, 10], reduction="mean")
+    with pytest.raises(NotImplementedError):
+        VoxelGenerator([0, 1, 0, 1, 0, 1], [10, 10, 10], max_points_filter="farthest_sampling")(cloud3.to(dev))
+
+
+def test_voxel_batch_equals_per_frame(dev, oracle):
+    """frame batching (C5): one launch sequence over 6 ragged frames == 6 independent calls == oracle"""
+    from d3d_b200.voxel import VoxelGenerator
+    frames = [lidar(np.random.default_rng(100 + i), n) for i, n in enumerate((9000, 1, 0, 12000, 777, 4096))]
+    bounds, shape = [0, 70.4, -40, 40, -3, 1], [352, 400, 40]
+    for kw in (dict(max_points=3, max_points_filter="trim", max_voxels=2500, max_voxels_filter="trim"),
+               dict(max_voxels=300, max_voxels_filter="descending", min_points=2),
+               dict(dense=True, max_points=4, max_voxels=3000, reduction="mean")):
+        gen = VoxelGenerator(bounds, shape, **kw)
+        res = gen.batch([_t(f, dev) for f in frames])
+        for f, r in zip(frames, res):
+            _cmp_vox(r, oracle.VoxelGenerator(bounds, shape, **kw)(f), kw, "batch " + str(kw))
+
+
+# ------------------------------------------------------------------ aligned scatter
+def test_scatter_golden_and_oracle(dev, oracle):
+    from d3d_b200.point import aligned_scatter
+    g = golden("scatter.npz")
+    for tag in ("f32", "f64"):
+        for dim in (1, 2, 3):
+            img, crd = g[f"{tag}.d{dim}.image"], g[f"{tag}.d{dim}.coord"]
+            for meth, at in (("mean", 1), ("linear", 2)):
+                out = aligned_scatter(_t(crd, dev), _t(img, dev), meth).cpu().numpy()
+                assert out.dtype == img.dtype and np.array_equal(out, g[f"{tag}.d{dim}.{meth}"]), (tag, dim, meth)
+                # backward against the oracle (reference CPU backward is a no-op at this commit, see make_golden.py)
+                ti = _t(img, dev).requires_grad_(True)
+                o = aligned_scatter(_t(crd, dev), ti, meth)
+                gr = np.random.default_rng(dim).random(o.shape).astype(img.dtype)
+                o.backward(_t(gr, dev))
+                exp = oracle.scatter_backward(crd, gr, at, img.shape)
+                tol = 1e-5 if tag == "f32" else 1e-12   # atomics add in arbitrary order
+                assert np.abs(ti.grad.cpu().numpy() - exp).max() < tol, (tag, dim, meth)
+
+
+def test_scatter_reference_test(dev):
+    """test/test_point.py:10-69 (drop / mean / linear forward and backward known answers)"""
+    from d3d_b200.point import aligned_scatter
+    coord = torch.tensor([[0, 0.25, 0.25, 0.25], [0, 1.25, 1.25, 1.25], [1, 2.25, 2.25, 2.25]], device=dev)
+    image_feat = torch.rand(2, 10, 3, 3, 3, device=dev)
+    image_feat.requires_grad = True
+    indexing = lambda icoord: (icoord[:, 0], slice(None)) + tuple(icoord[:, i] for i in range(1, coord.shape[1]))
+    lcoords = torch.tensor(np.array(np.meshgrid([0, 1], [0, 1], [0, 1])).T.reshape(-1, 3), device=dev)
+    pfeat = aligned_scatter(coord, image_feat, "drop")
+    assert torch.allclose(pfeat, image_feat[indexing(coord.long())])
+    pfeat.sum().backward()
+    assert torch.allclose(image_feat.grad[0, :, 0, 0, 0], torch.full([10], 1.0, device=dev))
+    pfeat = aligned_scatter(coord, image_feat, "mean")
+    icoord = torch.cat([torch.full((8, 1), 0, dtype=torch.long, device=dev), lcoords], dim=1)
+    assert torch.allclose(pfeat[0], torch.mean(image_feat[indexing(icoord)], dim=0))
+    icoord = torch.cat([torch.full((8, 1), 0, dtype=torch.long, device=dev), lcoords + 1], dim=1)
+    assert torch.allclose(pfeat[1], torch.mean(image_feat[indexing(icoord)], dim=0))
+    assert torch.allclose(pfeat[2], image_feat[1, :, 2, 2, 2])
+    image_feat.grad.zero_()
+    pfeat.sum().backward()
+    assert torch.allclose(image_feat.grad[0, :, 0, 0, 0], torch.full([10], 1 / 8, device=dev))
+    assert torch.allclose(image_feat.grad[0, :, 1, 1, 1], torch.full([10], 1 / 4, device=dev))
+    assert torch.allclose(image_feat.grad[1, :, 2, 2, 2], torch.full([10], 1.0, device=dev))
+    pfeat = aligned_scatter(coord, image_feat, "linear")
+    nhigh = torch.sum(lcoords, dim=1).long()
+    wmap = torch.tensor([0.25 ** i * 0.75 ** (3 - i) for i in range(4)], device=dev)
+    lweight = wmap[nhigh]
+    icoord = torch.cat([torch.full((8, 1), 0, dtype=torch.long, device=dev), lcoords], dim=1)
+    assert torch.allclose(pfeat[0], torch.sum(image_feat[indexing(icoord)] * lweight.unsqueeze(1), dim=0))
+    assert torch.allclose(pfeat[2], image_feat[1, :, 2, 2, 2])
+    image_feat.grad.zero_()
+    pfeat.sum().backward()
+    assert torch.allclose(image_feat.grad[0, :, 0, 0, 0], torch.full([10], .75 ** 3, device=dev))
+    assert torch.allclose(image_feat.grad[0, :, 1, 1, 1], torch.full([10], .75 ** 3 + .25 ** 3, device=dev))
+    assert torch.allclose(image_feat.grad[1, :, 2, 2, 2], torch.full([10], 1.0, device=dev))
+    with pytest.raises(AttributeError):
+        aligned_scatter(coord, image_feat, "bogus")
+    with pytest.raises(ValueError):
+        aligned_scatter(coord, image_feat, "max")
+
+
+def test_scatter_c2s_anchor(dev, oracle):
+    """88k points x 64 channels from a 1x64x704x800 map; checksum anchors + sampled oracle rows"""
+    from d3d_b200.point import aligned_scatter
+    pts = lidar(np.random.default_rng(1), 120000)
+    sel = (pts[:, 0] >= 0) & (pts[:, 0] < 70.4) & (pts[:, 1] >= -40) & (pts[:, 1] < 40)
+    p = pts[sel]
+    crd = np.stack([np.zeros(len(p), np.float32), p[:, 0] / np.float32(0.1), (p[:, 1] + np.float32(40)) / np.float32(0.1)], 1).astype(np.float32)
+    fm = torch.rand((1, 64, 704, 800), generator=torch.Generator().manual_seed(7))
+    tf, tc = fm.to(dev), _t(crd, dev)
+    om, ol = aligned_scatter(tc, tf, "mean"), aligned_scatter(tc, tf, "linear")
+    if len(p) == 88596:
+        assert abs(om.double().sum().item() - 2835634.619722) < 0.5 and abs(ol.double().sum().item() - 2834503.070217) < 0.5
+    idx = np.random.default_rng(0).integers(0, len(p), 200)
+    fmn = fm.numpy()
+    assert np.array_equal(om.cpu().numpy()[idx], oracle.scatter_forward(crd[idx], fmn, 1))
+    assert np.array_equal(ol.cpu().numpy()[idx], oracle.scatter_forward(crd[idx], fmn, 2))
