@@ -27,7 +27,7 @@ class VoxelParams(C.Structure):
     _fields_ = [("size", C.c_float * 3), ("vlo", C.c_int64 * 3), ("vhi", C.c_int64 * 3), ("offset", C.c_int32 * 3),
                 ("min_points", C.c_int32), ("max_points", C.c_int32), ("max_voxels", C.c_int32),
                 ("max_points_filter", C.c_int32), ("max_voxels_filter", C.c_int32), ("bound", C.c_float * 6),
-                ("shape", C.c_int32 * 3), ("reduction", C.c_int32)]
+                ("shape", C.c_int32 * 3), ("reduction", C.c_int32), ("algo", C.c_int32), ("max_frame_points", C.c_int64)]
 
 
 def _sig(name, restype, argtypes):
@@ -48,7 +48,7 @@ iou_count_candidates = _sig("d3d_iou_count_candidates", C.c_int, [_vp, _i64, _vp
 nms_workspace_bytes = _sig("d3d_nms2d_workspace_bytes", _sz, [_i64, C.c_int])
 _nms_sig = [_vp, _vp, _i64, C.c_int, C.c_int, _f, _f, _f, _vp, _vp, _sz, _vp]
 nms2d = {F32: _sig("d3d_nms2d_f32", C.c_int, _nms_sig), F64: _sig("d3d_nms2d_f64", C.c_int, _nms_sig)}
-voxelize_workspace_bytes = _sig("d3d_voxelize_workspace_bytes", _sz, [_i64, _i64])
+voxelize_workspace_bytes = _sig("d3d_voxelize_workspace_bytes", _sz, [_i64, _i64, _i64])
 voxelize_sparse = _sig("d3d_voxelize_sparse_f32", C.c_int,
                        [_vp, _i64, _i32, _vp, _i64, C.POINTER(VoxelParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp])
 voxelize_dense = _sig("d3d_voxelize_dense_f32", C.c_int,
@@ -58,7 +58,7 @@ scatter_forward = _sig("d3d_aligned_scatter_forward", C.c_int, _sc_sig)
 scatter_backward = _sig("d3d_aligned_scatter_backward", C.c_int, _sc_sig)
 fma_peak_probe = _sig("d3d_fma_peak_probe", C.c_int, [C.c_int, _i64, _vp, C.POINTER(C.c_double), _vp])
 
-if abi_version() != 1:
+if abi_version() != 2:
     raise ImportError("libd3d_b200.so ABI version mismatch")
 
 

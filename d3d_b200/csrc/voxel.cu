@@ -16,23 +16,10 @@
 // No atomics decide any output, so every tensor is bit-reproducible run to run and equal to the
 // reference's: coords, points_mapping, points_mask, voxel_npoints, dense voxels/pmask/aggregates
 // (MEAN sums a voxel's points sequentially in input order like voxelize.cpp:137-164).
-#include "common.cuh"
+#include "voxel.cuh"
 #include "prims.cuh"
 
 namespace d3d {
-
-constexpr uint64_t VOX_INVALID = ~0ull;
-
-struct VoxCfg {
-    int dense;
-    float size[3];      // voxel size (sparse: _size tensor; dense: (hi-lo)/shape in float)
-    float lo[3];        // dense lower bound
-    long long vlo[3];   // sparse: first kept coordinate; dense: 0
-    long long ext[3];   // kept extent per dim
-    int offset[3];      // sparse: coords_out = coord - offset
-    unsigned long long G;  // cells per frame
-    int min_points, max_points, max_voxels, pfilter, vfilter, reduction;
-};
 
 __device__ __forceinline__ int64_t frame_of(const int64_t *__restrict__ offs, int64_t nframes, int64_t i)
 {
@@ -54,23 +41,8 @@ __global__ void __launch_bounds__(256) vox_key_kernel(const float *__restrict__ 
         const float *q = pts + i * nfeat;
         p[0] = q[0]; p[1] = q[1]; p[2] = q[2];
     }
-    bool ok = true;
-    unsigned long long lin = 0;
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-        long long c;
-        if (cfg.dense) {
-            float v = __fdiv_rn(__fsub_rn(p[d], cfg.lo[d]), cfg.size[d]);   // voxelize.cpp:100, truncation toward zero
-            ok = ok && !isnan(v);
-            c = (long long)(int)v;
-        } else {
-            float v = floorf(__fdiv_rn(p[d], cfg.size[d]));                 // voxelize.cpp:309
-            ok = ok && !isnan(v);
-            c = (long long)(int)v - cfg.vlo[d];
-        }
-        ok = ok && c >= 0 && c < cfg.ext[d];
-        lin = lin * (unsigned long long)cfg.ext[d] + (unsigned long long)(ok ? c : 0);
-    }
+    unsigned long long lin;
+    const bool ok = vox_cell(cfg, p[0], p[1], p[2], &lin);
     uint64_t key = VOX_INVALID;
     if (ok) key = (uint64_t)frame_of(offs, nframes, i) * cfg.G + lin;
     keys[i] = key;
@@ -375,7 +347,22 @@ static int check_common(const float *points, int64_t total, int32_t nfeat, const
 
 using namespace d3d;
 
-extern "C" size_t d3d_voxelize_workspace_bytes(int64_t total_points, int64_t nframes) { return vox_ws_bytes(total_points > 0 ? total_points : 1, nframes); }
+extern "C" size_t d3d_voxelize_workspace_bytes(int64_t total_points, int64_t nframes, int64_t max_frame_points)
+{
+    const int64_t t = total_points > 0 ? total_points : 1;
+    const size_t a = vox_ws_bytes(t, nframes), b = vox_cluster_ws_bytes(t, nframes, max_frame_points);
+    return a > b ? a : b;
+}
+
+// AUTO: cluster path whenever it supports the configuration; an explicit request for an unsupported one is an error
+static int pick_algo(const d3d_voxel_params *P, const VoxCfg &cfg, int64_t total, int64_t nframes, bool *cluster)
+{
+    if (P->algo < D3D_VOXEL_AUTO || P->algo > D3D_VOXEL_CLUSTER) return D3D_ERR_INVALID_ARGUMENT;
+    const bool ok = vox_cluster_supported(cfg, total, nframes, P->max_frame_points > 0 ? P->max_frame_points : total);
+    if (P->algo == D3D_VOXEL_CLUSTER && !ok) return D3D_ERR_UNSUPPORTED;
+    *cluster = ok && P->algo != D3D_VOXEL_SORT;
+    return D3D_OK;
+}
 
 extern "C" int d3d_voxelize_sparse_f32(const float *points, int64_t total, int32_t nfeat, const int64_t *offs, int64_t nframes, const d3d_voxel_params *P,
                                        float *out_points, int64_t *out_mask, int64_t *out_mapping, int32_t *out_npoints, int64_t *out_coords, int64_t *counts,
@@ -386,10 +373,17 @@ extern "C" int d3d_voxelize_sparse_f32(const float *points, int64_t total, int32
     if (rc) return rc;
     if (nframes == 0) return D3D_OK;
     if (total > 0 && (!out_points || !out_mask || !out_mapping || !out_npoints || !out_coords)) return D3D_ERR_INVALID_ARGUMENT;
-    if (!ws || ws_bytes < vox_ws_bytes(total > 0 ? total : 1, nframes)) return D3D_ERR_WORKSPACE;
-    if (nframes >= 2048) return D3D_ERR_INVALID_ARGUMENT;   // DESCENDING key packs the frame in 11 bits
     VoxCfg cfg;
     if ((rc = build_cfg(P, 0, nframes, &cfg))) return rc;
+    bool cluster = false;
+    if ((rc = pick_algo(P, cfg, total, nframes, &cluster))) return rc;
+    if (cluster) {
+        if (!ws || ws_bytes < vox_cluster_ws_bytes(total > 0 ? total : 1, nframes, P->max_frame_points)) return D3D_ERR_WORKSPACE;
+        return vox_cluster_sparse(points, total, nfeat, offs, nframes, P->max_frame_points, cfg, out_points, out_mask, out_mapping, out_npoints, out_coords,
+                                  counts, ws, ws_bytes, st);
+    }
+    if (!ws || ws_bytes < vox_ws_bytes(total > 0 ? total : 1, nframes)) return D3D_ERR_WORKSPACE;
+    if (nframes >= 2048) return D3D_ERR_INVALID_ARGUMENT;   // DESCENDING key packs the frame in 11 bits
     VoxBufs B;
     if ((rc = vox_common(points, total, nfeat, offs, nframes, cfg, B, ws, ws_bytes, st))) return rc;
     const unsigned gb = (unsigned)cdiv(total + 1, 256);
@@ -423,15 +417,20 @@ extern "C" int d3d_voxelize_dense_f32(const float *points, int64_t total, int32_
     if (rc) return rc;
     if (nframes == 0) return D3D_OK;
     if (P->max_points < 0 || P->max_voxels < 0) return D3D_ERR_INVALID_ARGUMENT;
-    if (!voxels || !coords || !pmask || !npoints) return D3D_ERR_INVALID_ARGUMENT;
+    if (!coords || !npoints || (P->max_points > 0 && (!voxels || !pmask))) return D3D_ERR_INVALID_ARGUMENT;   // max_points 0: empty slot arrays
     if (P->reduction != D3D_RED_NONE && !aggregates) return D3D_ERR_INVALID_ARGUMENT;
-    if (!ws || ws_bytes < vox_ws_bytes(total > 0 ? total : 1, nframes)) return D3D_ERR_WORKSPACE;
     VoxCfg cfg;
     if ((rc = build_cfg(P, 1, nframes, &cfg))) return rc;
+    bool cluster = false;
+    if ((rc = pick_algo(P, cfg, total, nframes, &cluster))) return rc;
+    if (!ws || ws_bytes < (cluster ? vox_cluster_ws_bytes(total > 0 ? total : 1, nframes, P->max_frame_points) : vox_ws_bytes(total > 0 ? total : 1, nframes)))
+        return D3D_ERR_WORKSPACE;
     const size_t nslots = (size_t)nframes * (size_t)cfg.max_voxels * (size_t)cfg.max_points;
     D3D_CUDA_TRY(cudaMemsetAsync(voxels, 0, nslots * nfeat * sizeof(float), st));
     D3D_CUDA_TRY(cudaMemsetAsync(pmask, 0, nslots, st));
     D3D_CUDA_TRY(cudaMemsetAsync(npoints, 0, (size_t)nframes * cfg.max_voxels * sizeof(int32_t), st));
+    if (cluster)
+        return vox_cluster_dense(points, total, nfeat, offs, nframes, P->max_frame_points, cfg, voxels, coords, pmask, npoints, counts, ws, ws_bytes, st);
     VoxBufs B;
     if ((rc = vox_common(points, total, nfeat, offs, nframes, cfg, B, ws, ws_bytes, st))) return rc;
     const unsigned gb = (unsigned)cdiv(total + 1, 256);

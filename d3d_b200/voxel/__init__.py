@@ -46,6 +46,8 @@ class VoxelGenerator:
     '''
     Convert point cloud to voxels (same constructor and result keys as the reference)
     '''
+    default_algo = "auto"   # back end of new instances: "auto" | "sort" | "cluster" (results are identical)
+
     def __init__(self, bounds, shape,
         min_points=0, max_points=30, max_voxels=20000,
         max_points_filter=None, max_voxels_filter=None,
@@ -109,6 +111,9 @@ class VoxelGenerator:
         p.max_voxels_filter = int(self._max_voxels_filter)
         p.reduction = int(self._reduction)
         self._params = p
+        # execution back end, no effect on results: "auto" (cluster-per-frame hash path when it supports the
+        # configuration, else the sort pipeline), "sort", "cluster" (raises NotImplementedError if unsupported)
+        self.algo = VoxelGenerator.default_algo
 
     def __call__(self, points):
         '''
@@ -148,8 +153,10 @@ class VoxelGenerator:
         nframes = offs_host.numel() - 1
         offs = offs_host.to(dev, non_blocking=True)
         counts = torch.empty((nframes, 2), dtype=torch.int64, device=dev)
-        ws = _c.workspace(_c.voxelize_workspace_bytes(total, nframes), dev)
-        p = self._params
+        p = _c.VoxelParams.from_buffer_copy(self._params)
+        p.max_frame_points = int((offs_host[1:] - offs_host[:-1]).max()) if nframes > 0 else 0
+        p.algo = {"auto": 0, "sort": 1, "cluster": 2}[self.algo]
+        ws = _c.workspace(_c.voxelize_workspace_bytes(total, nframes, p.max_frame_points), dev)
         tcap = max(total, 1)
         with torch.cuda.device(dev):
             if self._dense:

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define D3D_B200_ABI_VERSION 1
+#define D3D_B200_ABI_VERSION 2
 
 enum d3d_status {
     D3D_OK = 0,
@@ -44,6 +44,9 @@ enum d3d_max_voxels_filter { D3D_VF_NONE = 0, D3D_VF_TRIM = 1, D3D_VF_DESCENDING
 /* reference d3d/point/scatter.h:37 */
 enum d3d_align_type { D3D_ALIGN_DROP = 0, D3D_ALIGN_MEAN = 1, D3D_ALIGN_LINEAR = 2, D3D_ALIGN_MAX = 3, D3D_ALIGN_NEAREST = 4 };
 enum d3d_dtype { D3D_F32 = 0, D3D_F64 = 1 };
+/* voxelization back ends: one thread-block cluster per frame with a hash table (fast path) or the
+ * sort / segmented-scan pipeline (general).  Both produce identical, deterministic outputs. */
+enum d3d_voxel_algo { D3D_VOXEL_AUTO = 0, D3D_VOXEL_SORT = 1, D3D_VOXEL_CLUSTER = 2 };
 
 int d3d_abi_version(void);
 const char *d3d_error_string(int status);
@@ -111,9 +114,13 @@ typedef struct d3d_voxel_params {
     float bound[6];     /* xmin,xmax,ymin,ymax,zmin,zmax; idx = (int)((p-lo)/((hi-lo)/shape)) */
     int32_t shape[3];
     int32_t reduction;  /* d3d_reduction_type */
+    /* execution hints (no effect on results) */
+    int32_t algo;              /* d3d_voxel_algo: AUTO picks the cluster path whenever it supports the configuration */
+    int64_t max_frame_points;  /* largest frame of the batch (host knows the offsets); 0 = unknown, assume `total` */
 } d3d_voxel_params;
 
-size_t d3d_voxelize_workspace_bytes(int64_t total_points, int64_t nframes);
+/* max_frame_points: largest frame of the batch (0 = unknown): bounds the per-frame scratch of the cluster path */
+size_t d3d_voxelize_workspace_bytes(int64_t total_points, int64_t nframes, int64_t max_frame_points);
 /* sparse + filter fused; replaces voxelize_3d_sparse + voxelize_3d_filter (voxelize.h:14-25).
  * out_points f32[total,nfeat], out_mask i64[total] (index of the surviving point INSIDE its frame),
  * out_mapping i64[total], out_npoints i32[total], out_coords i64[total,3]. */

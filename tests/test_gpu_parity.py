@@ -237,6 +237,21 @@ EXPECT_DTYPES = dict(points=torch.float32, points_mask=torch.int64, points_mappi
                      coords=torch.int64, voxels=torch.float32, voxel_pmask=torch.bool, aggregates=torch.float32)
 
 
+@pytest.fixture(autouse=True, params=["auto", "sort"])
+def voxel_backend(request):
+    """every voxel test runs on both back ends: "auto" (cluster-per-frame hash path wherever it supports the
+    configuration) and "sort" (the general pipeline); the outputs must be bit-identical"""
+    if "voxel" not in request.node.name:
+        if request.param == "sort":
+            pytest.skip("back-end parameter only applies to the voxel tests")
+        yield
+        return
+    from d3d_b200.voxel import VoxelGenerator
+    VoxelGenerator.default_algo = request.param
+    yield
+    VoxelGenerator.default_algo = "auto"
+
+
 def _cmp_vox(r, exp, kw, tag):
     assert set(r.keys()) == set(exp.keys()), (tag, r.keys(), exp.keys())
     for k, v in exp.items():
@@ -382,6 +397,10 @@ def test_voxel_reference_tests(dev):
         VoxelGenerator([0, 1, 0, 1, 0, 1], [10, 10, 10], reduction="mean")
     with pytest.raises(NotImplementedError):
         VoxelGenerator([0, 1, 0, 1, 0, 1], [10, 10, 10], max_points_filter="farthest_sampling")(cloud3.to(dev))
+    gen = VoxelGenerator([0, 1, 0, 1, 0, 1], [10, 10, 10], max_voxels=10, max_voxels_filter="descending")
+    gen.algo = "cluster"                      # the cluster back end does not order voxels by count: explicit request fails
+    with pytest.raises(NotImplementedError):
+        gen(cloud3.to(dev))
 
 
 def test_voxel_batch_equals_per_frame(dev, oracle):
@@ -475,3 +494,29 @@ def test_scatter_c2s_anchor(dev, oracle):
     fmn = fm.numpy()
     assert np.array_equal(om.cpu().numpy()[idx], oracle.scatter_forward(crd[idx], fmn, 1))
     assert np.array_equal(ol.cpu().numpy()[idx], oracle.scatter_forward(crd[idx], fmn, 2))
+
+
+@pytest.mark.gpu
+def test_voxel_rank_paths_stress(dev, oracle):
+    """the three rank regimes of the cluster back end (voxels with <= max_points points, up to 32, beyond 32) in
+    one frame, zero-padded clouds (thousands of identical points), max_points 0 / 1 / large, ragged batches"""
+    from d3d_b200.voxel import VoxelGenerator
+    rng = np.random.default_rng(21)
+    pts = lidar(rng, 40000)
+    pts[rng.integers(0, len(pts), 6000)] = np.array([0.5, 0.5, -0.5, 0], np.float32)   # padding-like duplicates
+    pts[:, 3] = np.arange(len(pts)) % 977                                                # feature identifies the point
+    b, s = [0, 70.4, -40, 40, -3, 1], [176, 200, 8]
+    cases = [dict(max_points=k, max_points_filter="trim") for k in (0, 1, 5, 33, 200)]
+    cases += [dict(max_points=5, max_points_filter="trim", min_points=3, max_voxels=700, max_voxels_filter="trim"),
+              dict(dense=True, max_points=0, max_voxels=100), dict(dense=True, max_points=1, max_voxels=30000),
+              dict(dense=True, max_points=40, max_voxels=2000), dict(dense=True, max_points=7, max_voxels=35000)]
+    for kw in cases:
+        _cmp_vox(VoxelGenerator(b, s, **kw)(_t(pts, dev)), oracle.VoxelGenerator(b, s, **kw)(pts), kw, "stress " + str(kw))
+    frames = [pts[:n] for n in (40000, 33, 0, 1025, 8192, 1, 20000, 31, 17000, 64, 5, 12345, 2, 30000, 999, 4097, 7, 26000, 513, 3000)]
+    for kw in (dict(max_points=5, max_points_filter="trim"), dict(dense=True, max_points=3, max_voxels=5000)):
+        gen = VoxelGenerator(b, s, **kw)
+        for f, r in zip(frames, gen.batch([_t(f, dev) for f in frames])):
+            _cmp_vox(r, oracle.VoxelGenerator(b, s, **kw)(f), kw, "ragged batch " + str(kw))
+    p3 = pts[:, :3].copy()                                                                # nfeat = 3 (no float4 path)
+    _cmp_vox(VoxelGenerator(b, s, max_points=2, max_points_filter="trim")(_t(p3, dev)),
+             oracle.VoxelGenerator(b, s, max_points=2, max_points_filter="trim")(p3), dict(max_points=2), "nfeat3")
