@@ -319,15 +319,16 @@ def bench_voxel(args, rank, world, barrier):
     offs[1:] = torch.tensor([len(f) for f in frames]).cumsum(0)
     dev_pts = torch.cat([h.cuda() for h in host], 0)
     gen = VoxelGenerator(C2_BOUNDS, C2_SHAPE, **C2_KW)
-    res = gen.batch_packed(dev_pts, offs)
-    K = sum(int(r.points.shape[0]) for r in res)
-    V = sum(int(r.coords.shape[0]) for r in res)
+    offs_dev = offs.cuda()
+    res = gen.batch_packed(dev_pts, offs, offs_dev)
+    rows = res.rows_host()
+    K, V = int(rows[-1, 0]), int(rows[-1, 1])
     N = int(dev_pts.shape[0])
     alg_bytes = 16.0 * N + 32.0 * K + 28.0 * V
     del res
     l0 = c.launch_count()
     with ClockSampler(torch.cuda.current_device()) as cs:
-        ms = timed(lambda: gen.batch_packed(dev_pts, offs), args.steps, args.warmup, barrier)
+        ms = timed(lambda: gen.batch_packed(dev_pts, offs, offs_dev), args.steps, args.warmup, barrier)
     launches = (c.launch_count() - l0) // (args.steps + args.warmup) * args.steps
     ms = max_over_ranks(ms, world)
     e2e_steps = max(2, min(args.steps, 4))
@@ -341,7 +342,7 @@ def bench_voxel(args, rank, world, barrier):
                             frames_per_gpu=F, points_per_frame=C2_POINTS, kept_points=K, voxels=V,
                             l2_policy=f"inputs larger than L2 ({N * 16 / 1e6:.0f} MB of points per step vs 126 MB L2)"),
                 e2e=dict(value=N * world / (ms_e2e * 1e-3), unit="points/s", h2d_bytes_per_step=int(N * 16 + offs.numel() * 8),
-                         d2h_bytes_per_step=int(32 * K + 28 * V + F * 16), ms_per_step=ms_e2e,
+                         d2h_bytes_per_step=int(32 * K + 28 * V + (F + 8) * 16), ms_per_step=ms_e2e,
                          api="VoxelGenerator.batch(list of pinned host tensors) -> host tensors"),
                 roofline=dict(bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm, traffic=None, peak_source=how,
                               kernel="whole voxelize_sparse pass (all kernels of one step); algorithmic bytes 16N+32K+28V'",

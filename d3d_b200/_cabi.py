@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libd3d_b200.so")
+LIB_PATH = os.environ.get("D3D_B200_LIB") or os.path.join(_HERE, "libd3d_b200.so")   # override: A/B builds while tuning
 if not os.path.exists(LIB_PATH):
     raise ImportError(f"{LIB_PATH} not found: build the CUDA extension first (make -C d3d_b200/csrc). "
                       "d3d_b200 has no CPU fallback.")

@@ -122,7 +122,8 @@ __global__ void __launch_bounds__(256) vox_desc_rank_kernel(const uint64_t *__re
 // per voxel segment: new id (or -1) and the per-voxel outputs
 __global__ void __launch_bounds__(256) vox_voxel_out_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ seg_app,
                                                             const uint32_t *__restrict__ app, const uint32_t *__restrict__ prank, const uint32_t *__restrict__ passflag,
-                                                            const uint32_t *__restrict__ desc_rank, const int64_t *__restrict__ offs, const uint32_t *__restrict__ nseg_ptr, VoxCfg cfg,
+                                                            const uint32_t *__restrict__ desc_rank, const int64_t *__restrict__ offs, const int64_t *__restrict__ voff,
+                                                            const uint32_t *__restrict__ nseg_ptr, VoxCfg cfg,
                                                             int32_t *__restrict__ newid, int32_t *__restrict__ out_npoints, int64_t *__restrict__ out_coords)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(256) vox_voxel_out_kernel(const uint64_t *__re
     long long cz = (long long)(lin % (unsigned long long)cfg.ext[2]); lin /= (unsigned long long)cfg.ext[2];
     long long cy = (long long)(lin % (unsigned long long)cfg.ext[1]); lin /= (unsigned long long)cfg.ext[1];
     long long cx = (long long)lin;
-    int64_t o = cfg.dense ? (int64_t)f * cfg.max_voxels + nid : offs[f] + nid;
+    int64_t o = cfg.dense ? (int64_t)f * cfg.max_voxels + nid : voff[f] + nid;   // sparse outputs are packed across frames
     out_coords[o * 3 + 0] = cx + cfg.vlo[0] - cfg.offset[0];
     out_coords[o * 3 + 1] = cy + cfg.vlo[1] - cfg.offset[1];
     out_coords[o * 3 + 2] = cz + cfg.vlo[2] - cfg.offset[2];
@@ -177,23 +178,56 @@ __global__ void __launch_bounds__(256) vox_point_out_kernel(const float *__restr
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total || !keepflag[i]) return;
     int64_t f = frame_of(offs, nframes, i);
-    int64_t o = offs[f] + (int64_t)(ppos[i] - ppos[offs[f]]);
+    int64_t o = (int64_t)ppos[i];   // global exclusive scan of the keep flags: rows are packed across frames
     if (nfeat == 4) reinterpret_cast<float4 *>(out_points)[o] = __ldg(reinterpret_cast<const float4 *>(pts) + i);
     else for (int k = 0; k < nfeat; k++) out_points[o * nfeat + k] = pts[i * nfeat + k];
     out_mask[o] = i - offs[f];
     out_mapping[o] = pmap[i];
 }
 
-__global__ void vox_counts_sparse_kernel(const uint32_t *__restrict__ ppos, const uint32_t *__restrict__ app, const uint32_t *__restrict__ prank,
-                                         const int64_t *__restrict__ offs, int64_t nframes, VoxCfg cfg, int64_t *__restrict__ counts)
+// voff[f] = first voxel row of frame f in the packed outputs = sum over earlier frames of their (capped) voxel counts
+__global__ void __launch_bounds__(1024) vox_voxel_rows_kernel(const uint32_t *__restrict__ app, const uint32_t *__restrict__ prank, const int64_t *__restrict__ offs,
+                                                              int64_t nframes, VoxCfg cfg, int64_t *__restrict__ voff)
+{
+    __shared__ long long wsum[32];
+    __shared__ long long carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < nframes; base += 1024) {
+        const int64_t f = base + threadIdx.x;
+        long long nv = 0;
+        if (f < nframes) {
+            nv = (long long)(prank[app[offs[f + 1]]] - prank[app[offs[f]]]);   // voxels passing min_points (and bounds)
+            if (cfg.vfilter != D3D_VF_NONE && nv > cfg.max_voxels) nv = cfg.max_voxels;
+        }
+        long long inc = nv;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { long long t = __shfl_up_sync(0xffffffffu, inc, d); if (lane_id() >= (unsigned)d) inc += t; }
+        if (lane_id() == 31) wsum[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            long long v = wsum[threadIdx.x], vi = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { long long t = __shfl_up_sync(0xffffffffu, vi, d); if (lane_id() >= (unsigned)d) vi += t; }
+            wsum[threadIdx.x] = vi - v;
+        }
+        __syncthreads();
+        const long long excl = carry_s + wsum[threadIdx.x >> 5] + inc - nv;
+        if (f < nframes) voff[f] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023 || f == nframes - 1) { carry_s = excl + nv; if (f == nframes - 1) voff[nframes] = excl + nv; }
+        __syncthreads();
+    }
+}
+
+// frame_rows[f] = {first kept-point row, first voxel row} of frame f; entry nframes holds the totals
+__global__ void vox_rows_sparse_kernel(const uint32_t *__restrict__ ppos, const int64_t *__restrict__ voff, const int64_t *__restrict__ offs, int64_t nframes,
+                                       int64_t *__restrict__ rows)
 {
     int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nframes) return;
-    int64_t b = offs[f], e = offs[f + 1];
-    counts[2 * f] = (int64_t)(ppos[e] - ppos[b]);
-    int64_t nv = (int64_t)(prank[app[e]] - prank[app[b]]);   // voxels passing min_points (and bounds)
-    if (cfg.vfilter != D3D_VF_NONE && nv > cfg.max_voxels) nv = cfg.max_voxels;
-    counts[2 * f + 1] = nv;
+    if (f > nframes) return;
+    rows[2 * f] = (int64_t)ppos[offs[f]];
+    rows[2 * f + 1] = voff[f];
 }
 
 // dense: slot writer, one thread per sorted position
@@ -259,9 +293,9 @@ static int key_bits_of(unsigned long long maxkey)
 
 static size_t vox_ws_bytes(int64_t total, int64_t nframes)
 {
-    (void)nframes;
     size_t n1 = (size_t)(total + 2);
-    return align_up(n1 * 8) * 2 + align_up(n1 * 4) * 12 + radix_sort_workspace_bytes(total + 1) + scan_workspace_bytes(total + 2) + 8192;
+    return align_up(n1 * 8) * 2 + align_up(n1 * 4) * 12 + radix_sort_workspace_bytes(total + 1) + scan_workspace_bytes(total + 2) +
+           align_up((size_t)(nframes + 2) * 8) + 8192;
 }
 
 static int build_cfg(const d3d_voxel_params *P, int dense, int64_t nframes, VoxCfg *cfg)
@@ -298,6 +332,7 @@ struct VoxBufs {
     int32_t *newid, *pmap;
     void *sort_ws, *scan_ws;
     size_t sort_bytes;
+    int64_t *voff;
 };
 
 static int vox_common(const float *points, int64_t total, int nfeat, const int64_t *offs, int64_t nframes, const VoxCfg &cfg, VoxBufs &B, void *ws, size_t ws_bytes,
@@ -314,6 +349,7 @@ static int vox_common(const float *points, int64_t total, int nfeat, const int64
     B.sort_bytes = radix_sort_workspace_bytes(total + 1);
     B.sort_ws = a.take<char>(B.sort_bytes);
     B.scan_ws = a.take<char>(scan_workspace_bytes(total + 2));
+    B.voff = a.take<int64_t>((size_t)nframes + 2);
     if (!a.ok()) return D3D_ERR_WORKSPACE;
     const unsigned gb = (unsigned)cdiv(total + 1, 256);
     int rc;
@@ -399,13 +435,14 @@ extern "C" int d3d_voxelize_sparse_f32(const float *points, int64_t total, int32
         if ((rc = radix_sort_pairs_u64(dk, dv, total + 1, 64, B.sort_ws, B.sort_bytes, st))) return rc;
         vox_desc_rank_kernel<<<gb, 256, 0, st>>>(dk, dv, B.app, offs, nseg, B.desc_rank); D3D_LAUNCHED();
     }
-    vox_voxel_out_kernel<<<gb, 256, 0, st>>>(B.keys, B.seg_start, B.seg_app, B.app, B.prank, B.passflag, B.desc_rank, offs, nseg, cfg, B.newid, out_npoints, out_coords);
+    vox_voxel_rows_kernel<<<1, 1024, 0, st>>>(B.app, B.prank, offs, nframes, cfg, B.voff); D3D_LAUNCHED();
+    vox_voxel_out_kernel<<<gb, 256, 0, st>>>(B.keys, B.seg_start, B.seg_app, B.app, B.prank, B.passflag, B.desc_rank, offs, B.voff, nseg, cfg, B.newid, out_npoints, out_coords);
     D3D_LAUNCHED();
     vox_point_flag_kernel<<<gb, 256, 0, st>>>(B.keys, B.sidx, B.segid, B.seg_start, B.newid, total, cfg, B.keepflag, B.pmap); D3D_LAUNCHED();
     D3D_CUDA_TRY(cudaMemsetAsync(B.keepflag + total, 0, 4, st));
     if ((rc = exclusive_scan_u32(B.keepflag, B.ppos, total + 1, nullptr, B.scan_ws, st))) return rc;
     vox_point_out_kernel<<<gb, 256, 0, st>>>(points, nfeat, B.keepflag, B.ppos, B.pmap, offs, nframes, total, out_points, out_mask, out_mapping); D3D_LAUNCHED();
-    vox_counts_sparse_kernel<<<(unsigned)cdiv(nframes, 64), 64, 0, st>>>(B.ppos, B.app, B.prank, offs, nframes, cfg, counts); D3D_LAUNCHED();
+    vox_rows_sparse_kernel<<<(unsigned)cdiv(nframes + 1, 64), 64, 0, st>>>(B.ppos, B.voff, offs, nframes, counts); D3D_LAUNCHED();
     return D3D_OK;
 }
 
@@ -437,7 +474,7 @@ extern "C" int d3d_voxelize_dense_f32(const float *points, int64_t total, int32_
     const uint32_t *nseg = B.segid + total;
     D3D_CUDA_TRY(cudaMemsetAsync(B.passflag, 0, (size_t)(total + 1) * 4, st));
     vox_pass_kernel<<<gb, 256, 0, st>>>(B.keys, B.seg_start, B.seg_first, B.app, nseg, cfg, B.seg_app, B.passflag); D3D_LAUNCHED();
-    vox_voxel_out_kernel<<<gb, 256, 0, st>>>(B.keys, B.seg_start, B.seg_app, B.app, B.passflag /*unused*/, B.passflag, B.desc_rank, offs, nseg, cfg, B.newid, npoints, coords);
+    vox_voxel_out_kernel<<<gb, 256, 0, st>>>(B.keys, B.seg_start, B.seg_app, B.app, B.passflag /*unused*/, B.passflag, B.desc_rank, offs, nullptr, nseg, cfg, B.newid, npoints, coords);
     D3D_LAUNCHED();
     vox_dense_point_kernel<<<gb, 256, 0, st>>>(points, nfeat, B.keys, B.sidx, B.segid, B.seg_start, B.newid, total, cfg, voxels, pmask); D3D_LAUNCHED();
     if (cfg.reduction != D3D_RED_NONE) {

@@ -124,7 +124,9 @@ class VoxelGenerator:
         return self.batch([points])[0]
 
     def batch(self, frames):
-        """Voxelize a list of frames in one launch sequence; returns one dict per frame."""
+        """Voxelize a list of frames in one launch; returns a sequence with one result dict per frame.
+        CUDA frames: results stay on the device.  Host frames: the batch is streamed through the GPU
+        (pinned staging, copies overlapped with compute) and the results come back as host tensors."""
         if len(frames) == 0:
             return []
         odev = frames[0].device
@@ -134,76 +136,118 @@ class VoxelGenerator:
                 raise RuntimeError("expected scalar type Float")  # reference: accessor<float,2> type error
             if f.dim() != 2 or f.shape[1] != nfeat:
                 raise ValueError("all frames must be [N, C] with the same C")
-        lens = [int(f.shape[0]) for f in frames]
-        pts = _c.to_device(frames[0]) if len(frames) == 1 else torch.cat([_c.to_device(f) for f in frames], 0)
+        lens = torch.tensor([int(f.shape[0]) for f in frames], dtype=torch.int64)
         offs_host = torch.zeros(len(frames) + 1, dtype=torch.int64)
-        offs_host[1:] = torch.tensor(lens, dtype=torch.int64).cumsum(0)
-        return self._run(pts, offs_host, odev)
+        offs_host[1:] = lens.cumsum(0)
+        if odev.type != "cuda":
+            from ._stream import host_batch
+            return host_batch(self, frames, offs_host)
+        pts = frames[0].contiguous() if len(frames) == 1 else torch.cat(list(frames), 0)
+        return self._run(pts, offs_host)
 
-    def batch_packed(self, points, offsets_host):
+    def batch_packed(self, points, offsets_host, offsets_dev=None):
         """Batch form without the concatenation: `points` f32[total, C] already holds the frames back to
-        back (CUDA tensor), `offsets_host` is the int64[nframes+1] CPU tensor of frame boundaries."""
+        back (CUDA tensor), `offsets_host` is the int64[nframes+1] CPU tensor of frame boundaries
+        (`offsets_dev`: the same offsets already on the device, saves the copy)."""
         if points.dtype != torch.float32:
             raise RuntimeError("expected scalar type Float")
-        return self._run(_c.to_device(points), offsets_host.to(torch.int64), points.device)
+        return self._run(_c.to_device(points), offsets_host.to(torch.int64), offs_dev=offsets_dev)
 
-    def _run(self, pts, offs_host, odev):
+    def _alloc(self, total, nfeat, nframes, max_frame_points, dev):
+        """device buffers of one launch: packed outputs, per-frame row table, scratch"""
+        tcap = max(total, 1)
+        if self._dense:
+            V, P = self._max_voxels, self._max_points
+            rows = torch.empty((nframes, 2), dtype=torch.int64, device=dev)
+            bufs = dict(voxels=torch.empty((nframes, V, P, nfeat), dtype=torch.float32, device=dev),
+                        coords=torch.empty((nframes, V, 3), dtype=torch.int64, device=dev),
+                        voxel_pmask=torch.empty((nframes, V, P), dtype=torch.uint8, device=dev),
+                        voxel_npoints=torch.empty((nframes, V), dtype=torch.int32, device=dev))
+            if self._reduction != ReductionType.NONE:
+                bufs["aggregates"] = torch.empty((nframes, V, nfeat), dtype=torch.float32, device=dev)
+        else:
+            rows = torch.empty((nframes + 1, 2), dtype=torch.int64, device=dev)
+            bufs = dict(points=torch.empty((tcap, nfeat), dtype=torch.float32, device=dev),
+                        points_mask=torch.empty(tcap, dtype=torch.int64, device=dev),
+                        points_mapping=torch.empty(tcap, dtype=torch.int64, device=dev),
+                        voxel_npoints=torch.empty(tcap, dtype=torch.int32, device=dev),
+                        coords=torch.empty((tcap, 3), dtype=torch.int64, device=dev))
+        ws = _c.workspace(_c.voxelize_workspace_bytes(total, nframes, max_frame_points), dev)
+        return bufs, rows, ws
+
+    def _launch(self, pts, offs, nframes, max_frame_points, bufs, rows, ws):
+        """one C-ABI call on the current stream; bufs/rows/ws may be larger than this launch needs"""
+        total, nfeat = int(pts.shape[0]), int(pts.shape[1])
+        p = _c.VoxelParams.from_buffer_copy(self._params)
+        p.max_frame_points = max_frame_points
+        p.algo = {"auto": 0, "sort": 1, "cluster": 2}[self.algo]
+        with torch.cuda.device(pts.device):
+            if self._dense:
+                if nframes < bufs["voxels"].shape[0]:
+                    bufs = {k: v[:nframes] for k, v in bufs.items()}
+                    rows = rows[:nframes]
+                st = _c.voxelize_dense(_c.ptr(pts), total, nfeat, _c.ptr(offs), nframes, C.byref(p), _c.ptr(bufs["voxels"]), _c.ptr(bufs["coords"]),
+                                       _c.ptr(bufs["voxel_pmask"]), _c.ptr(bufs["voxel_npoints"]), _c.ptr(bufs.get("aggregates")), _c.ptr(rows),
+                                       _c.ptr(ws), ws.numel(), _c.stream_ptr())
+                _c.check(st, "voxelize_3d_dense")
+                return VoxelBatch(bufs, rows, nframes, dense=True)
+            st = _c.voxelize_sparse(_c.ptr(pts), total, nfeat, _c.ptr(offs), nframes, C.byref(p), _c.ptr(bufs["points"]), _c.ptr(bufs["points_mask"]),
+                                    _c.ptr(bufs["points_mapping"]), _c.ptr(bufs["voxel_npoints"]), _c.ptr(bufs["coords"]), _c.ptr(rows),
+                                    _c.ptr(ws), ws.numel(), _c.stream_ptr())
+            _c.check(st, "voxelize_3d_sparse/filter")
+            return VoxelBatch(bufs, rows[:nframes + 1], nframes, dense=False)
+
+    def _run(self, pts, offs_host, offs_dev=None):
+        """launch on the current stream; nothing is read back until a frame of the result is indexed"""
         dev = pts.device
         total, nfeat = int(pts.shape[0]), int(pts.shape[1])
         nframes = offs_host.numel() - 1
-        offs = offs_host.to(dev, non_blocking=True)
-        counts = torch.empty((nframes, 2), dtype=torch.int64, device=dev)
-        p = _c.VoxelParams.from_buffer_copy(self._params)
-        p.max_frame_points = int((offs_host[1:] - offs_host[:-1]).max()) if nframes > 0 else 0
-        p.algo = {"auto": 0, "sort": 1, "cluster": 2}[self.algo]
-        ws = _c.workspace(_c.voxelize_workspace_bytes(total, nframes, p.max_frame_points), dev)
-        tcap = max(total, 1)
+        offs = offs_host.to(dev, non_blocking=True) if offs_dev is None else offs_dev
+        max_frame = int((offs_host[1:] - offs_host[:-1]).max()) if nframes > 0 else 0
         with torch.cuda.device(dev):
-            if self._dense:
-                V, P = self._max_voxels, self._max_points
-                voxels = torch.empty((nframes, V, P, nfeat), dtype=torch.float32, device=dev)
-                coords = torch.empty((nframes, V, 3), dtype=torch.int64, device=dev)
-                pmask = torch.empty((nframes, V, P), dtype=torch.uint8, device=dev)
-                npts = torch.empty((nframes, V), dtype=torch.int32, device=dev)
-                aggr = torch.empty((nframes, V, nfeat), dtype=torch.float32, device=dev) if self._reduction != ReductionType.NONE else None
-                st = _c.voxelize_dense(_c.ptr(pts), total, nfeat, _c.ptr(offs), nframes, C.byref(p), _c.ptr(voxels), _c.ptr(coords),
-                                       _c.ptr(pmask), _c.ptr(npts), _c.ptr(aggr), _c.ptr(counts), _c.ptr(ws), ws.numel(), _c.stream_ptr())
-                _c.check(st, "voxelize_3d_dense")
-                cnt = counts.cpu()   # the one readback: per-frame sizes
-                out = []
-                for f in range(nframes):
-                    nv = int(cnt[f, 1])
-                    r = Dict(voxels=voxels[f, :nv], coords=coords[f, :nv], voxel_pmask=pmask[f, :nv].view(torch.bool),
-                             voxel_npoints=npts[f, :nv])
-                    if aggr is not None:
-                        r["aggregates"] = aggr[f, :nv]
-                    out.append(self._home(r, odev))
-                return out
-            out_points = torch.empty((tcap, nfeat), dtype=torch.float32, device=dev)
-            out_mask = torch.empty(tcap, dtype=torch.int64, device=dev)
-            out_map = torch.empty(tcap, dtype=torch.int64, device=dev)
-            out_np = torch.empty(tcap, dtype=torch.int32, device=dev)
-            out_co = torch.empty((tcap, 3), dtype=torch.int64, device=dev)
-            st = _c.voxelize_sparse(_c.ptr(pts), total, nfeat, _c.ptr(offs), nframes, C.byref(p), _c.ptr(out_points), _c.ptr(out_mask),
-                                    _c.ptr(out_map), _c.ptr(out_np), _c.ptr(out_co), _c.ptr(counts), _c.ptr(ws), ws.numel(), _c.stream_ptr())
-            _c.check(st, "voxelize_3d_sparse/filter")
-            cnt = counts.cpu()
-            out = []
-            for f in range(nframes):
-                b = int(offs_host[f]); k = int(cnt[f, 0]); nv = int(cnt[f, 1])
-                out.append(self._home(Dict(points=out_points[b:b + k], points_mask=out_mask[b:b + k], points_mapping=out_map[b:b + k],
-                                           voxel_npoints=out_np[b:b + nv], coords=out_co[b:b + nv]), odev))
-            return out
+            bufs, rows, ws = self._alloc(total, nfeat, nframes, max_frame, dev)
+        return self._launch(pts, offs, nframes, max_frame, bufs, rows, ws)
 
-    @staticmethod
-    def _home(r, odev):
-        """results go back to where the input came from; host copies land in pinned memory and are
-        queued asynchronously (one stream sync per dict instead of one per tensor)"""
-        if odev.type != "cuda":
-            for k in list(r.keys()):
-                src = r[k]
-                dst = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
-                dst.copy_(src, non_blocking=True)
-                r[k] = dst
-            torch.cuda.current_stream().synchronize()
+
+class VoxelBatch:
+    """Result of a batched voxelization: behaves like a list of per-frame result dicts.
+
+    The per-frame tensors are views into packed buffers (`.packed`); the per-frame sizes live on the device
+    (`.rows`) and are read back -- the only synchronisation -- the first time a frame is indexed."""
+    POINT_KEYS = ("points", "points_mask", "points_mapping")
+
+    def __init__(self, bufs, rows, nframes, dense, rows_host=None):
+        self.packed, self.rows, self.nframes, self.dense = bufs, rows, nframes, dense
+        self._rows_host = rows_host
+        self._cache = {}
+
+    def __len__(self):
+        return self.nframes
+
+    def rows_host(self):
+        if self._rows_host is None:
+            self._rows_host = self.rows.cpu()
+        return self._rows_host
+
+    def __getitem__(self, f):
+        if isinstance(f, slice):
+            return [self[i] for i in range(*f.indices(self.nframes))]
+        if f < 0:
+            f += self.nframes
+        if not 0 <= f < self.nframes:
+            raise IndexError(f)
+        r = self._cache.get(f)
+        if r is None:
+            rh = self.rows_host()
+            if self.dense:
+                nv = int(rh[f, 1])
+                r = Dict((k, v[f, :nv]) for k, v in self.packed.items())
+                r["voxel_pmask"] = r["voxel_pmask"].view(torch.bool)
+            else:
+                k0, k1, v0, v1 = int(rh[f, 0]), int(rh[f + 1, 0]), int(rh[f, 1]), int(rh[f + 1, 1])
+                r = Dict((k, v[k0:k1] if k in self.POINT_KEYS else v[v0:v1]) for k, v in self.packed.items())
+            self._cache[f] = r
         return r
+
+    def __iter__(self):
+        return (self[i] for i in range(self.nframes))

@@ -95,9 +95,13 @@ int d3d_nms2d_f64(const double *boxes, const double *scores, int64_t n, int iou_
 /* ------------------------------------------------------------------------------------------------
  * Voxelization of a BATCH of frames (one frame = one reference VoxelGenerator.__call__).
  * points f32[total, nfeat] (first 3 columns xyz); frame_offsets DEVICE i64[nframes+1], ascending,
- * frame f owns points [frame_offsets[f], frame_offsets[f+1]).  All per-point / per-voxel outputs of
- * frame f are written starting at row frame_offsets[f] of the output arrays (a frame never has more
- * voxels than points), its sizes to counts[f] = {kept points K_f, voxels V_f} (device i64[nframes,2]).
+ * frame f owns points [frame_offsets[f], frame_offsets[f+1]).
+ * Sparse outputs are PACKED across frames in frame order: the kept points of frame f occupy rows
+ * [frame_rows[f][0], frame_rows[f+1][0]) of out_points / out_mask / out_mapping and its voxels rows
+ * [frame_rows[f][1], frame_rows[f+1][1]) of out_npoints / out_coords, where frame_rows is the DEVICE
+ * i64[nframes+1, 2] array the call fills (entry nframes = totals).  One contiguous device-to-host copy
+ * per array therefore moves a whole batch.  Dense outputs keep the regular [nframes, max_voxels, ...]
+ * layout and report counts[f] = {0, voxels V_f} (device i64[nframes, 2]).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct d3d_voxel_params {
     /* sparse path (reference voxelize.cpp:288-484 through d3d/voxel/__init__.py:96-103) */
@@ -122,11 +126,12 @@ typedef struct d3d_voxel_params {
 /* max_frame_points: largest frame of the batch (0 = unknown): bounds the per-frame scratch of the cluster path */
 size_t d3d_voxelize_workspace_bytes(int64_t total_points, int64_t nframes, int64_t max_frame_points);
 /* sparse + filter fused; replaces voxelize_3d_sparse + voxelize_3d_filter (voxelize.h:14-25).
- * out_points f32[total,nfeat], out_mask i64[total] (index of the surviving point INSIDE its frame),
- * out_mapping i64[total], out_npoints i32[total], out_coords i64[total,3]. */
+ * Capacities: out_points f32[total,nfeat], out_mask i64[total] (index of the surviving point INSIDE its
+ * frame), out_mapping i64[total] (voxel id inside the frame), out_npoints i32[total], out_coords i64[total,3];
+ * frame_rows i64[nframes+1,2] as described above. */
 int d3d_voxelize_sparse_f32(const float *points, int64_t total, int32_t nfeat, const int64_t *frame_offsets,
                             int64_t nframes, const d3d_voxel_params *params, float *out_points, int64_t *out_mask,
-                            int64_t *out_mapping, int32_t *out_npoints, int64_t *out_coords, int64_t *counts,
+                            int64_t *out_mapping, int32_t *out_npoints, int64_t *out_coords, int64_t *frame_rows,
                             void *workspace, size_t workspace_bytes, void *stream);
 /* dense; replaces voxelize_3d_dense (voxelize.h:9-12).  Per frame f the outputs live at
  * voxels f32[nframes,max_voxels,max_points,nfeat], coords i64[nframes,max_voxels,3],
