@@ -20,7 +20,11 @@
 namespace d3d {
 
 // ------------------------------------------------------------------ prep
-template <typename T>
+// TILE == 0: one 8-field record per box (rows of the IoU kernel, NMS, the candidate counter).
+// TILE > 0: field-major inside blocks of TILE boxes -- block t holds cx[TILE], cy[TILE], c, s, hw, hh, rho, area -- so that
+// a column tile is staged with one contiguous copy and a warp's shared-memory reads of one field of 32 different
+// columns of a 32-column chunk hit 32 different banks.
+template <typename T, int TILE>
 __global__ void __launch_bounds__(256) box_prep_kernel(const T *__restrict__ boxes, int64_t n, int64_t npad, BoxRec<T> *__restrict__ recs)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -33,7 +37,13 @@ __global__ void __launch_bounds__(256) box_prep_kernel(const T *__restrict__ box
         r.cx = r.cy = r.c = r.s = r.hw = r.hh = r.area = T(0);
         r.rho = T(NAN);  // padding: fails every candidate test
     }
-    recs[i] = r;
+    if (TILE == 0) {
+        recs[i] = r;
+    } else {
+        T *f = reinterpret_cast<T *>(recs + (i / TILE) * TILE) + (i % TILE);
+        f[0 * TILE] = r.cx; f[1 * TILE] = r.cy; f[2 * TILE] = r.c; f[3 * TILE] = r.s;
+        f[4 * TILE] = r.hw; f[5 * TILE] = r.hh; f[6 * TILE] = r.rho; f[7 * TILE] = r.area;
+    }
 }
 
 template <typename T>
@@ -52,21 +62,29 @@ template <> struct IouTile<double> { static constexpr int TR = 64, TC = 64; };
 
 constexpr int IOU_THREADS = 256;
 constexpr int IOU_WARPS = IOU_THREADS / 32;
-constexpr int IOU_QCAP = 256;  // per-warp ring of pending candidate pairs (uint16: row_local << 8 | col)
+
+// shared-memory image of one CTA (dynamic: more than the 48 KB static limit for fp32)
+template <typename T> struct IouSmem {
+    static constexpr int TR = IouTile<T>::TR, TC = IouTile<T>::TC;
+    static constexpr int RW = TR / IOU_WARPS;          // rows per warp
+    static constexpr int KC = TC / 32;                 // columns per lane
+    static constexpr int DEPTH = RW * KC;              // pairs one lane tests per tile (<= 32: one bit each)
+    BoxRec<T> sA[TR];                                   // row records
+    T sB[8][TC];                                        // column records, field-major: cx, cy, c, s, hw, hh, rho, area
+    T tile[TR][TC];
+    uint16_t queue[IOU_WARPS][DEPTH * 32 + 32];        // the warp's candidates packed back to back (row_local * TC + col)
+};
 
 template <typename T>
 __global__ void __launch_bounds__(IOU_THREADS, 3)
 iou2dr_tile_kernel(const BoxRec<T> *__restrict__ recA, int64_t n, const BoxRec<T> *__restrict__ recB, int64_t m,
                    T *__restrict__ out, int64_t ld, int64_t tiles_c)
 {
-    constexpr int TR = IouTile<T>::TR, TC = IouTile<T>::TC;
-    constexpr int RW = TR / IOU_WARPS;   // rows per warp
-    constexpr int KC = TC / 32;          // column chunks per lane
+    using S = IouSmem<T>;
+    constexpr int TR = S::TR, TC = S::TC, RW = S::RW, KC = S::KC;
     constexpr int V = 16 / sizeof(T);    // elements per 16-byte vector
-    __shared__ BoxRec<T> sA[TR];
-    __shared__ BoxRec<T> sB[TC];
-    __shared__ __align__(16) T tile[TR][TC];
-    __shared__ uint16_t queue[IOU_WARPS][IOU_QCAP];
+    extern __shared__ __align__(16) unsigned char iou_smem_raw[];
+    S &sm = *reinterpret_cast<S *>(iou_smem_raw);
 
     const int64_t tr = blockIdx.x / tiles_c, tc = blockIdx.x % tiles_c;   // column tiles fastest: A rows reused, B streams through L2
     const int64_t row0 = tr * TR, col0 = tc * TC;
@@ -75,7 +93,7 @@ iou2dr_tile_kernel(const BoxRec<T> *__restrict__ recA, int64_t n, const BoxRec<T
     {   // stage records (arrays are padded to tile multiples, so no bounds checks)
         const float4 *ga = reinterpret_cast<const float4 *>(recA + row0);
         const float4 *gb = reinterpret_cast<const float4 *>(recB + col0);
-        float4 *da = reinterpret_cast<float4 *>(sA), *db = reinterpret_cast<float4 *>(sB);
+        float4 *da = reinterpret_cast<float4 *>(sm.sA), *db = reinterpret_cast<float4 *>(&sm.sB[0][0]);
         constexpr int NA = TR * sizeof(BoxRec<T>) / 16, NB = TC * sizeof(BoxRec<T>) / 16;
         for (int i = threadIdx.x; i < NA; i += IOU_THREADS) da[i] = __ldg(ga + i);
         for (int i = threadIdx.x; i < NB; i += IOU_THREADS) db[i] = __ldg(gb + i);
@@ -84,41 +102,51 @@ iou2dr_tile_kernel(const BoxRec<T> *__restrict__ recA, int64_t n, const BoxRec<T
 #pragma unroll
     for (int r = 0; r < RW; r++)
 #pragma unroll
-        for (int k = 0; k < KC; k++) tile[w * RW + r][k * 32 + lane] = T(0);
+        for (int k = 0; k < KC; k++) sm.tile[w * RW + r][k * 32 + lane] = T(0);
     __syncthreads();
 
+    // ---- scan: bounding-circle test of this warp's RW x TC pairs: 6 flops, a compare, a ballot and a select per pair
+    // (no popc, no shared-memory traffic on the per-pair path).
     T bx[KC], by[KC], br[KC];
 #pragma unroll
-    for (int k = 0; k < KC; k++) { bx[k] = sB[k * 32 + lane].cx; by[k] = sB[k * 32 + lane].cy; br[k] = sB[k * 32 + lane].rho; }
-
-    uint16_t *q = queue[w];
-    unsigned head = 0, tail = 0;   // warp-uniform ring indices
-#pragma unroll 1
-    for (int r = 0; r <= RW; r++) {
-        if (r < RW) {
-            const BoxRec<T> &a = sA[w * RW + r];
-            const T ax = a.cx, ay = a.cy, ar = a.rho;
+    for (int k = 0; k < KC; k++) { bx[k] = sm.sB[0][k * 32 + lane]; by[k] = sm.sB[1][k * 32 + lane]; br[k] = sm.sB[6][k * 32 + lane]; }
+    static_assert(RW * KC <= 32, "one lane per tested (row, column chunk)");
+    unsigned mybal = 0;     // lane r*KC+k keeps the ballot of (row r, columns k*32 .. k*32+31)
 #pragma unroll
-            for (int k = 0; k < KC; k++) {
-                T dx = ax - bx[k], dy = ay - by[k], rs = ar + br[k];
-                bool cand = dx * dx + dy * dy <= rs * rs;           // false for NaN padding
-                unsigned bal = __ballot_sync(0xffffffffu, cand);
-                if (cand) q[(tail + __popc(bal & lanemask_lt())) & (IOU_QCAP - 1)] = (uint16_t)((r << 8) | (k * 32 + lane));
-                tail += __popc(bal);
-            }
+    for (int r = 0; r < RW; r++) {
+        const BoxRec<T> &a = sm.sA[w * RW + r];
+        const T ax = a.cx, ay = a.cy, ar = a.rho;
+#pragma unroll
+        for (int k = 0; k < KC; k++) {
+            T dx = ax - bx[k], dy = ay - by[k], rs = ar + br[k];
+            const unsigned bal = __ballot_sync(0xffffffffu, dx * dx + dy * dy <= rs * rs);   // false for NaN padding
+            if (lane == (unsigned)(r * KC + k)) mybal = bal;
         }
-        // drain full warps; on the extra last iteration drain the remainder too
-        while (tail - head >= 32u || (r == RW && tail != head)) {
-            __syncwarp();
-            unsigned cnt = min(tail - head, 32u);
-            unsigned e = q[(head + min(lane, cnt - 1)) & (IOU_QCAP - 1)];
-            const unsigned row = w * RW + (e >> 8), col = e & 255u;
-            BoxRec<T> A = sA[row], B = sB[col];
-            T v = rbox_iou<T>(A, B);
-            if (lane < cnt) tile[row][col] = v;
-            head += cnt;
-            __syncwarp();
-        }
+    }
+    // ---- pack: exclusive prefix of the per-(row, chunk) counts; lane r*KC+k expands its ballot into the warp queue, so
+    // the queue is ordered by row, then column: the 32 pairs of one clip step share (mostly) one row -> the row record is a
+    // broadcast read, and their columns are distinct modulo 32 -> the field-major column reads and the tile store are
+    // bank-conflict free.  Entry = row_local * TC + column.
+    const unsigned cnt = __popc(mybal);
+    unsigned incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (unsigned)d) incl += t; }
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    uint16_t *q = sm.queue[w];
+    for (unsigned pos = incl - cnt; mybal; mybal &= mybal - 1, pos++)
+        q[pos] = (uint16_t)((lane << 5) | (__ffs(mybal) - 1));
+    __syncwarp();
+
+    // ---- clip: full warps of 32 queued candidates (the last one padded with a repeat of the final entry)
+#pragma unroll 1
+    for (unsigned h = 0; h < total; h += 32) {
+        const unsigned e = q[min(h + lane, total - 1)];
+        const unsigned row = w * RW + e / TC, col = e % TC;
+        BoxRec<T> A = sm.sA[row], B;
+        B.cx = sm.sB[0][col]; B.cy = sm.sB[1][col]; B.c = sm.sB[2][col]; B.s = sm.sB[3][col];
+        B.hw = sm.sB[4][col]; B.hh = sm.sB[5][col]; B.area = sm.sB[7][col]; B.rho = T(0);
+        T v = rbox_iou<T>(A, B);
+        if (h + lane < total) sm.tile[row][col] = v;
     }
     __syncwarp();
 
@@ -129,7 +157,7 @@ iou2dr_tile_kernel(const BoxRec<T> *__restrict__ recA, int64_t n, const BoxRec<T
         const int64_t row = row0 + w * RW + r;
         if (row >= n) break;
         T *orow = out + row * ld + col0;
-        const T *trow = tile[w * RW + r];
+        const T *trow = sm.tile[w * RW + r];
         if (vec_ok && col0 + TC <= m) {
             for (int c = lane * V; c < TC; c += 32 * V)
                 __stcs(reinterpret_cast<float4 *>(orow + c), *reinterpret_cast<const float4 *>(trow + c));
@@ -184,11 +212,11 @@ template <typename T> static size_t iou_ws_bytes(int64_t n, int64_t m)
     return 256 + align_up((size_t)cdiv(n > 0 ? n : 1, TR) * TR * sizeof(BoxRec<T>)) + align_up((size_t)cdiv(m > 0 ? m : 1, TC) * TC * sizeof(BoxRec<T>));
 }
 
-template <typename T>
+template <typename T, int FIELD_MAJOR_TILE = 0>
 static int prep_boxes(const T *boxes, int64_t n, int tile, BoxRec<T> *recs, cudaStream_t st)
 {
     int64_t npad = cdiv(n, tile) * tile;
-    box_prep_kernel<T><<<(unsigned)cdiv(npad, 256), 256, 0, st>>>(boxes, n, npad, recs); D3D_LAUNCHED();
+    box_prep_kernel<T, FIELD_MAJOR_TILE><<<(unsigned)cdiv(npad, 256), 256, 0, st>>>(boxes, n, npad, recs); D3D_LAUNCHED();
     return D3D_OK;
 }
 
@@ -206,10 +234,15 @@ static int iou2dr_impl(const T *b1, int64_t n, const T *b2, int64_t m, T *out, i
     BoxRec<T> *ra = a.take<BoxRec<T>>(tiles_r * TR), *rb = a.take<BoxRec<T>>(tiles_c * TC);
     int rc;
     if ((rc = prep_boxes<T>(b1, n, TR, ra, st))) return rc;
-    if ((rc = prep_boxes<T>(b2, m, TC, rb, st))) return rc;
+    if ((rc = prep_boxes<T, TC>(b2, m, TC, rb, st))) return rc;
     int64_t nblocks = tiles_r * tiles_c;
     if (nblocks > 0x7fffffffll) return D3D_ERR_INVALID_ARGUMENT;
-    iou2dr_tile_kernel<T><<<(unsigned)nblocks, IOU_THREADS, 0, st>>>(ra, n, rb, m, out, ld, tiles_c); D3D_LAUNCHED();
+    static bool smem_opt_in = false;   // per instantiation; the attribute is per function and sticky
+    if (!smem_opt_in) {
+        D3D_CUDA_TRY(cudaFuncSetAttribute(iou2dr_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IouSmem<T>)));
+        smem_opt_in = true;
+    }
+    iou2dr_tile_kernel<T><<<(unsigned)nblocks, IOU_THREADS, sizeof(IouSmem<T>), st>>>(ra, n, rb, m, out, ld, tiles_c); D3D_LAUNCHED();
     return D3D_OK;
 }
 
