@@ -87,31 +87,81 @@ template <> struct Num<double> {
     static D3D_HD double abs_(double a) { return fabs(a); }
 };
 
-// signed integral contribution of one directed edge P->Q of A (in B's frame):
-//   (x0 - x1) * mean over the edge's clamped span of clamp(y, -hh, hh),  x0/x1 = clamp(Px/Qx, -hw, hw)
+// Pair arithmetic.  On sm_100a a float2 add / mul / fma is ONE instruction (FADD2 / FMUL2 / FFMA2: two fp32 results per
+// lane per issue slot, operand negation, half swaps and scalar broadcasts are free operand modifiers), and the clip
+// below is issue-bound, so its edge integrals are evaluated two edges at a time.  For double (and on the host, where
+// the CPU test-suite checks the algorithm) the same code is two scalar operations.
+template <typename T> struct Vec2;
+template <> struct Vec2<float>  { using type = float2; };
+template <> struct Vec2<double> { using type = double2; };
+
+template <typename T> struct P2 {
+    using V = typename Vec2<T>::type;
+    static D3D_HD V mk(T x, T y) { V r; r.x = x; r.y = y; return r; }
+    static D3D_HD V add(V a, V b)
+    {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+        if constexpr (sizeof(T) == 4) return __fadd2_rn(a, b);
+#endif
+        return mk(a.x + b.x, a.y + b.y);
+    }
+    static D3D_HD V sub(V a, V b)
+    {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+        if constexpr (sizeof(T) == 4) return __fadd2_rn(a, mk(-b.x, -b.y));
+#endif
+        return mk(a.x - b.x, a.y - b.y);
+    }
+    static D3D_HD V mul(V a, V b)
+    {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+        if constexpr (sizeof(T) == 4) return __fmul2_rn(a, b);
+#endif
+        return mk(a.x * b.x, a.y * b.y);
+    }
+    static D3D_HD V fma(V a, V b, V c)     // a*b + c
+    {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+        if constexpr (sizeof(T) == 4) return __ffma2_rn(a, b, c);
+#endif
+        return mk(a.x * b.x + c.x, a.y * b.y + c.y);
+    }
+    static D3D_HD V fnma(V a, V b, V c)    // c - a*b
+    {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+        if constexpr (sizeof(T) == 4) return __ffma2_rn(mk(-a.x, -a.y), b, c);
+#endif
+        return mk(c.x - a.x * b.x, c.y - a.y * b.y);
+    }
+};
+
+// Two directed edges of A at once (in B's frame).  ya / yb: the edge's ordinate at its start / end abscissa after the
+// abscissae were clamped to [-hw, hw].  Returns TWICE the mean over each edge's clamped span of clamp(y, -hh, hh):
+//   flo / fhi = fractions of the span below -hh / above +hh;  the part inside runs from cmin = ymin + flo*d to
+//   cmax = ymax - fhi*d, so cmin + cmax = ya + yb - d*(fhi - flo);   2*mean = 2*hh*(fhi - flo) + (1 - flo - fhi)*(cmin + cmax)
 template <typename T>
-D3D_HD T edge_term(T px, T py, T qx, T qy, T slope, T hw, T hh)
+D3D_HD typename P2<T>::V span_mean2(typename P2<T>::V ya, typename P2<T>::V yb, T hh)
 {
-    using N = Num<T>;
-    T x0 = N::fmin_(N::fmax_(px, -hw), hw);
-    T x1 = N::fmin_(N::fmax_(qx, -hw), hw);
-    T ya = py + slope * (x0 - px);
-    T yb = qy + slope * (x1 - qx);
-    T ymin = N::fmin_(ya, yb), ymax = N::fmax_(ya, yb);
-    T inv = N::rcp(ymax - ymin);                     // +inf for a horizontal span: fractions become 0/1
-    T flo = N::sat((-hh - ymin) * inv);              // fraction of the span below -hh  (sat(NaN) = 0)
-    T fhi = N::sat((ymax - hh) * inv);               // fraction above +hh
-    T cmin = N::fmin_(N::fmax_(ymin, -hh), hh);
-    T cmax = N::fmin_(N::fmax_(ymax, -hh), hh);
-    T mean = hh * (fhi - flo) + (T(1) - flo - fhi) * (T(0.5) * (cmin + cmax));
-    return (x0 - x1) * mean;
+    using N = Num<T>; using P = P2<T>; using V = typename P::V;
+    const V ymin = P::mk(N::fmin_(ya.x, yb.x), N::fmin_(ya.y, yb.y));
+    const V ymax = P::mk(N::fmax_(ya.x, yb.x), N::fmax_(ya.y, yb.y));
+    const V d = P::sub(ymax, ymin);
+    const T ix = N::rcp(d.x), iy = N::rcp(d.y);          // +inf for a horizontal span: the fractions become 0 / 1
+    const V nhh = P::mk(-hh, -hh);
+    const V tl = P::sub(nhh, ymin), th = P::add(ymax, nhh);
+    const V flo = P::mk(N::sat(tl.x * ix), N::sat(tl.y * iy));   // sat(NaN) = 0
+    const V fhi = P::mk(N::sat(th.x * ix), N::sat(th.y * iy));
+    const V diff = P::sub(fhi, flo);
+    const V csum = P::fnma(d, diff, P::add(ya, yb));
+    const V wmid = P::sub(P::sub(P::mk(T(1), T(1)), flo), fhi);
+    return P::fma(P::mk(hh + hh, hh + hh), diff, P::mul(wmid, csum));
 }
 
-// intersection-over-union of two rotated boxes given their records.  ~150 instructions, no branches.
+// intersection-over-union of two rotated boxes given their records.  No branches, registers only.
 template <typename T>
 D3D_HD T rbox_iou(const BoxRec<T> &A, const BoxRec<T> &B)
 {
-    using N = Num<T>;
+    using N = Num<T>; using P = P2<T>; using V = typename P::V;
     // A's centre and axes in B's frame
     T dx = A.cx - B.cx, dy = A.cy - B.cy;
     T cx = B.c * dx + B.s * dy;
@@ -120,22 +170,29 @@ D3D_HD T rbox_iou(const BoxRec<T> &A, const BoxRec<T> &B)
     // sin(rA - rB) from two separately rounded products: exactly 0 for equal headings (an FMA would leave
     // the rounding residue of one product, i.e. a 1e-8 rad tilt that costs 1e-4 of IoU on 1e4:1 slivers)
     T s = N::mul_rn(A.s, B.c) - N::mul_rn(A.c, B.s);
-    T ux = c * A.hw, uy = s * A.hw;    // half width axis
-    T vx = -s * A.hh, vy = c * A.hh;   // half height axis
-    // CCW vertices V0 = C-u-v, V1 = C+u-v, V2 = C+u+v, V3 = C-u+v  (same order as geometry.hpp:417-429)
-    T mx = cx - ux, px = cx + ux, my = cy - uy, py = cy + uy;
-    T x0 = mx - vx, y0 = my - vy;
-    T x1 = px - vx, y1 = py - vy;
-    T x2 = px + vx, y2 = py + vy;
-    T x3 = mx + vx, y3 = my + vy;
-    // slopes dy/dx of the u-edges (s/c) and v-edges (-c/s); a vertical edge has zero clamped x-extent,
-    // so any finite slope works for it
-    T mu = N::abs_(c) > N::tiny() ? s * N::rcp(c) : T(0);
-    T mv = N::abs_(s) > N::tiny() ? -c * N::rcp(s) : T(0);
-    T acc = edge_term<T>(x0, y0, x1, y1, mu, B.hw, B.hh);
-    acc += edge_term<T>(x1, y1, x2, y2, mv, B.hw, B.hh);
-    acc += edge_term<T>(x2, y2, x3, y3, mu, B.hw, B.hh);
-    acc += edge_term<T>(x3, y3, x0, y0, mv, B.hw, B.hh);
+    // half axes u (width) and v (height); a = u + v, b = u - v
+    const V u = P::mul(P::mk(c, s), P::mk(A.hw, A.hw)), v = P::mul(P::mk(-s, c), P::mk(A.hh, A.hh));
+    const V a = P::add(u, v), b = P::sub(u, v);
+    // CCW vertices V0 = C-a, V1 = C+b, V2 = C+a, V3 = C-b (same order as geometry.hpp:417-429), held as the pairs
+    // (V0, V2) and (V1, V3): edges e0 = V0->V1 and e2 = V2->V3 share the slope s/c, e1 = V1->V2 and e3 = V3->V0 share -c/s
+    const V pm = P::mk(T(-1), T(1)), mp = P::mk(T(1), T(-1));
+    const V X02 = P::fma(P::mk(a.x, a.x), pm, P::mk(cx, cx)), Y02 = P::fma(P::mk(a.y, a.y), pm, P::mk(cy, cy));
+    const V X13 = P::fma(P::mk(b.x, b.x), mp, P::mk(cx, cx)), Y13 = P::fma(P::mk(b.y, b.y), mp, P::mk(cy, cy));
+    // a vertical edge has zero clamped x-extent, so any finite slope works for it
+    const T mu = N::abs_(c) > N::tiny() ? s * N::rcp(c) : T(0);
+    const T mv = N::abs_(s) > N::tiny() ? -c * N::rcp(s) : T(0);
+    const T hw = B.hw, hh = B.hh;
+    const V CX02 = P::mk(N::fmin_(N::fmax_(X02.x, -hw), hw), N::fmin_(N::fmax_(X02.y, -hw), hw));
+    const V CX13 = P::mk(N::fmin_(N::fmax_(X13.x, -hw), hw), N::fmin_(N::fmax_(X13.y, -hw), hw));
+    const V D02 = P::sub(CX02, X02), D13 = P::sub(CX13, X13);       // how far the clamp moved each vertex abscissa
+    const V mu2 = P::mk(mu, mu), mv2 = P::mk(mv, mv);
+    const V ya02 = P::fma(mu2, D02, Y02), yb02 = P::fma(mu2, D13, Y13);   // e0, e2: start (V0, V2), end (V1, V3)
+    const V ya13 = P::fma(mv2, D13, Y13), t = P::fma(mv2, D02, Y02);      // e1, e3: start (V1, V3), end (V2, V0)
+    const V yb13 = P::mk(t.y, t.x);
+    // signed area under the clamped boundary: sum over the edges of (x_start - x_end) * mean clamp(y)
+    const V w02 = P::sub(CX02, CX13), w13 = P::sub(CX13, P::mk(CX02.y, CX02.x));
+    const V acc2 = P::fma(w13, span_mean2<T>(ya13, yb13, hh), P::mul(w02, span_mean2<T>(ya02, yb02, hh)));
+    const T acc = T(0.5) * (acc2.x + acc2.y);
     // the four edge integrals of two disjoint boxes cancel only up to rounding: snap residues below
     // snap()*(areaA+areaB) (IoU error <= 2*snap) to exactly +0 like the reference's empty intersection
     T asum = A.area + B.area;
