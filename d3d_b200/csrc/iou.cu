@@ -78,7 +78,7 @@ template <typename T> struct IouSmem {
 template <typename T>
 __global__ void __launch_bounds__(IOU_THREADS, 3)
 iou2dr_tile_kernel(const BoxRec<T> *__restrict__ recA, int64_t n, const BoxRec<T> *__restrict__ recB, int64_t m,
-                   T *__restrict__ out, int64_t ld, int64_t tiles_c)
+                   T *__restrict__ out, int64_t ld)
 {
     using S = IouSmem<T>;
     constexpr int TR = S::TR, TC = S::TC, RW = S::RW, KC = S::KC;
@@ -86,8 +86,9 @@ iou2dr_tile_kernel(const BoxRec<T> *__restrict__ recA, int64_t n, const BoxRec<T
     extern __shared__ __align__(16) unsigned char iou_smem_raw[];
     S &sm = *reinterpret_cast<S *>(iou_smem_raw);
 
-    const int64_t tr = blockIdx.x / tiles_c, tc = blockIdx.x % tiles_c;   // column tiles fastest: A rows reused, B streams through L2
-    const int64_t row0 = tr * TR, col0 = tc * TC;
+    // column tiles on grid.x (fastest): A rows reused, B streams through L2
+    const int64_t row0 = ((int64_t)blockIdx.y + (int64_t)blockIdx.z * 65535) * TR, col0 = (int64_t)blockIdx.x * TC;
+    if (row0 >= n) return;
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
 
     {   // stage records (arrays are padded to tile multiples, so no bounds checks)
@@ -99,10 +100,11 @@ iou2dr_tile_kernel(const BoxRec<T> *__restrict__ recA, int64_t n, const BoxRec<T
         for (int i = threadIdx.x; i < NB; i += IOU_THREADS) db[i] = __ldg(gb + i);
     }
     // zero this warp's rows of the output tile (rejected pairs are exactly +0)
+    {
+        float4 *z = reinterpret_cast<float4 *>(&sm.tile[w * RW][0]);
 #pragma unroll
-    for (int r = 0; r < RW; r++)
-#pragma unroll
-        for (int k = 0; k < KC; k++) sm.tile[w * RW + r][k * 32 + lane] = T(0);
+        for (int i = 0; i < RW * TC / (32 * V); i++) z[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     __syncthreads();
 
     // ---- scan: bounding-circle test of this warp's RW x TC pairs: 6 flops, a compare, a ballot and a select per pair
@@ -150,18 +152,23 @@ iou2dr_tile_kernel(const BoxRec<T> *__restrict__ recA, int64_t n, const BoxRec<T
     }
     __syncwarp();
 
-    // stream this warp's rows to HBM: 16-byte stores when the row pointers are 16-byte aligned
-    const bool vec_ok = (ld % V == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-#pragma unroll 1
-    for (int r = 0; r < RW; r++) {
-        const int64_t row = row0 + w * RW + r;
-        if (row >= n) break;
-        T *orow = out + row * ld + col0;
-        const T *trow = sm.tile[w * RW + r];
-        if (vec_ok && col0 + TC <= m) {
-            for (int c = lane * V; c < TC; c += 32 * V)
-                __stcs(reinterpret_cast<float4 *>(orow + c), *reinterpret_cast<const float4 *>(trow + c));
-        } else {
+    // stream this warp's rows to HBM: full-line 16-byte stores when the row pointers are 16-byte aligned
+    const int64_t wrow0 = row0 + w * RW;
+    const int nrows = (int)(n - wrow0 < RW ? (n - wrow0 > 0 ? n - wrow0 : 0) : RW);
+    const bool vec_ok = (ld % V == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && col0 + TC <= m;
+    T *orow = out + wrow0 * ld + col0;
+    if (vec_ok && nrows == RW) {
+        orow += lane * V;
+#pragma unroll
+        for (int r = 0; r < RW; r++) {
+#pragma unroll
+            for (int c = 0; c < TC; c += 32 * V)
+                __stcs(reinterpret_cast<float4 *>(orow + c), *reinterpret_cast<const float4 *>(&sm.tile[w * RW + r][lane * V + c]));
+            orow += ld;
+        }
+    } else {
+        for (int r = 0; r < nrows; r++, orow += ld) {
+            const T *trow = sm.tile[w * RW + r];
             for (int c = lane; c < TC; c += 32)
                 if (col0 + c < m) orow[c] = trow[c];
         }
@@ -235,14 +242,14 @@ static int iou2dr_impl(const T *b1, int64_t n, const T *b2, int64_t m, T *out, i
     int rc;
     if ((rc = prep_boxes<T>(b1, n, TR, ra, st))) return rc;
     if ((rc = prep_boxes<T, TC>(b2, m, TC, rb, st))) return rc;
-    int64_t nblocks = tiles_r * tiles_c;
-    if (nblocks > 0x7fffffffll) return D3D_ERR_INVALID_ARGUMENT;
+    if (tiles_c > 0x7fffffffll || tiles_r > 65535ll * 65535ll) return D3D_ERR_INVALID_ARGUMENT;
+    const dim3 grid((unsigned)tiles_c, (unsigned)(tiles_r < 65535 ? tiles_r : 65535), (unsigned)cdiv(tiles_r, 65535));
     static bool smem_opt_in = false;   // per instantiation; the attribute is per function and sticky
     if (!smem_opt_in) {
         D3D_CUDA_TRY(cudaFuncSetAttribute(iou2dr_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IouSmem<T>)));
         smem_opt_in = true;
     }
-    iou2dr_tile_kernel<T><<<(unsigned)nblocks, IOU_THREADS, sizeof(IouSmem<T>), st>>>(ra, n, rb, m, out, ld, tiles_c); D3D_LAUNCHED();
+    iou2dr_tile_kernel<T><<<grid, IOU_THREADS, sizeof(IouSmem<T>), st>>>(ra, n, rb, m, out, ld); D3D_LAUNCHED();
     return D3D_OK;
 }
 
