@@ -35,7 +35,7 @@ namespace d3d {
 
 constexpr int VC_THREADS = 1024;
 constexpr int VC_WARPS = VC_THREADS / 32;
-constexpr int VC_MAX_CSIZE = 16;
+constexpr int VC_MAX_CSIZE = 8;               // portable cluster sizes only
 constexpr int VC_MAX_CLUSTERS = 74;            // frames in flight the workspace is sized for
 constexpr uint32_t VC_NONE = 0xffffffffu;
 constexpr unsigned long long VC_EMPTY = ~0ull;
@@ -83,6 +83,19 @@ struct VcArgs {
     float *voxels; uint8_t *pmask;
     char *ws; VcLayout lay;
     unsigned long long *vstate, *kstate;   // sparse: cross-frame look-back words, one per frame (zeroed before the launch)
+    uint32_t dyn_bytes;                    // dynamic shared memory of the launch
+    int route;                             // sparse: try the shared-memory routed path first (vc_frame_route)
+};
+
+// per-CTA shared memory handed to the per-frame functions
+struct VcSh {
+    uint32_t *mytot, *wt1, *wt2, *vbase, *pbase;
+    unsigned long long *frow;      // first voxel row / first kept-point row of this frame in the packed outputs
+    uint2 *hbp;                    // routed path: first-of-voxel bits of every 32-point round (.x) and their exclusive prefix inside the warp's chunk (.y)
+    uint32_t *list, *lcount;       // routed path: work list
+    uint32_t *pool_min, *pool_acc0, *pool_acc1;   // routed path: records of the crowded voxels this CTA owns
+    uint32_t *qcount, *npool, *bail;
+    unsigned char *dyn;            // dynamic region: L2 path = per-warp probe rings; routed path = queue, slot table, reply words
 };
 
 __device__ __forceinline__ VcEntry vc_load_entry(const VcEntry *p)
@@ -185,7 +198,7 @@ __device__ __forceinline__ bool vc_cell(const VcDev &c, const float4 &p, uint32_
 #ifdef D3D_VC_TIMING   // tuning build only: per-phase time of a few frames, printed once per frame
 #define VC_TICK(slot) do { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tk_[slot] = (float)(t_ - t0_) * 1e-3f; t0_ = t_; } while (0)
 #define VC_TICK_INIT float tk_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; unsigned long long t0_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0_));
-#define VC_TICK_PRINT do { if (ct == 0 && (cid == 0 || cid == ncl - 1) && f < 2 * (int64_t)ncl) \
+#define VC_TICK_PRINT do { if (crank == 0 && tid == 0 && (cid == 0 || cid == ncl - 1) && f < 2 * (int64_t)ncl) \
     printf("frame %3d cl %2u  clear %6.1f insert %6.1f flags %6.1f join %6.1f big %6.1f ids %6.1f compact %6.1f us\n", (int)f, cid, tk_[0], tk_[1], tk_[2], tk_[3], tk_[4], tk_[5], tk_[6]); } while (0)
 #else
 #define VC_TICK(slot)
@@ -193,22 +206,24 @@ __device__ __forceinline__ bool vc_cell(const VcDev &c, const float4 &p, uint32_
 #define VC_TICK_PRINT
 #endif
 
+// ---------------------------------------------------------------------------------------------------------
+// L2 path: the frame's hash table and per-point words live in the cluster's workspace slice (L2-resident),
+// inserts are 64-bit CAS / atomicMin / RED on global memory.  Handles every supported configuration and
+// frame size; the routed path below falls back to it.
 template <bool DENSE>
-__global__ void __launch_bounds__(VC_THREADS, 1) vox_cluster_kernel(const VcArgs a, const VcDev dv)
+__device__ __forceinline__ void vc_frame_l2(const VcArgs &a, const VcDev &dv, const VcSh &sh, cg::cluster_group &cluster, const int64_t f,
+                                            const unsigned cid, const unsigned ncl)
 {
-    cg::cluster_group cluster = cg::this_cluster();
     const unsigned csize = cluster.num_blocks(), crank = cluster.block_rank();
-    const unsigned ncl = gridDim.x / csize, cid = blockIdx.x / csize;
     const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const unsigned W = csize * VC_WARPS, g = crank * VC_WARPS + w;     // warps per cluster, index of this warp
     const unsigned CT = csize * VC_THREADS, ct = crank * VC_THREADS + tid;
     const unsigned ltmask = lanemask_lt();
+    (void)ncl;
 
-    __shared__ uint32_t mytot[VC_WARPS];
-    __shared__ uint32_t wt1[VC_MAX_CSIZE * VC_WARPS], wt2[VC_MAX_CSIZE * VC_WARPS];
-    __shared__ uint32_t vbase[VC_MAX_CSIZE * VC_WARPS + 1], pbase[VC_MAX_CSIZE * VC_WARPS + 1];
-    __shared__ unsigned long long frow[2];   // first voxel row / first kept-point row of this frame in the packed outputs
-    __shared__ uint32_t q_key[VC_WARPS][VC_QCAP], q_pt[VC_WARPS][VC_QCAP];   // insert queue: cell key, (point index << 5 | probe number)
+    uint32_t *mytot = sh.mytot, *wt1 = sh.wt1, *wt2 = sh.wt2, *vbase = sh.vbase, *pbase = sh.pbase;
+    unsigned long long *frow = sh.frow;
+    uint32_t *q_key = reinterpret_cast<uint32_t *>(sh.dyn), *q_pt = q_key + VC_WARPS * VC_QCAP;   // insert queue: cell key, (point index << 5 | probe number)
 
     char *slice = a.ws + (size_t)cid * a.lay.total;
     VcEntry *tab = reinterpret_cast<VcEntry *>(slice + a.lay.tab);
@@ -228,7 +243,7 @@ __global__ void __launch_bounds__(VC_THREADS, 1) vox_cluster_kernel(const VcArgs
     const uint32_t vcap = (DENSE || cfg.vfilter != D3D_VF_NONE) ? (cfg.max_voxels > 0 ? (uint32_t)cfg.max_voxels : 0u) : VC_NONE;
     const int nfeat = a.nfeat;
 
-    for (int64_t f = cid; f < a.nframes; f += ncl) {
+    {
         const int64_t b = a.offs[f];
         const uint32_t L = (uint32_t)(a.offs[f + 1] - b);
         const uint32_t nslots = L + (L >> 1) + 64;
@@ -265,7 +280,7 @@ __global__ void __launch_bounds__(VC_THREADS, 1) vox_cluster_kernel(const VcArgs
         // the unluckiest one, points wait in a per-warp shared-memory ring between probes and every CAS instruction
         // is issued for 32 queued points (the same compaction the IoU kernel uses for its candidate pairs).
         {
-            uint32_t *qk = q_key[w], *qp = q_pt[w];
+            uint32_t *qk = q_key + w * VC_QCAP, *qp = q_pt + w * VC_QCAP;
             uint32_t head = 0, tail = 0;   // warp-uniform
             for (uint32_t k = 0; k <= nit; k++) {
                 if (k < nit) {
@@ -490,7 +505,7 @@ __global__ void __launch_bounds__(VC_THREADS, 1) vox_cluster_kernel(const VcArgs
             if (DENSE) {
                 if (ct == 0) { a.counts[2 * f] = 0; a.counts[2 * f + 1] = (long long)min(vbase[W], vcap); }
                 cluster.sync();   // the next frame clears the table other CTAs may still be reading
-                continue;
+                return;
             }
             if (lane == 0) mytot[w] = carry;
             vc_exchange(cluster, mytot, wt2, pbase, csize, crank);
@@ -535,6 +550,527 @@ __global__ void __launch_bounds__(VC_THREADS, 1) vox_cluster_kernel(const VcArgs
             }
         }
         VC_TICK(6); VC_TICK_PRINT;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Routed path (sparse): the frame never leaves the cluster's shared memory between the point load and the
+// output stores, and no global atomic is issued.
+//
+// Every CTA plays two roles.  As POINT OWNER it holds a contiguous range of the frame's points (the same
+// warp-chunk layout as the L2 path); as HASH OWNER it holds every point of the frame whose cell key hashes to
+// it, so all points of one voxel meet in one CTA.
+//   R1 push     point owners compute the cell keys (kept in registers) and append (key, index) to the hash
+//               owner's queue through distributed shared memory; a warp reserves its exact share of every
+//               queue with one remote atomicAdd per destination (8 per warp and frame).
+//   R2 resolve  hash owners find one slot per distinct key in a shared-memory table WITHOUT atomics: in
+//               round r every unresolved entry sits at probe position r of its key's double-hash sequence,
+//               writes its queue position into the slot if it is empty (plain store, any writer wins),
+//               and after a CTA barrier adopts the slot if the winner carries its key.  Entries of one key
+//               move in lock step, so they agree on the slot and on the winner; a slot never changes once
+//               it is filled.  Plain shared-memory loads/stores run at ~10 lanes/clk against 0.5 lanes/clk
+//               for shared-memory atomics, which only the ~8 % of points that join an existing voxel issue
+//               (atomicMin of the index, atomicAdd of the count on the winner's queue words).
+//   R3 ranks    voxels with more than max_points points extract their max_points smallest indices, one
+//               minimum per round (atomicMin on a per-voxel accumulator; the round number sits in the high
+//               bits so a later round always wins and nothing is reset).
+//   R4 reply    hash owners send every point one word back to its point owner: dropped | first point of its
+//               voxel + the voxel's point count | index of the voxel's first point, plus the keep decision.
+//   R5 ids      point owners turn the first-of-voxel bits into voxel ids (ballot/popc, DSMEM exchange of the
+//               warp totals, cross-frame look-back); a point that is not the first of its voxel reads the id
+//               at its first point's position (DSMEM when that lives in another CTA).
+//   R6 write    second prefix sum over the keep flags, then coalesced stores of the voxel rows (coordinates
+//               recomputed from the reloaded point, L2 hit) and of the packed point rows.
+// Results are identical to the L2 path and to the reference: every decision is a function of the point set
+// (smallest index, count, K smallest indices), never of the race order.
+// The frame falls back to the L2 path (cluster-uniform decision, nothing published yet) when it does not fit:
+// more than VR_NIT 32-point rounds per warp, a queue overflow (skewed hash or > ~85 % of a 120k-point frame in
+// bounds), or more crowded voxels per CTA than the pool holds.
+constexpr int VR_NIT = 16;                       // 32-point rounds per warp (cell keys live in registers during R1)
+constexpr int VR_E = 13;                         // queue entries per hash-owner thread
+constexpr int VR_POOL = 512;                     // crowded-voxel records per CTA
+constexpr uint32_t VR_HEAD = 1u << 31, VR_KEEP = 1u << 30, VR_VAL = (1u << 30) - 1;   // reply word
+constexpr uint32_t VR_IDX_BITS = 18, VR_IDX_MASK = (1u << VR_IDX_BITS) - 1;          // frame-local point index in packed words
+constexpr uint32_t VR_SLOT_EMPTY = 0xffffu;
+constexpr int VR_LIST = 2048;                    // work list: entries still probing (R2) / competing for a rank (R3)
+constexpr uint32_t VR_LOSER = 1u << 31;          // key word of a resolved entry that is not its voxel's winner (cell keys use <= 31 bits)
+constexpr uint32_t VR_KEPT = 1u << 31;           // index word: this entry of a crowded voxel is one of the K smallest
+
+struct VrPlan { uint32_t nit, Lc, lg, nslots, cap; };
+
+// shared-memory budget of one frame: reply words 4*Lc, slot table 2*nslots (power of two), queue 8*cap
+__host__ __device__ inline bool vr_plan(uint32_t L, uint32_t csize, uint32_t dyn, VrPlan *pl)
+{
+    if (csize < 1 || csize > (uint32_t)VC_MAX_CSIZE || L == 0) return false;
+    const uint32_t W = csize * VC_WARPS;
+    const uint32_t nit = (L + W * 32 - 1) / (W * 32);
+    if (nit > (uint32_t)VR_NIT || (uint64_t)nit * W * 32 > (1u << VR_IDX_BITS)) return false;
+    const uint32_t Lc = nit * VC_THREADS;
+    if (dyn < 4 * Lc + 4096) return false;
+    const uint32_t R = dyn - 4 * Lc;
+    uint32_t best = 0, blg = 0;
+    for (uint32_t lg = 10; lg <= 16; lg++) {
+        const uint32_t ns = 1u << lg;
+        if (2 * ns + 1024 > R) break;
+        uint32_t c = (R - 2 * ns) / 8;
+        if (c > ns - ns / 4) c = ns - ns / 4;                 // load factor <= 0.75
+        if (c > (uint32_t)VR_E * VC_THREADS) c = VR_E * VC_THREADS;
+        if (c > 0xfff0u) c = 0xfff0u;                         // 16-bit queue positions in the slot table
+        c &= ~3u;
+        if (c > best) { best = c; blg = lg; }
+    }
+    if ((uint64_t)best * 10 < (uint64_t)Lc * 6) return false;   // would overflow on ordinary frames: not worth the attempt
+    pl->nit = nit; pl->Lc = Lc; pl->lg = blg; pl->nslots = 1u << blg; pl->cap = best;
+    return true;
+}
+
+__device__ __forceinline__ uint32_t vr_hash(uint32_t key)
+{
+    uint32_t h = key * 0x85EBCA6Bu;
+    h ^= h >> 15; h *= 0xC2B2AE35u; h ^= h >> 13;
+    return h;
+}
+
+#ifdef D3D_VC_TIMING
+#define VR_TICK_PRINT do { if (crank == 0 && tid == 0 && (cid == 0 || cid == ncl - 1) && f < 2 * (int64_t)ncl) \
+    printf("frame %3d cl %2u  push %6.1f resolve %6.1f ranks %6.1f reply %6.1f heads %6.1f ids %6.1f write %6.1f us  (n %u)\n", (int)f, cid, tk_[0], tk_[1], tk_[2], tk_[3], tk_[4], tk_[5], tk_[6], n); } while (0)
+#else
+#define VR_TICK_PRINT
+#endif
+
+// returns false (cluster-uniform) when the frame has to be redone by the L2 path
+__device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv, const VcSh &sh, cg::cluster_group &cluster, const int64_t f,
+                                               const VrPlan &pl, const unsigned cid, const unsigned ncl)
+{
+    const unsigned csize = cluster.num_blocks(), crank = cluster.block_rank();
+    const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned W = csize * VC_WARPS, g = crank * VC_WARPS + w;
+    const unsigned ltmask = lanemask_lt();
+    (void)cid; (void)ncl;
+
+    const VoxCfg &cfg = a.cfg;
+    const uint32_t K = cfg.max_points > 0 ? (uint32_t)cfg.max_points : 0u;
+    const bool trim = cfg.pfilter == D3D_PF_TRIM;
+    const bool dropall = trim && K == 0;
+    const uint32_t cthr = (trim && K > 0) ? K : VC_NONE;
+    const uint32_t vcap = cfg.vfilter != D3D_VF_NONE ? (cfg.max_voxels > 0 ? (uint32_t)cfg.max_voxels : 0u) : VC_NONE;
+    const int nfeat = a.nfeat;
+
+    const int64_t b = a.offs[f];
+    const uint32_t L = (uint32_t)(a.offs[f + 1] - b);
+    const uint32_t nit = pl.nit, Lc = pl.Lc, cap = pl.cap, nslots = pl.nslots, smask = pl.nslots - 1, hshift = 32 - pl.lg;
+    const uint32_t wbeg = g * nit * 32;        // frame-local index of this warp's first point
+    const uint32_t lbeg = w * nit * 32;        // the same inside the CTA's range
+    const uint32_t magic = 65536u / nit + 1;   // x / nit == (x * magic) >> 16 for x < 4096
+
+    uint2 *q = reinterpret_cast<uint2 *>(sh.dyn);               // queue entry: .x cell key, .y point index.  After R2: winner .x = own index | joiners << 18,
+                                                                // winner .y = smallest index of the voxel (crowded voxel: its pool record), loser .x = VR_LOSER | winner
+    uint32_t *reply = reinterpret_cast<uint32_t *>(q + cap);    // one word per point of this CTA's range
+    uint16_t *slot = reinterpret_cast<uint16_t *>(reply + Lc);  // queue position of the entry that claimed the slot
+    uint2 *hbp = sh.hbp;
+    uint32_t *list = sh.list;
+    volatile uint32_t *vqcount = sh.qcount, *vbail = sh.bail, *vlcount = sh.lcount;
+
+    VC_TICK_INIT
+    // ---- R1: clear the slot table; keys; push to the hash owners
+    for (uint32_t s4 = tid; s4 < nslots / 8; s4 += VC_THREADS) reinterpret_cast<uint4 *>(slot)[s4] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    {
+        // a point that hears nothing back is the only point of its voxel
+        const uint32_t dflt = cfg.min_points <= 1 ? (VR_HEAD | VR_KEEP | 1u) : VC_NONE;
+        uint32_t keys[VR_NIT];
+        unsigned long long c0 = 0, c1 = 0;   // 16-bit fields: this thread's points per destination CTA (0-3 | 4-7)
+#pragma unroll
+        for (int k0 = 0; k0 < VR_NIT; k0 += 4) {
+            float4 p[4];
+            bool in[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = wbeg + (k0 + u) * 32 + lane;
+                in[u] = (uint32_t)(k0 + u) < nit && i < L;
+                p[u] = in[u] ? vc_load_point(a.pts, nfeat, b + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                uint32_t key;
+                const bool ok = vc_cell<false>(dv, p[u], &key) && in[u];
+                keys[k0 + u] = ok ? key : VC_NOKEY;
+                if (in[u]) reply[lbeg + (k0 + u) * 32 + lane] = ok ? dflt : VC_NONE;
+                if (ok) {
+                    const uint32_t own = __umulhi(key * 0x9E3779B1u, csize);
+                    const unsigned long long inc = 1ull << ((own & 3u) * 16u);
+                    if (own & 4u) c1 += inc; else c0 += inc;
+                }
+            }
+        }
+        unsigned long long i0 = c0, i1 = c1;   // inclusive prefix over the lanes
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t0 = __shfl_up_sync(0xffffffffu, i0, d), t1 = __shfl_up_sync(0xffffffffu, i1, d);
+            if (lane >= (unsigned)d) { i0 += t0; i1 += t1; }
+        }
+        const unsigned long long tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
+        uint32_t base = 0;
+        if (lane < csize) {   // lane d reserves the warp's share of CTA d's queue
+            const uint32_t mycnt = (uint32_t)(((lane & 4u) ? tot1 : tot0) >> ((lane & 3u) * 16u)) & 0xffffu;
+            if (mycnt) {
+                base = atomicAdd(cluster.map_shared_rank(sh.qcount, lane), mycnt);
+                if (base + mycnt > cap)   // the destination queue is full: every CTA of the cluster learns it before the barrier
+                    for (unsigned d = 0; d < csize; d++) *cluster.map_shared_rank(sh.bail, d) = 1u;
+            }
+        }
+        unsigned long long s0 = i0 - c0, s1 = i1 - c1;   // next queue position per destination (garbage, but bounded, after an overflow)
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            s0 += (unsigned long long)(__shfl_sync(0xffffffffu, base, d) & 0xffffu) << (16 * d);
+            s1 += (unsigned long long)(__shfl_sync(0xffffffffu, base, 4 + d) & 0xffffu) << (16 * d);
+        }
+#pragma unroll
+        for (int k = 0; k < VR_NIT; k++) {
+            const uint32_t key = keys[k];
+            if (key != VC_NOKEY) {
+                const uint32_t own = __umulhi(key * 0x9E3779B1u, csize), shf = (own & 3u) * 16u;
+                const uint32_t pos = (uint32_t)(((own & 4u) ? s1 : s0) >> shf) & 0xffffu;
+                if (own & 4u) s1 += 1ull << shf; else s0 += 1ull << shf;
+                if (pos < cap) cluster.map_shared_rank(q, own)[pos] = make_uint2(key, wbeg + k * 32 + lane);
+            }
+        }
+    }
+    cluster.sync();   // #1: every queue is complete
+    const uint32_t n = *vqcount;
+    {
+        const uint32_t ov = *vbail;
+        __syncthreads();
+        if (tid == 0) { *sh.qcount = 0; *sh.npool = 0; *sh.lcount = 0; if (ov) *sh.bail = 0; }
+#ifdef D3D_VC_TIMING
+        if (ov && tid == 0) printf("frame %d cl %u cta %u: queue overflow (n %u cap %u)\n", (int)f, cid, crank, n, cap);
+#endif
+        if (ov) return false;
+        __syncthreads();
+    }
+    VC_TICK(0);
+
+    // ---- R2: one slot per distinct key, by rounds of plain stores.  After two rounds over all entries (the
+    // unrolled loops) the few entries that are still looking move to a work list, so that a late round costs a
+    // handful of instructions per warp instead of a pass over every entry.
+    uint32_t s[VR_E];
+    {
+        uint32_t unres = 0, moved = 0;
+#pragma unroll
+        for (int e = 0; e < VR_E; e++) {
+            const uint32_t p = tid + e * VC_THREADS;
+            s[e] = 0;
+            if (p < n) { s[e] = vr_hash(q[p].x) >> hshift; unres |= 1u << e; }
+        }
+        uint32_t nl = 0;   // entries on the work list (CTA-uniform)
+        for (uint32_t round = 0;; round++) {
+            if (unres) {
+#pragma unroll
+                for (int e = 0; e < VR_E; e++)
+                    if ((unres >> e) & 1u) { if (slot[s[e]] == VR_SLOT_EMPTY) slot[s[e]] = (uint16_t)(tid + e * VC_THREADS); }
+            }
+            for (uint32_t j = tid; j < nl; j += VC_THREADS) {
+                const uint32_t ent = list[j];
+                if (ent != VC_NONE && slot[ent >> 16] == VR_SLOT_EMPTY) slot[ent >> 16] = (uint16_t)ent;
+            }
+            __syncthreads();
+            if (unres) {
+#pragma unroll
+                for (int e = 0; e < VR_E; e++)
+                    if ((unres >> e) & 1u) {
+                        const uint32_t kq = q[tid + e * VC_THREADS].x;
+                        const uint32_t wv = slot[s[e]];
+                        if (q[wv].x == kq) { unres &= ~(1u << e); s[e] = wv; }
+                        else s[e] = (s[e] + ((vr_hash(kq) & smask) | 1u)) & smask;
+                    }
+            }
+            uint32_t open = unres;
+            for (uint32_t j = tid; j < nl; j += VC_THREADS) {
+                const uint32_t ent = list[j];
+                if (ent != VC_NONE) {
+                    const uint32_t p = ent & 0xffffu, sl = ent >> 16;
+                    const uint32_t kq = q[p].x, wv = slot[sl];
+                    if (q[wv].x == kq) { list[j] = VC_NONE; if (wv != p) q[p].x = VR_LOSER | wv; }   // nobody else reads a loser's key
+                    else { list[j] = p | (((sl + ((vr_hash(kq) & smask) | 1u)) & smask) << 16); open = 1; }
+                }
+            }
+            if (round == 1 && unres) {   // hand the stragglers to the list (what does not fit stays with its thread)
+                const uint32_t cnt = __popc(unres);
+                const uint32_t at = atomicAdd(sh.lcount, cnt);
+                if (at + cnt <= (uint32_t)VR_LIST) {
+                    uint32_t o = at;
+#pragma unroll
+                    for (int e = 0; e < VR_E; e++)
+                        if ((unres >> e) & 1u) list[o++] = (tid + e * VC_THREADS) | (s[e] << 16);
+                    moved = unres; unres = 0;
+                } else {
+                    for (uint32_t o = at; o < (uint32_t)VR_LIST; o++) list[o] = VC_NONE;
+                }
+            }
+            if (!__syncthreads_or((int)open)) break;
+            if (round == 1) nl = min(*vlcount, (uint32_t)VR_LIST);
+        }
+        // entries resolved on the list left their winner in their key word (or kept the key: they are winners)
+#pragma unroll
+        for (int e = 0; e < VR_E; e++)
+            if ((moved >> e) & 1u) { const uint32_t p = tid + e * VC_THREADS, x = q[p].x; s[e] = (x & VR_LOSER) ? (x & 0xffffu) : p; }
+        // from here on s[e] is the queue position of the voxel's winner.  Winners: key word <- own index, 0 joiners
+        // (the index word becomes the voxel's minimum); every lookup of a winner's key is behind the barrier above.
+#pragma unroll
+        for (int e = 0; e < VR_E; e++) {
+            const uint32_t p = tid + e * VC_THREADS;
+            if (p < n && s[e] == p) q[p].x = q[p].y;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < VR_E; e++) {
+            const uint32_t p = tid + e * VC_THREADS;
+            if (p < n && s[e] != p) { atomicMin(&q[s[e]].y, q[p].y); atomicAdd(&q[s[e]].x, 1u << VR_IDX_BITS); }
+        }
+        if (tid == 0) *sh.lcount = 0;
+        __syncthreads();
+    }
+    VC_TICK(1);
+
+    // frame-local index of queue entry p whose voxel's winner is win: a winner's index word was taken over by its voxel
+    auto own_index = [&](uint32_t p, uint32_t win) -> uint32_t { return win == p ? (q[p].x & VR_IDX_MASK) : (q[p].y & VR_IDX_MASK); };
+
+    // ---- R3: the K smallest indices of every voxel that holds more than K points.  The first point opens a
+    // record for the voxel (the winner's index word now names the record), the other points go to the work
+    // list as (entry | winner << 16) and compete in K-1 rounds; a kept entry gets VR_KEPT in its index word.
+    if (cthr != VC_NONE) {
+        uint32_t cm = 0, hd = 0;
+#pragma unroll
+        for (int e = 0; e < VR_E; e++) {
+            const uint32_t p = tid + e * VC_THREADS;
+            if (p < n && (q[s[e]].x >> VR_IDX_BITS) + 1 > cthr) {
+                if (own_index(p, s[e]) == q[s[e]].y) hd |= 1u << e; else cm |= 1u << e;
+            }
+        }
+        if (__syncthreads_or((int)(cm | hd))) {
+            bool over = false;
+            if (hd) {
+#pragma unroll
+                for (int e = 0; e < VR_E; e++)
+                    if ((hd >> e) & 1u) {
+                        uint32_t r = atomicAdd(sh.npool, 1u);
+                        if (r >= (uint32_t)VR_POOL) { over = true; r = 0; }
+                        else { sh.pool_min[r] = q[s[e]].y; sh.pool_acc0[r] = 0xffffffffu; sh.pool_acc1[r] = 0xffffffffu; }
+                        q[s[e]].y = r;
+                    }
+            }
+            if (cm) {
+                const uint32_t cnt = __popc(cm);
+                uint32_t o = atomicAdd(sh.lcount, cnt);
+                if (o + cnt > (uint32_t)VR_LIST) {
+                    over = true;
+                    for (; o < (uint32_t)VR_LIST; o++) list[o] = VC_NONE;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < VR_E; e++)
+                        if ((cm >> e) & 1u) list[o++] = (tid + e * VC_THREADS) | (s[e] << 16);
+                }
+            }
+            if (over) for (unsigned d = 0; d < csize; d++) *cluster.map_shared_rank(sh.bail, d) = 1u;   // too crowded for this path
+            __syncthreads();
+            const uint32_t nc = min(*vlcount, (uint32_t)VR_LIST);
+            for (uint32_t r = 1; r < K; r++) {
+                uint32_t *acc = (r & 1u) ? sh.pool_acc1 : sh.pool_acc0;
+                const uint32_t pre = (0x3fffu - (r & 0x3fffu)) << VR_IDX_BITS;   // a later round always wins the minimum: nothing to reset
+                uint32_t open = 0;
+                for (uint32_t j = tid; j < nc; j += VC_THREADS) {
+                    const uint32_t ent = list[j];
+                    if (ent != VC_NONE) { atomicMin(&acc[q[ent >> 16].y & 0xffffu], pre | own_index(ent & 0xffffu, ent >> 16)); open = 1; }
+                }
+                if (!__syncthreads_or((int)open)) break;
+                for (uint32_t j = tid; j < nc; j += VC_THREADS) {
+                    const uint32_t ent = list[j];
+                    if (ent != VC_NONE) {
+                        const uint32_t p = ent & 0xffffu, wv = ent >> 16;
+                        if (acc[q[wv].y & 0xffffu] == (pre | own_index(p, wv))) { list[j] = VC_NONE; q[p].y |= VR_KEPT; }
+                    }
+                }
+            }
+            __syncthreads();   // VR_KEPT was set by whoever processed the list entry, R4 reads it from the entry's own thread
+        }
+    }
+    VC_TICK(2);
+
+    // ---- R4: one word back to every point that shares its voxel (or whose voxel fails min_points)
+#pragma unroll
+    for (int e = 0; e < VR_E; e++) {
+        const uint32_t p = tid + e * VC_THREADS;
+        if (p < n) {
+            const uint32_t total = (q[s[e]].x >> VR_IDX_BITS) + 1;
+            if (total > 1) {
+                const uint32_t my = own_index(p, s[e]);
+                const bool crowded = total > cthr;
+                const uint32_t wy = q[s[e]].y;
+                const uint32_t mn = crowded ? sh.pool_min[wy & 0xffffu] : wy;
+                uint32_t r;
+                if ((long long)total < (long long)cfg.min_points) r = VC_NONE;
+                else if (my == mn) r = VR_HEAD | VR_KEEP | total;                       // rank 0 is always kept (K >= 1 when crowded)
+                else r = ((!crowded || (q[p].y & VR_KEPT)) ? VR_KEEP : 0u) | mn;
+                const uint32_t c = ((my >> 10) * magic) >> 16;
+                cluster.map_shared_rank(reply, c)[my - c * Lc] = r;
+            }
+        }
+    }
+    cluster.sync();   // #2: every reply has arrived
+    {
+        const uint32_t cb = *vbail;
+        __syncthreads();
+        if (tid == 0) *sh.bail = 0;
+#ifdef D3D_VC_TIMING
+        if (cb && tid == 0 && crank == 0) printf("frame %d cl %u: too many crowded voxels\n", (int)f, cid);
+#endif
+        if (cb) return false;
+    }
+    VC_TICK(3);
+
+    // ---- R5: first-of-voxel bits -> voxel ids
+    {
+        uint32_t carry = 0;
+        for (uint32_t k = 0; k < nit; k++) {
+            const uint32_t i = wbeg + k * 32 + lane;
+            const uint32_t r = i < L ? reply[lbeg + k * 32 + lane] : VC_NONE;
+            const unsigned bal = __ballot_sync(0xffffffffu, r != VC_NONE && (r & VR_HEAD));
+            if (lane == 0) hbp[w * nit + k] = make_uint2(bal, carry);
+            carry += __popc(bal);
+        }
+        if (lane == 0) sh.mytot[w] = carry;
+        vc_exchange(cluster, sh.mytot, sh.wt1, sh.vbase, csize, crank);   // cluster barrier #3 inside
+        if (tid == 0) sh.frow[0] = vc_lookback(a.vstate, f, min(sh.vbase[W], vcap), crank == 0);
+        __syncthreads();
+    }
+    VC_TICK(4);
+    {
+        uint32_t carry = 0;
+        const uint32_t vb = sh.vbase[g];
+        for (uint32_t k = 0; k < nit; k++) {
+            const uint32_t i = wbeg + k * 32 + lane, li = lbeg + k * 32 + lane;
+            const uint32_t r = i < L ? reply[li] : VC_NONE;
+            uint32_t out = VC_NONE;
+            bool keep = false;
+            if (r != VC_NONE) {
+                uint32_t vid;
+                if (r & VR_HEAD) {
+                    const uint2 h = hbp[li >> 5];
+                    vid = vb + h.y + __popc(h.x & ltmask);
+                } else {   // the id lives where the voxel's first point lives
+                    const uint32_t m = r & VR_VAL;
+                    const uint32_t c = ((m >> 10) * magic) >> 16;
+                    const uint32_t lj = (m - c * Lc) >> 5;
+                    const uint32_t wv = (lj * magic) >> 16;
+                    const uint2 h = cluster.map_shared_rank(hbp, c)[lj];   // one remote load (2.7 clk per lane)
+                    vid = sh.vbase[c * VC_WARPS + wv] + h.y + __popc(h.x & ((1u << (m & 31u)) - 1u));
+                }
+                if (vid < vcap) {
+                    keep = (r & VR_KEEP) && !dropall;
+                    out = (r & VR_HEAD) ? ((r & ~VR_KEEP) | (keep ? VR_KEEP : 0u)) : ((keep ? VR_KEEP : 0u) | vid);
+                }
+            }
+            if (i < L) reply[li] = out;
+            carry += __popc(__ballot_sync(0xffffffffu, keep));
+        }
+        if (lane == 0) sh.mytot[w] = carry;
+        vc_exchange(cluster, sh.mytot, sh.wt2, sh.pbase, csize, crank);   // cluster barrier #4 inside
+        if (tid == 0) sh.frow[1] = vc_lookback(a.kstate, f, sh.pbase[W], crank == 0);
+        __syncthreads();
+    }
+    VC_TICK(5);
+
+    // ---- R6: voxel rows (written by the voxel's first point) and packed point rows, in input order
+    {
+        int64_t run = (int64_t)sh.frow[1] + sh.pbase[g];
+        const int64_t vrow = (int64_t)sh.frow[0];
+        const uint32_t vb = sh.vbase[g];
+        for (uint32_t k0 = 0; k0 < nit; k0 += VC_U) {
+            uint32_t r[VC_U];
+            float4 p[VC_U];
+#pragma unroll
+            for (int u = 0; u < VC_U; u++) {
+                const uint32_t i = wbeg + (k0 + u) * 32 + lane;
+                r[u] = (k0 + u < nit && i < L) ? reply[lbeg + (k0 + u) * 32 + lane] : VC_NONE;
+                if (r[u] != VC_NONE && !(r[u] & (VR_HEAD | VR_KEEP))) r[u] = VC_NONE;
+            }
+#pragma unroll
+            for (int u = 0; u < VC_U; u++)
+                if (r[u] != VC_NONE) p[u] = vc_load_point(a.pts, nfeat, b + wbeg + (k0 + u) * 32 + lane);
+#pragma unroll
+            for (int u = 0; u < VC_U; u++) {
+                const uint32_t i = wbeg + (k0 + u) * 32 + lane, lj = (lbeg >> 5) + k0 + u;
+                const bool valid = r[u] != VC_NONE;
+                const bool head = valid && (r[u] & VR_HEAD), keep = valid && (r[u] & VR_KEEP);
+                uint32_t nid = r[u] & VR_VAL;
+                if (head) {
+                    const uint32_t c = nid;   // points in the voxel
+                    const uint2 h = hbp[lj];
+                    nid = vb + h.y + __popc(h.x & ltmask);
+                    const int64_t o = vrow + nid;
+                    long long *co = reinterpret_cast<long long *>(a.out_coords) + o * 3;
+                    const int c0 = (int)floorf(__fdiv_rn(p[u].x, dv.size[0])), c1 = (int)floorf(__fdiv_rn(p[u].y, dv.size[1])),
+                              c2 = (int)floorf(__fdiv_rn(p[u].z, dv.size[2]));
+                    __stcs(co + 0, (long long)(uint32_t)(c0 - dv.vlo[0]) + dv.cadd[0]);
+                    __stcs(co + 1, (long long)(uint32_t)(c1 - dv.vlo[1]) + dv.cadd[1]);
+                    __stcs(co + 2, (long long)(uint32_t)(c2 - dv.vlo[2]) + dv.cadd[2]);
+                    __stcs(a.out_npoints + o, (trim && c > K) ? (int32_t)K : (int32_t)c);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    const int64_t o = run + __popc(bal & ltmask);
+                    if (nfeat == 4) __stcs(reinterpret_cast<float4 *>(a.out_points) + o, p[u]);
+                    else for (int q = 0; q < nfeat; q++) a.out_points[o * nfeat + q] = a.pts[(b + i) * nfeat + q];
+                    __stcs(reinterpret_cast<long long *>(a.out_mask) + o, (long long)i);
+                    __stcs(reinterpret_cast<long long *>(a.out_mapping) + o, (long long)nid);
+                }
+                run += __popc(bal);
+            }
+        }
+        if (crank == 0 && tid == 0) {
+            a.counts[2 * f] = (long long)sh.frow[1]; a.counts[2 * f + 1] = (long long)sh.frow[0];
+            if (f == a.nframes - 1) { a.counts[2 * f + 2] = (long long)(sh.frow[1] + sh.pbase[W]); a.counts[2 * f + 3] = (long long)(sh.frow[0] + min(sh.vbase[W], vcap)); }
+        }
+    }
+    __syncthreads();   // the next frame may map points to threads differently: its defaults must not overtake this frame's reads of the reply words
+    VC_TICK(6); VR_TICK_PRINT;
+    return true;
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(VC_THREADS, 1) vox_cluster_kernel(const VcArgs a, const VcDev dv)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned csize = cluster.num_blocks();
+    const unsigned ncl = gridDim.x / csize, cid = blockIdx.x / csize;
+
+    __shared__ uint32_t mytot[VC_WARPS];
+    __shared__ uint32_t wt1[VC_MAX_CSIZE * VC_WARPS], wt2[VC_MAX_CSIZE * VC_WARPS];
+    __shared__ uint32_t vbase[VC_MAX_CSIZE * VC_WARPS + 1], pbase[VC_MAX_CSIZE * VC_WARPS + 1];
+    __shared__ unsigned long long frow[2];
+    __shared__ uint2 hbp[DENSE ? 1 : VC_WARPS * VR_NIT];
+    __shared__ uint32_t list[DENSE ? 1 : VR_LIST];
+    __shared__ uint32_t pool[DENSE ? 3 : 3 * VR_POOL];
+    __shared__ uint32_t flags[4];
+    extern __shared__ __align__(16) unsigned char vc_dyn[];
+
+    VcSh sh;
+    sh.mytot = mytot; sh.wt1 = wt1; sh.wt2 = wt2; sh.vbase = vbase; sh.pbase = pbase; sh.frow = frow;
+    sh.hbp = hbp; sh.list = list; sh.lcount = flags + 3;
+    sh.pool_min = pool; sh.pool_acc0 = pool + (DENSE ? 1 : VR_POOL); sh.pool_acc1 = pool + (DENSE ? 2 : 2 * VR_POOL);
+    sh.qcount = flags; sh.npool = flags + 1; sh.bail = flags + 2;
+    sh.dyn = vc_dyn;
+
+    const bool route = !DENSE && a.route;
+    if (route) {
+        if (threadIdx.x < 4) flags[threadIdx.x] = 0;
+        cluster.sync();   // nobody pushes into a queue whose counter is not initialised yet
+    }
+    for (int64_t f = cid; f < a.nframes; f += ncl) {
+        if (route) {
+            VrPlan pl;
+            if (vr_plan((uint32_t)(a.offs[f + 1] - a.offs[f]), csize, a.dyn_bytes, &pl) && vc_frame_route(a, dv, sh, cluster, f, pl, cid, ncl)) continue;
+        }
+        vc_frame_l2<DENSE>(a, dv, sh, cluster, f, cid, ncl);
     }
 }
 
@@ -586,53 +1122,89 @@ size_t vox_cluster_ws_bytes(int64_t total, int64_t nframes, int64_t max_frame_po
 }
 
 // Cluster shape: CTAs of one cluster must sit in one GPC, and a B200's GPCs do not all expose a multiple of 8
-// SMs, so 8-CTA clusters leave SMs idle (15 clusters = 120 of 148 SMs on the boxes measured).  Pick the size
-// (<= 8, portable) that occupies the most SMs; the kernel is written for any cluster size.
-struct VcShape { int csize, max_clusters; };
+// SMs, so 8-CTA clusters leave SMs idle (15 clusters = 120 of 148 SMs on the boxes measured).  The L2 path
+// takes the size (<= 8, portable) that occupies the most SMs; the routed path needs the frame to fit the
+// cluster's shared memory, so among the sizes whose plan holds the largest frame it takes the one that
+// occupies the most SMs, and the kernel falls back to the L2 path frame by frame.
+struct VcShape { int csize, max_clusters; uint32_t dyn; int route; };
+
+constexpr uint32_t VC_L2_DYN = 2u * VC_WARPS * VC_QCAP * sizeof(uint32_t);   // per-warp probe rings of the L2 path
 
 template <bool DENSE>
-static int vc_shape(VcShape *out)
+static int vc_shape(VcShape *out, int64_t max_frame_points)
 {
-    static VcShape cached = {0, 0};
-    if (cached.csize == 0) {
-        auto kern = vox_cluster_kernel<DENSE>;
-        VcShape best = {0, 0};
-        int forced = 0;
-        if (const char *e = getenv("D3D_B200_VOX_CLUSTER")) forced = atoi(e);   // tuning override
-        for (int cs = 8; cs >= 4; cs -= 2) {   // 8, 6, 4: smaller clusters put more frames in flight than L2 holds
-            if (forced) cs = forced;
+    auto kern = vox_cluster_kernel<DENSE>;
+    static int occ[VC_MAX_CSIZE + 1];   // co-resident clusters per cluster size (0 = not queried yet, -1 = unavailable)
+    static uint32_t dyn = 0;
+    if (dyn == 0) {
+        dyn = VC_L2_DYN;
+        if (!DENSE) {
+            int dev = 0, optin = 0;
+            cudaFuncAttributes fa;
+            if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess ||
+                cudaFuncGetAttributes(&fa, kern) != cudaSuccess) { cudaGetLastError(); return D3D_ERR_CUDA; }
+            const long long d = ((long long)optin - (long long)fa.sharedSizeBytes) & ~1023ll;
+            if (d > (long long)dyn) dyn = (uint32_t)d;
+        }
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) { cudaGetLastError(); dyn = 0; return D3D_ERR_CUDA; }
+    }
+    auto query = [&](int cs) -> int {
+        if (occ[cs] == 0) {
             cudaLaunchConfig_t lc = {};
             lc.blockDim = dim3(VC_THREADS, 1, 1);
             lc.gridDim = dim3(cs, 1, 1);
+            lc.dynamicSmemBytes = dyn;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             lc.attrs = at; lc.numAttrs = 1;
             int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, kern, &lc) != cudaSuccess) { cudaGetLastError(); continue; }
-            if (n * cs > best.csize * best.max_clusters) best = {cs, n};
-            if (forced) break;
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &lc) != cudaSuccess || n < 1) { cudaGetLastError(); n = -1; }
+            occ[cs] = n;
         }
-        if (best.csize == 0) return D3D_ERR_CUDA;
-        cached = best;
+        return occ[cs];
+    };
+    int forced = 0, route = DENSE ? 0 : 1;
+    if (const char *e = getenv("D3D_B200_VOX_CLUSTER")) forced = atoi(e);   // tuning overrides
+    if (const char *e = getenv("D3D_B200_VOX_ROUTE")) route = DENSE ? 0 : atoi(e);
+    if (forced < 0 || forced > VC_MAX_CSIZE) forced = 0;
+    VcShape best = {0, 0, dyn, 0};
+    if (route) {
+        VrPlan pl;
+        for (int cs = 8; cs >= 4; cs -= 2) {
+            if (forced && cs != forced) continue;
+            if (!vr_plan((uint32_t)(max_frame_points > 0 ? max_frame_points : 1), cs, dyn, &pl)) continue;
+            const int n = query(cs);
+            if (n > 0 && n * cs > best.csize * best.max_clusters) best = {cs, n, dyn, 1};
+        }
     }
-    *out = cached;
+    if (best.csize == 0) {
+        for (int cs = 8; cs >= 4; cs -= 2) {   // 8, 6, 4: smaller clusters put more frames in flight than L2 holds
+            if (forced && cs != forced) continue;
+            const int n = query(cs);
+            if (n > 0 && n * cs > best.csize * best.max_clusters) best = {cs, n, dyn, route};
+        }
+    }
+    if (best.csize == 0 && forced) { const int n = query(forced); if (n > 0) best = {forced, n, dyn, route}; }
+    if (best.csize == 0) return D3D_ERR_CUDA;
+    *out = best;
     return D3D_OK;
 }
 
 template <bool DENSE>
-static int vc_launch(VcArgs &args, int64_t nframes, size_t ws_bytes, cudaStream_t st)
+static int vc_launch(VcArgs &args, int64_t nframes, int64_t max_frame_points, size_t ws_bytes, cudaStream_t st)
 {
     VcDev dv;
     if (!vc_make_dev(args.cfg, &dv)) return D3D_ERR_UNSUPPORTED;
     VcShape shape;
-    int rc = vc_shape<DENSE>(&shape);
+    int rc = vc_shape<DENSE>(&shape, max_frame_points);
     if (rc) return rc;
     const int csize = shape.csize;
+    args.dyn_bytes = shape.dyn; args.route = shape.route;
     auto kern = vox_cluster_kernel<DENSE>;
     cudaLaunchConfig_t lc = {};
     lc.blockDim = dim3(VC_THREADS, 1, 1);
-    lc.dynamicSmemBytes = 0;
+    lc.dynamicSmemBytes = shape.dyn;
     lc.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -665,7 +1237,7 @@ int vox_cluster_sparse(const float *points, int64_t total, int nfeat, const int6
     a.pts = points; a.nfeat = nfeat; a.offs = offs; a.nframes = nframes; a.cfg = cfg;
     a.out_points = out_points; a.out_mask = out_mask; a.out_mapping = out_mapping; a.out_npoints = out_npoints; a.out_coords = out_coords;
     a.counts = counts; a.ws = (char *)ws; a.lay = vc_layout(max_frame_points);
-    return vc_launch<false>(a, nframes, ws_bytes, st);
+    return vc_launch<false>(a, nframes, max_frame_points, ws_bytes, st);
 }
 
 int vox_cluster_dense(const float *points, int64_t total, int nfeat, const int64_t *offs, int64_t nframes, int64_t max_frame_points, const VoxCfg &cfg,
@@ -676,7 +1248,7 @@ int vox_cluster_dense(const float *points, int64_t total, int nfeat, const int64
     a.pts = points; a.nfeat = nfeat; a.offs = offs; a.nframes = nframes; a.cfg = cfg;
     a.out_npoints = npoints; a.out_coords = coords; a.counts = counts; a.voxels = voxels; a.pmask = pmask;
     a.ws = (char *)ws; a.lay = vc_layout(max_frame_points);
-    return vc_launch<true>(a, nframes, ws_bytes, st);
+    return vc_launch<true>(a, nframes, max_frame_points, ws_bytes, st);
 }
 
 }  // namespace d3d
