@@ -197,7 +197,7 @@ __device__ __forceinline__ bool vc_cell(const VcDev &c, const float4 &p, uint32_
 
 #ifdef D3D_VC_TIMING   // tuning build only: per-phase time of a few frames, printed once per frame
 #define VC_TICK(slot) do { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tk_[slot] = (float)(t_ - t0_) * 1e-3f; t0_ = t_; } while (0)
-#define VC_TICK_INIT float tk_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; unsigned long long t0_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0_));
+#define VC_TICK_INIT float tk_[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; unsigned long long t0_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0_));
 #define VC_TICK_PRINT do { if (crank == 0 && tid == 0 && (cid == 0 || cid == ncl - 1) && f < 2 * (int64_t)ncl) \
     printf("frame %3d cl %2u  clear %6.1f insert %6.1f flags %6.1f join %6.1f big %6.1f ids %6.1f compact %6.1f us\n", (int)f, cid, tk_[0], tk_[1], tk_[2], tk_[3], tk_[4], tk_[5], tk_[6]); } while (0)
 #else
@@ -624,16 +624,20 @@ __host__ __device__ inline bool vr_plan(uint32_t L, uint32_t csize, uint32_t dyn
     return true;
 }
 
-__device__ __forceinline__ uint32_t vr_hash(uint32_t key)
-{
-    uint32_t h = key * 0x85EBCA6Bu;
-    h ^= h >> 15; h *= 0xC2B2AE35u; h ^= h >> 13;
-    return h;
-}
+// One multiply serves both levels: the hash owner comes from the top of key * phi (umulhi with the cluster size),
+// the first slot from the bits below; the probe step (odd, so it visits every slot of the power-of-two table)
+// comes from a second multiply that only entries needing a second probe pay for.
+__device__ __forceinline__ uint32_t vr_h1(uint32_t key) { return key * 0x9E3779B1u; }
+__device__ __forceinline__ uint32_t vr_step(uint32_t key, uint32_t smask) { return (((key * 0x85EBCA6Bu) >> 15) | 1u) & smask; }
 
 #ifdef D3D_VC_TIMING
+#define VR_SUB(slot) do { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tk_[slot] = (float)(t_ - t0_) * 1e-3f; } while (0)
+#else
+#define VR_SUB(slot)
+#endif
+#ifdef D3D_VC_TIMING
 #define VR_TICK_PRINT do { if (crank == 0 && tid == 0 && (cid == 0 || cid == ncl - 1) && f < 2 * (int64_t)ncl) \
-    printf("frame %3d cl %2u  push %6.1f resolve %6.1f ranks %6.1f reply %6.1f heads %6.1f ids %6.1f write %6.1f us  (n %u)\n", (int)f, cid, tk_[0], tk_[1], tk_[2], tk_[3], tk_[4], tk_[5], tk_[6], n); } while (0)
+    printf("frame %3d cl %2u  push %6.1f resolve %6.1f (r0 %.1f r1 %.1f rounds %.1f [%u] fix %.1f) ranks %6.1f reply %6.1f heads %6.1f ids %6.1f write %6.1f us  (n %u)\n", (int)f, cid, tk_[0], tk_[1], tk_[8], tk_[9], tk_[10], (unsigned)tk_[12], tk_[11], tk_[2], tk_[3], tk_[4], tk_[5], tk_[6], n); } while (0)
 #else
 #define VR_TICK_PRINT
 #endif
@@ -654,10 +658,9 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
     const bool dropall = trim && K == 0;
     const uint32_t cthr = (trim && K > 0) ? K : VC_NONE;
     const uint32_t vcap = cfg.vfilter != D3D_VF_NONE ? (cfg.max_voxels > 0 ? (uint32_t)cfg.max_voxels : 0u) : VC_NONE;
-    const int nfeat = a.nfeat;
+    const float4 *pts4 = reinterpret_cast<const float4 *>(a.pts) + a.offs[f];   // the routed path serves xyz+1 clouds (nfeat == 4)
 
-    const int64_t b = a.offs[f];
-    const uint32_t L = (uint32_t)(a.offs[f + 1] - b);
+    const uint32_t L = (uint32_t)(a.offs[f + 1] - a.offs[f]);
     const uint32_t nit = pl.nit, Lc = pl.Lc, cap = pl.cap, nslots = pl.nslots, smask = pl.nslots - 1, hshift = 32 - pl.lg;
     const uint32_t wbeg = g * nit * 32;        // frame-local index of this warp's first point
     const uint32_t lbeg = w * nit * 32;        // the same inside the CTA's range
@@ -687,7 +690,7 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
             for (int u = 0; u < 4; u++) {
                 const uint32_t i = wbeg + (k0 + u) * 32 + lane;
                 in[u] = (uint32_t)(k0 + u) < nit && i < L;
-                p[u] = in[u] ? vc_load_point(a.pts, nfeat, b + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                p[u] = in[u] ? __ldg(pts4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -696,7 +699,7 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
                 keys[k0 + u] = ok ? key : VC_NOKEY;
                 if (in[u]) reply[lbeg + (k0 + u) * 32 + lane] = ok ? dflt : VC_NONE;
                 if (ok) {
-                    const uint32_t own = __umulhi(key * 0x9E3779B1u, csize);
+                    const uint32_t own = __umulhi(vr_h1(key), csize);
                     const unsigned long long inc = 1ull << ((own & 3u) * 16u);
                     if (own & 4u) c1 += inc; else c0 += inc;
                 }
@@ -728,7 +731,7 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
         for (int k = 0; k < VR_NIT; k++) {
             const uint32_t key = keys[k];
             if (key != VC_NOKEY) {
-                const uint32_t own = __umulhi(key * 0x9E3779B1u, csize), shf = (own & 3u) * 16u;
+                const uint32_t own = __umulhi(vr_h1(key), csize), shf = (own & 3u) * 16u;
                 const uint32_t pos = (uint32_t)(((own & 4u) ? s1 : s0) >> shf) & 0xffffu;
                 if (own & 4u) s1 += 1ull << shf; else s0 += 1ull << shf;
                 if (pos < cap) cluster.map_shared_rank(q, own)[pos] = make_uint2(key, wbeg + k * 32 + lane);
@@ -740,7 +743,7 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
     {
         const uint32_t ov = *vbail;
         __syncthreads();
-        if (tid == 0) { *sh.qcount = 0; *sh.npool = 0; *sh.lcount = 0; if (ov) *sh.bail = 0; }
+        if (tid == 0) { *sh.qcount = 0; *sh.npool = 0; sh.lcount[0] = 0; sh.lcount[1] = 0; if (ov) *sh.bail = 0; }
 #ifdef D3D_VC_TIMING
         if (ov && tid == 0) printf("frame %d cl %u cta %u: queue overflow (n %u cap %u)\n", (int)f, cid, crank, n, cap);
 #endif
@@ -749,9 +752,8 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
     }
     VC_TICK(0);
 
-    // ---- R2: one slot per distinct key, by rounds of plain stores.  After two rounds over all entries (the
-    // unrolled loops) the few entries that are still looking move to a work list, so that a late round costs a
-    // handful of instructions per warp instead of a pass over every entry.
+    // ---- R2: one slot per distinct key.  Two rounds of plain stores settle ~88 % of the entries; the stragglers
+    // move to a work list and finish with compare-and-swap probes, which need no barrier and no lock step.
     uint32_t s[VR_E];
     {
         uint32_t unres = 0, moved = 0;
@@ -759,56 +761,77 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
         for (int e = 0; e < VR_E; e++) {
             const uint32_t p = tid + e * VC_THREADS;
             s[e] = 0;
-            if (p < n) { s[e] = vr_hash(q[p].x) >> hshift; unres |= 1u << e; }
+            if (p < n) { s[e] = (vr_h1(q[p].x) << 3) >> hshift; unres |= 1u << e; }
         }
-        uint32_t nl = 0;   // entries on the work list (CTA-uniform)
-        for (uint32_t round = 0;; round++) {
-            if (unres) {
+#pragma unroll 1
+        for (int round = 0; round < 2; round++) {
 #pragma unroll
-                for (int e = 0; e < VR_E; e++)
-                    if ((unres >> e) & 1u) { if (slot[s[e]] == VR_SLOT_EMPTY) slot[s[e]] = (uint16_t)(tid + e * VC_THREADS); }
-            }
-            for (uint32_t j = tid; j < nl; j += VC_THREADS) {
-                const uint32_t ent = list[j];
-                if (ent != VC_NONE && slot[ent >> 16] == VR_SLOT_EMPTY) slot[ent >> 16] = (uint16_t)ent;
-            }
+            for (int e = 0; e < VR_E; e++)
+                if ((unres >> e) & 1u) { if (slot[s[e]] == VR_SLOT_EMPTY) slot[s[e]] = (uint16_t)(tid + e * VC_THREADS); }
             __syncthreads();
-            if (unres) {
+#pragma unroll
+            for (int e = 0; e < VR_E; e++)
+                if ((unres >> e) & 1u) {
+                    const uint32_t kq = q[tid + e * VC_THREADS].x;
+                    const uint32_t wv = slot[s[e]];
+                    if (q[wv].x == kq) { unres &= ~(1u << e); s[e] = wv; }
+                    else s[e] = (s[e] + vr_step(kq, smask)) & smask;
+                }
+            if (round == 0) { __syncthreads(); VR_SUB(8); }   // round 1 stores must not overtake round 0 lookups
+        }
+        VR_SUB(9);
+        if (unres) {   // hand the stragglers to the list (what does not fit stays with its thread)
+            const uint32_t cnt = __popc(unres);
+            const uint32_t at = atomicAdd(sh.lcount, cnt);
+            if (at + cnt <= (uint32_t)VR_LIST) {
+                uint32_t o = at;
 #pragma unroll
                 for (int e = 0; e < VR_E; e++)
-                    if ((unres >> e) & 1u) {
-                        const uint32_t kq = q[tid + e * VC_THREADS].x;
-                        const uint32_t wv = slot[s[e]];
-                        if (q[wv].x == kq) { unres &= ~(1u << e); s[e] = wv; }
-                        else s[e] = (s[e] + ((vr_hash(kq) & smask) | 1u)) & smask;
-                    }
+                    if ((unres >> e) & 1u) list[o++] = (tid + e * VC_THREADS) | (s[e] << 16);
+                moved = unres; unres = 0;
+            } else {
+                for (uint32_t o = at; o < (uint32_t)VR_LIST; o++) list[o] = VC_NONE;   // partial reservation: dead entries
             }
-            uint32_t open = unres;
+        }
+        __syncthreads();
+        // claim-or-join with a 32-bit CAS on the slot pair; slots only ever fill, so an entry that walks its probe
+        // sequence meets the slot its key settled in (or settles it) whatever the interleaving
+        auto settle = [&](uint32_t p, uint32_t sl) -> uint32_t {
+            const uint32_t kq = q[p].x;
+            const uint32_t step = vr_step(kq, smask);
+            for (;;) {
+                uint32_t *wp = reinterpret_cast<uint32_t *>(slot) + (sl >> 1);
+                const uint32_t sh16 = (sl & 1u) * 16u;
+                uint32_t cur = *reinterpret_cast<volatile uint32_t *>(wp), h;
+                for (;;) {
+                    h = (cur >> sh16) & 0xffffu;
+                    if (h != VR_SLOT_EMPTY) break;
+                    const uint32_t old = atomicCAS(wp, cur, (cur & ~(0xffffu << sh16)) | (p << sh16));
+                    if (old == cur) { h = p; break; }
+                    cur = old;
+                }
+                if (h == p || q[h].x == kq) return h;
+                sl = (sl + step) & smask;
+            }
+        };
+        {
+            const uint32_t nl = min(*vlcount, (uint32_t)VR_LIST);
             for (uint32_t j = tid; j < nl; j += VC_THREADS) {
                 const uint32_t ent = list[j];
                 if (ent != VC_NONE) {
-                    const uint32_t p = ent & 0xffffu, sl = ent >> 16;
-                    const uint32_t kq = q[p].x, wv = slot[sl];
-                    if (q[wv].x == kq) { list[j] = VC_NONE; if (wv != p) q[p].x = VR_LOSER | wv; }   // nobody else reads a loser's key
-                    else { list[j] = p | (((sl + ((vr_hash(kq) & smask) | 1u)) & smask) << 16); open = 1; }
+                    const uint32_t p = ent & 0xffffu;
+                    const uint32_t wv = settle(p, ent >> 16);
+                    if (wv != p) q[p].x = VR_LOSER | wv;   // a loser's key word is dead (only winners' keys are looked up): it carries the winner to the entry's own thread
                 }
             }
-            if (round == 1 && unres) {   // hand the stragglers to the list (what does not fit stays with its thread)
-                const uint32_t cnt = __popc(unres);
-                const uint32_t at = atomicAdd(sh.lcount, cnt);
-                if (at + cnt <= (uint32_t)VR_LIST) {
-                    uint32_t o = at;
+            if (unres) {
 #pragma unroll
-                    for (int e = 0; e < VR_E; e++)
-                        if ((unres >> e) & 1u) list[o++] = (tid + e * VC_THREADS) | (s[e] << 16);
-                    moved = unres; unres = 0;
-                } else {
-                    for (uint32_t o = at; o < (uint32_t)VR_LIST; o++) list[o] = VC_NONE;
-                }
+                for (int e = 0; e < VR_E; e++)
+                    if ((unres >> e) & 1u) s[e] = settle(tid + e * VC_THREADS, s[e]);
             }
-            if (!__syncthreads_or((int)open)) break;
-            if (round == 1) nl = min(*vlcount, (uint32_t)VR_LIST);
+            __syncthreads();
         }
+        VR_SUB(10);
         // entries resolved on the list left their winner in their key word (or kept the key: they are winners)
 #pragma unroll
         for (int e = 0; e < VR_E; e++)
@@ -826,8 +849,9 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
             const uint32_t p = tid + e * VC_THREADS;
             if (p < n && s[e] != p) { atomicMin(&q[s[e]].y, q[p].y); atomicAdd(&q[s[e]].x, 1u << VR_IDX_BITS); }
         }
-        if (tid == 0) *sh.lcount = 0;
+        if (tid == 0) { sh.lcount[0] = 0; sh.lcount[1] = 0; }
         __syncthreads();
+        VR_SUB(11);
     }
     VC_TICK(1);
 
@@ -995,7 +1019,7 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
             }
 #pragma unroll
             for (int u = 0; u < VC_U; u++)
-                if (r[u] != VC_NONE) p[u] = vc_load_point(a.pts, nfeat, b + wbeg + (k0 + u) * 32 + lane);
+                if (r[u] != VC_NONE) p[u] = __ldg(pts4 + wbeg + (k0 + u) * 32 + lane);
 #pragma unroll
             for (int u = 0; u < VC_U; u++) {
                 const uint32_t i = wbeg + (k0 + u) * 32 + lane, lj = (lbeg >> 5) + k0 + u;
@@ -1018,8 +1042,7 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
                 const unsigned bal = __ballot_sync(0xffffffffu, keep);
                 if (keep) {
                     const int64_t o = run + __popc(bal & ltmask);
-                    if (nfeat == 4) __stcs(reinterpret_cast<float4 *>(a.out_points) + o, p[u]);
-                    else for (int q = 0; q < nfeat; q++) a.out_points[o * nfeat + q] = a.pts[(b + i) * nfeat + q];
+                    __stcs(reinterpret_cast<float4 *>(a.out_points) + o, p[u]);
                     __stcs(reinterpret_cast<long long *>(a.out_mask) + o, (long long)i);
                     __stcs(reinterpret_cast<long long *>(a.out_mapping) + o, (long long)nid);
                 }
@@ -1050,19 +1073,19 @@ __global__ void __launch_bounds__(VC_THREADS, 1) vox_cluster_kernel(const VcArgs
     __shared__ uint2 hbp[DENSE ? 1 : VC_WARPS * VR_NIT];
     __shared__ uint32_t list[DENSE ? 1 : VR_LIST];
     __shared__ uint32_t pool[DENSE ? 3 : 3 * VR_POOL];
-    __shared__ uint32_t flags[4];
+    __shared__ uint32_t flags[8];
     extern __shared__ __align__(16) unsigned char vc_dyn[];
 
     VcSh sh;
     sh.mytot = mytot; sh.wt1 = wt1; sh.wt2 = wt2; sh.vbase = vbase; sh.pbase = pbase; sh.frow = frow;
-    sh.hbp = hbp; sh.list = list; sh.lcount = flags + 3;
+    sh.hbp = hbp; sh.list = list; sh.lcount = flags + 4;
     sh.pool_min = pool; sh.pool_acc0 = pool + (DENSE ? 1 : VR_POOL); sh.pool_acc1 = pool + (DENSE ? 2 : 2 * VR_POOL);
     sh.qcount = flags; sh.npool = flags + 1; sh.bail = flags + 2;
     sh.dyn = vc_dyn;
 
-    const bool route = !DENSE && a.route;
+    const bool route = !DENSE && a.route && a.nfeat == 4;
     if (route) {
-        if (threadIdx.x < 4) flags[threadIdx.x] = 0;
+        if (threadIdx.x < 8) flags[threadIdx.x] = 0;
         cluster.sync();   // nobody pushes into a queue whose counter is not initialised yet
     }
     for (int64_t f = cid; f < a.nframes; f += ncl) {
