@@ -118,22 +118,34 @@ __device__ __forceinline__ float4 vc_load_point(const float *pts, int nfeat, int
 // starts at the sum of the row counts of frames < f.  Frames are processed in index order by co-resident
 // clusters, every frame publishes its own count as soon as it knows it (flag 1) and its inclusive prefix once
 // it has looked back (flag 2); a frame only ever waits for lower-numbered frames, which are running or done.
+// The clusters run in step, so the nearest inclusive prefix is usually a whole wave of frames away: one warp
+// reads 32 predecessors per round trip instead of walking them one acquire-load at a time.
 __device__ __forceinline__ unsigned long long vc_lookback(unsigned long long *state, int64_t f, unsigned long long mine, bool publish)
 {
     constexpr unsigned long long VAL = (1ull << 62) - 1;
-    if (publish && f > 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(state + f), "l"((1ull << 62) | mine) : "memory");
+    const unsigned lane = threadIdx.x & 31u;
+    if (publish && f > 0 && lane == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(state + f), "l"((1ull << 62) | mine) : "memory");
     unsigned long long excl = 0;
-    for (int64_t j = f - 1; j >= 0; j--) {
-        unsigned long long v;
+    for (int64_t j = f - 1; j >= 0; j -= 32) {
+        const int64_t idx = j - (int64_t)lane;
+        unsigned long long v = 2ull << 62;   // before the first frame: an inclusive prefix of zero
+        unsigned first2, need;
         for (;;) {
-            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(state + j) : "memory");
-            if (v >> 62) break;
+            if (idx >= 0) asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(state + idx) : "memory");
+            const unsigned flag = (unsigned)(v >> 62);
+            const unsigned b2 = __ballot_sync(0xffffffffu, flag == 2), b0 = __ballot_sync(0xffffffffu, flag == 0);
+            first2 = b2 ? (unsigned)__ffs((int)b2) - 1u : 32u;                       // nearest predecessor that already knows its prefix
+            need = first2 >= 31u ? 0xffffffffu : ((2u << first2) - 1u);          // it and every frame after it must have published
+            if (!(b0 & need)) break;
             __nanosleep(64);
         }
-        excl += v & VAL;
-        if ((v >> 62) == 2) break;
+        unsigned long long x = ((need >> lane) & 1u) ? (v & VAL) : 0ull;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+        excl += x;
+        if (first2 < 32u) break;
     }
-    if (publish) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(state + f), "l"((2ull << 62) | (excl + mine)) : "memory");
+    if (publish && lane == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(state + f), "l"((2ull << 62) | (excl + mine)) : "memory");
     return excl;
 }
 
@@ -384,7 +396,7 @@ __device__ __forceinline__ void vc_frame_l2(const VcArgs &a, const VcDev &dv, co
             if (lane == 0) mytot[w] = carry;
             vc_exchange(cluster, mytot, wt1, vbase, csize, crank);
             if (!DENSE) {
-                if (tid == 0) frow[0] = vc_lookback(a.vstate, f, min(vbase[W], vcap), crank == 0);
+                if (w == 0) { const unsigned long long x = vc_lookback(a.vstate, f, min(vbase[W], vcap), crank == 0); if (lane == 0) frow[0] = x; }
                 __syncthreads();
             }
         }
@@ -509,7 +521,7 @@ __device__ __forceinline__ void vc_frame_l2(const VcArgs &a, const VcDev &dv, co
             }
             if (lane == 0) mytot[w] = carry;
             vc_exchange(cluster, mytot, wt2, pbase, csize, crank);
-            if (tid == 0) frow[1] = vc_lookback(a.kstate, f, pbase[W], crank == 0);
+            if (w == 0) { const unsigned long long x = vc_lookback(a.kstate, f, pbase[W], crank == 0); if (lane == 0) frow[1] = x; }
             __syncthreads();
         }
         VC_TICK(5);
@@ -596,6 +608,7 @@ constexpr int VR_LIST = 2048;                    // work list: entries still pro
 constexpr uint32_t VR_LOSER = 1u << 31;          // key word of a resolved entry that is not its voxel's winner (cell keys use <= 31 bits)
 constexpr uint32_t VR_KEPT = 1u << 31;           // index word: this entry of a crowded voxel is one of the K smallest
 
+constexpr uint32_t VR_STAGE = VC_WARPS * 96 * 8;   // bytes: 32 voxel rows x 3 coordinates x 8 B per warp
 struct VrPlan { uint32_t nit, Lc, lg, nslots, cap; };
 
 // shared-memory budget of one frame: reply words 4*Lc, slot table 2*nslots (power of two), queue 8*cap
@@ -611,8 +624,9 @@ __host__ __device__ inline bool vr_plan(uint32_t L, uint32_t csize, uint32_t dyn
     uint32_t best = 0, blg = 0;
     for (uint32_t lg = 10; lg <= 16; lg++) {
         const uint32_t ns = 1u << lg;
-        if (2 * ns + 1024 > R) break;
-        uint32_t c = (R - 2 * ns) / 8;
+        const uint32_t sb = 2 * ns > VR_STAGE ? 2 * ns : VR_STAGE;   // the idle slot table doubles as R6's coordinate staging
+        if (sb + 1024 > R) break;
+        uint32_t c = (R - sb) / 8;
         if (c > ns - ns / 4) c = ns - ns / 4;                 // load factor <= 0.75
         if (c > (uint32_t)VR_E * VC_THREADS) c = VR_E * VC_THREADS;
         if (c > 0xfff0u) c = 0xfff0u;                         // 16-bit queue positions in the slot table
@@ -963,7 +977,7 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
         }
         if (lane == 0) sh.mytot[w] = carry;
         vc_exchange(cluster, sh.mytot, sh.wt1, sh.vbase, csize, crank);   // cluster barrier #3 inside
-        if (tid == 0) sh.frow[0] = vc_lookback(a.vstate, f, min(sh.vbase[W], vcap), crank == 0);
+        if (w == 0) { const unsigned long long x = vc_lookback(a.vstate, f, min(sh.vbase[W], vcap), crank == 0); if (lane == 0) sh.frow[0] = x; }
         __syncthreads();
     }
     VC_TICK(4);
@@ -998,7 +1012,7 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
         }
         if (lane == 0) sh.mytot[w] = carry;
         vc_exchange(cluster, sh.mytot, sh.wt2, sh.pbase, csize, crank);   // cluster barrier #4 inside
-        if (tid == 0) sh.frow[1] = vc_lookback(a.kstate, f, sh.pbase[W], crank == 0);
+        if (w == 0) { const unsigned long long x = vc_lookback(a.kstate, f, sh.pbase[W], crank == 0); if (lane == 0) sh.frow[1] = x; }
         __syncthreads();
     }
     VC_TICK(5);
@@ -1008,6 +1022,7 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
         int64_t run = (int64_t)sh.frow[1] + sh.pbase[g];
         const int64_t vrow = (int64_t)sh.frow[0];
         const uint32_t vb = sh.vbase[g];
+        long long *stg = reinterpret_cast<long long *>(slot) + w * 96;   // the slot table is idle until the next frame
         for (uint32_t k0 = 0; k0 < nit; k0 += VC_U) {
             uint32_t r[VC_U];
             float4 p[VC_U];
@@ -1026,18 +1041,28 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
                 const bool valid = r[u] != VC_NONE;
                 const bool head = valid && (r[u] & VR_HEAD), keep = valid && (r[u] & VR_KEEP);
                 uint32_t nid = r[u] & VR_VAL;
-                if (head) {
-                    const uint32_t c = nid;   // points in the voxel
-                    const uint2 h = hbp[lj];
-                    nid = vb + h.y + __popc(h.x & ltmask);
-                    const int64_t o = vrow + nid;
-                    long long *co = reinterpret_cast<long long *>(a.out_coords) + o * 3;
-                    const int c0 = (int)floorf(__fdiv_rn(p[u].x, dv.size[0])), c1 = (int)floorf(__fdiv_rn(p[u].y, dv.size[1])),
-                              c2 = (int)floorf(__fdiv_rn(p[u].z, dv.size[2]));
-                    __stcs(co + 0, (long long)(uint32_t)(c0 - dv.vlo[0]) + dv.cadd[0]);
-                    __stcs(co + 1, (long long)(uint32_t)(c1 - dv.vlo[1]) + dv.cadd[1]);
-                    __stcs(co + 2, (long long)(uint32_t)(c2 - dv.vlo[2]) + dv.cadd[2]);
-                    __stcs(a.out_npoints + o, (trim && c > K) ? (int32_t)K : (int32_t)c);
+                // voxel rows of this round are consecutive: the coordinates go through a per-warp staging row so that
+                // the global stores are three dense 256-byte lines instead of three 24-byte-strided ones
+                const unsigned hbal = __ballot_sync(0xffffffffu, head);
+                if (hbal) {
+                    const uint32_t rank = __popc(hbal & ltmask), nh3 = 3u * __popc(hbal);
+                    const uint32_t first = vb + hbp[lj].y;
+                    if (head) {
+                        const uint32_t c = nid;   // points in the voxel
+                        nid = first + rank;
+                        const int c0 = (int)floorf(__fdiv_rn(p[u].x, dv.size[0])), c1 = (int)floorf(__fdiv_rn(p[u].y, dv.size[1])),
+                                  c2 = (int)floorf(__fdiv_rn(p[u].z, dv.size[2]));
+                        stg[rank * 3 + 0] = (long long)(uint32_t)(c0 - dv.vlo[0]) + dv.cadd[0];
+                        stg[rank * 3 + 1] = (long long)(uint32_t)(c1 - dv.vlo[1]) + dv.cadd[1];
+                        stg[rank * 3 + 2] = (long long)(uint32_t)(c2 - dv.vlo[2]) + dv.cadd[2];
+                        __stcs(a.out_npoints + vrow + nid, (trim && c > K) ? (int32_t)K : (int32_t)c);
+                    }
+                    __syncwarp();
+                    long long *co = reinterpret_cast<long long *>(a.out_coords) + (vrow + first) * 3;
+#pragma unroll
+                    for (int t = 0; t < 3; t++)
+                        if (t * 32 + lane < nh3) __stcs(co + t * 32 + lane, stg[t * 32 + lane]);
+                    __syncwarp();
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, keep);
                 if (keep) {
