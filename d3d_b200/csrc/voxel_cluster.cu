@@ -89,7 +89,7 @@ struct VcArgs {
 
 // per-CTA shared memory handed to the per-frame functions
 struct VcSh {
-    uint32_t *mytot, *wt1, *wt2, *vbase, *pbase;
+    uint32_t *mytot, *mytot2, *wt1, *wt2, *vbase, *pbase;
     unsigned long long *frow;      // first voxel row / first kept-point row of this frame in the packed outputs
     uint2 *hbp;                    // routed path: first-of-voxel bits of every 32-point round (.x) and their exclusive prefix inside the warp's chunk (.y)
     uint32_t *list, *lcount;       // routed path: work list
@@ -171,6 +171,36 @@ __device__ __forceinline__ void vc_exchange(cg::cluster_group &cluster, uint32_t
         if (lane == 31) base[csize * VC_WARPS] = run;
     }
     __syncthreads();
+}
+
+// both prefix sums of a frame (voxel rows, kept-point rows) behind ONE cluster barrier, for configurations whose keep
+// decision does not depend on the voxel id; warp 0 / warp 1 scan and look back concurrently
+__device__ __forceinline__ void vc_exchange2(cg::cluster_group &cluster, const uint32_t *mytot1, const uint32_t *mytot2, uint32_t *wt1, uint32_t *wt2,
+                                             uint32_t *base1, uint32_t *base2, unsigned csize, unsigned crank)
+{
+    const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned nw = csize * VC_WARPS;
+    __syncthreads();   // mytot1[], mytot2[] complete
+    for (unsigned t = tid; t < 2 * nw; t += VC_THREADS) {
+        const bool second = t >= nw;
+        const unsigned tt = second ? t - nw : t;
+        uint32_t *remote = cluster.map_shared_rank(second ? wt2 : wt1, tt / VC_WARPS);
+        remote[crank * VC_WARPS + (tt % VC_WARPS)] = (second ? mytot2 : mytot1)[tt % VC_WARPS];
+    }
+    cluster.sync();
+    if (w < 2) {
+        const uint32_t *wt = w ? wt2 : wt1;
+        uint32_t *base = w ? base2 : base1;
+        uint32_t s = 0;
+        for (unsigned j = 0; j < csize; j++) s += wt[lane * csize + j];
+        uint32_t inc = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (unsigned)d) inc += t; }
+        uint32_t run = inc - s;
+        for (unsigned j = 0; j < csize; j++) { base[lane * csize + j] = run; run += wt[lane * csize + j]; }
+        if (lane == 31) base[nw] = run;
+        __syncwarp();
+    }
 }
 
 // per-launch constants in the 32-bit form the kernel computes with
@@ -644,6 +674,19 @@ __host__ __device__ inline bool vr_plan(uint32_t L, uint32_t csize, uint32_t dyn
 __device__ __forceinline__ uint32_t vr_h1(uint32_t key) { return key * 0x9E3779B1u; }
 __device__ __forceinline__ uint32_t vr_step(uint32_t key, uint32_t smask) { return (((key * 0x85EBCA6Bu) >> 15) | 1u) & smask; }
 
+// every lane asks for cnt consecutive list positions: one shared-memory atomic per warp instead of one per thread
+// (same-address atomics with a result serialise)
+__device__ __forceinline__ uint32_t vr_reserve(uint32_t *counter, uint32_t cnt, unsigned lane)
+{
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (unsigned)d) inc += t; }
+    const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+    uint32_t base = 0;
+    if (lane == 31 && tot) base = atomicAdd(counter, tot);
+    return __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
+}
+
 #ifdef D3D_VC_TIMING
 #define VR_SUB(slot) do { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tk_[slot] = (float)(t_ - t0_) * 1e-3f; } while (0)
 #else
@@ -794,10 +837,11 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
             if (round == 0) { __syncthreads(); VR_SUB(8); }   // round 1 stores must not overtake round 0 lookups
         }
         VR_SUB(9);
-        if (unres) {   // hand the stragglers to the list (what does not fit stays with its thread)
+        {   // hand the stragglers to the list (what does not fit stays with its thread); one reservation per warp
             const uint32_t cnt = __popc(unres);
-            const uint32_t at = atomicAdd(sh.lcount, cnt);
-            if (at + cnt <= (uint32_t)VR_LIST) {
+            const uint32_t at = vr_reserve(sh.lcount, cnt, lane);
+            if (cnt == 0) {
+            } else if (at + cnt <= (uint32_t)VR_LIST) {
                 uint32_t o = at;
 #pragma unroll
                 for (int e = 0; e < VR_E; e++)
@@ -896,10 +940,11 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
                         q[s[e]].y = r;
                     }
             }
-            if (cm) {
+            {
                 const uint32_t cnt = __popc(cm);
-                uint32_t o = atomicAdd(sh.lcount, cnt);
-                if (o + cnt > (uint32_t)VR_LIST) {
+                uint32_t o = vr_reserve(sh.lcount, cnt, lane);
+                if (cnt == 0) {
+                } else if (o + cnt > (uint32_t)VR_LIST) {
                     over = true;
                     for (; o < (uint32_t)VR_LIST; o++) list[o] = VC_NONE;
                 } else {
@@ -965,23 +1010,32 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
     }
     VC_TICK(3);
 
-    // ---- R5: first-of-voxel bits -> voxel ids
+    // ---- R5: first-of-voxel bits -> voxel ids.  Without a voxel cap the keep decision is already in the reply word, so both
+    // prefix sums share one exchange and the ids of the points that are not first of their voxel are looked up in R6.
+    const bool twopass = vcap != VC_NONE;
     {
-        uint32_t carry = 0;
+        uint32_t carry = 0, kcarry = 0;
         for (uint32_t k = 0; k < nit; k++) {
             const uint32_t i = wbeg + k * 32 + lane;
             const uint32_t r = i < L ? reply[lbeg + k * 32 + lane] : VC_NONE;
             const unsigned bal = __ballot_sync(0xffffffffu, r != VC_NONE && (r & VR_HEAD));
             if (lane == 0) hbp[w * nit + k] = make_uint2(bal, carry);
             carry += __popc(bal);
+            if (!twopass) kcarry += __popc(__ballot_sync(0xffffffffu, r != VC_NONE && (r & VR_KEEP) && !dropall));
         }
-        if (lane == 0) sh.mytot[w] = carry;
-        vc_exchange(cluster, sh.mytot, sh.wt1, sh.vbase, csize, crank);   // cluster barrier #3 inside
-        if (w == 0) { const unsigned long long x = vc_lookback(a.vstate, f, min(sh.vbase[W], vcap), crank == 0); if (lane == 0) sh.frow[0] = x; }
+        if (lane == 0) { sh.mytot[w] = carry; sh.mytot2[w] = kcarry; }
+        if (twopass) {
+            vc_exchange(cluster, sh.mytot, sh.wt1, sh.vbase, csize, crank);   // cluster barrier #3 inside
+            if (w == 0) { const unsigned long long x = vc_lookback(a.vstate, f, min(sh.vbase[W], vcap), crank == 0); if (lane == 0) sh.frow[0] = x; }
+        } else {
+            vc_exchange2(cluster, sh.mytot, sh.mytot2, sh.wt1, sh.wt2, sh.vbase, sh.pbase, csize, crank);   // cluster barrier #3 inside
+            if (w == 0) { const unsigned long long x = vc_lookback(a.vstate, f, sh.vbase[W], crank == 0); if (lane == 0) sh.frow[0] = x; }
+            if (w == 1) { const unsigned long long x = vc_lookback(a.kstate, f, sh.pbase[W], crank == 0); if (lane == 0) sh.frow[1] = x; }
+        }
         __syncthreads();
     }
     VC_TICK(4);
-    {
+    if (twopass) {   // the voxel cap decides which points stay: ids first, then the second prefix sum
         uint32_t carry = 0;
         const uint32_t vb = sh.vbase[g];
         for (uint32_t k = 0; k < nit; k++) {
@@ -1026,11 +1080,22 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
         for (uint32_t k0 = 0; k0 < nit; k0 += VC_U) {
             uint32_t r[VC_U];
             float4 p[VC_U];
+            uint2 hrem[VC_U];
+            uint32_t hoff[VC_U];
 #pragma unroll
             for (int u = 0; u < VC_U; u++) {
                 const uint32_t i = wbeg + (k0 + u) * 32 + lane;
                 r[u] = (k0 + u < nit && i < L) ? reply[lbeg + (k0 + u) * 32 + lane] : VC_NONE;
+                if (r[u] != VC_NONE && dropall) r[u] &= ~VR_KEEP;
                 if (r[u] != VC_NONE && !(r[u] & (VR_HEAD | VR_KEEP))) r[u] = VC_NONE;
+                hrem[u] = make_uint2(0u, 0u); hoff[u] = 0;
+                if (!twopass && r[u] != VC_NONE && !(r[u] & VR_HEAD)) {   // id of a voxel whose first point lives elsewhere: loads of all rounds in flight together
+                    const uint32_t m = r[u] & VR_VAL;
+                    const uint32_t c = ((m >> 10) * magic) >> 16;
+                    const uint32_t lj = (m - c * Lc) >> 5;
+                    hrem[u] = cluster.map_shared_rank(hbp, c)[lj];
+                    hoff[u] = sh.vbase[c * VC_WARPS + ((lj * magic) >> 16)];
+                }
             }
 #pragma unroll
             for (int u = 0; u < VC_U; u++)
@@ -1041,6 +1106,7 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
                 const bool valid = r[u] != VC_NONE;
                 const bool head = valid && (r[u] & VR_HEAD), keep = valid && (r[u] & VR_KEEP);
                 uint32_t nid = r[u] & VR_VAL;
+                if (!twopass && valid && !head) nid = hoff[u] + hrem[u].y + __popc(hrem[u].x & ((1u << (nid & 31u)) - 1u));
                 // voxel rows of this round are consecutive: the coordinates go through a per-warp staging row so that
                 // the global stores are three dense 256-byte lines instead of three 24-byte-strided ones
                 const unsigned hbal = __ballot_sync(0xffffffffu, head);
@@ -1091,7 +1157,7 @@ __global__ void __launch_bounds__(VC_THREADS, 1) vox_cluster_kernel(const VcArgs
     const unsigned csize = cluster.num_blocks();
     const unsigned ncl = gridDim.x / csize, cid = blockIdx.x / csize;
 
-    __shared__ uint32_t mytot[VC_WARPS];
+    __shared__ uint32_t mytot[VC_WARPS], mytot2[VC_WARPS];
     __shared__ uint32_t wt1[VC_MAX_CSIZE * VC_WARPS], wt2[VC_MAX_CSIZE * VC_WARPS];
     __shared__ uint32_t vbase[VC_MAX_CSIZE * VC_WARPS + 1], pbase[VC_MAX_CSIZE * VC_WARPS + 1];
     __shared__ unsigned long long frow[2];
@@ -1102,7 +1168,7 @@ __global__ void __launch_bounds__(VC_THREADS, 1) vox_cluster_kernel(const VcArgs
     extern __shared__ __align__(16) unsigned char vc_dyn[];
 
     VcSh sh;
-    sh.mytot = mytot; sh.wt1 = wt1; sh.wt2 = wt2; sh.vbase = vbase; sh.pbase = pbase; sh.frow = frow;
+    sh.mytot = mytot; sh.mytot2 = mytot2; sh.wt1 = wt1; sh.wt2 = wt2; sh.vbase = vbase; sh.pbase = pbase; sh.frow = frow;
     sh.hbp = hbp; sh.list = list; sh.lcount = flags + 4;
     sh.pool_min = pool; sh.pool_acc0 = pool + (DENSE ? 1 : VR_POOL); sh.pool_acc1 = pool + (DENSE ? 2 : 2 * VR_POOL);
     sh.qcount = flags; sh.npool = flags + 1; sh.bail = flags + 2;
@@ -1120,6 +1186,7 @@ __global__ void __launch_bounds__(VC_THREADS, 1) vox_cluster_kernel(const VcArgs
         }
         vc_frame_l2<DENSE>(a, dv, sh, cluster, f, cid, ncl);
     }
+    if (route) cluster.sync();   // R6 of the last frame reads other CTAs' shared memory: nobody leaves before everybody is done
 }
 
 // ------------------------------------------------------------------ host side
