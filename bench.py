@@ -335,6 +335,14 @@ def bench_voxel(args, rank, world, barrier):
     ms_e2e = max_over_ranks(timed(lambda: gen.batch(host), e2e_steps, 1, barrier), world)
     hbm, how = peaks()
     ach = alg_bytes / (ms * 1e-3) / 1e9
+    traffic = None   # DRAM bytes per launch from the committed ncu capture, when it was taken on this workload
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as fh:
+            t = json.load(fh)["voxel"]
+        if t["frames"] == F and t["points_per_frame"] == C2_POINTS:
+            traffic = float(t["bytes"])
+    except (OSError, KeyError, ValueError):
+        pass
     return dict(metric="voxelized points/sec", unit="points/s", value=N * world / (ms * 1e-3), ms_per_step=ms, dtype="f32",
                 scaling="weak", gpu_launches=int(launches),
                 config=dict(workload=f"C2 KITTI-shaped voxelization: {F} frames/GPU x {C2_POINTS} pts/frame, voxel 0.05x0.05x0.1 m "
@@ -344,8 +352,9 @@ def bench_voxel(args, rank, world, barrier):
                 e2e=dict(value=N * world / (ms_e2e * 1e-3), unit="points/s", h2d_bytes_per_step=int(N * 16 + offs.numel() * 8),
                          d2h_bytes_per_step=int(32 * K + 28 * V + (F + 8) * 16), ms_per_step=ms_e2e,
                          api="VoxelGenerator.batch(list of pinned host tensors) -> host tensors"),
-                roofline=dict(bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm, traffic=None, peak_source=how,
-                              kernel="whole voxelize_sparse pass (all kernels of one step); algorithmic bytes 16N+32K+28V'",
+                roofline=dict(bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm, traffic=traffic, peak_source=how,
+                              traffic_source="profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch)",
+                              kernel="vox_cluster_kernel<sparse>: one persistent launch per step, shared-memory routed path; algorithmic bytes 16N+32K+28V'",
                               algorithmic_bytes_per_step=alg_bytes),
                 clocks=cs.summary())
 

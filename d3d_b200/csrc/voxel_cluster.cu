@@ -694,7 +694,7 @@ __device__ __forceinline__ uint32_t vr_reserve(uint32_t *counter, uint32_t cnt, 
 #endif
 #ifdef D3D_VC_TIMING
 #define VR_TICK_PRINT do { if (crank == 0 && tid == 0 && (cid == 0 || cid == ncl - 1) && f < 2 * (int64_t)ncl) \
-    printf("frame %3d cl %2u  push %6.1f resolve %6.1f (r0 %.1f r1 %.1f rounds %.1f [%u] fix %.1f) ranks %6.1f reply %6.1f heads %6.1f ids %6.1f write %6.1f us  (n %u)\n", (int)f, cid, tk_[0], tk_[1], tk_[8], tk_[9], tk_[10], (unsigned)tk_[12], tk_[11], tk_[2], tk_[3], tk_[4], tk_[5], tk_[6], n); } while (0)
+    printf("frame %3d cl %2u  push %6.1f resolve %6.1f (r0 %.1f r1 %.1f rounds %.1f [handoff %.1f] fix %.1f) ranks %6.1f reply %6.1f heads %6.1f ids %6.1f write %6.1f us  (n %u)\n", (int)f, cid, tk_[0], tk_[1], tk_[8], tk_[9], tk_[10], tk_[12], tk_[11], tk_[2], tk_[3], tk_[4], tk_[5], tk_[6], n); } while (0)
 #else
 #define VR_TICK_PRINT
 #endif
@@ -852,6 +852,7 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
             }
         }
         __syncthreads();
+        VR_SUB(12);
         // claim-or-join with a 32-bit CAS on the slot pair; slots only ever fill, so an entry that walks its probe
         // sequence meets the slot its key settled in (or settles it) whatever the interleaving
         auto settle = [&](uint32_t p, uint32_t sl) -> uint32_t {
