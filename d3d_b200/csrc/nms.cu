@@ -14,8 +14,14 @@
 //      resolved by a single thread with register bit-ops; the rows of the survivors are then OR-ed
 //      into the removal bitmap by all threads in parallel (coalesced, independent loads).  The
 //      reference does this whole phase in a <<<1,1>>> kernel (nms_cuda.cu:79-106,201).
+//      The suppression matrix is sparse (a proposal overlaps a few dozen others): the mask kernels also
+//      append every non-zero word to a list per 64-row block, and the resolve walks those lists, streamed
+//      through shared memory four blocks ahead with cp.async, so that a block costs a few hundred cycles of
+//      shared-memory work instead of two dependent L2 round trips.  The dense matrix remains the fallback
+//      (a list overflow, or more than 8192 blocks).
 #include "geom.cuh"
 #include "prims.cuh"
+#include <cuda_pipeline.h>
 
 namespace d3d {
 
@@ -100,9 +106,45 @@ __device__ __forceinline__ bool over_threshold<float>(float v, float thr, const 
     return v > thr;
 }
 
+// ---- sparse side product of the mask kernels: the non-zero words of row block rb, in any order
+constexpr uint32_t NMS_LIST_CAP = 4096;      // entries per 64-row block (64 rows x 64 words); more -> dense resolve
+struct NmsLists {
+    uint32_t *blkcnt;      // [nwords] entries appended per row block; blkcnt[nwords] = overflow flag
+    uint32_t *ent_w;       // [nwords * NMS_LIST_CAP] column word index | row inside the block << 16
+    uint64_t *ent_bits;    // [nwords * NMS_LIST_CAP]
+};
+
+// called by every thread of the CTA after the tile's words are final in smask[] (one per row, threads < NMS_TILE own them)
+__device__ __forceinline__ void nms_append_tile(const NmsLists &L, const unsigned long long *smask, int64_t rb, int64_t cb, int64_t n, int64_t nwords,
+                                                uint32_t *s_cnt, uint32_t *s_base)
+{
+    if (!L.blkcnt) return;
+    const unsigned tid = threadIdx.x;
+    if (tid == 0) *s_cnt = 0;
+    __syncthreads();
+    unsigned long long bits = 0;
+    uint32_t rank = 0;
+    if (tid < NMS_TILE && rb * NMS_TILE + tid < n) bits = smask[tid];
+    if (bits) rank = atomicAdd(s_cnt, 1u);
+    __syncthreads();
+    const uint32_t cnt = *s_cnt;
+    if (cnt == 0) return;   // CTA-uniform
+    if (tid == 0) {
+        const uint32_t base = atomicAdd(L.blkcnt + rb, cnt);
+        if (base + cnt > NMS_LIST_CAP) L.blkcnt[nwords] = 1u;
+        *s_base = base;
+    }
+    __syncthreads();
+    const uint32_t at = *s_base + rank;
+    if (bits && at < NMS_LIST_CAP) {
+        L.ent_w[rb * NMS_LIST_CAP + at] = (uint32_t)cb | (tid << 16);
+        L.ent_bits[rb * NMS_LIST_CAP + at] = bits;
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(NMS_THREADS)
-nms_mask_rbox_kernel(const BoxRec<T> *__restrict__ recs, const T *__restrict__ raw, int64_t n, int64_t nwords, T thr, uint64_t *__restrict__ mask)
+nms_mask_rbox_kernel(const BoxRec<T> *__restrict__ recs, const T *__restrict__ raw, int64_t n, int64_t nwords, T thr, uint64_t *__restrict__ mask, const NmsLists lists)
 {
     const int64_t rb = blockIdx.y, cb = blockIdx.x;
     if (cb < rb) return;   // strictly upper triangle (plus the diagonal tile)
@@ -112,6 +154,7 @@ nms_mask_rbox_kernel(const BoxRec<T> *__restrict__ recs, const T *__restrict__ r
     __shared__ BoxRec<T> sB[NMS_TILE];
     __shared__ unsigned long long smask[NMS_TILE];
     __shared__ uint16_t queue[NMS_WARPS][128];
+    __shared__ uint32_t s_cnt, s_base;
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
     {
         const float4 *ga = reinterpret_cast<const float4 *>(recs + rb * NMS_TILE);
@@ -161,38 +204,62 @@ nms_mask_rbox_kernel(const BoxRec<T> *__restrict__ recs, const T *__restrict__ r
         int64_t row = rb * NMS_TILE + threadIdx.x;
         if (row < n) mask[row * nwords + cb] = smask[threadIdx.x];
     }
+    nms_append_tile(lists, smask, rb, cb, n, nwords, &s_cnt, &s_base);
 }
 
 // AABB variant: every pair is a handful of instructions, no queue needed
 template <typename T>
 __global__ void __launch_bounds__(NMS_TILE)
-nms_mask_aabb_kernel(const AABBRec<T> *__restrict__ recs, int64_t n, int64_t nwords, T thr, uint64_t *__restrict__ mask)
+nms_mask_aabb_kernel(const AABBRec<T> *__restrict__ recs, int64_t n, int64_t nwords, T thr, uint64_t *__restrict__ mask, const NmsLists lists)
 {
     const int64_t rb = blockIdx.y, cb = blockIdx.x;
     if (cb < rb) return;
     __shared__ AABBRec<T> sB[NMS_TILE];
+    __shared__ unsigned long long smask[NMS_TILE];
+    __shared__ uint32_t s_cnt, s_base;
     sB[threadIdx.x] = recs[cb * NMS_TILE + threadIdx.x];
     __syncthreads();
     const int64_t row = rb * NMS_TILE + threadIdx.x;
-    if (row >= n) return;
-    const AABBRec<T> a = recs[row];
     unsigned long long bits = 0;
-    const int start = (rb == cb) ? threadIdx.x + 1 : 0;
-    for (int c = start; c < NMS_TILE; c++) {
-        if (cb * NMS_TILE + c >= n) break;
-        if (aabb_iou<T>(a, sB[c]) > thr) bits |= 1ull << c;
+    if (row < n) {
+        const AABBRec<T> a = recs[row];
+        const int start = (rb == cb) ? threadIdx.x + 1 : 0;
+        for (int c = start; c < NMS_TILE; c++) {
+            if (cb * NMS_TILE + c >= n) break;
+            if (aabb_iou<T>(a, sB[c]) > thr) bits |= 1ull << c;
+        }
+        mask[row * nwords + cb] = bits;
     }
-    mask[row * nwords + cb] = bits;
+    smask[threadIdx.x] = bits;
+    __syncthreads();
+    nms_append_tile(lists, smask, rb, cb, n, nwords, &s_cnt, &s_base);
 }
 
 constexpr int RESOLVE_THREADS = 1024;
 
+constexpr int RS_STAGES = 6;          // blocks of list entries in flight
+
+// greedy pass over one 64-box block: cur = boxes already removed, diag[t] = boxes of the block that box t removes.
+// Jumps from survivor to survivor (a handful per block) instead of testing all 64 positions.
+__device__ __forceinline__ unsigned long long nms_resolve_diag(unsigned long long cur, const unsigned long long *diag)
+{
+    unsigned long long kept = 0, cand = ~cur;
+    while (cand) {
+        const int t = __ffsll((long long)cand) - 1;
+        kept |= 1ull << t;
+        cur |= diag[t];
+        cand = ~cur & ~((2ull << t) - 1ull);   // alive boxes after t (t == 63: the shift wraps to 0, the mask clears everything)
+        if (t == 63) break;
+    }
+    return kept;
+}
+
 __global__ void __launch_bounds__(RESOLVE_THREADS)
 nms_resolve_kernel(const uint64_t *__restrict__ mask, int64_t n, int64_t nwords, const uint8_t *__restrict__ valid,
-                   const uint32_t *__restrict__ order, uint8_t *__restrict__ suppressed)
+                   const uint32_t *__restrict__ order, uint8_t *__restrict__ suppressed, const NmsLists lists, const uint32_t stage_cap)
 {
-    extern __shared__ unsigned long long remv[];   // [nwords] removal bitmap in sorted order
-    __shared__ unsigned long long diag[64];
+    extern __shared__ unsigned long long remv[];   // [nwords] removal bitmap in sorted order (+ the sparse path's arrays behind it)
+    __shared__ unsigned long long diag[2][64];
     __shared__ unsigned long long keptbits;
     const int tid = threadIdx.x;
     // boxes at or below the score threshold (and the padding past n) start out removed
@@ -204,21 +271,81 @@ nms_resolve_kernel(const uint64_t *__restrict__ mask, int64_t n, int64_t nwords,
         }
         remv[w] = b;
     }
+    const bool sparse = lists.blkcnt != nullptr && lists.blkcnt[nwords] == 0u;   // CTA-uniform: no list overflowed
+    if (sparse) {
+        // ---- sparse walk.  Per block: thread 0 resolves the diagonal tile while the other warps pick the diagonal words of the
+        // NEXT block out of its staged list; barrier; everybody ORs the survivors' words into the bitmap; barrier.  The lists
+        // arrive through cp.async RS_STAGES-1 blocks ahead, the keep bits leave in one pass at the end.
+        const uint32_t SC = stage_cap;
+        unsigned long long *keptw = remv + nwords;                                   // [nwords]
+        unsigned long long *sbits = keptw + nwords;                                  // [RS_STAGES][SC]
+        uint32_t *sw = reinterpret_cast<uint32_t *>(sbits + (size_t)RS_STAGES * SC); // [RS_STAGES][SC]
+        uint32_t *cnts = sw + (size_t)RS_STAGES * SC;                                // [nwords]
+        for (int64_t w = tid; w < nwords; w += RESOLVE_THREADS) cnts[w] = min(lists.blkcnt[w], NMS_LIST_CAP);
+        if (tid < 128) diag[tid >> 6][tid & 63] = 0ull;
+        __syncthreads();
+        auto issue = [&](int64_t b) {
+            if (b < nwords) {
+                const uint32_t c = min(cnts[b], SC);
+                const int st = (int)(b % RS_STAGES);
+                for (uint32_t e = tid; e < c; e += RESOLVE_THREADS) {
+                    __pipeline_memcpy_async(sw + st * SC + e, lists.ent_w + b * NMS_LIST_CAP + e, 4);
+                    __pipeline_memcpy_async(sbits + st * SC + e, lists.ent_bits + b * NMS_LIST_CAP + e, 8);
+                }
+            }
+            __pipeline_commit();
+        };
+        auto extract = [&](int64_t b, uint32_t first, uint32_t stride) {   // diagonal words of block b -> diag[b & 1] (zeroed beforehand)
+            if (b >= nwords) return;
+            const int st = (int)(b % RS_STAGES);
+            const uint32_t c = cnts[b];
+            const uint32_t *gw = lists.ent_w + b * NMS_LIST_CAP;
+            const uint64_t *gb = lists.ent_bits + b * NMS_LIST_CAP;
+            for (uint32_t e = first; e < c; e += stride) {
+                const uint32_t we = e < SC ? sw[st * SC + e] : gw[e];
+                if ((we & 0xffffu) == (uint32_t)b) diag[b & 1][we >> 16] = e < SC ? sbits[st * SC + e] : gb[e];
+            }
+        };
+        for (int b = 0; b < RS_STAGES - 1; b++) issue(b);
+        __pipeline_wait_prior(RS_STAGES - 3);   // blocks 0 and 1 have landed (this thread's copies)
+        __syncthreads();
+        extract(0, tid, RESOLVE_THREADS);
+        __syncthreads();
+        for (int64_t blk = 0; blk < nwords; blk++) {
+            // phase A: resolve blk (thread 0) | diagonal words of blk + 1 (everybody else)
+            if (tid == 0) { const unsigned long long k = nms_resolve_diag(remv[blk], diag[blk & 1]); keptbits = k; keptw[blk] = k; }
+            else if (tid >= 32) extract(blk + 1, tid - 32, RESOLVE_THREADS - 32);
+            __syncthreads();
+            // phase B: the survivors' words of blk into the bitmap; recycle buffers; keep the pipeline full
+            const unsigned long long kept = keptbits;
+            if (tid < 64) diag[blk & 1][tid] = 0ull;   // next used by block blk + 2
+            if (kept) {
+                const int st = (int)(blk % RS_STAGES);
+                const uint32_t c = cnts[blk];
+                const uint32_t *gw = lists.ent_w + blk * NMS_LIST_CAP;
+                const uint64_t *gb = lists.ent_bits + blk * NMS_LIST_CAP;
+                for (uint32_t e = tid; e < c; e += RESOLVE_THREADS) {
+                    const uint32_t we = e < SC ? sw[st * SC + e] : gw[e];
+                    if ((kept >> (we >> 16)) & 1ull) atomicOr(&remv[we & 0xffffu], e < SC ? sbits[st * SC + e] : gb[e]);
+                }
+            }
+            issue(blk + RS_STAGES - 1);             // into stage (blk - 1) % RS_STAGES, last read before the previous iteration's final barrier
+            __pipeline_wait_prior(RS_STAGES - 3);   // this thread's copies of block blk + 2 have landed ...
+            __syncthreads();                        // ... and everybody's are visible; remv[blk + 1] is final
+        }
+        __syncthreads();
+        for (int64_t row = tid; row < n; row += RESOLVE_THREADS) suppressed[order[row]] = ((keptw[row >> 6] >> (row & 63)) & 1ull) ? 0 : 1;
+        return;
+    }
+    unsigned long long *diag0 = diag[0];
     __syncthreads();
     for (int64_t blk = 0; blk < nwords; blk++) {
         if (tid < 64) {
             int64_t row = blk * 64 + tid;
-            diag[tid] = row < n ? mask[row * nwords + blk] : 0ull;
+            diag0[tid] = row < n ? mask[row * nwords + blk] : 0ull;
         }
         __syncthreads();
-        if (tid == 0) {
-            unsigned long long cur = remv[blk], kept = 0;
-#pragma unroll 8
-            for (int t = 0; t < 64; t++) {
-                if (!((cur >> t) & 1ull)) { kept |= 1ull << t; cur |= diag[t]; }
-            }
-            keptbits = kept;
-        }
+        if (tid == 0) keptbits = nms_resolve_diag(remv[blk], diag0);
         __syncthreads();
         const unsigned long long kept = keptbits;
         if (tid < 64) {
@@ -244,13 +371,16 @@ nms_resolve_kernel(const uint64_t *__restrict__ mask, int64_t n, int64_t nwords,
     }
 }
 
+constexpr int64_t NMS_SPARSE_MAX_WORDS = 8192;   // block counters + staging must fit shared memory next to the bitmap
+
 template <typename T> static size_t nms_ws_bytes(int64_t n)
 {
     if (n <= 0) n = 1;
     int64_t npad = cdiv(n, NMS_TILE) * NMS_TILE, nwords = npad / 64;
     size_t recs = sizeof(BoxRec<T>) > sizeof(AABBRec<T>) ? sizeof(BoxRec<T>) : sizeof(AABBRec<T>);
     return align_up((size_t)n * 8) + align_up((size_t)n * 4) + radix_sort_workspace_bytes(n) + align_up((size_t)npad * recs) +
-           align_up((size_t)npad * 5 * sizeof(T)) + align_up((size_t)npad) + align_up((size_t)npad * nwords * 8) + 4096;
+           align_up((size_t)npad * 5 * sizeof(T)) + align_up((size_t)npad) + align_up((size_t)npad * nwords * 8) +
+           align_up((size_t)(nwords + 1) * 4) + align_up((size_t)nwords * NMS_LIST_CAP * 4) + align_up((size_t)nwords * NMS_LIST_CAP * 8) + 4096;
 }
 
 template <typename T>
@@ -277,7 +407,15 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
     T *raw = a.take<T>((size_t)npad * 5);
     uint8_t *valid = a.take<uint8_t>(npad);
     uint64_t *mask = a.take<uint64_t>((size_t)npad * nwords);
+    NmsLists lists = {nullptr, nullptr, nullptr};
+    uint32_t *blkcnt = a.take<uint32_t>((size_t)nwords + 1);
+    uint32_t *ent_w = a.take<uint32_t>((size_t)nwords * NMS_LIST_CAP);
+    uint64_t *ent_bits = a.take<uint64_t>((size_t)nwords * NMS_LIST_CAP);
     if (!a.ok()) return D3D_ERR_WORKSPACE;
+    if (nwords <= NMS_SPARSE_MAX_WORDS) {
+        lists.blkcnt = blkcnt; lists.ent_w = ent_w; lists.ent_bits = ent_bits;
+        D3D_CUDA_TRY(cudaMemsetAsync(blkcnt, 0, (size_t)(nwords + 1) * 4, st));
+    }
 
     nms_keys_kernel<T><<<(unsigned)cdiv(n, 256), 256, 0, st>>>(scores, n, keys, order); D3D_LAUNCHED();
     int rc = radix_sort_pairs_u64(keys, order, n, KeyBits<T>::bits, sort_ws, sort_bytes, st);
@@ -291,12 +429,20 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
     const T thr = (T)iou_thr;   // (T)(float): SURVEY.md 8(c) T2
     if (nwords > 65535) return D3D_ERR_INVALID_ARGUMENT;
     dim3 grid((unsigned)nwords, (unsigned)nwords);
-    if (aabb) nms_mask_aabb_kernel<T><<<grid, NMS_TILE, 0, st>>>((const AABBRec<T> *)recs, n, nwords, thr, mask);
-    else nms_mask_rbox_kernel<T><<<grid, NMS_THREADS, 0, st>>>((const BoxRec<T> *)recs, recheck ? raw : nullptr, n, nwords, thr, mask);
+    if (aabb) nms_mask_aabb_kernel<T><<<grid, NMS_TILE, 0, st>>>((const AABBRec<T> *)recs, n, nwords, thr, mask, lists);
+    else nms_mask_rbox_kernel<T><<<grid, NMS_THREADS, 0, st>>>((const BoxRec<T> *)recs, recheck ? raw : nullptr, n, nwords, thr, mask, lists);
     D3D_LAUNCHED();
     size_t smem = (size_t)nwords * 8;
+    uint32_t stage_cap = 0;
+    if (lists.blkcnt) {   // bitmap + keep words + block counts, the rest of ~200 KB goes to the list stages
+        const size_t fixed = (size_t)nwords * 20;
+        size_t sc = (200 * 1024 - fixed) / ((size_t)RS_STAGES * 12);
+        if (sc > NMS_LIST_CAP) sc = NMS_LIST_CAP;
+        stage_cap = (uint32_t)(sc & ~(size_t)1);   // even: the 64-bit stage arrays stay 8-byte aligned
+        smem = fixed + (size_t)RS_STAGES * stage_cap * 12;
+    }
     if (smem > 40 * 1024) D3D_CUDA_TRY(cudaFuncSetAttribute(nms_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_resolve_kernel<<<1, RESOLVE_THREADS, smem, st>>>(mask, n, nwords, valid, order, suppressed); D3D_LAUNCHED();
+    nms_resolve_kernel<<<1, RESOLVE_THREADS, smem, st>>>(mask, n, nwords, valid, order, suppressed, lists, stage_cap); D3D_LAUNCHED();
     return D3D_OK;
 }
 
