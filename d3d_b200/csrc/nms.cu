@@ -22,6 +22,7 @@
 #include "geom.cuh"
 #include "prims.cuh"
 #include <cuda_pipeline.h>
+#include <stdlib.h>
 
 namespace d3d {
 
@@ -142,12 +143,154 @@ __device__ __forceinline__ void nms_append_tile(const NmsLists &L, const unsigne
     }
 }
 
+// ---- spatial candidate search (rbox).  Boxes whose bounding circles overlap lie in adjacent cells of a grid whose cell
+// is wider than 2 * max rho, so a box meets all its candidates in 3x3 cells instead of the whole upper triangle of
+// the sorted matrix (C3: ~500 candidates per box instead of 25 000).  Everything is decided on the device: when the
+// geometry does not allow a grid (non-finite boxes, no extent, too few cells) or a list overflows, the dense tile
+// kernel below runs instead -- otherwise its CTAs exit on their first instruction.
+constexpr int NMS_GRID_MAX = 256;                                   // cells per axis
+constexpr int NMS_GRID_CELLS = NMS_GRID_MAX * NMS_GRID_MAX;
+struct NmsGrid { double minx, miny, inv_cell; int nx, ny; uint32_t ok; uint32_t pad; };
+
+template <typename T>
+__global__ void __launch_bounds__(1024) nms_grid_kernel(const BoxRec<T> *__restrict__ recs, int64_t n, NmsGrid *__restrict__ g)
+{
+    __shared__ double smin[2][32], smax[2][32], srho[32];
+    __shared__ int sbad[32];
+    double mnx = 1e300, mny = 1e300, mxx = -1e300, mxy = -1e300, mr = 0;
+    int bad = 0;
+    for (int64_t p = threadIdx.x; p < n; p += blockDim.x) {
+        const double x = (double)recs[p].cx, y = (double)recs[p].cy, r = (double)recs[p].rho;
+        if (!(fabs(x) < 1e150) || !(fabs(y) < 1e150) || !(r < 1e150) || !(r >= 0)) bad = 1;
+        mnx = fmin(mnx, x); mny = fmin(mny, y); mxx = fmax(mxx, x); mxy = fmax(mxy, y); mr = fmax(mr, r);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        mnx = fmin(mnx, __shfl_xor_sync(0xffffffffu, mnx, d)); mny = fmin(mny, __shfl_xor_sync(0xffffffffu, mny, d));
+        mxx = fmax(mxx, __shfl_xor_sync(0xffffffffu, mxx, d)); mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
+        mr = fmax(mr, __shfl_xor_sync(0xffffffffu, mr, d)); bad |= __shfl_xor_sync(0xffffffffu, bad, d);
+    }
+    const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { smin[0][w] = mnx; smin[1][w] = mny; smax[0][w] = mxx; smax[1][w] = mxy; srho[w] = mr; sbad[w] = bad; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (unsigned k = 1; k < blockDim.x / 32; k++) {
+            mnx = fmin(mnx, smin[0][k]); mny = fmin(mny, smin[1][k]); mxx = fmax(mxx, smax[0][k]); mxy = fmax(mxy, smax[1][k]);
+            mr = fmax(mr, srho[k]); bad |= sbad[k];
+        }
+        NmsGrid o;
+        o.minx = mnx; o.miny = mny; o.inv_cell = 0; o.nx = o.ny = 1; o.ok = 0; o.pad = 0;
+        const double ex = mxx - mnx, ey = mxy - mny;
+        double cell = 2.0 * mr * (1.0 + 1e-6);     // the margin absorbs the rounding of the cell index
+        cell = fmax(cell, fmax(ex, ey) / NMS_GRID_MAX * (1.0 + 1e-6));
+        if (!bad && n > 0 && cell > 0 && cell < 1e150) {
+            const int nx = (int)fmin((double)NMS_GRID_MAX, floor(ex / cell) + 1), ny = (int)fmin((double)NMS_GRID_MAX, floor(ey / cell) + 1);
+            if ((int64_t)nx * ny >= 16) { o.inv_cell = 1.0 / cell; o.nx = nx; o.ny = ny; o.ok = 1; }
+        }
+        *g = o;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void nms_cell_of(const NmsGrid &g, const BoxRec<T> &r, int *ix, int *iy)
+{
+    // clamping merges cells at the border: a superset of candidates, never a miss
+    *ix = min(g.nx - 1, max(0, (int)floor(((double)r.cx - g.minx) * g.inv_cell)));
+    *iy = min(g.ny - 1, max(0, (int)floor(((double)r.cy - g.miny) * g.inv_cell)));
+}
+
+// pass 0: count boxes per cell; pass 1: fill the cell lists (order inside a cell is arbitrary: results are ORs)
+template <typename T, int PASS>
+__global__ void __launch_bounds__(256) nms_bin_kernel(const BoxRec<T> *__restrict__ recs, int64_t n, const NmsGrid *__restrict__ g,
+                                                      uint32_t *__restrict__ cellcnt, const uint32_t *__restrict__ cellptr, uint32_t *__restrict__ celllist)
+{
+    if (!g->ok) return;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int ix, iy;
+    nms_cell_of<T>(*g, recs[p], &ix, &iy);
+    const uint32_t c = (uint32_t)(iy * g->nx + ix);
+    const uint32_t at = atomicAdd(cellcnt + c, 1u);
+    if (PASS == 1) celllist[cellptr[c] + at] = (uint32_t)p;
+}
+
+constexpr int NMS_PAIR_THREADS = 256;
+template <typename T>
+__global__ void __launch_bounds__(NMS_PAIR_THREADS) nms_pairs_kernel(const BoxRec<T> *__restrict__ recs, const T *__restrict__ raw, int64_t n, int64_t nwords, T thr,
+                                                                    const NmsGrid *__restrict__ g, const uint32_t *__restrict__ cellptr,
+                                                                    const uint32_t *__restrict__ celllist, const NmsLists lists)
+{
+    if (!g->ok) return;
+    __shared__ uint32_t queue[NMS_PAIR_THREADS / 32][64];
+    const unsigned lane = lane_id(), w = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * (NMS_PAIR_THREADS / 32) + w;   // one warp per row of the sorted matrix
+    if (i >= n) return;
+    const BoxRec<T> A = recs[i];
+    const NmsGrid G = *g;
+    int ix, iy;
+    nms_cell_of<T>(G, A, &ix, &iy);
+    uint32_t *q = queue[w];
+    unsigned head = 0, tail = 0;
+    const uint32_t rb = (uint32_t)(i >> 6), trow = (uint32_t)(i & 63);
+    auto drain = [&](bool all) {
+        while (tail - head >= 32u || (all && tail != head)) {
+            __syncwarp();
+            const unsigned cnt = min(tail - head, 32u);
+            const uint32_t j = q[(head + min(lane, cnt - 1)) & 63];
+            const BoxRec<T> B = recs[j];
+            const T v = rbox_iou<T>(A, B);   // iou(higher score box, lower score box), nms.cpp:50
+            const bool hit = lane < cnt && over_threshold<T>(v, thr, raw, (unsigned)i, j);
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (bal) {   // one reservation per warp: every hit of this row goes to the list of its 64-row block
+                uint32_t at = 0;
+                if (lane == 0) at = atomicAdd(lists.blkcnt + rb, (uint32_t)__popc(bal));
+                at = __shfl_sync(0xffffffffu, at, 0) + __popc(bal & lanemask_lt());
+                if (hit) {
+                    if (at < NMS_LIST_CAP) {
+                        lists.ent_w[(size_t)rb * NMS_LIST_CAP + at] = (j >> 6) | (trow << 16);
+                        lists.ent_bits[(size_t)rb * NMS_LIST_CAP + at] = 1ull << (j & 63u);
+                    } else lists.blkcnt[nwords] = 1u;
+                }
+            }
+            head += cnt;
+            __syncwarp();
+        }
+    };
+    for (int dy = -1; dy <= 1; dy++) {
+        const int cy = iy + dy;
+        if (cy < 0 || cy >= G.ny) continue;
+        const int x0 = max(ix - 1, 0), x1 = min(ix + 1, G.nx - 1);
+        const uint32_t beg = cellptr[cy * G.nx + x0], end = cellptr[cy * G.nx + x1 + 1];   // the three cells of a grid row are contiguous
+        for (uint32_t k0 = beg; k0 < end; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            bool cand = false;
+            uint32_t j = 0;
+            if (k < end) {
+                j = celllist[k];
+                if ((int64_t)j > i) {
+                    const T dx = A.cx - recs[j].cx, dyy = A.cy - recs[j].cy, rs = A.rho + recs[j].rho;
+                    cand = dx * dx + dyy * dyy <= rs * rs;
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, cand);
+            if (cand) q[(tail + __popc(bal & lanemask_lt())) & 63] = j;
+            tail += __popc(bal);
+            drain(false);
+        }
+    }
+    drain(true);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(NMS_THREADS)
-nms_mask_rbox_kernel(const BoxRec<T> *__restrict__ recs, const T *__restrict__ raw, int64_t n, int64_t nwords, T thr, uint64_t *__restrict__ mask, const NmsLists lists)
+nms_mask_rbox_kernel(const BoxRec<T> *__restrict__ recs, const T *__restrict__ raw, int64_t n, int64_t nwords, T thr, uint64_t *__restrict__ mask, const NmsLists lists,
+                     const NmsGrid *__restrict__ grid)
 {
-    const int64_t rb = blockIdx.y, cb = blockIdx.x;
-    if (cb < rb) return;   // strictly upper triangle (plus the diagonal tile)
+    // one CTA per column tile cb and per residue of the row tile: rb = blockIdx.y, blockIdx.y + gridDim.y, ... <= cb.  The short grid
+    // keeps the launch cheap when the spatial path has already produced the lists and every CTA leaves at once.
+    const int64_t cb = blockIdx.x;
+    if (cb < (int64_t)blockIdx.y) return;
+    if (grid && grid->ok && lists.blkcnt[nwords] == 0u) return;   // the spatial path produced the lists: nothing to do
     constexpr int RW = NMS_TILE / NMS_WARPS;  // 16 rows per warp
     constexpr int KC = NMS_TILE / 32;         // 2 column chunks
     __shared__ BoxRec<T> sA[NMS_TILE];
@@ -156,19 +299,25 @@ nms_mask_rbox_kernel(const BoxRec<T> *__restrict__ recs, const T *__restrict__ r
     __shared__ uint16_t queue[NMS_WARPS][128];
     __shared__ uint32_t s_cnt, s_base;
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
+    constexpr int NV = NMS_TILE * sizeof(BoxRec<T>) / 16;
     {
-        const float4 *ga = reinterpret_cast<const float4 *>(recs + rb * NMS_TILE);
         const float4 *gb = reinterpret_cast<const float4 *>(recs + cb * NMS_TILE);
-        float4 *da = reinterpret_cast<float4 *>(sA), *db = reinterpret_cast<float4 *>(sB);
-        constexpr int NV = NMS_TILE * sizeof(BoxRec<T>) / 16;
-        for (int i = threadIdx.x; i < NV; i += NMS_THREADS) { da[i] = __ldg(ga + i); db[i] = __ldg(gb + i); }
-        if (threadIdx.x < NMS_TILE) smask[threadIdx.x] = 0ull;
+        float4 *db = reinterpret_cast<float4 *>(sB);
+        for (int i = threadIdx.x; i < NV; i += NMS_THREADS) db[i] = __ldg(gb + i);
     }
     __syncthreads();
     T bx[KC], by[KC], br[KC];
 #pragma unroll
     for (int k = 0; k < KC; k++) { bx[k] = sB[k * 32 + lane].cx; by[k] = sB[k * 32 + lane].cy; br[k] = sB[k * 32 + lane].rho; }
     uint16_t *q = queue[w];
+  for (int64_t rb = blockIdx.y; rb <= cb; rb += gridDim.y) {
+    {
+        const float4 *ga = reinterpret_cast<const float4 *>(recs + rb * NMS_TILE);
+        float4 *da = reinterpret_cast<float4 *>(sA);
+        for (int i = threadIdx.x; i < NV; i += NMS_THREADS) da[i] = __ldg(ga + i);
+        if (threadIdx.x < NMS_TILE) smask[threadIdx.x] = 0ull;
+    }
+    __syncthreads();
     unsigned head = 0, tail = 0;
     const bool diag = (rb == cb);
 #pragma unroll 1
@@ -205,6 +354,8 @@ nms_mask_rbox_kernel(const BoxRec<T> *__restrict__ recs, const T *__restrict__ r
         if (row < n) mask[row * nwords + cb] = smask[threadIdx.x];
     }
     nms_append_tile(lists, smask, rb, cb, n, nwords, &s_cnt, &s_base);
+    __syncthreads();   // sA, smask and the counters are reused by the next row tile
+  }
 }
 
 // AABB variant: every pair is a handful of instructions, no queue needed
@@ -238,6 +389,15 @@ nms_mask_aabb_kernel(const AABBRec<T> *__restrict__ recs, int64_t n, int64_t nwo
 constexpr int RESOLVE_THREADS = 1024;
 
 constexpr int RS_STAGES = 6;          // blocks of list entries in flight
+
+// shared-memory OR of a 64-bit word through its 32-bit halves (native ATOMS.OR; the 64-bit form is a CAS loop)
+__device__ __forceinline__ void smem_or64(unsigned long long *word, unsigned long long bits)
+{
+    uint32_t *h = reinterpret_cast<uint32_t *>(word);
+    const uint32_t lo = (uint32_t)bits, hi = (uint32_t)(bits >> 32);
+    if (lo) atomicOr(h, lo);
+    if (hi) atomicOr(h + 1, hi);
+}
 
 // greedy pass over one 64-box block: cur = boxes already removed, diag[t] = boxes of the block that box t removes.
 // Jumps from survivor to survivor (a handful per block) instead of testing all 64 positions.
@@ -303,7 +463,7 @@ nms_resolve_kernel(const uint64_t *__restrict__ mask, int64_t n, int64_t nwords,
             const uint64_t *gb = lists.ent_bits + b * NMS_LIST_CAP;
             for (uint32_t e = first; e < c; e += stride) {
                 const uint32_t we = e < SC ? sw[st * SC + e] : gw[e];
-                if ((we & 0xffffu) == (uint32_t)b) diag[b & 1][we >> 16] = e < SC ? sbits[st * SC + e] : gb[e];
+                if ((we & 0xffffu) == (uint32_t)b) smem_or64(&diag[b & 1][we >> 16], e < SC ? sbits[st * SC + e] : gb[e]);   // several entries may share a word
             }
         };
         for (int b = 0; b < RS_STAGES - 1; b++) issue(b);
@@ -326,7 +486,7 @@ nms_resolve_kernel(const uint64_t *__restrict__ mask, int64_t n, int64_t nwords,
                 const uint64_t *gb = lists.ent_bits + blk * NMS_LIST_CAP;
                 for (uint32_t e = tid; e < c; e += RESOLVE_THREADS) {
                     const uint32_t we = e < SC ? sw[st * SC + e] : gw[e];
-                    if ((kept >> (we >> 16)) & 1ull) atomicOr(&remv[we & 0xffffu], e < SC ? sbits[st * SC + e] : gb[e]);
+                    if ((kept >> (we >> 16)) & 1ull) smem_or64(&remv[we & 0xffffu], e < SC ? sbits[st * SC + e] : gb[e]);
                 }
             }
             issue(blk + RS_STAGES - 1);             // into stage (blk - 1) % RS_STAGES, last read before the previous iteration's final barrier
@@ -380,7 +540,8 @@ template <typename T> static size_t nms_ws_bytes(int64_t n)
     size_t recs = sizeof(BoxRec<T>) > sizeof(AABBRec<T>) ? sizeof(BoxRec<T>) : sizeof(AABBRec<T>);
     return align_up((size_t)n * 8) + align_up((size_t)n * 4) + radix_sort_workspace_bytes(n) + align_up((size_t)npad * recs) +
            align_up((size_t)npad * 5 * sizeof(T)) + align_up((size_t)npad) + align_up((size_t)npad * nwords * 8) +
-           align_up((size_t)(nwords + 1) * 4) + align_up((size_t)nwords * NMS_LIST_CAP * 4) + align_up((size_t)nwords * NMS_LIST_CAP * 8) + 4096;
+           align_up((size_t)(nwords + 1) * 4) + align_up((size_t)nwords * NMS_LIST_CAP * 4) + align_up((size_t)nwords * NMS_LIST_CAP * 8) +
+           align_up(sizeof(NmsGrid)) + 2 * align_up((size_t)2 * (NMS_GRID_CELLS + 1) * 4) + align_up((size_t)npad * 4) + scan_workspace_bytes(NMS_GRID_CELLS + 1) + 4096;
 }
 
 template <typename T>
@@ -411,8 +572,16 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
     uint32_t *blkcnt = a.take<uint32_t>((size_t)nwords + 1);
     uint32_t *ent_w = a.take<uint32_t>((size_t)nwords * NMS_LIST_CAP);
     uint64_t *ent_bits = a.take<uint64_t>((size_t)nwords * NMS_LIST_CAP);
+    NmsGrid *grid = a.take<NmsGrid>(1);
+    uint32_t *cellcnt = a.take<uint32_t>((size_t)2 * (NMS_GRID_CELLS + 1));   // [0] counts (pass 0), [1] fill cursors (pass 1)
+    uint32_t *cellptr = a.take<uint32_t>((size_t)2 * (NMS_GRID_CELLS + 1));
+    uint32_t *celllist = a.take<uint32_t>((size_t)npad);
+    void *cell_scan_ws = a.take<char>(scan_workspace_bytes(NMS_GRID_CELLS + 1));
     if (!a.ok()) return D3D_ERR_WORKSPACE;
-    if (nwords <= NMS_SPARSE_MAX_WORDS) {
+    // tuning / test override: D3D_B200_NMS_PATH=dense (dense matrix, dense resolve) | tiles (dense tiles + list resolve); default: spatial
+    const char *path_env = getenv("D3D_B200_NMS_PATH");
+    const bool force_dense = path_env && path_env[0] == 'd', force_tiles = path_env && path_env[0] == 't';
+    if (nwords <= NMS_SPARSE_MAX_WORDS && !force_dense) {
         lists.blkcnt = blkcnt; lists.ent_w = ent_w; lists.ent_bits = ent_bits;
         D3D_CUDA_TRY(cudaMemsetAsync(blkcnt, 0, (size_t)(nwords + 1) * 4, st));
     }
@@ -428,9 +597,22 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
     D3D_LAUNCHED();
     const T thr = (T)iou_thr;   // (T)(float): SURVEY.md 8(c) T2
     if (nwords > 65535) return D3D_ERR_INVALID_ARGUMENT;
-    dim3 grid((unsigned)nwords, (unsigned)nwords);
-    if (aabb) nms_mask_aabb_kernel<T><<<grid, NMS_TILE, 0, st>>>((const AABBRec<T> *)recs, n, nwords, thr, mask, lists);
-    else nms_mask_rbox_kernel<T><<<grid, NMS_THREADS, 0, st>>>((const BoxRec<T> *)recs, recheck ? raw : nullptr, n, nwords, thr, mask, lists);
+    // spatial candidate search: pairs with disjoint bounding circles have IoU 0, which never exceeds a threshold >= 0
+    const bool spatial = !aabb && lists.blkcnt && thr >= T(0) && !force_tiles;
+    if (spatial) {
+        const BoxRec<T> *br = (const BoxRec<T> *)recs;
+        const unsigned gb = (unsigned)cdiv(n, 256);
+        D3D_CUDA_TRY(cudaMemsetAsync(cellcnt, 0, (size_t)2 * (NMS_GRID_CELLS + 1) * 4, st));
+        nms_grid_kernel<T><<<1, 1024, 0, st>>>(br, n, grid); D3D_LAUNCHED();
+        nms_bin_kernel<T, 0><<<gb, 256, 0, st>>>(br, n, grid, cellcnt, nullptr, nullptr); D3D_LAUNCHED();
+        if ((rc = exclusive_scan_u32(cellcnt, cellptr, NMS_GRID_CELLS + 1, nullptr, cell_scan_ws, st))) return rc;
+        nms_bin_kernel<T, 1><<<gb, 256, 0, st>>>(br, n, grid, cellcnt + NMS_GRID_CELLS + 1, cellptr, celllist); D3D_LAUNCHED();
+        nms_pairs_kernel<T><<<(unsigned)cdiv(n, NMS_PAIR_THREADS / 32), NMS_PAIR_THREADS, 0, st>>>(br, recheck ? raw : nullptr, n, nwords, thr, grid, cellptr, celllist, lists);
+        D3D_LAUNCHED();
+    }
+    dim3 tiles((unsigned)nwords, (unsigned)nwords);
+    if (aabb) nms_mask_aabb_kernel<T><<<tiles, NMS_TILE, 0, st>>>((const AABBRec<T> *)recs, n, nwords, thr, mask, lists);
+    else nms_mask_rbox_kernel<T><<<dim3((unsigned)nwords, (unsigned)(nwords < 24 ? nwords : 24)), NMS_THREADS, 0, st>>>((const BoxRec<T> *)recs, recheck ? raw : nullptr, n, nwords, thr, mask, lists, spatial ? grid : nullptr);
     D3D_LAUNCHED();
     size_t smem = (size_t)nwords * 8;
     uint32_t stage_cap = 0;

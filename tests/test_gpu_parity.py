@@ -196,6 +196,23 @@ def test_nms_vs_oracle_sizes_and_thresholds(dev, oracle):
                           oracle.box2d_nms(P, s, "rbox", iou_threshold=0.4, cuda_score_rule=True))
 
 
+def test_nms_back_ends_agree(dev, monkeypatch):
+    """the three NMS back ends (spatial candidate grid, dense tiles + list resolve, dense matrix + dense resolve) give the
+    same keep mask; D3D_B200_NMS_PATH is read per call"""
+    from d3d_b200.box import box2d_nms
+    rng = np.random.default_rng(5)
+    for n, nobj, extent in ((20000, 800, 75.0), (3000, 40, 30.0), (700, 700, 400.0)):
+        P, s = proposals(rng, n, nobj, extent=extent)
+        for dt in (np.float64, np.float32):
+            out = {}
+            for path in ("", "tiles", "dense"):
+                monkeypatch.setenv("D3D_B200_NMS_PATH", path)
+                out[path] = box2d_nms(_t(P.astype(dt), dev), _t(s.astype(dt), dev), "rbox", iou_threshold=0.45, precise=dt == np.float64).cpu().numpy()
+            monkeypatch.delenv("D3D_B200_NMS_PATH")
+            assert np.array_equal(out[""], out["dense"]) and np.array_equal(out["tiles"], out["dense"]), (n, dt)
+            assert 0 < out[""].sum() < n
+
+
 def test_nms_c3_scale_properties(dev, oracle):
     """config C3: 50k clustered proposals, rbox thr 0.5, fp64.  The oracle needs ~25 s for this, so the
     full mask is checked through NMS invariants plus an oracle run on a prefix in score order."""
