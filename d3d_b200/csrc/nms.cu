@@ -23,6 +23,7 @@
 #include "prims.cuh"
 #include <cuda_pipeline.h>
 #include <stdlib.h>
+#include <stdio.h>
 
 namespace d3d {
 
@@ -400,18 +401,31 @@ __device__ __forceinline__ void smem_or64(unsigned long long *word, unsigned lon
 }
 
 // greedy pass over one 64-box block: cur = boxes already removed, diag[t] = boxes of the block that box t removes.
-// Jumps from survivor to survivor (a handful per block) instead of testing all 64 positions.
+// This chain is the critical path of the whole resolve (one thread, every step depends on the previous one), so it
+// jumps from survivor to survivor (a handful per block) and works on 32-bit halves: find-first-set, one shared-memory
+// load, two ORs and one mask per survivor.
 __device__ __forceinline__ unsigned long long nms_resolve_diag(unsigned long long cur, const unsigned long long *diag)
 {
-    unsigned long long kept = 0, cand = ~cur;
-    while (cand) {
-        const int t = __ffsll((long long)cand) - 1;
-        kept |= 1ull << t;
-        cur |= diag[t];
-        cand = ~cur & ~((2ull << t) - 1ull);   // alive boxes after t (t == 63: the shift wraps to 0, the mask clears everything)
-        if (t == 63) break;
+    uint32_t clo = (uint32_t)cur, chi = (uint32_t)(cur >> 32), klo = 0, khi = 0;
+    const uint2 *d2 = reinterpret_cast<const uint2 *>(diag);
+    uint32_t cand = ~clo;
+#pragma unroll 1
+    while (cand) {          // boxes 0..31: a survivor removes boxes of both halves
+        const int t = __ffs((int)cand) - 1;
+        klo |= 1u << t;
+        const uint2 row = d2[t];
+        clo |= row.x; chi |= row.y;
+        cand = ~clo & (0xfffffffeu << t);
     }
-    return kept;
+    cand = ~chi;
+#pragma unroll 1
+    while (cand) {          // boxes 32..63
+        const int t = __ffs((int)cand) - 1;
+        khi |= 1u << t;
+        chi |= d2[32 + t].y;
+        cand = ~chi & (0xfffffffeu << t);
+    }
+    return (unsigned long long)klo | ((unsigned long long)khi << 32);
 }
 
 __global__ void __launch_bounds__(RESOLVE_THREADS)
@@ -422,8 +436,9 @@ nms_resolve_kernel(const uint64_t *__restrict__ mask, int64_t n, int64_t nwords,
     __shared__ unsigned long long diag[2][64];
     __shared__ unsigned long long keptbits;
     const int tid = threadIdx.x;
+    const uint32_t NT = blockDim.x;   // >= 128
     // boxes at or below the score threshold (and the padding past n) start out removed
-    for (int64_t w = tid; w < nwords; w += RESOLVE_THREADS) {
+    for (int64_t w = tid; w < nwords; w += NT) {
         unsigned long long b = 0;
         for (int t = 0; t < 64; t++) {
             int64_t p = w * 64 + t;
@@ -441,14 +456,14 @@ nms_resolve_kernel(const uint64_t *__restrict__ mask, int64_t n, int64_t nwords,
         unsigned long long *sbits = keptw + nwords;                                  // [RS_STAGES][SC]
         uint32_t *sw = reinterpret_cast<uint32_t *>(sbits + (size_t)RS_STAGES * SC); // [RS_STAGES][SC]
         uint32_t *cnts = sw + (size_t)RS_STAGES * SC;                                // [nwords]
-        for (int64_t w = tid; w < nwords; w += RESOLVE_THREADS) cnts[w] = min(lists.blkcnt[w], NMS_LIST_CAP);
+        for (int64_t w = tid; w < nwords; w += NT) cnts[w] = min(lists.blkcnt[w], NMS_LIST_CAP);
         if (tid < 128) diag[tid >> 6][tid & 63] = 0ull;
         __syncthreads();
         auto issue = [&](int64_t b) {
             if (b < nwords) {
                 const uint32_t c = min(cnts[b], SC);
                 const int st = (int)(b % RS_STAGES);
-                for (uint32_t e = tid; e < c; e += RESOLVE_THREADS) {
+                for (uint32_t e = tid; e < c; e += NT) {
                     __pipeline_memcpy_async(sw + st * SC + e, lists.ent_w + b * NMS_LIST_CAP + e, 4);
                     __pipeline_memcpy_async(sbits + st * SC + e, lists.ent_bits + b * NMS_LIST_CAP + e, 8);
                 }
@@ -469,13 +484,21 @@ nms_resolve_kernel(const uint64_t *__restrict__ mask, int64_t n, int64_t nwords,
         for (int b = 0; b < RS_STAGES - 1; b++) issue(b);
         __pipeline_wait_prior(RS_STAGES - 3);   // blocks 0 and 1 have landed (this thread's copies)
         __syncthreads();
-        extract(0, tid, RESOLVE_THREADS);
+        extract(0, tid, NT);
         __syncthreads();
+#ifdef D3D_NMS_TIMING
+        long long tA = 0, tB1 = 0, tB = 0, tB2 = 0, t0 = clock64(), t1;
+#define NMS_TK(acc) do { t1 = clock64(); acc += t1 - t0; t0 = t1; } while (0)
+#else
+#define NMS_TK(acc)
+#endif
         for (int64_t blk = 0; blk < nwords; blk++) {
             // phase A: resolve blk (thread 0) | diagonal words of blk + 1 (everybody else)
             if (tid == 0) { const unsigned long long k = nms_resolve_diag(remv[blk], diag[blk & 1]); keptbits = k; keptw[blk] = k; }
-            else if (tid >= 32) extract(blk + 1, tid - 32, RESOLVE_THREADS - 32);
+            else if (tid >= 32) extract(blk + 1, tid - 32, NT - 32);
+            NMS_TK(tA);
             __syncthreads();
+            NMS_TK(tB1);
             // phase B: the survivors' words of blk into the bitmap; recycle buffers; keep the pipeline full
             const unsigned long long kept = keptbits;
             if (tid < 64) diag[blk & 1][tid] = 0ull;   // next used by block blk + 2
@@ -484,17 +507,22 @@ nms_resolve_kernel(const uint64_t *__restrict__ mask, int64_t n, int64_t nwords,
                 const uint32_t c = cnts[blk];
                 const uint32_t *gw = lists.ent_w + blk * NMS_LIST_CAP;
                 const uint64_t *gb = lists.ent_bits + blk * NMS_LIST_CAP;
-                for (uint32_t e = tid; e < c; e += RESOLVE_THREADS) {
+                for (uint32_t e = tid; e < c; e += NT) {
                     const uint32_t we = e < SC ? sw[st * SC + e] : gw[e];
                     if ((kept >> (we >> 16)) & 1ull) smem_or64(&remv[we & 0xffffu], e < SC ? sbits[st * SC + e] : gb[e]);
                 }
             }
             issue(blk + RS_STAGES - 1);             // into stage (blk - 1) % RS_STAGES, last read before the previous iteration's final barrier
             __pipeline_wait_prior(RS_STAGES - 3);   // this thread's copies of block blk + 2 have landed ...
+            NMS_TK(tB);
             __syncthreads();                        // ... and everybody's are visible; remv[blk + 1] is final
+            NMS_TK(tB2);
         }
+#ifdef D3D_NMS_TIMING
+        if (tid == 0 || tid == 40 || tid == 255) printf("resolve tid %d: per block cycles  A %lld  barrier1 %lld  B %lld  barrier2 %lld\n", tid, tA / nwords, tB1 / nwords, tB / nwords, tB2 / nwords);
+#endif
         __syncthreads();
-        for (int64_t row = tid; row < n; row += RESOLVE_THREADS) suppressed[order[row]] = ((keptw[row >> 6] >> (row & 63)) & 1ull) ? 0 : 1;
+        for (int64_t row = tid; row < n; row += NT) suppressed[order[row]] = ((keptw[row >> 6] >> (row & 63)) & 1ull) ? 0 : 1;
         return;
     }
     unsigned long long *diag0 = diag[0];
@@ -513,7 +541,7 @@ nms_resolve_kernel(const uint64_t *__restrict__ mask, int64_t n, int64_t nwords,
             if (row < n) suppressed[order[row]] = ((kept >> tid) & 1ull) ? 0 : 1;
         }
         if (kept) {
-            for (int64_t w = blk + 1 + tid; w < nwords; w += RESOLVE_THREADS) {
+            for (int64_t w = blk + 1 + tid; w < nwords; w += NT) {
                 unsigned long long acc = remv[w], k = kept;
                 const uint64_t *col = mask + (blk * 64) * nwords + w;
                 while (k) {   // up to 4 independent row loads in flight
@@ -621,10 +649,13 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
         size_t sc = (200 * 1024 - fixed) / ((size_t)RS_STAGES * 12);
         if (sc > NMS_LIST_CAP) sc = NMS_LIST_CAP;
         stage_cap = (uint32_t)(sc & ~(size_t)1);   // even: the 64-bit stage arrays stay 8-byte aligned
+        if (const char *e = getenv("D3D_B200_NMS_STAGE")) { const long v = atol(e); if (v >= 0 && v < (long)stage_cap) stage_cap = (uint32_t)(v & ~1l); }   // tuning override
         smem = fixed + (size_t)RS_STAGES * stage_cap * 12;
     }
     if (smem > 40 * 1024) D3D_CUDA_TRY(cudaFuncSetAttribute(nms_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_resolve_kernel<<<1, RESOLVE_THREADS, smem, st>>>(mask, n, nwords, valid, order, suppressed, lists, stage_cap); D3D_LAUNCHED();
+    int resolve_nt = lists.blkcnt ? 512 : RESOLVE_THREADS;   // list walk: 64 1.9x slower, 256 +10 %, 512 = 1024 (tools/nms_stage_probe.sh)
+    if (const char *e = getenv("D3D_B200_NMS_NT")) { const int v = atoi(e); if (v >= 128 && v <= 1024 && v % 32 == 0) resolve_nt = v; }   // tuning override
+    nms_resolve_kernel<<<1, resolve_nt, smem, st>>>(mask, n, nwords, valid, order, suppressed, lists, stage_cap); D3D_LAUNCHED();
     return D3D_OK;
 }
 
