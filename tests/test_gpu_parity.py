@@ -434,6 +434,28 @@ def test_voxel_batch_equals_per_frame(dev, oracle):
             _cmp_vox(r, oracle.VoxelGenerator(bounds, shape, **kw)(f), kw, "batch " + str(kw))
 
 
+def test_voxel_routed_and_l2_frames_in_one_launch(dev):
+    """one batch whose frames take different per-frame back ends inside the same persistent launch: routed (fits the cluster's
+    shared memory), L2 (more than 131072 points), routed-then-bailed (40 % of the points in one cell: queue overflow) --
+    packed outputs and per-frame results equal the sort pipeline's"""
+    from d3d_b200.voxel import VoxelGenerator
+    rng = np.random.default_rng(77)
+    sizes = (120000, 140000, 3000, 131072, 150000, 60000, 1, 90000)
+    frames = [lidar(rng, n) for n in sizes]
+    frames[5][rng.integers(0, 60000, 24000)] = np.array([10.01, 0.01, -1.0, 0.5], np.float32)
+    bounds, shape = [0, 70.4, -40, 40, -3, 1], [1408, 1600, 40]
+    for kw in (dict(max_points=5, max_points_filter="trim"), dict(max_points=3, max_points_filter="trim", max_voxels=30000, max_voxels_filter="trim", min_points=2)):
+        out = {}
+        for algo in ("cluster", "sort"):
+            gen = VoxelGenerator(bounds, shape, **kw)
+            gen.algo = algo
+            out[algo] = gen.batch([_t(f, dev) for f in frames])
+        for a, b in zip(out["cluster"], out["sort"]):
+            assert set(a.keys()) == set(b.keys())
+            for k in a:
+                assert torch.equal(a[k], b[k]), (kw, k)
+
+
 # ------------------------------------------------------------------ aligned scatter
 def test_scatter_golden_and_oracle(dev, oracle):
     from d3d_b200.point import aligned_scatter
