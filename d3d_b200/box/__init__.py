@@ -100,6 +100,45 @@ def box2d_iou(boxes1, boxes2, method="box", precise=True):
     return result
 
 
+def box3d_iou_distance(src_boxes, dst_boxes, metric="riou"):
+    '''
+    Distance matrix of the detection evaluator / tracking matcher: ``1 - iou2d * ziou`` in float32, the array
+    ``ScoreMatcher.prepare_boxes`` caches (reference d3d/tracking/matcher.pyx:24-82 over box3dr_iou / box3d_iou,
+    d3d/dgal_wrap.h:45-91).
+
+    :param src_boxes: boxes to match, shape N x 7: x, y, z, lx, ly, lz, rz (the columns 2..8 of ``Target3DArray.to_numpy()``)
+    :param dst_boxes: fixed boxes (such as ground truth boxes), shape M x 7
+    :param metric: 'riou' - rotated BEV IoU times the z overlap ratio (DistanceTypes.RIoU), 'iou' - IoU of the BEV
+        axis-aligned bounding boxes times the z overlap ratio (DistanceTypes.IoU)
+    :return: float32 N x M; numpy in -> numpy out, host tensors in -> host tensor out
+    '''
+    convert_numpy = False
+    if isinstance(src_boxes, np.ndarray):
+        assert isinstance(dst_boxes, np.ndarray), "Input should be both numpy tensor or pytorch tensor!"
+        src_boxes, dst_boxes = torch.from_numpy(src_boxes), torch.from_numpy(dst_boxes)
+        convert_numpy = True
+    if len(src_boxes.shape) != 2 or len(dst_boxes.shape) != 2 or src_boxes.shape[1] != 7 or dst_boxes.shape[1] != 7:
+        raise ValueError("Input boxes should be Nx7 tensors: x, y, z, lx, ly, lz, rz")
+    if metric.lower() not in ("riou", "iou"):
+        raise ValueError("Unrecognized distance metric!")
+    odev = src_boxes.device
+    b1 = _c.to_device(src_boxes).to(torch.float32).contiguous().clone()
+    b2 = _c.to_device(dst_boxes).to(torch.float32).contiguous().clone()
+    b1[:, 3:6].clamp_(-1e3, 1e3)   # "prevent really weird boxes with unusual size" (matcher.pyx:50-52)
+    b2[:, 3:6].clamp_(-1e3, 1e3)
+    n, m = b1.shape[0], b2.shape[0]
+    out = torch.empty((n, m), dtype=torch.float32, device=b1.device)
+    if n and m:
+        ws = _c.workspace(_c.iou3d_distance_workspace_bytes(n, m), b1.device)
+        with torch.cuda.device(b1.device):
+            st = _c.iou3d_distance(_c.ptr(b1), n, _c.ptr(b2), m, 1 if metric.lower() == "riou" else 0, _c.ptr(out), out.stride(0),
+                                   _c.ptr(ws), ws.numel(), _c.stream_ptr())
+        _c.check(st, "box3d_iou_distance")
+    if odev.type != "cuda":
+        out = out.cpu()
+    return out.numpy() if convert_numpy else out
+
+
 def nms2d_cuda(boxes, scores, iou_type, supression_type, iou_threshold, score_threshold, supression_param):
     """Suppressed mask bool[N] in original order (reference d3d/box/nms.h:6-10, nms_cuda.cu:217-244)."""
     code = _c.dtype_code(boxes.dtype)

@@ -75,10 +75,23 @@ template <typename T> struct IouSmem {
     uint16_t queue[IOU_WARPS][DEPTH * 32 + 32];        // the warp's candidates packed back to back (row_local * TC + col)
 };
 
-template <typename T>
+// z extent of a 3-D box (zmin, zmax), for the detection-evaluation distance matrix
+struct ZRange { float lo, hi; };
+
+// z overlap ratio of two boxes with the reference's float arithmetic (d3d/dgal_wrap.h:55-66): i / max(u, 1e-6)
+__device__ __forceinline__ float z_iou(const ZRange &a, const ZRange &b)
+{
+    const float i = fmaxf(__fsub_rn(fminf(a.hi, b.hi), fmaxf(a.lo, b.lo)), 0.f);
+    const float u = fmaxf(__fsub_rn(fmaxf(a.hi, b.hi), fminf(a.lo, b.lo)), 1e-6f);
+    return __fdiv_rn(i, u);
+}
+
+// ZD: the stored value is the matcher's distance 1 - iou2d * ziou (d3d/tracking/matcher.pyx:55-76) instead of iou2d;
+// the z factor is applied while the tile streams out, so the detection-evaluation matrix costs what the IoU matrix costs.
+template <typename T, bool ZD = false>
 __global__ void __launch_bounds__(IOU_THREADS, 3)
 iou2dr_tile_kernel(const BoxRec<T> *__restrict__ recA, int64_t n, const BoxRec<T> *__restrict__ recB, int64_t m,
-                   T *__restrict__ out, int64_t ld)
+                   T *__restrict__ out, int64_t ld, const ZRange *__restrict__ zA = nullptr, const ZRange *__restrict__ zB = nullptr)
 {
     using S = IouSmem<T>;
     constexpr int TR = S::TR, TC = S::TC, RW = S::RW, KC = S::KC;
@@ -152,6 +165,21 @@ iou2dr_tile_kernel(const BoxRec<T> *__restrict__ recA, int64_t n, const BoxRec<T
     }
     __syncwarp();
 
+    if (ZD) {   // distance epilogue on this warp's rows of the tile (rejected pairs: 1 - 0 * ziou = 1)
+        ZRange zb[KC];
+#pragma unroll
+        for (int k = 0; k < KC; k++) zb[k] = zB[col0 + k * 32 + lane];
+#pragma unroll
+        for (int r = 0; r < RW; r++) {
+            const ZRange za = zA[row0 + w * RW + r];
+#pragma unroll
+            for (int k = 0; k < KC; k++) {
+                T &v = sm.tile[w * RW + r][k * 32 + lane];
+                v = (T)__fsub_rn(1.f, __fmul_rn((float)v, z_iou(za, zb[k])));
+            }
+        }
+        __syncwarp();
+    }
     // stream this warp's rows to HBM: full-line 16-byte stores when the row pointers are 16-byte aligned
     const int64_t wrow0 = row0 + w * RW;
     const int nrows = (int)(n - wrow0 < RW ? (n - wrow0 > 0 ? n - wrow0 : 0) : RW);
@@ -187,6 +215,49 @@ __global__ void __launch_bounds__(256) iou2d_kernel(const AABBRec<T> *__restrict
 #pragma unroll
     for (int k = 0; k < 4; k++)
         if (c0 + k < m) out[row * ld + c0 + k] = aabb_iou<T>(a, recB[c0 + k]);
+}
+
+// AABB variant of the matcher distance (DistanceTypes.IoU, d3d/dgal_wrap.h:70-91): 1 - iou(AABBs) * ziou
+__global__ void __launch_bounds__(256) dist3d_aabb_kernel(const AABBRec<float> *__restrict__ recA, const ZRange *__restrict__ zA, int64_t n,
+                                                          const AABBRec<float> *__restrict__ recB, const ZRange *__restrict__ zB, int64_t m,
+                                                          float *__restrict__ out, int64_t ld)
+{
+    const int64_t row = blockIdx.y;
+    const int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (row >= n || c0 >= m) return;
+    const AABBRec<float> a = recA[row];
+    const ZRange za = zA[row];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (c0 + k < m) out[row * ld + c0 + k] = __fsub_rn(1.f, __fmul_rn(aabb_iou<float>(a, recB[c0 + k]), z_iou(za, zB[c0 + k])));
+}
+
+// 3-D boxes (x, y, z, lx, ly, lz, rz) -> BEV records + z extents.  MODE 0: row records, 1: field-major column records, 2: AABB records
+template <int MODE, int TILE>
+__global__ void __launch_bounds__(256) box3d_prep_kernel(const float *__restrict__ boxes, int64_t n, int64_t npad, BoxRec<float> *__restrict__ recs,
+                                                         AABBRec<float> *__restrict__ arecs, ZRange *__restrict__ z)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npad) return;
+    BoxRec<float> r;
+    ZRange zr = {0.f, 0.f};
+    if (i < n) {
+        const float *b = boxes + 7 * i;
+        if (MODE == 2) arecs[i] = make_aabb_rec<float>(b[0], b[1], b[3], b[4], b[6]);
+        else r = make_box_rec<float>(b[0], b[1], b[3], b[4], b[6]);
+        const float h = __fdiv_rn(b[5], 2.f);
+        zr.lo = __fsub_rn(b[2], h); zr.hi = __fadd_rn(b[2], h);   // z -+ lz / 2 in float (dgal_wrap.h:50-53)
+    } else {
+        r.cx = r.cy = r.c = r.s = r.hw = r.hh = r.area = 0.f;
+        r.rho = NAN;
+    }
+    z[i] = zr;
+    if (MODE == 0) recs[i] = r;
+    else if (MODE == 1) {
+        float *f = reinterpret_cast<float *>(recs + (i / TILE) * TILE) + (i % TILE);
+        f[0 * TILE] = r.cx; f[1 * TILE] = r.cy; f[2 * TILE] = r.c; f[3 * TILE] = r.s;
+        f[4 * TILE] = r.hw; f[5 * TILE] = r.hh; f[6 * TILE] = r.rho; f[7 * TILE] = r.area;
+    }
 }
 
 // ------------------------------------------------------------------ candidate counter (measurement only; SURVEY.md 8(d) accounting)
@@ -275,6 +346,51 @@ static int iou2d_impl(const T *b1, int64_t n, const T *b2, int64_t m, T *out, in
     return D3D_OK;
 }
 
+static size_t dist3d_ws_bytes(int64_t n, int64_t m)
+{
+    constexpr int TR = IouTile<float>::TR, TC = IouTile<float>::TC;
+    const size_t np = (size_t)cdiv(n > 0 ? n : 1, TR) * TR, mp = (size_t)cdiv(m > 0 ? m : 1, TC) * TC;
+    return iou_ws_bytes<float>(n, m) + align_up(np * sizeof(ZRange)) + align_up(mp * sizeof(ZRange));
+}
+
+// replaces the pair loops of ScoreMatcher.prepare_boxes (d3d/tracking/matcher.pyx:55-76) over box3dr_iou / box3d_iou (d3d/dgal_wrap.h:45-91)
+static int dist3d_impl(const float *b1, int64_t n, const float *b2, int64_t m, int rotated, float *out, int64_t ld, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    if (n < 0 || m < 0 || ld < m) return D3D_ERR_INVALID_ARGUMENT;
+    if (n == 0 || m == 0) return D3D_OK;
+    if (!b1 || !b2 || !out) return D3D_ERR_INVALID_ARGUMENT;
+    if (ws_bytes < dist3d_ws_bytes(n, m) || !ws) return D3D_ERR_WORKSPACE;
+    constexpr int TR = IouTile<float>::TR, TC = IouTile<float>::TC;
+    Arena a(ws, ws_bytes);
+    a.take<char>(256);
+    const int64_t tiles_r = cdiv(n, TR), tiles_c = cdiv(m, TC), np = tiles_r * TR, mp = tiles_c * TC;
+    BoxRec<float> *ra = a.take<BoxRec<float>>(np), *rb = a.take<BoxRec<float>>(mp);
+    ZRange *za = a.take<ZRange>(np), *zb = a.take<ZRange>(mp);
+    if (!a.ok()) return D3D_ERR_WORKSPACE;
+    if (!rotated) {
+        if (n > 65535ll * 65535ll) return D3D_ERR_INVALID_ARGUMENT;
+        AABBRec<float> *aa = reinterpret_cast<AABBRec<float> *>(ra), *ab = reinterpret_cast<AABBRec<float> *>(rb);   // 16-byte records fit the 32-byte slots
+        box3d_prep_kernel<2, 1><<<(unsigned)cdiv(n, 256), 256, 0, st>>>(b1, n, n, nullptr, aa, za); D3D_LAUNCHED();
+        box3d_prep_kernel<2, 1><<<(unsigned)cdiv(m, 256), 256, 0, st>>>(b2, m, m, nullptr, ab, zb); D3D_LAUNCHED();
+        for (int64_t r0 = 0; r0 < n; r0 += 65535) {
+            const int64_t nr = n - r0 < 65535 ? n - r0 : 65535;
+            dist3d_aabb_kernel<<<dim3((unsigned)cdiv(m, 1024), (unsigned)nr), 256, 0, st>>>(aa + r0, za + r0, nr, ab, zb, m, out + r0 * ld, ld); D3D_LAUNCHED();
+        }
+        return D3D_OK;
+    }
+    box3d_prep_kernel<0, 1><<<(unsigned)cdiv(np, 256), 256, 0, st>>>(b1, n, np, ra, nullptr, za); D3D_LAUNCHED();
+    box3d_prep_kernel<1, TC><<<(unsigned)cdiv(mp, 256), 256, 0, st>>>(b2, m, mp, rb, nullptr, zb); D3D_LAUNCHED();
+    if (tiles_c > 0x7fffffffll || tiles_r > 65535ll * 65535ll) return D3D_ERR_INVALID_ARGUMENT;
+    const dim3 grid((unsigned)tiles_c, (unsigned)(tiles_r < 65535 ? tiles_r : 65535), (unsigned)cdiv(tiles_r, 65535));
+    static bool smem_opt_in = false;
+    if (!smem_opt_in) {
+        D3D_CUDA_TRY(cudaFuncSetAttribute(iou2dr_tile_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IouSmem<float>)));
+        smem_opt_in = true;
+    }
+    iou2dr_tile_kernel<float, true><<<grid, IOU_THREADS, sizeof(IouSmem<float>), st>>>(ra, n, rb, m, out, ld, za, zb); D3D_LAUNCHED();
+    return D3D_OK;
+}
+
 template <typename T>
 static int count_cand_impl(const T *b1, int64_t n, const T *b2, int64_t m, unsigned long long *counters64, void *ws, size_t ws_bytes, cudaStream_t st)
 {
@@ -312,6 +428,10 @@ extern "C" int d3d_iou2d_f32(const float *b1, int64_t n, const float *b2, int64_
 { return iou2d_impl<float>(b1, n, b2, m, ious, ld, ws, wsb, (cudaStream_t)stream); }
 extern "C" int d3d_iou2d_f64(const double *b1, int64_t n, const double *b2, int64_t m, double *ious, int64_t ld, void *ws, size_t wsb, void *stream)
 { return iou2d_impl<double>(b1, n, b2, m, ious, ld, ws, wsb, (cudaStream_t)stream); }
+extern "C" size_t d3d_iou3d_distance_workspace_bytes(int64_t n, int64_t m) { return dist3d_ws_bytes(n, m); }
+extern "C" int d3d_iou3d_distance_f32(const float *boxes1, int64_t n, const float *boxes2, int64_t m, int rotated, float *dist, int64_t ld, void *ws, size_t wsb,
+                                      void *stream)
+{ return dist3d_impl(boxes1, n, boxes2, m, rotated, dist, ld, ws, wsb, (cudaStream_t)stream); }
 extern "C" int d3d_iou_count_candidates(const void *b1, int64_t n, const void *b2, int64_t m, int dtype, uint64_t *counters64, void *ws, size_t wsb, void *stream)
 {
     return dtype == D3D_F64 ? count_cand_impl<double>((const double *)b1, n, (const double *)b2, m, (unsigned long long *)counters64, ws, wsb, (cudaStream_t)stream)

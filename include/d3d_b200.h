@@ -71,6 +71,14 @@ int d3d_iou2d_f32(const float *boxes1, int64_t n, const float *boxes2, int64_t m
                   void *workspace, size_t workspace_bytes, void *stream);
 int d3d_iou2d_f64(const double *boxes1, int64_t n, const double *boxes2, int64_t m, double *ious, int64_t ld,
                   void *workspace, size_t workspace_bytes, void *stream);
+/* Detection-evaluation distance matrix: dist[i][j] = 1 - iou2d(BEV boxes) * ziou, fp32,
+ * for 3-D boxes [n,7] / [m,7] with rows (x, y, z, lx, ly, lz, rz).  rotated != 0: rotated BEV IoU, replaces the pair
+ * loop over box3dr_iou in ScoreMatcher.prepare_boxes (reference d3d/tracking/matcher.pyx:66-76, d3d/dgal_wrap.h:45-68);
+ * rotated == 0: IoU of the BEV axis-aligned boxes, replaces the loop over box3d_iou (matcher.pyx:55-65,
+ * dgal_wrap.h:70-91).  The z factor is applied while the IoU tile streams out (same kernel, same cost). */
+size_t d3d_iou3d_distance_workspace_bytes(int64_t n, int64_t m);
+int d3d_iou3d_distance_f32(const float *boxes1, int64_t n, const float *boxes2, int64_t m, int rotated, float *dist,
+                           int64_t ld, void *workspace, size_t workspace_bytes, void *stream);
 /* optional statistics of the last d3d_iou2dr_* call that used this workspace: counters[0] = candidate
  * pairs (bounding circles overlap) -- what roofline accounting needs.  Device i64[2]
  * at the start of the workspace; read it back after synchronising the stream. */

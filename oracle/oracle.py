@@ -87,6 +87,29 @@ def box2d_iou(b1, b2, method="box", precise=True, alg=ALG_RC):
     return r.astype(otype) if precise else r
 
 
+def box3d_iou_distance(src, dst, metric="riou", alg=ALG_RC):
+    """Distance cache of ScoreMatcher.prepare_boxes: 1 - iou2d * ziou in float32 for [N,7] / [M,7] boxes
+    (x, y, z, lx, ly, lz, rz): reference d3d/tracking/matcher.pyx:45-76 over box3dr_iou / box3d_iou,
+    d3d/dgal_wrap.h:45-91.  The BEV IoU comes from the pinned fp32 restatement above (alg: the reference's RC, or
+    ALG_TRUTH for geometric truth); the z factor follows dgal_wrap.h:50-66 operation by operation in float32.
+    PARITY NOTE: the reference's matcher is a Cython module that cannot be built here, so this function is pinned
+    through its 2-D part only (reference extension + golden vectors); the z arithmetic is a restatement."""
+    f = np.float32
+    a, b = np.array(src, dtype=f, copy=True), np.array(dst, dtype=f, copy=True)
+    a[:, 3:6] = np.clip(a[:, 3:6], -1e3, 1e3)          # matcher.pyx:50-52
+    b[:, 3:6] = np.clip(b[:, 3:6], -1e3, 1e3)
+    a2, b2 = a[:, [0, 1, 3, 4, 6]], b[:, [0, 1, 3, 4, 6]]
+    if metric == "riou":
+        iou = iou2dr_truth(a2.astype(np.float64), b2.astype(np.float64)).astype(f) if alg == ALG_TRUTH else iou2dr(a2, b2, alg)
+    else:
+        iou = iou2d(a2, b2)
+    z1max, z1min = (a[:, 2] + a[:, 5] / f(2))[:, None], (a[:, 2] - a[:, 5] / f(2))[:, None]
+    z2max, z2min = (b[:, 2] + b[:, 5] / f(2))[None, :], (b[:, 2] - b[:, 5] / f(2))[None, :]
+    i = np.maximum(np.minimum(z1max, z2max) - np.maximum(z1min, z2min), f(0))
+    u = np.maximum(np.maximum(z1max, z2max) - np.minimum(z1min, z2min), f(1e-6))
+    return (f(1) - iou.astype(f) * (i / u).astype(f)).astype(f)
+
+
 def nms2d(boxes, scores, iou_type=IOU_BOX, sup_type=SUP_HARD, iou_threshold=0.0, score_threshold=0.0,
           sup_param=0.0, alg=ALG_RC, cuda_score_rule=False, return_evals=False):
     """Suppressed mask u8[n]: d3d/box/nms.cpp:98-119 (order = stable descending argsort)."""

@@ -144,6 +144,45 @@ def test_iou_large_properties(dev, oracle):
 
 
 # ------------------------------------------------------------------ NMS
+def _boxes3d(rng, n, extent=40.0):
+    return np.stack([(rng.random(n) - .5) * extent, (rng.random(n) - .5) * extent, rng.normal(-1, 0.5, n),
+                     3.5 + rng.random(n) * 2, 1.5 + rng.random(n), 1.4 + rng.random(n) * 0.6, (rng.random(n) - .5) * 7], 1).astype(np.float32)
+
+
+def test_box3d_iou_distance_vs_oracle(dev, oracle):
+    """the evaluator's distance matrix 1 - iou2d * ziou (fp32).  Against geometric truth everywhere
+    (tolerance 1e-4, north_star's fp32 bound), against the reference's own fp32 Rotating-Calipers path on the pairs where
+    that path is sane, and bit-exact for the axis-aligned metric, whose arithmetic has no transcendental in the pair loop."""
+    from d3d_b200.box import box3d_iou_distance
+    rng = np.random.default_rng(31)
+    for n, m in ((1, 1), (37, 129), (300, 257), (1000, 700)):
+        A, B = _boxes3d(rng, n), _boxes3d(rng, m)
+        B[: min(n, m) // 3] = A[: min(n, m) // 3] + rng.normal(0, 0.15, (min(n, m) // 3, 7)).astype(np.float32)   # true matches
+        d = box3d_iou_distance(_t(A, dev), _t(B, dev), "riou")
+        assert d.dtype == torch.float32 and tuple(d.shape) == (n, m)
+        d = d.cpu().numpy()
+        truth = oracle.box3d_iou_distance(A, B, "riou", alg=oracle.ALG_TRUTH)
+        assert np.abs(d - truth).max() < 1e-4, (n, m, float(np.abs(d - truth).max()))
+        ref = oracle.box3d_iou_distance(A, B, "riou")
+        sane = np.abs(ref - truth) < 1e-4                                    # the fp32 RC path blows up on rare pairs (SURVEY 8(c))
+        assert sane.mean() > 0.999 and np.abs(d - ref)[sane].max() < 2e-4
+        assert d.min() >= -1e-6 and d.max() <= 1.0 + 1e-6
+        da = box3d_iou_distance(_t(A, dev), _t(B, dev), "iou").cpu().numpy()
+        assert np.abs(da - oracle.box3d_iou_distance(A, B, "iou")).max() < 2e-6
+    # z semantics: identical boxes -> 0, disjoint in z -> 1, half z overlap of the same footprint -> 1 - 1/3, flat boxes (u clamp)
+    a = np.array([[0, 0, 0, 4, 2, 2, 0.3]], np.float32)
+    cases = np.array([[0, 0, 0, 4, 2, 2, 0.3], [0, 0, 5, 4, 2, 2, 0.3], [0, 0, 1, 4, 2, 2, 0.3], [0, 0, 0, 4, 2, 0, 0.3]], np.float32)
+    got = box3d_iou_distance(a, cases, "riou")
+    assert isinstance(got, np.ndarray) and np.allclose(got[0], [0.0, 1.0, 1 - 1 / 3, 1.0], atol=2e-6)
+    flat = np.array([[0, 0, 0, 4, 2, 0, 0.3]], np.float32)
+    assert np.allclose(box3d_iou_distance(flat, flat, "riou"), oracle.box3d_iou_distance(flat, flat, "riou", alg=oracle.ALG_TRUTH), atol=1e-6)
+    assert box3d_iou_distance(torch.zeros((0, 7)), torch.zeros((5, 7))).shape == (0, 5)
+    with pytest.raises(ValueError):
+        box3d_iou_distance(torch.zeros((3, 5)), torch.zeros((3, 7)))
+    with pytest.raises(ValueError):
+        box3d_iou_distance(torch.zeros((3, 7)), torch.zeros((3, 7)), metric="giou")
+
+
 def test_nms_known_answer_and_golden(dev):
     from d3d_b200.box import box2d_nms
     g = golden("nms.npz")

@@ -221,3 +221,19 @@ def test_oracle_vs_live_reference(oracle):
     b = R.VoxelGenerator([0, 70.4, -40, 40, -3, 1], [352, 400, 40], **kw)(pts)
     for k in b:
         assert np.array_equal(a[k], b[k]), k
+
+
+def test_box3d_iou_distance_known_answers(oracle):
+    """SURVEY 8(f) f1 (evaluator distance 1 - iou2d * ziou, d3d/dgal_wrap.h:45-91): z semantics of the restatement"""
+    a = np.array([[0, 0, 0, 4, 2, 2, 0.3]], np.float32)
+    cases = np.array([[0, 0, 0, 4, 2, 2, 0.3],      # identical -> 0
+                      [0, 0, 5, 4, 2, 2, 0.3],      # disjoint in z -> 1
+                      [0, 0, 1, 4, 2, 2, 0.3],      # same footprint, half z overlap: 1 - 1 * (1 / 3)
+                      [0, 0, 0, 4, 2, 0, 0.3],      # flat box: i = 0
+                      [50, 0, 0, 4, 2, 2, 0.3]], np.float32)
+    for metric in ("riou", "iou"):
+        d = oracle.box3d_iou_distance(a, cases, metric)
+        assert d.dtype == np.float32 and np.allclose(d[0], [0, 1, 1 - 1 / 3, 1, 1], atol=1e-6)
+    big = np.array([[0, 0, 0, 5000, 2, 2, 0.0]], np.float32)   # sizes are clipped to 1e3 (matcher.pyx:50-52)
+    ref = np.array([[0, 0, 0, 1000, 2, 2, 0.0]], np.float32)
+    assert np.allclose(oracle.box3d_iou_distance(big, ref, "iou"), 0, atol=1e-6)
