@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the d3d hot path on B200 next to the reference's CPU path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--op all|voxel|iou|nms] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--op all|voxel|iou|nms|dist3d] [--impl reference]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W      (N > 1)
 
 One JSON line on rank 0.  BASELINE.json's metric is a triple (rotated-IoU pairs/s, NMS boxes/s, voxelized
@@ -108,6 +108,23 @@ def _cpu_iou_block(args):
     return time.perf_counter() - t0, (hi - lo) * 4000
 
 
+def gen_boxes3d(rng, n):
+    b = gen_boxes(rng, n)
+    return np.stack([b[:, 0], b[:, 1], rng.normal(-1.0, 0.5, n), b[:, 2], b[:, 3], 1.4 + rng.random(n) * 0.6, b[:, 4]], 1)
+
+
+def _cpu_dist3d_block(args):
+    import torch
+    torch.set_num_threads(1)
+    seed, lo, hi = args
+    rng = np.random.default_rng(seed)
+    A, B = gen_boxes3d(rng, hi).astype(np.float32)[lo:hi], gen_boxes3d(rng, 4000).astype(np.float32)
+    from oracle import oracle as O
+    t0 = time.perf_counter()
+    O.box3d_iou_distance(A, B, "riou")
+    return time.perf_counter() - t0, (hi - lo) * 4000
+
+
 def _cpu_nms(n):
     import torch
     torch.set_num_threads(1)
@@ -187,6 +204,14 @@ def cpu_baseline(op, cores, rounds=2):
                     sample=f"{len(res)} row-blocks of {rows} x 4000 fp32 boxes (C4 distribution, precise=False), one block per "
                            f"process on {cores} cores; {len(res) - len(ok)} block(s) aborted inside the reference "
                            f"(dgal fp32 Rotating-Calipers overflows its Poly2<T,8> buffer: 'stack smashing detected') and are not counted")
+    if op == "dist3d":
+        rows = 256
+        res, wall = cpu_pool(_cpu_dist3d_block, [(3, i * rows, (i + 1) * rows) for i in range(cores * rounds)], cores)
+        ok = [r for r in res if r is not None]
+        return dict(value=sum(r[1] for r in ok) / wall, unit="pairs/s", cores=cores, kind="port", crashed_blocks=len(res) - len(ok),
+                    sample=f"{len(res)} row-blocks of {rows} x 4000 fp32 3-D boxes, one block per process on {cores} cores; C restatement of the "
+                           f"reference's fp32 Rotating-Calipers IoU + the z arithmetic of d3d/dgal_wrap.h:45-68 (the reference's Cython matcher "
+                           f"cannot be built in this image)")
     if op == "nms":
         n = 10000
         res, wall = cpu_pool(_cpu_nms, [n] * (cores * rounds), cores)
@@ -450,6 +475,64 @@ def bench_iou(args, rank, world, barrier):
                 clocks=cs.summary())
 
 
+def bench_dist3d(args, rank, world, barrier):
+    """the detection evaluator's distance matrix 1 - iou2d * ziou over C4-sized 3-D box sets"""
+    import torch
+    from d3d_b200 import _cabi as c
+    from d3d_b200.box import box3d_iou_distance
+    from d3d_b200.parallel import row_block
+    n = m = args.iou_n
+    rng = np.random.default_rng(3)
+    A, B = gen_boxes3d(rng, n).astype(np.float32), gen_boxes3d(rng, m).astype(np.float32)
+    lo, hi = row_block(n, rank, world)
+    tA, tB = torch.from_numpy(A[lo:hi]).cuda(), torch.from_numpy(B).cuda()
+    out = torch.empty((hi - lo, m), dtype=torch.float32, device="cuda")
+    bevA, bevB = tA[:, [0, 1, 3, 4, 6]].contiguous(), tB[:, [0, 1, 3, 4, 6]].contiguous()
+    cnt = torch.zeros(64, dtype=torch.int64, device="cuda")
+    ws = c.workspace(c.iou_workspace_bytes(hi - lo, m, 0), tA.device)
+    c.check(c.iou_count_candidates(c.ptr(bevA), hi - lo, c.ptr(bevB), m, 0, c.ptr(cnt), c.ptr(ws), ws.numel(), c.stream_ptr()), "count")
+    ncand, pairs = float(cnt.sum().item()), float(hi - lo) * m
+    ws3 = c.workspace(c.iou3d_distance_workspace_bytes(hi - lo, m), tA.device)
+
+    def step():
+        c.check(c.iou3d_distance(c.ptr(tA), hi - lo, c.ptr(tB), m, 1, c.ptr(out), out.stride(0), c.ptr(ws3), ws3.numel(), c.stream_ptr()), "dist3d")
+    l0 = c.launch_count()
+    with ClockSampler(torch.cuda.current_device()) as cs:
+        ms = timed(step, args.steps, args.warmup, barrier)
+        l1 = c.launch_count()
+        cs.hold(step)
+    launches = (l1 - l0) // (args.steps + args.warmup) * args.steps
+    ms = max_over_ranks(ms, world)
+    tot_pairs, tot_cand = sum_over_ranks(pairs, world), sum_over_ranks(ncand, world)
+    peak32 = fma_peak(0)
+    W_Z = 10.0   # z factor per CANDIDATE pair: 4 min/max, 2 subtractions, 2 clamps, divide, multiply, subtract (a rejected pair is the constant 1)
+    flops = tot_cand * (W_CAND + W_Z) + (tot_pairs - tot_cand) * W_REJ
+    ach = flops / (ms * 1e-3) / 1e12 / world
+    er = min(hi - lo, args.iou_e2e_rows)
+    hA, hB = torch.from_numpy(A[lo:lo + er]).pin_memory(), torch.from_numpy(B).pin_memory()
+    hout = torch.empty((er, m), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        r = box3d_iou_distance(hA.cuda(non_blocking=True), hB.cuda(non_blocking=True), "riou")
+        hout.copy_(r, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    ms_e2e = max_over_ranks(timed(e2e_step, 3, 1, barrier), world)
+    hbm, _ = peaks()
+    return dict(metric="evaluator distance-matrix pairs/sec", unit="pairs/s", value=tot_pairs / (ms * 1e-3), ms_per_step=ms, dtype="f32", scaling="strong",
+                gpu_launches=int(launches),
+                config=dict(workload=f"SURVEY 8(f) f1: ScoreMatcher distance cache 1 - riou2d * ziou, {n}x{m} fp32 3-D boxes (C4 BEV distribution), "
+                                     f"row-block sharded over {world} GPU(s)", candidate_fraction=tot_cand / tot_pairs,
+                            l2_policy=f"output slab {pairs * 4 / 1e9:.1f} GB per GPU streams through HBM, far larger than L2"),
+                e2e=dict(value=er * m * world / (ms_e2e * 1e-3), unit="pairs/s", h2d_bytes_per_step=int((er + m) * 28),
+                         d2h_bytes_per_step=int(er * m * 4), ms_per_step=ms_e2e,
+                         api=f"box3d_iou_distance(pinned host boxes [{er},7],[{m},7]) -> host [{er},{m}] slab"),
+                roofline=dict(bound="fp32_alu", achieved=ach, peak=peak32, unit="TFLOP/s", frac=ach / peak32, traffic=None,
+                              peak_source="measured with d3d_fma_peak_probe in this run",
+                              algorithmic_flops=f"{W_CAND:.0f} + {W_Z:.0f} (z factor) per candidate pair + {W_REJ:.0f} per rejected pair",
+                              store_gbs=tot_pairs * 4 / (ms * 1e-3) / 1e9 / world),
+                clocks=cs.summary())
+
+
 def bench_nms(args, rank, world, barrier):
     import torch
     from d3d_b200 import _cabi as c
@@ -496,14 +579,15 @@ def run_reference(args):
     vals = vals[args.warmup:] or vals
     v = float(np.median([x["value"] for x in vals]))
     cb = dict(vals[-1]); cb["value"] = v
-    metric = {"voxel": "voxelized points/sec", "iou": "rotated-IoU pairs/sec", "nms": "NMS boxes/sec"}[op]
+    metric = {"voxel": "voxelized points/sec", "iou": "rotated-IoU pairs/sec", "nms": "NMS boxes/sec", "dist3d": "evaluator distance-matrix pairs/sec"}[op]
     unit = cb["unit"]
     line = dict(impl="reference", metric=metric, value=v, unit=unit, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=None, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype={"voxel": "f32", "iou": "f32", "nms": "f64"}[op], data="synthetic",
+                dtype={"voxel": "f32", "iou": "f32", "nms": "f64", "dist3d": "f32"}[op], data="synthetic",
                 config=dict(workload={"voxel": "C2 KITTI-shaped voxelization 120k pts/frame, 0.05x0.05x0.1 m voxels, max 5 pts/voxel (reference CPU path)",
                                       "iou": "C4 rotated IoU fp32, C1 distribution (reference CPU path, row-block sample)",
-                                      "nms": "C3-style rotated NMS fp64, 5000-proposal frames (reference CPU path)"}[op]),
+                                      "nms": "C3-style rotated NMS fp64, 5000-proposal frames (reference CPU path)",
+                                      "dist3d": "evaluator distance matrix 1 - riou2d * ziou fp32 (C restatement of the reference path, row-block sample)"}[op]),
                 cpu_baseline=cb, e2e=dict(value=v, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
 
@@ -515,7 +599,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--op", default="all", choices=["all", "voxel", "iou", "nms"])
+    ap.add_argument("--op", default="all", choices=["all", "voxel", "iou", "nms", "dist3d"])
     ap.add_argument("--frames", type=int, default=128, help="C2 frames per GPU per voxelization step")
     ap.add_argument("--iou-n", type=int, default=100_000)
     ap.add_argument("--iou-e2e-rows", type=int, default=8192)
@@ -528,7 +612,7 @@ def main():
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    ops = ["voxel", "iou", "nms"] if args.op == "all" else [args.op]
+    ops = ["voxel", "iou", "nms", "dist3d"] if args.op == "all" else [args.op]
 
     # CPU baseline first: the fork-based pool must run before this process touches CUDA
     cpu = {}
@@ -550,7 +634,7 @@ def main():
         barrier = lambda: None
     import d3d_b200  # noqa: F401  (raises if the CUDA extension is missing: no fallback)
 
-    fns = dict(voxel=bench_voxel, iou=bench_iou, nms=bench_nms)
+    fns = dict(voxel=bench_voxel, iou=bench_iou, nms=bench_nms, dist3d=bench_dist3d)
     res = {}
     for op in ops:
         res[op] = fns[op](args, rank, world, barrier)

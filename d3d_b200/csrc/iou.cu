@@ -86,8 +86,9 @@ __device__ __forceinline__ float z_iou(const ZRange &a, const ZRange &b)
     return __fdiv_rn(i, u);
 }
 
-// ZD: the stored value is the matcher's distance 1 - iou2d * ziou (d3d/tracking/matcher.pyx:55-76) instead of iou2d;
-// the z factor is applied while the tile streams out, so the detection-evaluation matrix costs what the IoU matrix costs.
+// ZD: the stored value is the matcher's distance 1 - iou2d * ziou (d3d/tracking/matcher.pyx:55-76) instead of iou2d.
+// The z factor is applied to the clipped candidates only (the tile is pre-filled with 1 = the distance of a rejected
+// pair), so the detection-evaluation matrix costs little more than the IoU matrix.
 template <typename T, bool ZD = false>
 __global__ void __launch_bounds__(IOU_THREADS, 3)
 iou2dr_tile_kernel(const BoxRec<T> *__restrict__ recA, int64_t n, const BoxRec<T> *__restrict__ recB, int64_t m,
@@ -112,11 +113,18 @@ iou2dr_tile_kernel(const BoxRec<T> *__restrict__ recA, int64_t n, const BoxRec<T
         for (int i = threadIdx.x; i < NA; i += IOU_THREADS) da[i] = __ldg(ga + i);
         for (int i = threadIdx.x; i < NB; i += IOU_THREADS) db[i] = __ldg(gb + i);
     }
-    // zero this warp's rows of the output tile (rejected pairs are exactly +0)
+    // zero this warp's rows of the output tile (rejected pairs are exactly +0; distance matrix: 1 - 0 * ziou = 1)
     {
         float4 *z = reinterpret_cast<float4 *>(&sm.tile[w * RW][0]);
+        const float fill = ZD ? 1.f : 0.f;
 #pragma unroll
-        for (int i = 0; i < RW * TC / (32 * V); i++) z[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < RW * TC / (32 * V); i++) z[i * 32 + lane] = make_float4(fill, fill, fill, fill);
+    }
+    __shared__ ZRange szA[ZD ? TR : 1], szB[ZD ? TC : 1];   // z extents of the tile's rows / columns (distance matrix only)
+    if (ZD) {
+        for (int i = threadIdx.x; i < TR + TC; i += IOU_THREADS) {
+            if (i < TR) szA[i] = zA[row0 + i]; else szB[i - TR] = zB[col0 + i - TR];
+        }
     }
     __syncthreads();
 
@@ -161,25 +169,11 @@ iou2dr_tile_kernel(const BoxRec<T> *__restrict__ recA, int64_t n, const BoxRec<T
         B.cx = sm.sB[0][col]; B.cy = sm.sB[1][col]; B.c = sm.sB[2][col]; B.s = sm.sB[3][col];
         B.hw = sm.sB[4][col]; B.hh = sm.sB[5][col]; B.area = sm.sB[7][col]; B.rho = T(0);
         T v = rbox_iou<T>(A, B);
+        if (ZD) v = (T)__fsub_rn(1.f, __fmul_rn((float)v, z_iou(szA[row], szB[col])));   // only candidates pay for the z factor
         if (h + lane < total) sm.tile[row][col] = v;
     }
     __syncwarp();
 
-    if (ZD) {   // distance epilogue on this warp's rows of the tile (rejected pairs: 1 - 0 * ziou = 1)
-        ZRange zb[KC];
-#pragma unroll
-        for (int k = 0; k < KC; k++) zb[k] = zB[col0 + k * 32 + lane];
-#pragma unroll
-        for (int r = 0; r < RW; r++) {
-            const ZRange za = zA[row0 + w * RW + r];
-#pragma unroll
-            for (int k = 0; k < KC; k++) {
-                T &v = sm.tile[w * RW + r][k * 32 + lane];
-                v = (T)__fsub_rn(1.f, __fmul_rn((float)v, z_iou(za, zb[k])));
-            }
-        }
-        __syncwarp();
-    }
     // stream this warp's rows to HBM: full-line 16-byte stores when the row pointers are 16-byte aligned
     const int64_t wrow0 = row0 + w * RW;
     const int nrows = (int)(n - wrow0 < RW ? (n - wrow0 > 0 ? n - wrow0 : 0) : RW);
