@@ -100,6 +100,62 @@ def box2d_iou(boxes1, boxes2, method="box", precise=True):
     return result
 
 
+def crop_2dr_cuda(points, boxes):
+    """bool[M, N] mask of the points [N,2] inside the rotated boxes [M,5] (reference crop_2dr, d3d/box/utils.h:45; CUDA tensors)"""
+    code = _c.dtype_code(points.dtype)
+    if boxes.dtype != points.dtype:
+        raise RuntimeError("points and boxes must have the same dtype")
+    n, m = points.shape[0], boxes.shape[0]
+    mask = torch.empty((m, n), dtype=torch.bool, device=points.device)
+    if n and m:
+        ws = _c.workspace(_c.crop_workspace_bytes(m, code), points.device)
+        with torch.cuda.device(points.device):
+            st = _c.crop2dr[code](_c.ptr(points), n, _c.ptr(boxes), m, _c.ptr(mask), _c.ptr(ws), ws.numel(), _c.stream_ptr())
+        _c.check(st, "box2dr_crop")
+    return mask
+
+
+def box2dr_crop(points, boxes):
+    '''
+    Crop point points points out given rotated boxes (reference d3d/box/__init__.py:278-287).
+    The result is the M x N indicator mask of the points lying in each box (what the reference's crop_2dr returns).
+
+    :param points: The input point points, shape: N x 2
+    :param boxes: Input boxes array, shape: M x 5
+    '''
+    if len(points.shape) != 2 or points.shape[1] != 2:
+        raise ValueError("Input points should be Nx2 tensors!")
+    if len(boxes.shape) != 2 or boxes.shape[1] != 5:
+        raise ValueError("Input boxes should have 5 fields: x, y, w, h, r")
+    odev = points.device
+    r = crop_2dr_cuda(_c.to_device(points).contiguous(), _c.to_device(boxes).contiguous())
+    return r if odev.type == "cuda" else r.cpu()
+
+
+def box3dp_crop(points, boxes, project_axis=2):
+    '''
+    Crop point points points out given rotated boxes with boxes projected to given axis (reference d3d/box/__init__.py:289-314)
+
+    :param points: The input point points, shape: N x 3
+    :param boxes: Input boxes array, shape: M x 7
+    :param project_axis: Axis for the box to be projected to. {0: x, 1: y, 2: z}
+    '''
+    if project_axis == 0:
+        points_2d, boxes_2d = points[:, [1, 2]], boxes[:, [1, 2, 4, 5, 6]]
+    elif project_axis == 1:
+        points_2d, boxes_2d = points[:, [0, 2]], boxes[:, [0, 2, 3, 5, 6]]
+    elif project_axis == 2:
+        points_2d, boxes_2d = points[:, [0, 1]], boxes[:, [0, 1, 3, 4, 6]]
+    else:
+        raise ValueError("The projection axis can only be 0-x, 1-y and 2-z!")
+    mask_2d = box2dr_crop(points_2d, boxes_2d)
+    points_p = points[:, [project_axis]].t()
+    boxes_p = boxes[:, [project_axis]]
+    boxes_pd = boxes[:, [3 + project_axis]] / 2
+    mask_p = (points_p - boxes_pd < boxes_p) & (boxes_p < points_p + boxes_pd)
+    return mask_2d & mask_p.to(mask_2d.device)
+
+
 def box3d_iou_distance(src_boxes, dst_boxes, metric="riou"):
     '''
     Distance matrix of the detection evaluator / tracking matcher: ``1 - iou2d * ziou`` in float32, the array

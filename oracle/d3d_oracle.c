@@ -117,6 +117,39 @@ void orc_iou2d_f64(const double *b1, int64_t n, const double *b2, int64_t m, dou
         for (int64_t j = 0; j < m; j++) out[i * m + j] = aabb_iou_d(b1 + 5 * i, b2 + 5 * j);
 }
 
+/* ---- point-in-rotated-box mask: d3d/box/utils.cpp:10-47 crop_2dr.  out is u8[m boxes, n points].
+ * Vertices as dgal::poly2_from_xywhr (geometry.hpp:417-429), bounding box as aabox2_from_poly2 (:398-414) with the open
+ * test of AABox2::contains (:185-188), then Poly2::contains (:218-229): no edge may have _cross(...) < 0 (:160-163). */
+#define ORC_CROP_BODY(T, SFX, SIN, COS)                                                                       \
+    void orc_crop2dr_##SFX(const T *pts, int64_t n, const T *boxes, int64_t m, uint8_t *out)                  \
+    {                                                                                                         \
+        for (int64_t i = 0; i < m; i++) {                                                                     \
+            const T x = boxes[5 * i], y = boxes[5 * i + 1], w = boxes[5 * i + 2], h = boxes[5 * i + 3], r = boxes[5 * i + 4]; \
+            const T dxsin = w * SIN(r) / 2, dxcos = w * COS(r) / 2, dysin = h * SIN(r) / 2, dycos = h * COS(r) / 2; \
+            const T vx[4] = {x - dxcos + dysin, x + dxcos + dysin, x + dxcos - dysin, x - dxcos - dysin};       \
+            const T vy[4] = {y - dxsin - dycos, y + dxsin - dycos, y + dxsin + dycos, y - dxsin + dycos};       \
+            T minx = vx[0], maxx = vx[0], miny = vy[0], maxy = vy[0];                                         \
+            for (int k = 1; k < 4; k++) {                                                                     \
+                if (vx[k] < minx) minx = vx[k];                                                               \
+                if (vx[k] > maxx) maxx = vx[k];                                                               \
+                if (vy[k] < miny) miny = vy[k];                                                               \
+                if (vy[k] > maxy) maxy = vy[k];                                                               \
+            }                                                                                                 \
+            for (int64_t j = 0; j < n; j++) {                                                                 \
+                const T px = pts[2 * j], py = pts[2 * j + 1];                                                 \
+                int in = px > minx && px < maxx && py > miny && py < maxy;                                    \
+                for (int k = 0; k < 4 && in; k++) {                                                           \
+                    const int a = (k + 3) & 3;   /* edge a -> k; order 3->0, 0->1, 1->2, 2->3 as geometry.hpp:221-226 */ \
+                    const T c = (vx[k] - vx[a]) * (py - vy[k]) - (vy[k] - vy[a]) * (px - vx[k]);              \
+                    if (c < 0) in = 0;                                                                        \
+                }                                                                                             \
+                out[i * n + j] = (uint8_t)in;                                                                 \
+            }                                                                                                 \
+        }                                                                                                     \
+    }
+ORC_CROP_BODY(float, f32, sinf, cosf)
+ORC_CROP_BODY(double, f64, sin, cos)
+
 /* ---- NMS: d3d/box/nms.cpp:9-96 nms2d_templated.
  * `order` (i64[n], descending score; computed by the caller exactly like nms.cpp:103) and `scores`
  * (copied by the caller like nms.cpp:104-105) are mutated by the soft variants.

@@ -87,6 +87,26 @@ def box2d_iou(b1, b2, method="box", precise=True, alg=ALG_RC):
     return r.astype(otype) if precise else r
 
 
+def crop_2dr(points, boxes):
+    """Point-in-rotated-box mask bool[M boxes, N points]: reference d3d/box/utils.cpp:10-47 (bound as crop_2dr,
+    front door box2dr_crop d3d/box/__init__.py:278-287)."""
+    dt = np.float32 if points.dtype == np.float32 else np.float64
+    pts, bx = np.ascontiguousarray(points, dtype=dt), _boxes(boxes, dt)
+    assert pts.ndim == 2 and pts.shape[1] == 2
+    out = np.empty((len(bx), len(pts)), np.uint8)
+    f = lib().orc_crop2dr_f32 if dt == np.float32 else lib().orc_crop2dr_f64
+    f(_p(pts), C.c_int64(len(pts)), _p(bx), C.c_int64(len(bx)), _p(out))
+    return out.astype(bool)
+
+
+def box3dp_crop(points, boxes, project_axis=2):
+    """d3d/box/__init__.py:289-314: 2-D crop of the projection & the open interval test along the projection axis."""
+    ax2 = {0: ([1, 2], [1, 2, 4, 5, 6]), 1: ([0, 2], [0, 2, 3, 5, 6]), 2: ([0, 1], [0, 1, 3, 4, 6])}[project_axis]
+    m2 = crop_2dr(np.ascontiguousarray(points[:, ax2[0]]), np.ascontiguousarray(boxes[:, ax2[1]]))
+    pp, bp, bd = points[:, [project_axis]].T, boxes[:, [project_axis]], boxes[:, [3 + project_axis]] / 2
+    return m2 & ((pp - bd < bp) & (bp < pp + bd))
+
+
 def box3d_iou_distance(src, dst, metric="riou", alg=ALG_RC):
     """Distance cache of ScoreMatcher.prepare_boxes: 1 - iou2d * ziou in float32 for [N,7] / [M,7] boxes
     (x, y, z, lx, ly, lz, rz): reference d3d/tracking/matcher.pyx:45-76 over box3dr_iou / box3d_iou,

@@ -49,6 +49,11 @@ def box2d_iou(boxes1, boxes2, method="box", precise=True):
     return r.numpy()
 
 
+def crop_2dr(points, boxes):
+    """the reference's own crop_2dr (d3d/box/utils.cpp:36-47): bool[M, N]"""
+    return _box().crop_2dr(_t(points), _t(boxes)).numpy()
+
+
 def box2d_nms(boxes, scores, iou_method="box", supression_method="hard", iou_threshold=0, score_threshold=0,
               supression_param=0, precise=True):
     b, s = _t(boxes), _t(scores)

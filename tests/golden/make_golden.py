@@ -46,8 +46,23 @@ def proposals(rng, n, n_obj, extent=75.0):
     return np.concatenate([xy, wh, r[:, None]], 1), scores
 
 
+def write_crop():
+    """point-in-rotated-box masks of the reference's own crop_2dr (d3d/box/utils.cpp:10-47), bits packed"""
+    rng = np.random.default_rng(9)
+    out = {}
+    for tag, dt in (("f32", np.float32), ("f64", np.float64)):
+        pts = ((rng.random((3000, 2)) - .5) * 12).astype(dt)
+        bx = gen_boxes(rng, 96).astype(dt)
+        bx[:4] = np.array([[0, 0, 1, 1, 0], [0, 0, 1, 1, np.pi / 2], [0, 0, 0, 2, 0.3], [1, 1, 2, 2, 100.0]], dt)   # test_box.py:191-205 boxes, a flat box, a huge angle
+        out[f"{tag}.points"], out[f"{tag}.boxes"] = pts, bx
+        out[f"{tag}.mask"] = np.packbits(R.crop_2dr(pts, bx))
+    np.savez_compressed(os.path.join(OUT, "crop.npz"), **out)
+
+
 def main():
     assert R.available(), "build oracle/_ref first"
+    if "--only-crop" in sys.argv:
+        return write_crop()
     # ---------------- IoU: C1-style random, 160x96 block (fp64 + fp32, rbox + box)
     rng = np.random.default_rng(0)
     A, B = gen_boxes(rng, 1000), gen_boxes(rng, 1000)
@@ -187,6 +202,7 @@ def main():
             for meth in ("mean", "linear"):
                 sc[f"{tag}.d{dim}.{meth}"] = R.aligned_scatter_forward(crd, img, meth)
     np.savez_compressed(os.path.join(OUT, "scatter.npz"), **sc)
+    write_crop()
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT) if f.endswith(".npz"))
     print("golden fixtures written, total bytes:", tot)
 

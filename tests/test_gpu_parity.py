@@ -183,6 +183,43 @@ def test_box3d_iou_distance_vs_oracle(dev, oracle):
         box3d_iou_distance(torch.zeros((3, 7)), torch.zeros((3, 7)), metric="giou")
 
 
+def test_box_crop_vs_reference_and_oracle(dev, oracle):
+    """box2dr_crop / box3dp_crop.  Masks are compared bit for bit with the golden fixture written by the
+    reference's own crop_2dr and with the oracle on ragged sizes; points closer than a few ulps to an edge could flip with
+    the last-ulp difference between CUDA's and glibc's sin/cos (none do on these inputs)."""
+    from d3d_b200.box import box2dr_crop, box3dp_crop
+    g = golden("crop.npz")
+    for tag in ("f32", "f64"):
+        pts, bx = g[f"{tag}.points"], g[f"{tag}.boxes"]
+        exp = np.unpackbits(g[f"{tag}.mask"])[:len(bx) * len(pts)].reshape(len(bx), len(pts)).astype(bool)
+        got = box2dr_crop(_t(pts, dev), _t(bx, dev))
+        assert got.dtype == torch.bool and tuple(got.shape) == exp.shape
+        assert np.array_equal(got.cpu().numpy(), exp), (tag, int((got.cpu().numpy() != exp).sum()))
+    rng = np.random.default_rng(17)
+    for n, m in ((1, 1), (15, 3), (16, 17), (4099, 33), (70000, 40), (65536, 16)):
+        for dt in (np.float32, np.float64):
+            pts = ((rng.random((n, 2)) - .5) * 12).astype(dt)
+            bx = gen_boxes(rng, m).astype(dt)
+            got = box2dr_crop(_t(pts, dev), _t(bx, dev)).cpu().numpy()
+            assert np.array_equal(got, oracle.crop_2dr(pts, bx)), (n, m, dt)
+    # reference test/test_box.py:191-205
+    cloud = (rng.random((100, 2)) * 2 - 1).astype(np.float32)
+    boxes = np.array([[0, 0, 1, 1, 0], [0, 0, 1, 1, np.pi / 4]], np.float32)
+    r = box2dr_crop(torch.from_numpy(cloud), torch.from_numpy(boxes))
+    assert r.device.type == "cpu"
+    ab = np.abs(cloud)
+    assert np.array_equal(r[0].numpy(), np.all(ab < 0.5, 1)) and np.array_equal(r[1].numpy(), np.abs(ab[:, 0] + ab[:, 1]) < np.sqrt(2) / 2)
+    p3 = np.concatenate([(rng.random((5000, 2)) - .5) * 12, rng.normal(0, 1, (5000, 1))], 1).astype(np.float32)
+    b3 = np.concatenate([gen_boxes(rng, 20)[:, :2], rng.normal(0, .5, (20, 1)), gen_boxes(rng, 20)[:, 2:4], 1 + rng.random((20, 1)), rng.normal(0, 2, (20, 1))], 1).astype(np.float32)
+    for ax in (0, 1, 2):
+        assert np.array_equal(box3dp_crop(_t(p3, dev), _t(b3, dev), ax).cpu().numpy(), oracle.box3dp_crop(p3, b3, ax)), ax
+    assert tuple(box2dr_crop(torch.zeros((0, 2), device=dev), torch.zeros((4, 5), device=dev)).shape) == (4, 0)
+    with pytest.raises(ValueError):
+        box2dr_crop(torch.zeros((3, 3), device=dev), torch.zeros((4, 5), device=dev))
+    with pytest.raises(ValueError):
+        box3dp_crop(_t(p3, dev), _t(b3, dev), 3)
+
+
 def test_nms_known_answer_and_golden(dev):
     from d3d_b200.box import box2d_nms
     g = golden("nms.npz")

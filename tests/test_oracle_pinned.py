@@ -237,3 +237,24 @@ def test_box3d_iou_distance_known_answers(oracle):
     big = np.array([[0, 0, 0, 5000, 2, 2, 0.0]], np.float32)   # sizes are clipped to 1e3 (matcher.pyx:50-52)
     ref = np.array([[0, 0, 0, 1000, 2, 2, 0.0]], np.float32)
     assert np.allclose(oracle.box3d_iou_distance(big, ref, "iou"), 0, atol=1e-6)
+
+
+def test_crop_2dr_pinned(oracle):
+    """point-in-rotated-box mask -- oracle == the reference's own crop_2dr (golden fixture, and the live
+    extension when oracle/_ref exists) bit for bit, plus the known answers of reference test/test_box.py:191-205"""
+    g = golden("crop.npz")
+    for tag in ("f32", "f64"):
+        pts, bx = g[f"{tag}.points"], g[f"{tag}.boxes"]
+        exp = np.unpackbits(g[f"{tag}.mask"])[:len(bx) * len(pts)].reshape(len(bx), len(pts)).astype(bool)
+        assert np.array_equal(oracle.crop_2dr(pts, bx), exp), tag
+    rng = np.random.default_rng(3)
+    cloud = (rng.random((100, 2)) * 2 - 1).astype(np.float32)
+    boxes = np.array([[0, 0, 1, 1, 0], [0, 0, 1, 1, np.pi / 2 / 2]], np.float32)
+    m = oracle.crop_2dr(cloud, boxes)
+    ab = np.abs(cloud)
+    assert np.array_equal(m[0], np.all(ab < 0.5, 1))
+    assert np.array_equal(m[1], np.abs(ab[:, 0] + ab[:, 1]) < np.sqrt(2) / 2)
+    p3 = np.concatenate([cloud, rng.normal(0, 1, (100, 1)).astype(np.float32)], 1)
+    b3 = np.array([[0, 0, 0.2, 1, 1, 1.5, 0.3]], np.float32)
+    m3 = oracle.box3dp_crop(p3, b3)
+    assert m3.shape == (1, 100) and np.array_equal(m3[0], oracle.crop_2dr(p3[:, :2], b3[:, [0, 1, 3, 4, 6]])[0] & (np.abs(p3[:, 2] - 0.2) < 0.75))
