@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the d3d hot path on B200 next to the reference's CPU path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--op all|voxel|iou|nms|dist3d] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--op all|voxel|iou|nms|dist3d|crop] [--impl reference]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W      (N > 1)
 
 One JSON line on rank 0.  BASELINE.json's metric is a triple (rotated-IoU pairs/s, NMS boxes/s, voxelized
@@ -125,6 +125,23 @@ def _cpu_dist3d_block(args):
     return time.perf_counter() - t0, (hi - lo) * 4000
 
 
+def _cpu_crop_block(args):
+    import torch
+    torch.set_num_threads(1)
+    seed, nb = args
+    rng = np.random.default_rng(seed)
+    pts = lidar(seed, 180_000)[:, :2].copy()
+    bx = proposals(seed, nb, max(1, nb // 2), extent=75.0)[0].astype(np.float32)
+    t0 = time.perf_counter()
+    if _CPU_KIND == "reference":
+        from oracle import ref as R
+        R.crop_2dr(pts, bx)
+    else:
+        from oracle import oracle as O
+        O.crop_2dr(pts, bx)
+    return time.perf_counter() - t0, len(pts) * nb
+
+
 def _cpu_nms(n):
     import torch
     torch.set_num_threads(1)
@@ -212,6 +229,12 @@ def cpu_baseline(op, cores, rounds=2):
                     sample=f"{len(res)} row-blocks of {rows} x 4000 fp32 3-D boxes, one block per process on {cores} cores; C restatement of the "
                            f"reference's fp32 Rotating-Calipers IoU + the z arithmetic of d3d/dgal_wrap.h:45-68 (the reference's Cython matcher "
                            f"cannot be built in this image)")
+    if op == "crop":
+        nb = 256
+        res, wall = cpu_pool(_cpu_crop_block, [(200 + i, nb) for i in range(cores * rounds)], cores)
+        ok = [r for r in res if r is not None]
+        return dict(value=sum(r[1] for r in ok) / wall, unit="pairs/s", cores=cores, kind=_CPU_KIND,
+                    sample=f"{len(ok)} blocks of {nb} boxes x 180000 points (fp32), one block per process on {cores} cores")
     if op == "nms":
         n = 10000
         res, wall = cpu_pool(_cpu_nms, [n] * (cores * rounds), cores)
@@ -533,6 +556,49 @@ def bench_dist3d(args, rank, world, barrier):
                 clocks=cs.summary())
 
 
+def bench_crop(args, rank, world, barrier):
+    """point-in-rotated-box mask, one C3-sized frame (180k points) against 4096 boxes per GPU per step"""
+    import torch
+    from d3d_b200 import _cabi as c
+    from d3d_b200.box import box2dr_crop
+    n, m = 180_000 // 16 * 16, 4096
+    pts = torch.from_numpy(lidar(300 + rank, 180_000)[:n, :2].copy()).cuda()
+    bx = torch.from_numpy(proposals(300 + rank, m, m // 2)[0].astype(np.float32)).cuda()
+    mask = torch.empty((m, n), dtype=torch.bool, device="cuda")
+    ws = c.workspace(c.crop_workspace_bytes(m, 0), pts.device)
+
+    def step():
+        c.check(c.crop2dr[0](c.ptr(pts), n, c.ptr(bx), m, c.ptr(mask), c.ptr(ws), ws.numel(), c.stream_ptr()), "crop")
+    l0 = c.launch_count()
+    with ClockSampler(torch.cuda.current_device()) as cs:
+        ms = timed(step, args.steps, args.warmup, barrier)
+        l1 = c.launch_count()
+        cs.hold(step)
+    launches = (l1 - l0) // (args.steps + args.warmup) * args.steps
+    ms = max_over_ranks(ms, world)
+    hP, hB = pts.cpu().pin_memory(), bx.cpu().pin_memory()
+    hout = torch.empty((m, n), dtype=torch.bool).pin_memory()
+
+    def e2e_step():
+        r = box2dr_crop(hP.cuda(non_blocking=True), hB.cuda(non_blocking=True))
+        hout.copy_(r, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    ms_e2e = max_over_ranks(timed(e2e_step, 3, 1, barrier), world)
+    hbm, how = peaks()
+    alg = float(m) * n + 8.0 * n + 20.0 * m
+    ach = alg / (ms * 1e-3) / 1e9
+    return dict(metric="point-in-box pairs/sec", unit="pairs/s", value=float(m) * n * world / (ms * 1e-3), ms_per_step=ms, dtype="f32", scaling="weak",
+                gpu_launches=int(launches),
+                config=dict(workload=f"SURVEY 8(f) f4: box2dr_crop, {n} points x {m} rotated boxes fp32, one frame per GPU per step",
+                            l2_policy=f"the {m * n / 1e6:.0f} MB mask streams through HBM, larger than L2"),
+                e2e=dict(value=float(m) * n * world / (ms_e2e * 1e-3), unit="pairs/s", h2d_bytes_per_step=int(8 * n + 20 * m), d2h_bytes_per_step=int(m * n),
+                         ms_per_step=ms_e2e, api="box2dr_crop(pinned host points, boxes) -> host bool mask"),
+                roofline=dict(bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm, traffic=None, peak_source=how,
+                              algorithmic_bytes_per_step=alg, note="1 mask byte per pair; ~4 compares per rejected pair and ~35 flops per pair inside the "
+                                                                    "box's AABB keep the kernel between the store stream and the fp32 issue rate"),
+                clocks=cs.summary())
+
+
 def bench_nms(args, rank, world, barrier):
     import torch
     from d3d_b200 import _cabi as c
@@ -579,14 +645,15 @@ def run_reference(args):
     vals = vals[args.warmup:] or vals
     v = float(np.median([x["value"] for x in vals]))
     cb = dict(vals[-1]); cb["value"] = v
-    metric = {"voxel": "voxelized points/sec", "iou": "rotated-IoU pairs/sec", "nms": "NMS boxes/sec", "dist3d": "evaluator distance-matrix pairs/sec"}[op]
+    metric = {"voxel": "voxelized points/sec", "iou": "rotated-IoU pairs/sec", "nms": "NMS boxes/sec", "dist3d": "evaluator distance-matrix pairs/sec", "crop": "point-in-box pairs/sec"}[op]
     unit = cb["unit"]
     line = dict(impl="reference", metric=metric, value=v, unit=unit, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=None, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype={"voxel": "f32", "iou": "f32", "nms": "f64", "dist3d": "f32"}[op], data="synthetic",
+                dtype={"voxel": "f32", "iou": "f32", "nms": "f64", "dist3d": "f32", "crop": "f32"}[op], data="synthetic",
                 config=dict(workload={"voxel": "C2 KITTI-shaped voxelization 120k pts/frame, 0.05x0.05x0.1 m voxels, max 5 pts/voxel (reference CPU path)",
                                       "iou": "C4 rotated IoU fp32, C1 distribution (reference CPU path, row-block sample)",
                                       "nms": "C3-style rotated NMS fp64, 5000-proposal frames (reference CPU path)",
+                                      "crop": "box2dr_crop 180k points x 256-box blocks fp32 (reference CPU path)",
                                       "dist3d": "evaluator distance matrix 1 - riou2d * ziou fp32 (C restatement of the reference path, row-block sample)"}[op]),
                 cpu_baseline=cb, e2e=dict(value=v, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
@@ -599,7 +666,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--op", default="all", choices=["all", "voxel", "iou", "nms", "dist3d"])
+    ap.add_argument("--op", default="all", choices=["all", "voxel", "iou", "nms", "dist3d", "crop"])
     ap.add_argument("--frames", type=int, default=128, help="C2 frames per GPU per voxelization step")
     ap.add_argument("--iou-n", type=int, default=100_000)
     ap.add_argument("--iou-e2e-rows", type=int, default=8192)
@@ -612,7 +679,7 @@ def main():
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    ops = ["voxel", "iou", "nms", "dist3d"] if args.op == "all" else [args.op]
+    ops = ["voxel", "iou", "nms", "dist3d", "crop"] if args.op == "all" else [args.op]
 
     # CPU baseline first: the fork-based pool must run before this process touches CUDA
     cpu = {}
@@ -634,7 +701,7 @@ def main():
         barrier = lambda: None
     import d3d_b200  # noqa: F401  (raises if the CUDA extension is missing: no fallback)
 
-    fns = dict(voxel=bench_voxel, iou=bench_iou, nms=bench_nms, dist3d=bench_dist3d)
+    fns = dict(voxel=bench_voxel, iou=bench_iou, nms=bench_nms, dist3d=bench_dist3d, crop=bench_crop)
     res = {}
     for op in ops:
         res[op] = fns[op](args, rank, world, barrier)
