@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the d3d hot path on B200 next to the reference's CPU path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--op all|voxel|iou|nms|dist3d|crop] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--op all|voxel|iou|nms|scatter|dist3d|crop] [--impl reference]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W      (N > 1)
 
 One JSON line on rank 0.  BASELINE.json's metric is a triple (rotated-IoU pairs/s, NMS boxes/s, voxelized
@@ -142,6 +142,31 @@ def _cpu_crop_block(args):
     return time.perf_counter() - t0, len(pts) * nb
 
 
+def c2s_inputs(seed=1):
+    """the in-range points of a C2 cloud as (batch 0, x / 0.1, (y + 40) / 0.1) against f32[1,64,704,800]"""
+    import torch
+    pts = lidar(seed)
+    ok = (pts[:, 0] >= 0) & (pts[:, 0] < 70.4) & (pts[:, 1] >= -40) & (pts[:, 1] < 40)
+    p = pts[ok]
+    coords = np.stack([np.zeros(len(p), np.float32), p[:, 0] / np.float32(0.1), (p[:, 1] + np.float32(40)) / np.float32(0.1)], 1).astype(np.float32)
+    fmap = torch.rand((1, 64, 704, 800), generator=torch.Generator().manual_seed(7))
+    return coords, fmap
+
+
+def _cpu_scatter(method):
+    import torch
+    torch.set_num_threads(1)
+    coords, fmap = c2s_inputs()
+    t0 = time.perf_counter()
+    if _CPU_KIND == "reference":
+        from oracle import ref as R
+        R.aligned_scatter_forward(coords, fmap.numpy(), method)
+    else:
+        from oracle import oracle as O
+        O.scatter_forward(coords, fmap.numpy(), {"mean": 1, "linear": 2}[method])
+    return time.perf_counter() - t0, len(coords)
+
+
 def _cpu_nms(n):
     import torch
     torch.set_num_threads(1)
@@ -229,6 +254,12 @@ def cpu_baseline(op, cores, rounds=2):
                     sample=f"{len(res)} row-blocks of {rows} x 4000 fp32 3-D boxes, one block per process on {cores} cores; C restatement of the "
                            f"reference's fp32 Rotating-Calipers IoU + the z arithmetic of d3d/dgal_wrap.h:45-68 (the reference's Cython matcher "
                            f"cannot be built in this image)")
+    if op == "scatter":
+        res, wall = cpu_pool(_cpu_scatter, ["linear"] * cores, cores)
+        ok = [r for r in res if r is not None]
+        return dict(value=sum(r[1] for r in ok) / wall, unit="points/s", cores=cores, kind=_CPU_KIND,
+                    sample=f"{len(ok)} C2s forward passes (method linear, {ok[0][1] if ok else 0} points x 64 channels), one per process on {cores} cores; "
+                           f"single-pass latency {np.median([r[0] for r in ok]) * 1e3:.0f} ms")
     if op == "crop":
         nb = 256
         res, wall = cpu_pool(_cpu_crop_block, [(200 + i, nb) for i in range(cores * rounds)], cores)
@@ -599,6 +630,66 @@ def bench_crop(args, rank, world, barrier):
                 clocks=cs.summary())
 
 
+def bench_scatter(args, rank, world, barrier):
+    """aligned_scatter forward + backward (method linear) of one C2 frame's points on a 64-channel BEV map"""
+    import torch
+    from d3d_b200 import _cabi as c
+    from d3d_b200.point import aligned_scatter, aligned_scatter_forward_cuda, aligned_scatter_backward_cuda, AlignType
+    coords_np, fmap = c2s_inputs(1 + rank)
+    coords, fm = torch.from_numpy(coords_np).cuda(), fmap.cuda()
+    n, ch = coords.shape[0], fm.shape[1]
+    grad = torch.ones((n, ch), dtype=torch.float32, device="cuda")
+    image_grad = torch.zeros_like(fm)
+
+    def fwd():
+        return aligned_scatter_forward_cuda(coords, fm, AlignType.LINEAR)
+
+    def step():
+        fwd()
+        aligned_scatter_backward_cuda(coords, grad, AlignType.LINEAR, image_grad)   # accumulates in place (the caller zeroes once, d3d/point/__init__.py:32)
+    anchor = float(fwd().double().sum().item())
+    l0 = c.launch_count()
+    with ClockSampler(torch.cuda.current_device()) as cs:
+        ms = timed_flushed(step, args.steps, args.warmup, barrier)
+        l1 = c.launch_count()
+        ms_fwd = timed_flushed(fwd, args.steps, 1, barrier)
+        cs.hold(step)
+    launches = (l1 - l0) // (args.steps + args.warmup) * args.steps
+    ms, ms_fwd = max_over_ranks(ms, world), max_over_ranks(ms_fwd, world)
+    hC = torch.from_numpy(coords_np).pin_memory()
+
+    def e2e_step():
+        r = aligned_scatter(hC.cuda(non_blocking=True), fm, "linear")   # the feature map is an activation that already lives on the device
+        r.cpu()
+    ms_e2e = max_over_ranks(timed(e2e_step, 3, 1, barrier), world)
+    hbm, how = peaks()
+    dim = 2
+    alg_f = n * ch * (2 ** dim + 1) * 4.0 + n * (1 + dim) * 4.0          # SURVEY 8(d): gather 2^Dim neighbours + write, per channel
+    alg = 2 * alg_f                                                      # backward: read grad, read-modify-write 2^Dim neighbours
+    ach = alg / (ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as fh:
+            t = json.load(fh)["scatter"]
+        if t["points"] == n:
+            traffic = float(t["bytes"])
+    except (OSError, KeyError, ValueError):
+        pass
+    return dict(metric="aligned_scatter points/sec (forward + backward)", unit="points/s", value=n * world / (ms * 1e-3), ms_per_step=ms, dtype="f32",
+                scaling="weak", gpu_launches=int(launches),
+                config=dict(workload=f"SURVEY 8(d) C2s: {n} in-range points of a C2 frame, feature map f32[1,64,704,800], method linear, "
+                                     f"forward + backward per step, one frame per GPU", forward_ms=ms_fwd, forward_sum_anchor=anchor,
+                            l2_policy="256 MB memset evicts L2 between timed steps (the 144 MB map itself exceeds L2)"),
+                e2e=dict(value=n * world / (ms_e2e * 1e-3), unit="points/s", h2d_bytes_per_step=int(n * 12), d2h_bytes_per_step=int(n * ch * 4),
+                         ms_per_step=ms_e2e, api="aligned_scatter(pinned host coordinates, device feature map, 'linear') -> host [N,64]"),
+                roofline=dict(bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm, traffic=traffic, peak_source=how,
+                              algorithmic_bytes_per_step=alg, forward_gbs=alg_f / (ms_fwd * 1e-3) / 1e9,
+                              note="N*C*(2^Dim+1)*4 + N*(1+Dim)*4 bytes per pass (SURVEY 8(d)).  Every 4-byte neighbour of a random point costs a 32-byte "
+                                   "sector, so the DRAM traffic (ncu, profiles/r1_scatter_ncu.txt) is 3x the algorithmic bytes: the forward kernel moves "
+                                   "352 MB in 95 us = 57 % of the measured HBM peak, the backward (RED.ADD per neighbour) 328 MB in 206 us"),
+                clocks=cs.summary())
+
+
 def bench_nms(args, rank, world, barrier):
     import torch
     from d3d_b200 import _cabi as c
@@ -645,14 +736,15 @@ def run_reference(args):
     vals = vals[args.warmup:] or vals
     v = float(np.median([x["value"] for x in vals]))
     cb = dict(vals[-1]); cb["value"] = v
-    metric = {"voxel": "voxelized points/sec", "iou": "rotated-IoU pairs/sec", "nms": "NMS boxes/sec", "dist3d": "evaluator distance-matrix pairs/sec", "crop": "point-in-box pairs/sec"}[op]
+    metric = {"voxel": "voxelized points/sec", "iou": "rotated-IoU pairs/sec", "nms": "NMS boxes/sec", "dist3d": "evaluator distance-matrix pairs/sec", "crop": "point-in-box pairs/sec", "scatter": "aligned_scatter points/sec (forward)"}[op]
     unit = cb["unit"]
     line = dict(impl="reference", metric=metric, value=v, unit=unit, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=None, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype={"voxel": "f32", "iou": "f32", "nms": "f64", "dist3d": "f32", "crop": "f32"}[op], data="synthetic",
+                dtype={"voxel": "f32", "iou": "f32", "nms": "f64", "dist3d": "f32", "crop": "f32", "scatter": "f32"}[op], data="synthetic",
                 config=dict(workload={"voxel": "C2 KITTI-shaped voxelization 120k pts/frame, 0.05x0.05x0.1 m voxels, max 5 pts/voxel (reference CPU path)",
                                       "iou": "C4 rotated IoU fp32, C1 distribution (reference CPU path, row-block sample)",
                                       "nms": "C3-style rotated NMS fp64, 5000-proposal frames (reference CPU path)",
+                                      "scatter": "C2s aligned_scatter forward, method linear (reference CPU path)",
                                       "crop": "box2dr_crop 180k points x 256-box blocks fp32 (reference CPU path)",
                                       "dist3d": "evaluator distance matrix 1 - riou2d * ziou fp32 (C restatement of the reference path, row-block sample)"}[op]),
                 cpu_baseline=cb, e2e=dict(value=v, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
@@ -666,7 +758,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--op", default="all", choices=["all", "voxel", "iou", "nms", "dist3d", "crop"])
+    ap.add_argument("--op", default="all", choices=["all", "voxel", "iou", "nms", "scatter", "dist3d", "crop"])
     ap.add_argument("--frames", type=int, default=128, help="C2 frames per GPU per voxelization step")
     ap.add_argument("--iou-n", type=int, default=100_000)
     ap.add_argument("--iou-e2e-rows", type=int, default=8192)
@@ -679,7 +771,7 @@ def main():
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    ops = ["voxel", "iou", "nms", "dist3d", "crop"] if args.op == "all" else [args.op]
+    ops = ["voxel", "iou", "nms", "scatter", "dist3d", "crop"] if args.op == "all" else [args.op]
 
     # CPU baseline first: the fork-based pool must run before this process touches CUDA
     cpu = {}
@@ -701,7 +793,7 @@ def main():
         barrier = lambda: None
     import d3d_b200  # noqa: F401  (raises if the CUDA extension is missing: no fallback)
 
-    fns = dict(voxel=bench_voxel, iou=bench_iou, nms=bench_nms, dist3d=bench_dist3d, crop=bench_crop)
+    fns = dict(voxel=bench_voxel, iou=bench_iou, nms=bench_nms, dist3d=bench_dist3d, crop=bench_crop, scatter=bench_scatter)
     res = {}
     for op in ops:
         res[op] = fns[op](args, rank, world, barrier)

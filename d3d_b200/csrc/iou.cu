@@ -309,10 +309,12 @@ static int iou2dr_impl(const T *b1, int64_t n, const T *b2, int64_t m, T *out, i
     if ((rc = prep_boxes<T, TC>(b2, m, TC, rb, st))) return rc;
     if (tiles_c > 0x7fffffffll || tiles_r > 65535ll * 65535ll) return D3D_ERR_INVALID_ARGUMENT;
     const dim3 grid((unsigned)tiles_c, (unsigned)(tiles_r < 65535 ? tiles_r : 65535), (unsigned)cdiv(tiles_r, 65535));
-    static bool smem_opt_in = false;   // per instantiation; the attribute is per function and sticky
-    if (!smem_opt_in) {
+    static bool smem_opt_in[64] = {};   // per instantiation and per device: the attribute is per function and context, and sticky
+    int dev = 0;
+    D3D_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !smem_opt_in[dev]) {
         D3D_CUDA_TRY(cudaFuncSetAttribute(iou2dr_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IouSmem<T>)));
-        smem_opt_in = true;
+        if (dev >= 0 && dev < 64) smem_opt_in[dev] = true;
     }
     iou2dr_tile_kernel<T><<<grid, IOU_THREADS, sizeof(IouSmem<T>), st>>>(ra, n, rb, m, out, ld); D3D_LAUNCHED();
     return D3D_OK;
@@ -376,10 +378,12 @@ static int dist3d_impl(const float *b1, int64_t n, const float *b2, int64_t m, i
     box3d_prep_kernel<1, TC><<<(unsigned)cdiv(mp, 256), 256, 0, st>>>(b2, m, mp, rb, nullptr, zb); D3D_LAUNCHED();
     if (tiles_c > 0x7fffffffll || tiles_r > 65535ll * 65535ll) return D3D_ERR_INVALID_ARGUMENT;
     const dim3 grid((unsigned)tiles_c, (unsigned)(tiles_r < 65535 ? tiles_r : 65535), (unsigned)cdiv(tiles_r, 65535));
-    static bool smem_opt_in = false;
-    if (!smem_opt_in) {
+    static bool smem_opt_in[64] = {};
+    int dev = 0;
+    D3D_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !smem_opt_in[dev]) {
         D3D_CUDA_TRY(cudaFuncSetAttribute(iou2dr_tile_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IouSmem<float>)));
-        smem_opt_in = true;
+        if (dev >= 0 && dev < 64) smem_opt_in[dev] = true;
     }
     iou2dr_tile_kernel<float, true><<<grid, IOU_THREADS, sizeof(IouSmem<float>), st>>>(ra, n, rb, m, out, ld, za, zb); D3D_LAUNCHED();
     return D3D_OK;

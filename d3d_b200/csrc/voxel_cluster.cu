@@ -1250,14 +1250,19 @@ template <bool DENSE>
 static int vc_shape(VcShape *out, int64_t max_frame_points)
 {
     auto kern = vox_cluster_kernel<DENSE>;
-    static int occ[VC_MAX_CSIZE + 1];   // co-resident clusters per cluster size (0 = not queried yet, -1 = unavailable)
-    static uint32_t dyn = 0;
+    // cached per device: function attributes and occupancy belong to the device's context (one process may drive several GPUs)
+    static int occ_dev[64][VC_MAX_CSIZE + 1];   // co-resident clusters per cluster size (0 = not queried yet, -1 = unavailable)
+    static uint32_t dyn_dev[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return D3D_ERR_CUDA; }
+    int *occ = occ_dev[dev];
+    uint32_t &dyn = dyn_dev[dev];
     if (dyn == 0) {
         dyn = VC_L2_DYN;
         if (!DENSE) {
-            int dev = 0, optin = 0;
+            int optin = 0;
             cudaFuncAttributes fa;
-            if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess ||
+            if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess ||
                 cudaFuncGetAttributes(&fa, kern) != cudaSuccess) { cudaGetLastError(); return D3D_ERR_CUDA; }
             const long long d = ((long long)optin - (long long)fa.sharedSizeBytes) & ~1023ll;
             if (d > (long long)dyn) dyn = (uint32_t)d;
