@@ -152,6 +152,8 @@ __device__ __forceinline__ void nms_append_tile(const NmsLists &L, const unsigne
 constexpr int NMS_GRID_MAX = 256;                                   // cells per axis
 constexpr int NMS_GRID_CELLS = NMS_GRID_MAX * NMS_GRID_MAX;
 struct NmsGrid { double minx, miny, inv_cell; int nx, ny; uint32_t ok; uint32_t pad; };
+// what the candidate scan needs of a box, stored in cell order so that a warp reads consecutive records
+template <typename T> struct __align__(16) NmsCand { T cx, cy, rho; uint32_t idx, pad; };
 
 template <typename T>
 __global__ void __launch_bounds__(1024) nms_grid_kernel(const BoxRec<T> *__restrict__ recs, int64_t n, NmsGrid *__restrict__ g)
@@ -203,23 +205,24 @@ __device__ __forceinline__ void nms_cell_of(const NmsGrid &g, const BoxRec<T> &r
 // pass 0: count boxes per cell; pass 1: fill the cell lists (order inside a cell is arbitrary: results are ORs)
 template <typename T, int PASS>
 __global__ void __launch_bounds__(256) nms_bin_kernel(const BoxRec<T> *__restrict__ recs, int64_t n, const NmsGrid *__restrict__ g,
-                                                      uint32_t *__restrict__ cellcnt, const uint32_t *__restrict__ cellptr, uint32_t *__restrict__ celllist)
+                                                      uint32_t *__restrict__ cellcnt, const uint32_t *__restrict__ cellptr, NmsCand<T> *__restrict__ celllist)
 {
     if (!g->ok) return;
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     int ix, iy;
-    nms_cell_of<T>(*g, recs[p], &ix, &iy);
+    const BoxRec<T> r = recs[p];
+    nms_cell_of<T>(*g, r, &ix, &iy);
     const uint32_t c = (uint32_t)(iy * g->nx + ix);
     const uint32_t at = atomicAdd(cellcnt + c, 1u);
-    if (PASS == 1) celllist[cellptr[c] + at] = (uint32_t)p;
+    if (PASS == 1) { NmsCand<T> e; e.cx = r.cx; e.cy = r.cy; e.rho = r.rho; e.idx = (uint32_t)p; e.pad = 0; celllist[cellptr[c] + at] = e; }
 }
 
 constexpr int NMS_PAIR_THREADS = 256;
 template <typename T>
 __global__ void __launch_bounds__(NMS_PAIR_THREADS) nms_pairs_kernel(const BoxRec<T> *__restrict__ recs, const T *__restrict__ raw, int64_t n, int64_t nwords, T thr,
                                                                     const NmsGrid *__restrict__ g, const uint32_t *__restrict__ cellptr,
-                                                                    const uint32_t *__restrict__ celllist, const NmsLists lists)
+                                                                    const NmsCand<T> *__restrict__ celllist, const NmsLists lists)
 {
     if (!g->ok) return;
     __shared__ uint32_t queue[NMS_PAIR_THREADS / 32][64];
@@ -267,9 +270,10 @@ __global__ void __launch_bounds__(NMS_PAIR_THREADS) nms_pairs_kernel(const BoxRe
             bool cand = false;
             uint32_t j = 0;
             if (k < end) {
-                j = celllist[k];
+                const NmsCand<T> e = celllist[k];   // coalesced: the cell lists hold the three numbers the circle test needs
+                j = e.idx;
                 if ((int64_t)j > i) {
-                    const T dx = A.cx - recs[j].cx, dyy = A.cy - recs[j].cy, rs = A.rho + recs[j].rho;
+                    const T dx = A.cx - e.cx, dyy = A.cy - e.cy, rs = A.rho + e.rho;
                     cand = dx * dx + dyy * dyy <= rs * rs;
                 }
             }
@@ -569,7 +573,7 @@ template <typename T> static size_t nms_ws_bytes(int64_t n)
     return align_up((size_t)n * 8) + align_up((size_t)n * 4) + radix_sort_workspace_bytes(n) + align_up((size_t)npad * recs) +
            align_up((size_t)npad * 5 * sizeof(T)) + align_up((size_t)npad) + align_up((size_t)npad * nwords * 8) +
            align_up((size_t)(nwords + 1) * 4) + align_up((size_t)nwords * NMS_LIST_CAP * 4) + align_up((size_t)nwords * NMS_LIST_CAP * 8) +
-           align_up(sizeof(NmsGrid)) + 2 * align_up((size_t)2 * (NMS_GRID_CELLS + 1) * 4) + align_up((size_t)npad * 4) + scan_workspace_bytes(NMS_GRID_CELLS + 1) + 4096;
+           align_up(sizeof(NmsGrid)) + 2 * align_up((size_t)2 * (NMS_GRID_CELLS + 1) * 4) + align_up((size_t)npad * sizeof(NmsCand<T>)) + scan_workspace_bytes(NMS_GRID_CELLS + 1) + 4096;
 }
 
 template <typename T>
@@ -603,7 +607,7 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
     NmsGrid *grid = a.take<NmsGrid>(1);
     uint32_t *cellcnt = a.take<uint32_t>((size_t)2 * (NMS_GRID_CELLS + 1));   // [0] counts (pass 0), [1] fill cursors (pass 1)
     uint32_t *cellptr = a.take<uint32_t>((size_t)2 * (NMS_GRID_CELLS + 1));
-    uint32_t *celllist = a.take<uint32_t>((size_t)npad);
+    NmsCand<T> *celllist = a.take<NmsCand<T>>((size_t)npad);
     void *cell_scan_ws = a.take<char>(scan_workspace_bytes(NMS_GRID_CELLS + 1));
     if (!a.ok()) return D3D_ERR_WORKSPACE;
     // tuning / test override: D3D_B200_NMS_PATH=dense (dense matrix, dense resolve) | tiles (dense tiles + list resolve); default: spatial
