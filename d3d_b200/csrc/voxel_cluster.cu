@@ -820,8 +820,11 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
             s[e] = 0;
             if (p < n) { s[e] = (vr_h1(q[p].x) << 3) >> hshift; unres |= 1u << e; }
         }
+#ifndef D3D_VR_ROUNDS
+#define D3D_VR_ROUNDS 2
+#endif
 #pragma unroll 1
-        for (int round = 0; round < 2; round++) {
+        for (int round = 0; round < D3D_VR_ROUNDS; round++) {
 #pragma unroll
             for (int e = 0; e < VR_E; e++)
                 if ((unres >> e) & 1u) { if (slot[s[e]] == VR_SLOT_EMPTY) slot[s[e]] = (uint16_t)(tid + e * VC_THREADS); }
@@ -834,7 +837,7 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
                     if (q[wv].x == kq) { unres &= ~(1u << e); s[e] = wv; }
                     else s[e] = (s[e] + vr_step(kq, smask)) & smask;
                 }
-            if (round == 0) { __syncthreads(); VR_SUB(8); }   // round 1 stores must not overtake round 0 lookups
+            if (round + 1 < D3D_VR_ROUNDS) { __syncthreads(); VR_SUB(8); }   // the next round's stores must not overtake this round's lookups
         }
         VR_SUB(9);
         {   // hand the stragglers to the list (what does not fit stays with its thread); one reservation per warp
