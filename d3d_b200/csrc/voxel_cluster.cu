@@ -827,7 +827,7 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
         for (int round = 0; round < D3D_VR_ROUNDS; round++) {
 #pragma unroll
             for (int e = 0; e < VR_E; e++)
-                if ((unres >> e) & 1u) { if (slot[s[e]] == VR_SLOT_EMPTY) slot[s[e]] = (uint16_t)(tid + e * VC_THREADS); }
+                if ((unres >> e) & 1u) { if (slot[s[e]] == VR_SLOT_EMPTY) slot[s[e]] = (uint16_t)(tid + e * VC_THREADS); }   // racy on purpose: any writer wins
             __syncthreads();
 #pragma unroll
             for (int e = 0; e < VR_E; e++)
@@ -973,6 +973,8 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
                     const uint32_t ent = list[j];
                     if (ent != VC_NONE) {
                         const uint32_t p = ent & 0xffffu, wv = ent >> 16;
+                        // (racecheck flags this store against the next round's read of q[wv].y by faster threads when p == wv: only bit 31
+                        // changes and every reader masks it off, so both values name the same record)
                         if (acc[q[wv].y & 0xffffu] == (pre | own_index(p, wv))) { list[j] = VC_NONE; q[p].y |= VR_KEPT; }
                     }
                 }
