@@ -130,20 +130,30 @@ iou2dr_tile_kernel(const BoxRec<T> *__restrict__ recA, int64_t n, const BoxRec<T
 
     // ---- scan: bounding-circle test of this warp's RW x TC pairs: 6 flops, a compare, a ballot and a select per pair
     // (no popc, no shared-memory traffic on the per-pair path).
-    T bx[KC], by[KC], br[KC];
+    // The six flops of the circle test run on pairs of column chunks (FADD2 / FMUL2 / FFMA2 on sm_100a: two pairs per issue slot).
+    using PV = typename Vec2<T>::type;
+    static_assert(KC % 2 == 0, "column chunks are tested two at a time");
+    PV bx2[KC / 2], by2[KC / 2], br2[KC / 2];
 #pragma unroll
-    for (int k = 0; k < KC; k++) { bx[k] = sm.sB[0][k * 32 + lane]; by[k] = sm.sB[1][k * 32 + lane]; br[k] = sm.sB[6][k * 32 + lane]; }
+    for (int k = 0; k < KC / 2; k++) {
+        bx2[k] = P2<T>::mk(sm.sB[0][(2 * k) * 32 + lane], sm.sB[0][(2 * k + 1) * 32 + lane]);
+        by2[k] = P2<T>::mk(sm.sB[1][(2 * k) * 32 + lane], sm.sB[1][(2 * k + 1) * 32 + lane]);
+        br2[k] = P2<T>::mk(sm.sB[6][(2 * k) * 32 + lane], sm.sB[6][(2 * k + 1) * 32 + lane]);
+    }
     static_assert(RW * KC <= 32, "one lane per tested (row, column chunk)");
     unsigned mybal = 0;     // lane r*KC+k keeps the ballot of (row r, columns k*32 .. k*32+31)
 #pragma unroll
     for (int r = 0; r < RW; r++) {
         const BoxRec<T> &a = sm.sA[w * RW + r];
-        const T ax = a.cx, ay = a.cy, ar = a.rho;
+        const PV ax2 = P2<T>::mk(a.cx, a.cx), ay2 = P2<T>::mk(a.cy, a.cy), ar2 = P2<T>::mk(a.rho, a.rho);
 #pragma unroll
-        for (int k = 0; k < KC; k++) {
-            T dx = ax - bx[k], dy = ay - by[k], rs = ar + br[k];
-            const unsigned bal = __ballot_sync(0xffffffffu, dx * dx + dy * dy <= rs * rs);   // false for NaN padding
-            if (lane == (unsigned)(r * KC + k)) mybal = bal;
+        for (int k = 0; k < KC / 2; k++) {
+            const PV dx = P2<T>::sub(ax2, bx2[k]), dy = P2<T>::sub(ay2, by2[k]), rs = P2<T>::add(ar2, br2[k]);
+            const PV d2 = P2<T>::fma(dy, dy, P2<T>::mul(dx, dx)), r2 = P2<T>::mul(rs, rs);
+            const unsigned bal0 = __ballot_sync(0xffffffffu, d2.x <= r2.x);   // false for NaN padding
+            const unsigned bal1 = __ballot_sync(0xffffffffu, d2.y <= r2.y);
+            if (lane == (unsigned)(r * KC + 2 * k)) mybal = bal0;
+            if (lane == (unsigned)(r * KC + 2 * k + 1)) mybal = bal1;
         }
     }
     // ---- pack: exclusive prefix of the per-(row, chunk) counts; lane r*KC+k expands its ballot into the warp queue, so
