@@ -219,8 +219,11 @@ __global__ void __launch_bounds__(256) nms_bin_kernel(const BoxRec<T> *__restric
 }
 
 constexpr int NMS_PAIR_THREADS = 256;
+#ifndef D3D_NMS_PAIR_CTAS
+#define D3D_NMS_PAIR_CTAS 3   // 85 registers: 1.54 ms on C3 against 1.62 ms with 2 CTAs (92 registers) and 1.55 ms with 4 (tools/nms_occ_probe.sh)
+#endif
 template <typename T>
-__global__ void __launch_bounds__(NMS_PAIR_THREADS) nms_pairs_kernel(const BoxRec<T> *__restrict__ recs, const T *__restrict__ raw, int64_t n, int64_t nwords, T thr,
+__global__ void __launch_bounds__(NMS_PAIR_THREADS, D3D_NMS_PAIR_CTAS) nms_pairs_kernel(const BoxRec<T> *__restrict__ recs, const T *__restrict__ raw, int64_t n, int64_t nwords, T thr,
                                                                     const NmsGrid *__restrict__ g, const uint32_t *__restrict__ cellptr,
                                                                     const NmsCand<T> *__restrict__ celllist, const NmsLists lists)
 {
