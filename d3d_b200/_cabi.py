@@ -46,7 +46,7 @@ iou2dr = {F32: _sig("d3d_iou2dr_f32", C.c_int, _iou_sig), F64: _sig("d3d_iou2dr_
 iou2d = {F32: _sig("d3d_iou2d_f32", C.c_int, _iou_sig), F64: _sig("d3d_iou2d_f64", C.c_int, _iou_sig)}
 iou3d_distance_workspace_bytes = _sig("d3d_iou3d_distance_workspace_bytes", _sz, [_i64, _i64])
 iou3d_distance = _sig("d3d_iou3d_distance_f32", C.c_int, [_vp, _i64, _vp, _i64, C.c_int, _vp, _i64, _vp, _sz, _vp])
-crop_workspace_bytes = _sig("d3d_crop2dr_workspace_bytes", _sz, [_i64, C.c_int])
+crop_workspace_bytes = _sig("d3d_crop2dr_workspace_bytes", _sz, [_i64, _i64, C.c_int])
 _crop_sig = [_vp, _i64, _vp, _i64, _vp, _vp, _sz, _vp]
 crop2dr = {F32: _sig("d3d_crop2dr_f32", C.c_int, _crop_sig), F64: _sig("d3d_crop2dr_f64", C.c_int, _crop_sig)}
 iou_count_candidates = _sig("d3d_iou_count_candidates", C.c_int, [_vp, _i64, _vp, _i64, C.c_int, _vp, _vp, _sz, _vp])

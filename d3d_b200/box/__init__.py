@@ -108,7 +108,7 @@ def crop_2dr_cuda(points, boxes):
     n, m = points.shape[0], boxes.shape[0]
     mask = torch.empty((m, n), dtype=torch.bool, device=points.device)
     if n and m:
-        ws = _c.workspace(_c.crop_workspace_bytes(m, code), points.device)
+        ws = _c.workspace(_c.crop_workspace_bytes(n, m, code), points.device)
         with torch.cuda.device(points.device):
             st = _c.crop2dr[code](_c.ptr(points), n, _c.ptr(boxes), m, _c.ptr(mask), _c.ptr(ws), ws.numel(), _c.stream_ptr())
         _c.check(st, "box2dr_crop")

@@ -12,6 +12,8 @@
 // The per-pair arithmetic uses the explicit round-to-nearest intrinsics: the reference is compiled without FMA
 // contraction and the mask is compared bit for bit.
 #include "common.cuh"
+#include "prims.cuh"
+#include <stdlib.h>
 
 namespace d3d {
 
@@ -55,10 +57,14 @@ __global__ void __launch_bounds__(256) crop_prep_kernel(const T *__restrict__ bo
 
 constexpr int CROP_THREADS = 256, CROP_PPT = 16, CROP_BT = 16;   // points per thread, boxes per CTA
 
+struct CropGrid;
+__device__ __forceinline__ bool crop_grid_ok(const CropGrid *g);
+
 template <typename T>
 __global__ void __launch_bounds__(CROP_THREADS) crop2dr_kernel(const T *__restrict__ pts, int64_t n, const CropBox<T> *__restrict__ recs, int64_t m,
-                                                               uint8_t *__restrict__ mask)
+                                                               uint8_t *__restrict__ mask, const CropGrid *__restrict__ skip_if_grid)
 {
+    if (skip_if_grid && crop_grid_ok(skip_if_grid)) return;   // the grid path produced the mask
     __shared__ CropBox<T> sb[CROP_BT];
     const int64_t box0 = (int64_t)blockIdx.y * CROP_BT;
     const int nb = (int)(m - box0 < CROP_BT ? m - box0 : CROP_BT);
@@ -100,7 +106,123 @@ __global__ void __launch_bounds__(CROP_THREADS) crop2dr_kernel(const T *__restri
     }
 }
 
-template <typename T> static size_t crop_ws_bytes(int64_t m) { return align_up((size_t)(m > 0 ? m : 1) * sizeof(CropBox<T>)) + 256; }
+// ------------------------------------------------------------------ grid path
+// The brute-force kernel above spends ~10 ALU instructions on every (box, point) pair although a box contains a tiny
+// fraction of the cloud.  For large problems the points are binned once into a 256 x 256 grid over their extent
+// (cell-sorted records x, y, index); the mask is zero-filled at memset speed and one warp per box visits only the
+// cells its AABB touches -- a contiguous run of the sorted list per grid row -- and stores a 1 for the points inside.
+// The decision per point is the same code as above, so the mask is identical; the cell of a coordinate is a monotone
+// function of it (subtract, multiply by a positive constant, floor, clamp), so every point strictly inside the AABB
+// lies in a cell between the cells of the AABB's bounds.
+constexpr int CG = 256, CG_CELLS = CG * CG;
+struct CropGrid { float minx, miny, invx, invy; uint32_t ok, pad[3]; };
+__device__ __forceinline__ bool crop_grid_ok(const CropGrid *g) { return g->ok != 0u; }
+template <typename T> struct __align__(16) CropPt { T x, y; uint32_t idx, pad; };
+
+__device__ __forceinline__ uint32_t f2ord(float f) { const uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float ord2f(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); }
+
+// acc[0..3] = ordered-int min x, max x, min y, max y; acc[4] = a non-finite coordinate was seen
+template <typename T>
+__global__ void __launch_bounds__(256) crop_bounds_kernel(const T *__restrict__ pts, int64_t n, uint32_t *__restrict__ acc)
+{
+    float mnx = 3e38f, mxx = -3e38f, mny = 3e38f, mxy = -3e38f;
+    int bad = 0;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        const float x = (float)pts[2 * j], y = (float)pts[2 * j + 1];   // the grid only needs float bounds (rounded outwards below)
+        if (!(fabsf(x) < 1e30f) || !(fabsf(y) < 1e30f)) bad = 1;
+        mnx = fminf(mnx, x); mxx = fmaxf(mxx, x); mny = fminf(mny, y); mxy = fmaxf(mxy, y);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, d)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, d)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
+        bad |= __shfl_xor_sync(0xffffffffu, bad, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(acc + 0, f2ord(mnx)); atomicMax(acc + 1, f2ord(mxx)); atomicMin(acc + 2, f2ord(mny)); atomicMax(acc + 3, f2ord(mxy));
+        if (bad) acc[4] = 1u;
+    }
+}
+
+__global__ void crop_grid_kernel(const uint32_t *__restrict__ acc, CropGrid *__restrict__ g)
+{
+    CropGrid o;
+    const float mnx = ord2f(acc[0]), mxx = ord2f(acc[1]), mny = ord2f(acc[2]), mxy = ord2f(acc[3]);
+    o.minx = mnx; o.miny = mny; o.ok = 0; o.pad[0] = o.pad[1] = o.pad[2] = 0;
+    const float ex = mxx - mnx, ey = mxy - mny;
+    o.invx = ex > 0 ? (float)CG / ex : 0.f; o.invy = ey > 0 ? (float)CG / ey : 0.f;
+    if (!acc[4] && ex >= 0 && ey >= 0 && ex < 1e30f && ey < 1e30f && (ex > 0 || ey > 0)) o.ok = 1;
+    *g = o;
+}
+
+// cell coordinate of a value: monotone in v (the double -> float conversion of the fp64 instantiation is monotone too)
+__device__ __forceinline__ int crop_cell(float v, float lo, float inv) { return min(CG - 1, max(0, (int)floorf((v - lo) * inv))); }
+
+template <typename T, int PASS>
+__global__ void __launch_bounds__(256) crop_bin_kernel(const T *__restrict__ pts, int64_t n, const CropGrid *__restrict__ g, uint32_t *__restrict__ cellcnt,
+                                                       const uint32_t *__restrict__ cellptr, CropPt<T> *__restrict__ sorted)
+{
+    if (!g->ok) return;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const T x = pts[2 * j], y = pts[2 * j + 1];
+    const uint32_t c = (uint32_t)(crop_cell((float)y, g->miny, g->invy) * CG + crop_cell((float)x, g->minx, g->invx));
+    const uint32_t at = atomicAdd(cellcnt + c, 1u);
+    if (PASS == 1) { CropPt<T> e; e.x = x; e.y = y; e.idx = (uint32_t)j; e.pad = 0; sorted[cellptr[c] + at] = e; }
+}
+
+template <typename T>
+__device__ __forceinline__ bool crop_inside(const CropBox<T> &B, T px, T py)
+{
+    bool in = px > B.minx && px < B.maxx && py > B.miny && py < B.maxy;
+    if (in) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int a = (e + 3) & 3;
+            const T c = rn_sub(rn_mul(rn_sub(B.vx[e], B.vx[a]), rn_sub(py, B.vy[e])), rn_mul(rn_sub(B.vy[e], B.vy[a]), rn_sub(px, B.vx[e])));
+            in = in && !(c < T(0));
+        }
+    }
+    return in;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) crop_grid_boxes_kernel(const CropPt<T> *__restrict__ sorted, int64_t n, const CropBox<T> *__restrict__ recs, int64_t m,
+                                                              const CropGrid *__restrict__ g, const uint32_t *__restrict__ cellptr, uint8_t *__restrict__ mask)
+{
+    if (!g->ok) return;
+    // one CTA per box, one warp per grid row of its AABB, one lane per point of the row's run: a box that sits on a dense part
+    // of the cloud (a lidar's first metres hold a third of the points) spreads over 256 threads instead of one warp
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int64_t i = blockIdx.x;
+    if (i >= m) return;
+    const CropBox<T> B = recs[i];
+    if (!(B.minx < B.maxx) || !(B.miny < B.maxy)) return;   // empty or NaN box: no point passes the open AABB test
+    const CropGrid G = *g;
+    // float bounds rounded outwards, so that the cell range covers the exact AABB of the fp64 instantiation as well
+    const float lx = sizeof(T) == 8 ? __double2float_rd((double)B.minx) : (float)B.minx, hx = sizeof(T) == 8 ? __double2float_ru((double)B.maxx) : (float)B.maxx;
+    const float ly = sizeof(T) == 8 ? __double2float_rd((double)B.miny) : (float)B.miny, hy = sizeof(T) == 8 ? __double2float_ru((double)B.maxy) : (float)B.maxy;
+    const int x0 = crop_cell(lx, G.minx, G.invx), x1 = crop_cell(hx, G.minx, G.invx);
+    const int y0 = crop_cell(ly, G.miny, G.invy), y1 = crop_cell(hy, G.miny, G.invy);
+    uint8_t *row = mask + i * n;
+    for (int cy = y0 + (int)warp; cy <= y1; cy += (int)nwarps) {
+        const uint32_t beg = cellptr[cy * CG + x0], end = cellptr[cy * CG + x1 + 1];   // the cells of one grid row are contiguous in the sorted list
+        for (uint32_t k = beg + lane; k < end; k += 32) {
+            const CropPt<T> p = sorted[k];
+            if (crop_inside<T>(B, p.x, p.y)) row[p.idx] = 1;
+        }
+    }
+}
+
+template <typename T> static size_t crop_grid_ws_bytes(int64_t n)
+{
+    return align_up(64) + align_up(sizeof(CropGrid)) + 2 * align_up((size_t)2 * (CG_CELLS + 1) * 4) + align_up((size_t)(n > 0 ? n : 1) * sizeof(CropPt<T>)) +
+           align_up(scan_workspace_bytes(CG_CELLS + 1));
+}
+template <typename T> static size_t crop_ws_bytes(int64_t m, int64_t n) { return align_up((size_t)(m > 0 ? m : 1) * sizeof(CropBox<T>)) + 256 + crop_grid_ws_bytes<T>(n); }
+
+constexpr int64_t CROP_GRID_MIN_PAIRS = 64ll << 20;   // below this the binning costs more than the brute-force pass
 
 template <typename T>
 static int crop_impl(const T *pts, int64_t n, const T *boxes, int64_t m, uint8_t *mask, void *ws, size_t ws_bytes, cudaStream_t st)
@@ -108,19 +230,47 @@ static int crop_impl(const T *pts, int64_t n, const T *boxes, int64_t m, uint8_t
     if (n < 0 || m < 0) return D3D_ERR_INVALID_ARGUMENT;
     if (n == 0 || m == 0) return D3D_OK;
     if (!pts || !boxes || !mask) return D3D_ERR_INVALID_ARGUMENT;
-    if (!ws || ws_bytes < crop_ws_bytes<T>(m)) return D3D_ERR_WORKSPACE;
+    if (!ws || ws_bytes < crop_ws_bytes<T>(m, n)) return D3D_ERR_WORKSPACE;
     const int64_t gy = cdiv(m, CROP_BT), gx = cdiv(n, (int64_t)CROP_THREADS * CROP_PPT);
-    if (gy > 65535 || gx > 0x7fffffffll) return D3D_ERR_INVALID_ARGUMENT;   // up to ~1M boxes per call
-    CropBox<T> *recs = reinterpret_cast<CropBox<T> *>(ws);
+    if (gy > 65535 || gx > 0x7fffffffll || n >= (1ll << 32)) return D3D_ERR_INVALID_ARGUMENT;   // up to ~1M boxes per call
+    Arena a(ws, ws_bytes);
+    CropBox<T> *recs = a.take<CropBox<T>>(m);
     crop_prep_kernel<T><<<(unsigned)cdiv(m, 256), 256, 0, st>>>(boxes, m, recs); D3D_LAUNCHED();
-    crop2dr_kernel<T><<<dim3((unsigned)gx, (unsigned)gy), CROP_THREADS, 0, st>>>(pts, n, recs, m, mask); D3D_LAUNCHED();
+    int mode = 0;   // tuning / test override: D3D_B200_CROP_PATH=brute | grid
+    if (const char *e = getenv("D3D_B200_CROP_PATH")) mode = e[0] == 'b' ? 1 : (e[0] == 'g' ? 2 : 0);
+    const bool grid = mode == 2 || (mode == 0 && m * n >= CROP_GRID_MIN_PAIRS);
+    if (!grid) {
+        crop2dr_kernel<T><<<dim3((unsigned)gx, (unsigned)gy), CROP_THREADS, 0, st>>>(pts, n, recs, m, mask, nullptr); D3D_LAUNCHED();
+        return D3D_OK;
+    }
+    uint32_t *acc = a.take<uint32_t>(16);
+    CropGrid *g = a.take<CropGrid>(1);
+    uint32_t *cellcnt = a.take<uint32_t>((size_t)2 * (CG_CELLS + 1));
+    uint32_t *cellptr = a.take<uint32_t>((size_t)2 * (CG_CELLS + 1));
+    CropPt<T> *sorted = a.take<CropPt<T>>(n);
+    void *scan_ws = a.take<char>(scan_workspace_bytes(CG_CELLS + 1));
+    if (!a.ok()) return D3D_ERR_WORKSPACE;
+    const uint32_t init[5] = {0xffffffffu, 0u, 0xffffffffu, 0u, 0u};
+    D3D_CUDA_TRY(cudaMemcpyAsync(acc, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    D3D_CUDA_TRY(cudaMemsetAsync(cellcnt, 0, (size_t)2 * (CG_CELLS + 1) * 4, st));
+    D3D_CUDA_TRY(cudaMemsetAsync(mask, 0, (size_t)m * n, st));
+    const unsigned gb = (unsigned)cdiv(n, 256);
+    crop_bounds_kernel<T><<<gb < 592 ? gb : 592, 256, 0, st>>>(pts, n, acc); D3D_LAUNCHED();
+    crop_grid_kernel<<<1, 1, 0, st>>>(acc, g); D3D_LAUNCHED();
+    crop_bin_kernel<T, 0><<<gb, 256, 0, st>>>(pts, n, g, cellcnt, nullptr, nullptr); D3D_LAUNCHED();
+    int rc = exclusive_scan_u32(cellcnt, cellptr, CG_CELLS + 1, nullptr, scan_ws, st);
+    if (rc) return rc;
+    crop_bin_kernel<T, 1><<<gb, 256, 0, st>>>(pts, n, g, cellcnt + CG_CELLS + 1, cellptr, sorted); D3D_LAUNCHED();
+    crop_grid_boxes_kernel<T><<<(unsigned)m, 256, 0, st>>>(sorted, n, recs, m, g, cellptr, mask); D3D_LAUNCHED();
+    // geometry that admits no grid (non-finite points, all points identical): the brute-force pass runs instead (it leaves at once otherwise)
+    crop2dr_kernel<T><<<dim3((unsigned)gx, (unsigned)gy), CROP_THREADS, 0, st>>>(pts, n, recs, m, mask, g); D3D_LAUNCHED();
     return D3D_OK;
 }
 
 }  // namespace d3d
 
 using namespace d3d;
-extern "C" size_t d3d_crop2dr_workspace_bytes(int64_t m, int dtype) { return dtype == D3D_F64 ? crop_ws_bytes<double>(m) : crop_ws_bytes<float>(m); }
+extern "C" size_t d3d_crop2dr_workspace_bytes(int64_t n, int64_t m, int dtype) { return dtype == D3D_F64 ? crop_ws_bytes<double>(m, n) : crop_ws_bytes<float>(m, n); }
 extern "C" int d3d_crop2dr_f32(const float *points, int64_t n, const float *boxes, int64_t m, uint8_t *mask, void *ws, size_t wsb, void *stream)
 { return crop_impl<float>(points, n, boxes, m, mask, ws, wsb, (cudaStream_t)stream); }
 extern "C" int d3d_crop2dr_f64(const double *points, int64_t n, const double *boxes, int64_t m, uint8_t *mask, void *ws, size_t wsb, void *stream)

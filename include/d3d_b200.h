@@ -82,8 +82,9 @@ int d3d_iou3d_distance_f32(const float *boxes1, int64_t n, const float *boxes2, 
 /* Point-in-rotated-box mask: mask u8[m boxes, n points] row-major, 1 where the point lies inside
  * the box.  points [n,2], boxes [m,5] (x, y, w, h, r).  Replaces crop_2dr (reference d3d/box/utils.h:45, utils.cpp:10-47,
  * bound at d3d/box/impl.cpp:26 and called by box2dr_crop / box3dp_crop, d3d/box/__init__.py:278-314); the reference
- * has no CUDA version.  Same decision rule as dgal: open AABB test, then no edge with a negative cross product. */
-size_t d3d_crop2dr_workspace_bytes(int64_t m, int dtype);
+ * has no CUDA version.  Same decision rule as dgal: open AABB test, then no edge with a negative cross product.
+ * Large problems bin the points into a grid first and zero-fill the mask; the result does not depend on the back end. */
+size_t d3d_crop2dr_workspace_bytes(int64_t n, int64_t m, int dtype);
 int d3d_crop2dr_f32(const float *points, int64_t n, const float *boxes, int64_t m, uint8_t *mask, void *workspace,
                     size_t workspace_bytes, void *stream);
 int d3d_crop2dr_f64(const double *points, int64_t n, const double *boxes, int64_t m, uint8_t *mask, void *workspace,

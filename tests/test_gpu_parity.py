@@ -183,7 +183,7 @@ def test_box3d_iou_distance_vs_oracle(dev, oracle):
         box3d_iou_distance(torch.zeros((3, 7)), torch.zeros((3, 7)), metric="giou")
 
 
-def test_box_crop_vs_reference_and_oracle(dev, oracle):
+def test_box_crop_vs_reference_and_oracle(dev, oracle, monkeypatch):
     """box2dr_crop / box3dp_crop.  Masks are compared bit for bit with the golden fixture written by the
     reference's own crop_2dr and with the oracle on ragged sizes; points closer than a few ulps to an edge could flip with
     the last-ulp difference between CUDA's and glibc's sin/cos (none do on these inputs)."""
@@ -200,8 +200,22 @@ def test_box_crop_vs_reference_and_oracle(dev, oracle):
         for dt in (np.float32, np.float64):
             pts = ((rng.random((n, 2)) - .5) * 12).astype(dt)
             bx = gen_boxes(rng, m).astype(dt)
-            got = box2dr_crop(_t(pts, dev), _t(bx, dev)).cpu().numpy()
-            assert np.array_equal(got, oracle.crop_2dr(pts, bx)), (n, m, dt)
+            exp = oracle.crop_2dr(pts, bx)
+            for path in ("brute", "grid"):   # both back ends (the grid over the points is the default from 64 M pairs on)
+                monkeypatch.setenv("D3D_B200_CROP_PATH", path)
+                got = box2dr_crop(_t(pts, dev), _t(bx, dev)).cpu().numpy()
+                assert np.array_equal(got, exp), (n, m, dt, path)
+            monkeypatch.delenv("D3D_B200_CROP_PATH")
+    # grid path corner cases: boxes far outside the cloud, a degenerate (flat) box, clustered points, a NaN point (falls back to brute force)
+    pts = np.concatenate([rng.normal(0, 0.01, (5000, 2)), (rng.random((5000, 2)) - .5) * 200]).astype(np.float32)
+    bx = np.array([[0, 0, 0.05, 0.05, 0.4], [1e6, 1e6, 5, 5, 0], [0, 0, 0, 3, 1], [0, 0, 400, 400, 0.1], [-90, 95, 30, 2, 2.0]], np.float32)
+    monkeypatch.setenv("D3D_B200_CROP_PATH", "grid")
+    assert np.array_equal(box2dr_crop(_t(pts, dev), _t(bx, dev)).cpu().numpy(), oracle.crop_2dr(pts, bx))
+    pts[17] = np.nan
+    assert np.array_equal(box2dr_crop(_t(pts, dev), _t(bx, dev)).cpu().numpy(), oracle.crop_2dr(pts, bx))
+    one = np.zeros((300, 2), np.float32)
+    assert np.array_equal(box2dr_crop(_t(one, dev), _t(bx, dev)).cpu().numpy(), oracle.crop_2dr(one, bx))
+    monkeypatch.delenv("D3D_B200_CROP_PATH")
     # reference test/test_box.py:191-205
     cloud = (rng.random((100, 2)) * 2 - 1).astype(np.float32)
     boxes = np.array([[0, 0, 1, 1, 0], [0, 0, 1, 1, np.pi / 4]], np.float32)
