@@ -55,6 +55,36 @@ class _Arena:
         return self.buf[start:start + nbytes].view(dtype).view(*shape)
 
 
+class _Chunked:
+    """The per-frame results of all chunks as one list-like object.  Frame dicts are created when they are asked for
+    (a batch of 128 frames is 640 tensor views: building them eagerly costs more host time than a chunk's kernel)."""
+
+    def __init__(self, parts):
+        self.parts, self.starts, n = parts, [], 0
+        for p in parts:
+            self.starts.append(n)
+            n += len(p)
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self.n))]
+        if i < 0:
+            i += self.n
+        if not 0 <= i < self.n:
+            raise IndexError(i)
+        import bisect
+        c = bisect.bisect_right(self.starts, i) - 1
+        return self.parts[c][i - self.starts[c]]
+
+    def __iter__(self):
+        for p in self.parts:
+            yield from p
+
+
 def _slots(gen, nslots, cap_points, cap_frames, max_frame, nfeat, dev):
     """per-stream device buffers (input points, packed outputs, scratch), kept on the generator between calls:
     allocating them per chunk costs more host time than the chunk's kernel takes"""
@@ -90,7 +120,10 @@ def host_batch(gen, frames, offs_host):
     cap_frames = max(f1 - f0 for f0, f1 in chunks)
     nstreams = min(NSTREAMS, len(chunks))
     slots = _slots(gen, nstreams, cap_points, cap_frames, max_frame, nfeat, dev)
-    streams = [torch.cuda.Stream(dev) for _ in range(nstreams)]
+    streams = getattr(gen, "_stream_pool", None)
+    if streams is None or len(streams) < nstreams or streams[0].device != dev:
+        streams = gen._stream_pool = [torch.cuda.Stream(dev) for _ in range(nstreams)]
+    streams = streams[:nstreams]
     cur = torch.cuda.current_stream(dev)
     for s in streams:
         s.wait_stream(cur)
@@ -164,7 +197,4 @@ def host_batch(gen, frames, offs_host):
     for s in streams:
         s.synchronize()
         cur.wait_stream(s)
-    out = []
-    for kind, r in results:
-        out.extend(r if kind == "dense" else list(r))
-    return out
+    return _Chunked([r for _, r in results])
