@@ -138,7 +138,9 @@ typedef struct d3d_voxel_params {
     int32_t reduction;  /* d3d_reduction_type */
     /* execution hints (no effect on results) */
     int32_t algo;              /* d3d_voxel_algo: AUTO picks the cluster path whenever it supports the configuration */
-    int64_t max_frame_points;  /* largest frame of the batch (host knows the offsets); 0 = unknown, assume `total` */
+    int64_t max_frame_points;  /* largest frame of the batch (host knows the offsets); 0 = unknown, assume `total`.
+                                * Pass it: it sizes the scratch AND selects the shared-memory routed path (frames of up to
+                                * 131072 points); with 0 a multi-frame batch runs on the slower L2 hash path. */
 } d3d_voxel_params;
 
 /* max_frame_points: largest frame of the batch (0 = unknown): bounds the per-frame scratch of the cluster path */
