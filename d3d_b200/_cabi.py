@@ -63,7 +63,7 @@ scatter_forward = _sig("d3d_aligned_scatter_forward", C.c_int, _sc_sig)
 scatter_backward = _sig("d3d_aligned_scatter_backward", C.c_int, _sc_sig)
 fma_peak_probe = _sig("d3d_fma_peak_probe", C.c_int, [C.c_int, _i64, _vp, C.POINTER(C.c_double), _vp])
 
-if abi_version() != 2:
+if abi_version() != 3:
     raise ImportError("libd3d_b200.so ABI version mismatch")
 
 
