@@ -386,17 +386,21 @@ using namespace d3d;
 extern "C" size_t d3d_voxelize_workspace_bytes(int64_t total_points, int64_t nframes, int64_t max_frame_points)
 {
     const int64_t t = total_points > 0 ? total_points : 1;
-    const size_t a = vox_ws_bytes(t, nframes), b = vox_cluster_ws_bytes(t, nframes, max_frame_points);
-    return a > b ? a : b;
+    const size_t a = vox_ws_bytes(t, nframes), b = vox_cluster_ws_bytes(t, nframes, max_frame_points), c = vox_tiles_ws_bytes(t, nframes, max_frame_points);
+    return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
-// AUTO: cluster path whenever it supports the configuration; an explicit request for an unsupported one is an error
-static int pick_algo(const d3d_voxel_params *P, const VoxCfg &cfg, int64_t total, int64_t nframes, bool *cluster)
+// AUTO: tile pipeline, else cluster path, whenever they support the configuration; an explicit request for an unsupported one is an error
+static int pick_algo(const d3d_voxel_params *P, const VoxCfg &cfg, int64_t total, int64_t nframes, bool *cluster, bool *tiles)
 {
-    if (P->algo < D3D_VOXEL_AUTO || P->algo > D3D_VOXEL_CLUSTER) return D3D_ERR_INVALID_ARGUMENT;
-    const bool ok = vox_cluster_supported(cfg, total, nframes, P->max_frame_points > 0 ? P->max_frame_points : total);
+    if (P->algo < D3D_VOXEL_AUTO || P->algo > D3D_VOXEL_AUTO_NO_TILES) return D3D_ERR_INVALID_ARGUMENT;
+    const int64_t mfp = P->max_frame_points > 0 ? P->max_frame_points : total;
+    const bool ok = vox_cluster_supported(cfg, total, nframes, mfp);
+    const bool okt = vox_tiles_supported(cfg, total, nframes, mfp);
     if (P->algo == D3D_VOXEL_CLUSTER && !ok) return D3D_ERR_UNSUPPORTED;
-    *cluster = ok && P->algo != D3D_VOXEL_SORT;
+    if (P->algo == D3D_VOXEL_TILES && !okt) return D3D_ERR_UNSUPPORTED;
+    *tiles = okt && (P->algo == D3D_VOXEL_AUTO || P->algo == D3D_VOXEL_TILES);
+    *cluster = !*tiles && ok && P->algo != D3D_VOXEL_SORT && P->algo != D3D_VOXEL_TILES;
     return D3D_OK;
 }
 
@@ -411,8 +415,13 @@ extern "C" int d3d_voxelize_sparse_f32(const float *points, int64_t total, int32
     if (total > 0 && (!out_points || !out_mask || !out_mapping || !out_npoints || !out_coords)) return D3D_ERR_INVALID_ARGUMENT;
     VoxCfg cfg;
     if ((rc = build_cfg(P, 0, nframes, &cfg))) return rc;
-    bool cluster = false;
-    if ((rc = pick_algo(P, cfg, total, nframes, &cluster))) return rc;
+    bool cluster = false, tiles = false;
+    if ((rc = pick_algo(P, cfg, total, nframes, &cluster, &tiles))) return rc;
+    if (tiles) {
+        if (!ws || ws_bytes < vox_tiles_ws_bytes(total > 0 ? total : 1, nframes, P->max_frame_points)) return D3D_ERR_WORKSPACE;
+        return vox_tiles_sparse(points, total, nfeat, offs, nframes, P->max_frame_points, cfg, out_points, out_mask, out_mapping, out_npoints, out_coords,
+                                counts, ws, ws_bytes, st);
+    }
     if (cluster) {
         if (!ws || ws_bytes < vox_cluster_ws_bytes(total > 0 ? total : 1, nframes, P->max_frame_points)) return D3D_ERR_WORKSPACE;
         return vox_cluster_sparse(points, total, nfeat, offs, nframes, P->max_frame_points, cfg, out_points, out_mask, out_mapping, out_npoints, out_coords,
@@ -458,8 +467,8 @@ extern "C" int d3d_voxelize_dense_f32(const float *points, int64_t total, int32_
     if (P->reduction != D3D_RED_NONE && !aggregates) return D3D_ERR_INVALID_ARGUMENT;
     VoxCfg cfg;
     if ((rc = build_cfg(P, 1, nframes, &cfg))) return rc;
-    bool cluster = false;
-    if ((rc = pick_algo(P, cfg, total, nframes, &cluster))) return rc;
+    bool cluster = false, tiles = false;
+    if ((rc = pick_algo(P, cfg, total, nframes, &cluster, &tiles))) return rc;
     if (!ws || ws_bytes < (cluster ? vox_cluster_ws_bytes(total > 0 ? total : 1, nframes, P->max_frame_points) : vox_ws_bytes(total > 0 ? total : 1, nframes)))
         return D3D_ERR_WORKSPACE;
     const size_t nslots = (size_t)nframes * (size_t)cfg.max_voxels * (size_t)cfg.max_points;

@@ -44,14 +44,76 @@ __device__ __forceinline__ bool vox_cell(const VoxCfg &cfg, float px, float py, 
     return ok;
 }
 
+// ---- 32-bit cell keys shared by the cluster path (voxel_cluster.cu) and the tile pipeline (voxel_tiles.cu)
+constexpr uint32_t VC_NOKEY = 0xffffffffu;   // cell keys use at most 31 bits
+// per-launch constants in the 32-bit form the kernel computes with
+struct VcDev {
+    float size[3], lo[3];
+    int vlo[3];
+    uint32_t ext[3];
+    uint32_t sh_x, sh_y;     // cell key = cx << sh_x | cy << sh_y | cz (bit fields: decoding is two shifts and two masks)
+    long long cadd[3];       // coords_out = c + vlo - offset
+};
+
+template <bool DENSE>
+__device__ __forceinline__ bool vc_cell(const VcDev &c, const float4 &p, uint32_t *key)
+{
+    float v0, v1, v2;
+    if (DENSE) {
+        v0 = __fdiv_rn(__fsub_rn(p.x, c.lo[0]), c.size[0]);
+        v1 = __fdiv_rn(__fsub_rn(p.y, c.lo[1]), c.size[1]);
+        v2 = __fdiv_rn(__fsub_rn(p.z, c.lo[2]), c.size[2]);
+    } else {
+        v0 = floorf(__fdiv_rn(p.x, c.size[0]));
+        v1 = floorf(__fdiv_rn(p.y, c.size[1]));
+        v2 = floorf(__fdiv_rn(p.z, c.size[2]));
+    }
+    const uint32_t c0 = (uint32_t)((int)v0 - c.vlo[0]), c1 = (uint32_t)((int)v1 - c.vlo[1]), c2 = (uint32_t)((int)v2 - c.vlo[2]);
+    *key = (c0 << c.sh_x) | (c1 << c.sh_y) | c2;
+    return v0 == v0 && v1 == v1 && v2 == v2 && c0 < c.ext[0] && c1 < c.ext[1] && c2 < c.ext[2];
+}
+
+static inline int vox_bits_for(long long ext)   // bits needed for coordinates 0 .. ext-1
+{
+    int b = 0;
+    while ((1ll << b) < ext) b++;
+    return b;
+}
+
+static inline bool vc_make_dev(const VoxCfg &cfg, VcDev *d)
+{
+    int bits[3];
+    for (int k = 0; k < 3; k++) {
+        if (cfg.ext[k] <= 0 || cfg.ext[k] > (1ll << 30)) return false;
+        if (cfg.vlo[k] <= -(1ll << 30) || cfg.vlo[k] >= (1ll << 30)) return false;   // 32-bit cell arithmetic in vc_cell
+        bits[k] = vox_bits_for(cfg.ext[k]);
+        d->size[k] = cfg.size[k]; d->lo[k] = cfg.lo[k];
+        d->vlo[k] = (int)cfg.vlo[k]; d->ext[k] = (uint32_t)cfg.ext[k];
+        d->cadd[k] = cfg.vlo[k] - cfg.offset[k];
+    }
+    if (bits[2] < 1) bits[2] = 1;   // keep the masks well defined for single-cell extents
+    if (bits[1] < 1) bits[1] = 1;
+    if (bits[0] + bits[1] + bits[2] > 31) return false;               // cell keys use at most 31 bits (VC_NOKEY is all ones)
+    d->sh_y = (uint32_t)bits[2];
+    d->sh_x = (uint32_t)(bits[2] + bits[1]);
+    return true;
+}
+
 // ---- cluster-per-frame back end (voxel_cluster.cu)
 // true when this configuration / problem size is served by the cluster path
 bool vox_cluster_supported(const VoxCfg &cfg, int64_t total, int64_t nframes, int64_t max_frame_points);
 size_t vox_cluster_ws_bytes(int64_t total, int64_t nframes, int64_t max_frame_points);
 int vox_cluster_sparse(const float *points, int64_t total, int nfeat, const int64_t *offs, int64_t nframes, int64_t max_frame_points, const VoxCfg &cfg,
                        float *out_points, int64_t *out_mask, int64_t *out_mapping, int32_t *out_npoints, int64_t *out_coords, int64_t *counts,
-                       void *ws, size_t ws_bytes, cudaStream_t st);
+                       void *ws, size_t ws_bytes, cudaStream_t st, const uint32_t *run_if = nullptr);
 int vox_cluster_dense(const float *points, int64_t total, int nfeat, const int64_t *offs, int64_t nframes, int64_t max_frame_points, const VoxCfg &cfg,
                       float *voxels, int64_t *coords, uint8_t *pmask, int32_t *npoints, int64_t *counts, void *ws, size_t ws_bytes, cudaStream_t st);
+
+// ---- tile pipeline (voxel_tiles.cu): sparse, no voxel cap, TRIM up to 8 points per voxel
+bool vox_tiles_supported(const VoxCfg &cfg, int64_t total, int64_t nframes, int64_t max_frame_points);
+size_t vox_tiles_ws_bytes(int64_t total, int64_t nframes, int64_t max_frame_points);
+int vox_tiles_sparse(const float *points, int64_t total, int nfeat, const int64_t *offs, int64_t nframes, int64_t max_frame_points, const VoxCfg &cfg,
+                     float *out_points, int64_t *out_mask, int64_t *out_mapping, int32_t *out_npoints, int64_t *out_coords, int64_t *counts,
+                     void *ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace d3d

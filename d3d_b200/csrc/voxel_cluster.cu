@@ -84,6 +84,9 @@ struct VcArgs {
     char *ws; VcLayout lay;
     unsigned long long *vstate, *kstate;   // sparse: cross-frame look-back words, one per frame (zeroed before the launch)
     uint32_t dyn_bytes;                    // dynamic shared memory of the launch
+    uint32_t *ticket;                      // frames are handed out in index order to the clusters that are running (zeroed before the launch)
+    uint32_t lmax;                         // hard upper bound of a frame's length: the scratch is sized for it, longer frames are cut
+    const uint32_t *run_if;                // optional device flag: the launch does nothing when it is zero (fallback of the tile pipeline)
     int route;                             // sparse: try the shared-memory routed path first (vc_frame_route)
 };
 
@@ -203,39 +206,11 @@ __device__ __forceinline__ void vc_exchange2(cg::cluster_group &cluster, const u
     }
 }
 
-// per-launch constants in the 32-bit form the kernel computes with
-struct VcDev {
-    float size[3], lo[3];
-    int vlo[3];
-    uint32_t ext[3];
-    uint32_t sh_x, sh_y;     // cell key = cx << sh_x | cy << sh_y | cz (bit fields: decoding is two shifts and two masks)
-    long long cadd[3];       // coords_out = c + vlo - offset
-};
-
 #ifndef D3D_VC_U
 #define D3D_VC_U 2
 #endif
 constexpr int VC_U = D3D_VC_U;     // points per thread in flight in the streaming phases: independent loads are issued back to back
 constexpr int VC_QCAP = 128;       // per-warp ring of points waiting for their next hash probe
-constexpr uint32_t VC_NOKEY = 0xffffffffu;   // cell keys use at most 31 bits
-
-template <bool DENSE>
-__device__ __forceinline__ bool vc_cell(const VcDev &c, const float4 &p, uint32_t *key)
-{
-    float v0, v1, v2;
-    if (DENSE) {
-        v0 = __fdiv_rn(__fsub_rn(p.x, c.lo[0]), c.size[0]);
-        v1 = __fdiv_rn(__fsub_rn(p.y, c.lo[1]), c.size[1]);
-        v2 = __fdiv_rn(__fsub_rn(p.z, c.lo[2]), c.size[2]);
-    } else {
-        v0 = floorf(__fdiv_rn(p.x, c.size[0]));
-        v1 = floorf(__fdiv_rn(p.y, c.size[1]));
-        v2 = floorf(__fdiv_rn(p.z, c.size[2]));
-    }
-    const uint32_t c0 = (uint32_t)((int)v0 - c.vlo[0]), c1 = (uint32_t)((int)v1 - c.vlo[1]), c2 = (uint32_t)((int)v2 - c.vlo[2]);
-    *key = (c0 << c.sh_x) | (c1 << c.sh_y) | c2;
-    return v0 == v0 && v1 == v1 && v2 == v2 && c0 < c.ext[0] && c1 < c.ext[1] && c2 < c.ext[2];
-}
 
 #ifdef D3D_VC_TIMING   // tuning build only: per-phase time of a few frames, printed once per frame
 #define VC_TICK(slot) do { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tk_[slot] = (float)(t_ - t0_) * 1e-3f; t0_ = t_; } while (0)
@@ -287,7 +262,7 @@ __device__ __forceinline__ void vc_frame_l2(const VcArgs &a, const VcDev &dv, co
 
     {
         const int64_t b = a.offs[f];
-        const uint32_t L = (uint32_t)(a.offs[f + 1] - b);
+        const uint32_t L = (uint32_t)min((long long)(a.offs[f + 1] - b), (long long)a.lmax);
         const uint32_t nslots = L + (L >> 1) + 64;
         const uint32_t nit = (L + W * 32 - 1) / (W * 32);   // 32-point rounds per warp
         const uint32_t wbeg = g * nit * 32;                 // this warp owns points [wbeg, wbeg + nit*32)
@@ -717,7 +692,7 @@ __device__ __forceinline__ bool vc_frame_route(const VcArgs &a, const VcDev &dv,
     const uint32_t vcap = cfg.vfilter != D3D_VF_NONE ? (cfg.max_voxels > 0 ? (uint32_t)cfg.max_voxels : 0u) : VC_NONE;
     const float4 *pts4 = reinterpret_cast<const float4 *>(a.pts) + a.offs[f];   // the routed path serves xyz+1 clouds (nfeat == 4)
 
-    const uint32_t L = (uint32_t)(a.offs[f + 1] - a.offs[f]);
+    const uint32_t L = (uint32_t)min((long long)(a.offs[f + 1] - a.offs[f]), (long long)a.lmax);
     const uint32_t nit = pl.nit, Lc = pl.Lc, cap = pl.cap, nslots = pl.nslots, smask = pl.nslots - 1, hshift = 32 - pl.lg;
     const uint32_t wbeg = g * nit * 32;        // frame-local index of this warp's first point
     const uint32_t lbeg = w * nit * 32;        // the same inside the CTA's range
@@ -1180,48 +1155,31 @@ __global__ void __launch_bounds__(VC_THREADS, 1) vox_cluster_kernel(const VcArgs
     sh.qcount = flags; sh.npool = flags + 1; sh.bail = flags + 2;
     sh.dyn = vc_dyn;
 
+    if (a.run_if && *a.run_if == 0) return;   // grid-uniform
     const bool route = !DENSE && a.route && a.nfeat == 4;
-    if (route) {
-        if (threadIdx.x < 8) flags[threadIdx.x] = 0;
-        cluster.sync();   // nobody pushes into a queue whose counter is not initialised yet
-    }
-    for (int64_t f = cid; f < a.nframes; f += ncl) {
+    __shared__ uint32_t s_frame;
+    if (threadIdx.x < 8) flags[threadIdx.x] = 0;
+    // Frames are taken from a ticket counter, not from the cluster index: a frame is only ever started by a cluster that
+    // is running, so the look-back (which waits for lower-numbered frames) cannot wait for a cluster that the hardware
+    // has not scheduled yet (other kernels on the GPU, MPS limits, out-of-order dispatch).
+    for (;;) {
+        if (cluster.block_rank() == 0 && threadIdx.x == 0) {
+            const uint32_t t = atomicAdd(a.ticket, 1u);
+            for (unsigned d = 0; d < csize; d++) *cluster.map_shared_rank(&s_frame, d) = t;
+        }
+        cluster.sync();   // also: nobody pushes into a queue whose counter is not initialised yet
+        const int64_t f = (int64_t)s_frame;
+        if (f >= a.nframes) break;
         if (route) {
             VrPlan pl;
-            if (vr_plan((uint32_t)(a.offs[f + 1] - a.offs[f]), csize, a.dyn_bytes, &pl) && vc_frame_route(a, dv, sh, cluster, f, pl, cid, ncl)) continue;
+            const uint32_t L = (uint32_t)min((long long)(a.offs[f + 1] - a.offs[f]), (long long)a.lmax);
+            if (vr_plan(L, csize, a.dyn_bytes, &pl) && vc_frame_route(a, dv, sh, cluster, f, pl, cid, ncl)) continue;
         }
         vc_frame_l2<DENSE>(a, dv, sh, cluster, f, cid, ncl);
-    }
-    if (route) cluster.sync();   // R6 of the last frame reads other CTAs' shared memory: nobody leaves before everybody is done
+    }   // the barrier at the top of the loop also separates this frame's remote shared-memory reads from the next frame's writes
 }
 
 // ------------------------------------------------------------------ host side
-static int bits_for(long long ext)   // bits needed for coordinates 0 .. ext-1
-{
-    int b = 0;
-    while ((1ll << b) < ext) b++;
-    return b;
-}
-
-static bool vc_make_dev(const VoxCfg &cfg, VcDev *d)
-{
-    int bits[3];
-    for (int k = 0; k < 3; k++) {
-        if (cfg.ext[k] <= 0 || cfg.ext[k] > (1ll << 30)) return false;
-        if (cfg.vlo[k] <= -(1ll << 30) || cfg.vlo[k] >= (1ll << 30)) return false;   // 32-bit cell arithmetic in vc_cell
-        bits[k] = bits_for(cfg.ext[k]);
-        d->size[k] = cfg.size[k]; d->lo[k] = cfg.lo[k];
-        d->vlo[k] = (int)cfg.vlo[k]; d->ext[k] = (uint32_t)cfg.ext[k];
-        d->cadd[k] = cfg.vlo[k] - cfg.offset[k];
-    }
-    if (bits[2] < 1) bits[2] = 1;   // keep the masks well defined for single-cell extents
-    if (bits[1] < 1) bits[1] = 1;
-    if (bits[0] + bits[1] + bits[2] > 31) return false;               // cell keys use at most 31 bits (VC_NOKEY is all ones)
-    d->sh_y = (uint32_t)bits[2];
-    d->sh_x = (uint32_t)(bits[2] + bits[1]);
-    return true;
-}
-
 bool vox_cluster_supported(const VoxCfg &cfg, int64_t total, int64_t nframes, int64_t max_frame_points)
 {
     (void)total; (void)nframes;
@@ -1239,7 +1197,7 @@ size_t vox_cluster_ws_bytes(int64_t total, int64_t nframes, int64_t max_frame_po
     if (max_frame_points <= 0 || max_frame_points > total) max_frame_points = total;
     int64_t ncl = nframes < VC_MAX_CLUSTERS ? nframes : VC_MAX_CLUSTERS;
     if (ncl < 1) ncl = 1;
-    return vc_layout(max_frame_points).total * (size_t)ncl + 256 + align_up((size_t)(nframes > 0 ? nframes : 1) * 16);
+    return vc_layout(max_frame_points).total * (size_t)ncl + 512 + align_up((size_t)(nframes > 0 ? nframes : 1) * 16);
 }
 
 // Cluster shape: CTAs of one cluster must sit in one GPC, and a B200's GPCs do not all expose a multiple of 8
@@ -1340,14 +1298,17 @@ static int vc_launch(VcArgs &args, int64_t nframes, int64_t max_frame_points, si
     if (const char *e = getenv("D3D_B200_VOX_MAXCL")) { int m = atoi(e); if (m > 0 && m < ncl) ncl = m; }   // tuning override
     if (ncl > nframes) ncl = nframes;
     if (ncl > VC_MAX_CLUSTERS) ncl = VC_MAX_CLUSTERS;
-    const size_t state_bytes = align_up((size_t)nframes * 16);
+    const size_t state_bytes = 256 + align_up((size_t)nframes * 16);
     while (ncl > 1 && args.lay.total * (size_t)ncl + 256 + state_bytes > ws_bytes) ncl--;
     if (args.lay.total * (size_t)ncl + 256 + state_bytes > ws_bytes) return D3D_ERR_WORKSPACE;
-    if (!DENSE) {   // look-back words live behind the cluster slices
-        args.vstate = reinterpret_cast<unsigned long long *>(args.ws + align_up(args.lay.total * (size_t)ncl));
+    {   // ticket counter and (sparse) look-back words live behind the cluster slices
+        char *state = args.ws + align_up(args.lay.total * (size_t)ncl);
+        args.ticket = reinterpret_cast<uint32_t *>(state);
+        args.vstate = reinterpret_cast<unsigned long long *>(state + 256);
         args.kstate = args.vstate + nframes;
-        D3D_CUDA_TRY(cudaMemsetAsync(args.vstate, 0, (size_t)nframes * 16, st));
+        D3D_CUDA_TRY(cudaMemsetAsync(state, 0, DENSE ? 256 : 256 + (size_t)nframes * 16, st));
     }
+    args.lmax = (uint32_t)(max_frame_points > 0 ? max_frame_points : 1);
     lc.gridDim = dim3((unsigned)(ncl * csize), 1, 1);
     D3D_CUDA_TRY(cudaLaunchKernelEx(&lc, kern, args, dv));
     D3D_LAUNCHED();
@@ -1356,10 +1317,11 @@ static int vc_launch(VcArgs &args, int64_t nframes, int64_t max_frame_points, si
 
 int vox_cluster_sparse(const float *points, int64_t total, int nfeat, const int64_t *offs, int64_t nframes, int64_t max_frame_points, const VoxCfg &cfg,
                        float *out_points, int64_t *out_mask, int64_t *out_mapping, int32_t *out_npoints, int64_t *out_coords, int64_t *counts,
-                       void *ws, size_t ws_bytes, cudaStream_t st)
+                       void *ws, size_t ws_bytes, cudaStream_t st, const uint32_t *run_if)
 {
     if (max_frame_points <= 0 || max_frame_points > total) max_frame_points = total;
     VcArgs a = {};
+    a.run_if = run_if;
     a.pts = points; a.nfeat = nfeat; a.offs = offs; a.nframes = nframes; a.cfg = cfg;
     a.out_points = out_points; a.out_mask = out_mask; a.out_mapping = out_mapping; a.out_npoints = out_npoints; a.out_coords = out_coords;
     a.counts = counts; a.ws = (char *)ws; a.lay = vc_layout(max_frame_points);

@@ -46,7 +46,7 @@ class VoxelGenerator:
     '''
     Convert point cloud to voxels (same constructor and result keys as the reference)
     '''
-    default_algo = "auto"   # back end of new instances: "auto" | "sort" | "cluster" (results are identical)
+    default_algo = "auto"   # back end of new instances: "auto" | "sort" | "cluster" | "tiles" | "auto_no_tiles" (results are identical)
 
     def __init__(self, bounds, shape,
         min_points=0, max_points=30, max_voxels=20000,
@@ -111,8 +111,9 @@ class VoxelGenerator:
         p.max_voxels_filter = int(self._max_voxels_filter)
         p.reduction = int(self._reduction)
         self._params = p
-        # execution back end, no effect on results: "auto" (cluster-per-frame hash path when it supports the
-        # configuration, else the sort pipeline), "sort", "cluster" (raises NotImplementedError if unsupported)
+        # execution back end, no effect on results: "auto" (tile pipeline, else cluster-per-frame hash path, else the sort
+        # pipeline -- the first that supports the configuration), "sort", "cluster" / "tiles" (raise NotImplementedError if
+        # unsupported), "auto_no_tiles" (auto without the tile pipeline)
         self.algo = VoxelGenerator.default_algo
 
     def __call__(self, points):
@@ -180,7 +181,7 @@ class VoxelGenerator:
         total, nfeat = int(pts.shape[0]), int(pts.shape[1])
         p = _c.VoxelParams.from_buffer_copy(self._params)
         p.max_frame_points = max_frame_points
-        p.algo = {"auto": 0, "sort": 1, "cluster": 2}[self.algo]
+        p.algo = {"auto": 0, "sort": 1, "cluster": 2, "tiles": 3, "auto_no_tiles": 4}[self.algo]
         with torch.cuda.device(pts.device):
             if self._dense:
                 if nframes < bufs["voxels"].shape[0]:

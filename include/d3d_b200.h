@@ -44,9 +44,11 @@ enum d3d_max_voxels_filter { D3D_VF_NONE = 0, D3D_VF_TRIM = 1, D3D_VF_DESCENDING
 /* reference d3d/point/scatter.h:37 */
 enum d3d_align_type { D3D_ALIGN_DROP = 0, D3D_ALIGN_MEAN = 1, D3D_ALIGN_LINEAR = 2, D3D_ALIGN_MAX = 3, D3D_ALIGN_NEAREST = 4 };
 enum d3d_dtype { D3D_F32 = 0, D3D_F64 = 1 };
-/* voxelization back ends: one thread-block cluster per frame with a hash table (fast path) or the
- * sort / segmented-scan pipeline (general).  Both produce identical, deterministic outputs. */
-enum d3d_voxel_algo { D3D_VOXEL_AUTO = 0, D3D_VOXEL_SORT = 1, D3D_VOXEL_CLUSTER = 2 };
+/* voxelization back ends: a software pipeline of streaming tiles (default fast path: sparse, no voxel cap, TRIM up
+ * to 8 points per voxel), one thread-block cluster per frame with a hash table, or the sort / segmented-scan
+ * pipeline (general).  All produce identical, deterministic outputs. */
+enum d3d_voxel_algo { D3D_VOXEL_AUTO = 0, D3D_VOXEL_SORT = 1, D3D_VOXEL_CLUSTER = 2, D3D_VOXEL_TILES = 3,
+                      D3D_VOXEL_AUTO_NO_TILES = 4 /* AUTO restricted to the cluster and sort back ends (A/B runs, tests) */ };
 
 int d3d_abi_version(void);
 const char *d3d_error_string(int status);
@@ -137,11 +139,12 @@ typedef struct d3d_voxel_params {
     float bound[6];     /* xmin,xmax,ymin,ymax,zmin,zmax; idx = (int)((p-lo)/((hi-lo)/shape)) */
     int32_t shape[3];
     int32_t reduction;  /* d3d_reduction_type */
-    /* execution hints (no effect on results) */
-    int32_t algo;              /* d3d_voxel_algo: AUTO picks the cluster path whenever it supports the configuration */
-    int64_t max_frame_points;  /* largest frame of the batch (host knows the offsets); 0 = unknown, assume `total`.
-                                * Pass it: it sizes the scratch AND selects the shared-memory routed path (frames of up to
-                                * 131072 points); with 0 a multi-frame batch runs on the slower L2 hash path. */
+    /* execution parameters */
+    int32_t algo;              /* d3d_voxel_algo: AUTO picks the fastest back end that supports the configuration (no effect on results) */
+    int64_t max_frame_points;  /* HARD UPPER BOUND of the frame lengths of the batch (the host knows the offsets); 0 = unknown,
+                                * assume `total`.  It sizes the per-frame scratch and the launch geometry of the fast paths: a
+                                * frame longer than this bound is cut to its first max_frame_points points.  With 0 a multi-frame
+                                * batch runs with scratch sized for one frame of `total` points (slower, never wrong). */
 } d3d_voxel_params;
 
 /* max_frame_points: largest frame of the batch (0 = unknown): bounds the per-frame scratch of the cluster path */

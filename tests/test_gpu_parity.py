@@ -344,12 +344,13 @@ EXPECT_DTYPES = dict(points=torch.float32, points_mask=torch.int64, points_mappi
                      coords=torch.int64, voxels=torch.float32, voxel_pmask=torch.bool, aggregates=torch.float32)
 
 
-@pytest.fixture(autouse=True, params=["auto", "sort"])
+@pytest.fixture(autouse=True, params=["auto", "sort", "auto_no_tiles"])
 def voxel_backend(request):
-    """every voxel test runs on both back ends: "auto" (cluster-per-frame hash path wherever it supports the
-    configuration) and "sort" (the general pipeline); the outputs must be bit-identical"""
+    """every voxel test runs on all back ends: "auto" (tile pipeline wherever it supports the configuration, else as
+    below), "auto_no_tiles" (cluster-per-frame hash path wherever it supports the configuration) and "sort" (the
+    general pipeline); the outputs must be bit-identical"""
     if "voxel" not in request.node.name:
-        if request.param == "sort":
+        if request.param != "auto":
             pytest.skip("back-end parameter only applies to the voxel tests")
         yield
         return
