@@ -1,31 +1,34 @@
-// voxel_tiles.cu -- sparse voxelization as a software pipeline of streaming tiles (the default fast path).
+// voxel_tiles.cu -- sparse voxelization as a pipeline of streaming tile kernels (the default fast path).
 //
 // Replaces voxelize_sparse + voxelize_filter (reference d3d/voxel/voxelize.cpp:288-484) for the common
-// configurations (no voxel cap, max_points filter NONE or TRIM with max_points <= 8); everything else goes to
-// the cluster path (voxel_cluster.cu) or the sort path (voxel.cu).  Same packed outputs, bit for bit.
+// configurations (no voxel cap, max_points filter NONE or TRIM with max_points <= 8, cell keys of <= 30 bits);
+// everything else goes to the cluster path (voxel_cluster.cu) or the sort path (voxel.cu).  Same packed outputs,
+// bit for bit.
 //
 // Why not one cluster per frame (voxel_cluster.cu): that kernel keeps a whole frame in the shared memory of 8 SMs,
 // which pins one 1024-thread CTA per SM, all warps of an SM in the same phase, on the 120 SMs that 8-CTA clusters
-// reach -- it is bound by exposed latency, not by HBM (ncu: issue slots 52 % busy, DRAM 15 %).  Here every stage is
-// an ordinary tile of 256 threads, several CTAs per SM on all 148 SMs, and the stages of different frames run side
-// by side in one launch ("tick"):
+// reach -- it is bound by exposed latency, not by HBM (ncu: issue slots 52 % busy, DRAM 15 %).  Here a chunk of
+// frames runs through four ordinary kernels, each with the block size, register budget and occupancy its stage
+// wants, on all 148 SMs:
 //
 //   split   (1024 points / CTA)  cell keys with the reference's fp32 arithmetic; a point's (key, index) goes to
-//                                the queue of the BUCKET its key hashes to (128 buckets for a 120k-point frame);
-//                                the tile reserves its share of every queue with one atomic per bucket.  The point's
-//                                word is its key: a point that hears nothing back is the only point of its voxel.
+//                                the queue of the BUCKET its key hashes to (256 buckets for a 120k-point frame);
+//                                the tile counts per bucket in shared memory and reserves its share of every queue
+//                                with one global atomic per bucket.  The point's word is its key: a point that
+//                                hears nothing back is the only point of its voxel.
 //   bucket  (one CTA / bucket)   all points of a voxel meet in one bucket: hash table in shared memory (CAS claim,
-//                                atomicMin of the point index, count), the K smallest indices of voxels with more
-//                                than K points by a min-cascade (level j keeps the j-th smallest of everything it
-//                                is offered and passes the larger value on: the result does not depend on the
+//                                atomicMin of the point index, count -- B200 issues a shared-memory atomic in
+//                                ~1.3 clk per warp, tools/warp_prims_probe.cu), the K smallest indices of voxels with
+//                                more than K points by a min-cascade (level j keeps the j-th smallest of everything
+//                                it is offered and passes the larger value on: the result does not depend on the
 //                                arrival order); the points that share a voxel get a new word.
 //   scan    (8192 points / CTA)  first-of-voxel and keep bits -> ballots -> one chained scan over all tiles of all
 //                                frames (decoupled look-back): voxel ids in order of first appearance, packed rows.
 //   write   (1024 points / CTA)  voxel rows and kept point rows streamed out; no barrier, no waiting.
 //
-// Tick k launches split(chunk k) + bucket(chunk k-1) + scan(chunk k-2) + write(chunk k-3), a chunk being a few
-// frames, so the scratch of the frames in flight (queues, words, row tables: ~1.3 MB per frame, plus the frame
-// itself) lives in L2 and HBM sees the algorithmic traffic only: 16 B/point in, 32 B/kept point + 28 B/voxel out.
+// A chunk is a few frames (16 by default), so the scratch of the chunk (queues, words, row tables: ~1.3 MB per
+// frame, plus the frame itself) lives in L2 between the kernels and HBM sees the algorithmic traffic only:
+// 16 B/point in, 32 B/kept point + 28 B/voxel out.
 //
 // Determinism: every output is a function of the point set (smallest index, count, K smallest indices, prefix
 // sums in point order), never of the race order of the queues and tables.
@@ -43,9 +46,12 @@ constexpr int VT_PPT = 4;                         // points per thread (split, w
 constexpr int VT_TILE = VT_THREADS * VT_PPT;      // 1024 points per tile
 constexpr int VT_SPT = 32;                        // points per thread (scan): lane u of a warp keeps the warp's row u
 constexpr int VT_STILE = VT_THREADS * VT_SPT;     // 8192 points per scan tile
-constexpr int VT_STAGES = 4;
+constexpr int VT_BT = 128;                        // threads of a bucket CTA
+constexpr int VT_EPT = 8;                         // queue entries per bucket thread, all in registers
+constexpr int VT_QCAP = VT_BT * VT_EPT;           // largest queue a bucket CTA takes
+constexpr int VT_SMAX = 1024;                     // table slots per bucket (maximum)
 constexpr int VT_MAXK = 8;                        // deepest min-cascade (max_points of the TRIM filter)
-constexpr int VT_POOL = 128;                      // crowded-voxel records per bucket
+constexpr int VT_POOL = 64;                       // crowded-voxel records per bucket
 constexpr uint32_t VT_NONE = 0xffffffffu;         // empty table slot / queue entry
 // point word, category in bits 31:30 -- 0: cell key (<= 30 bits) of a point that is alone in its voxel | 1: nothing to write |
 // 2: kept point of a shared voxel + index of the voxel's first point | 3: first point of a shared voxel + point count
@@ -55,7 +61,7 @@ constexpr uint32_t VT_F31 = 0x7fffffffu;
 
 struct VtGeom {
     uint32_t lmax, lpad, tpf, spf; // longest frame, padded to whole scan tiles, tiles / scan tiles per frame
-    uint32_t lgP, P, lgS, S, qcap; // buckets per frame, table slots per bucket (maximum), queue entries per bucket
+    uint32_t lgP, P, qcap;         // buckets per frame, queue entries per bucket
     uint32_t CF, nchunks;          // frames per chunk, chunks
 };
 
@@ -122,29 +128,24 @@ __device__ __forceinline__ void vt_decode(const VtArgs &a, uint32_t w, bool *hea
 
 // ------------------------------------------------------------------------------------------------ split
 template <bool NF4>
-__device__ __forceinline__ void vt_split(const VtArgs &a, const VcDev &dv, uint32_t lt, uint32_t chunk, unsigned char *dyn)
+__global__ void __launch_bounds__(VT_THREADS, 6) vt_split_kernel(const VtArgs a, const VcDev dv, uint32_t chunk)
 {
+    extern __shared__ __align__(16) unsigned char vt_dyn[];
     const VtGeom &g = a.g;
-    const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
-    const unsigned ltmask = lanemask_lt();
-    const uint32_t fl = lt / g.tpf, t = lt - fl * g.tpf;
+    const unsigned tid = threadIdx.x;
+    const uint32_t fl = blockIdx.y, t = blockIdx.x;
     const int64_t f = (int64_t)chunk * g.CF + fl;
-    const uint32_t slot = (chunk % VT_STAGES) * g.CF + fl;
     const int64_t b = a.offs[f];
     const uint32_t L = (uint32_t)min((long long)(a.offs[f + 1] - b), (long long)g.lmax);
     const uint32_t t0 = t * VT_TILE;
     if (t0 >= L) return;
 
-    // Shared-memory atomics run at ~0.5 lanes per clock: the tile's histogram over the buckets is kept per warp instead
-    // (lanes of a warp that hit the same bucket find each other with match.any, the first of them does a plain
-    // read-modify-write of the warp's counter), and the warps' counters are chained afterwards.
-    uint32_t *base = reinterpret_cast<uint32_t *>(dyn);                         // [P] first queue position of the tile per bucket
-    uint16_t *wh = reinterpret_cast<uint16_t *>(base + g.P), *whw = wh + w * g.P;   // [8][P] per-warp counts, then exclusive offsets
-    uint32_t *word = a.word + (size_t)slot * g.lpad;
-    uint32_t *qcount = a.qcount + (size_t)slot * g.P;
-    uint2 *queue = a.queue + (size_t)slot * g.P * g.qcap;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(vt_dyn), *base = hist + g.P;
+    uint32_t *word = a.word + (size_t)fl * g.lpad;
+    uint32_t *qcount = a.qcount + (size_t)fl * g.P;
+    uint2 *queue = a.queue + (size_t)fl * g.P * g.qcap;
 
-    for (uint32_t p = tid; p < g.P * (VT_WARPS / 2); p += VT_THREADS) reinterpret_cast<uint32_t *>(wh)[p] = 0u;
+    for (uint32_t p = tid; p < g.P; p += VT_THREADS) hist[p] = 0;
     __syncthreads();
 
     float4 p4[VT_PPT];
@@ -165,21 +166,14 @@ __device__ __forceinline__ void vt_split(const VtArgs &a, const VcDev &dv, uint3
         uint32_t key;
         const bool ok = vc_cell<false>(dv, p4[u], &key) && in[u];
         keys[u] = ok ? key : VC_NOKEY;
+        rank[u] = 0;
         if (in[u]) word[t0 + u * VT_THREADS + tid] = (ok && a.single_ok) ? key : VT_W_NONE;   // min_points > 1: a lone point is dropped
-        const uint32_t bk = ok ? vt_bucket(key, g.lgP) : VT_NONE;
-        const unsigned m = __match_any_sync(0xffffffffu, bk);
-        const int leader = __ffs((int)m) - 1;
-        uint32_t old = 0;
-        if (ok && lane == (unsigned)leader) { old = whw[bk]; whw[bk] = (uint16_t)(old + __popc(m)); }
-        rank[u] = __shfl_sync(0xffffffffu, old, leader) + __popc(m & ltmask);
-        __syncwarp();
+        if (ok) rank[u] = atomicAdd(&hist[vt_bucket(key, g.lgP)], 1u);
     }
     __syncthreads();
     for (uint32_t p = tid; p < g.P; p += VT_THREADS) {
-        uint32_t run = 0;
-#pragma unroll
-        for (int k = 0; k < VT_WARPS; k++) { const uint32_t c = wh[k * g.P + p]; wh[k * g.P + p] = (uint16_t)run; run += c; }
-        base[p] = run ? atomicAdd(&qcount[p], run) : 0u;
+        const uint32_t c = hist[p];
+        base[p] = c ? atomicAdd(&qcount[p], c) : 0u;
     }
     __syncthreads();
     bool over = false;
@@ -187,7 +181,7 @@ __device__ __forceinline__ void vt_split(const VtArgs &a, const VcDev &dv, uint3
     for (int u = 0; u < VT_PPT; u++) {
         if (keys[u] != VC_NOKEY) {
             const uint32_t bk = vt_bucket(keys[u], g.lgP);
-            const uint32_t pos = base[bk] + whw[bk] + rank[u];
+            const uint32_t pos = base[bk] + rank[u];
             if (pos < g.qcap) queue[bk * g.qcap + pos] = make_uint2(keys[u], t0 + u * VT_THREADS + tid);
             else over = true;
         }
@@ -196,169 +190,137 @@ __device__ __forceinline__ void vt_split(const VtArgs &a, const VcDev &dv, uint3
 }
 
 // ------------------------------------------------------------------------------------------------ bucket
-// Shared-memory atomics are the scarce resource here too, so the voxels of a bucket are resolved with plain stores: every entry
-// of the bucket's queue writes its queue position into the slot its key hashes to if the slot is empty (any writer wins),
-// and after a barrier adopts the slot if the winner carries its key, else moves on to the next slot.  Entries of one key move in
-// lock step, so they agree on the slot and on the winner; slots only ever fill.  Two such rounds settle most entries, the
-// stragglers finish with compare-and-swap.  Only the ~8 % of entries that join another entry's voxel issue atomics (smallest index,
-// count) -- on the winner's words.
-constexpr uint32_t VT_E_WIN = 1u << 30, VT_E_JOIN = 2u << 30, VT_E_VAL = (1u << 30) - 1;   // entry state: probing slot | winner: smallest index | joiner: winner
-constexpr int VT_ROUNDS = 2;
-
-__device__ __forceinline__ void vt_bucket_role(const VtArgs &a, uint32_t lb, uint32_t chunk, unsigned char *dyn)
+// table slot: .x cell key, .y smallest point index, .z points, .w record of a crowded voxel
+__global__ void __launch_bounds__(VT_BT, 12) vt_bucket_kernel(const VtArgs a)
 {
+    __shared__ uint4 tab[VT_SMAX];
+    __shared__ uint32_t pool[VT_POOL * VT_MAXK];   // records of VT_MAXK indices
+    __shared__ uint32_t misc[4];                   // [1] records in use, [2] failure
     const VtGeom &g = a.g;
     const unsigned tid = threadIdx.x;
-    const uint32_t fl = lb >> g.lgP, bk = lb & (g.P - 1);
-    const uint32_t slot_id = (chunk % VT_STAGES) * g.CF + fl;
+    const uint32_t fl = blockIdx.y, bk = blockIdx.x;
     const uint32_t K = a.K, cthr = a.cthr;
+    uint32_t *qcount = a.qcount + (size_t)fl * g.P;
+    const uint2 *q = a.queue + ((size_t)fl * g.P + bk) * g.qcap;
+    uint32_t *word = a.word + (size_t)fl * g.lpad, *hkey = a.hkey + (size_t)fl * g.lpad;
 
-    uint2 *qs = reinterpret_cast<uint2 *>(dyn);                    // [qcap] the bucket's queue: key, point index
-    uint32_t *st = reinterpret_cast<uint32_t *>(qs + g.qcap);      // [qcap] entry state
-    uint32_t *cnt = st + g.qcap;                                   // [qcap] winners: points in the voxel | (record + 1) << 16
-    uint32_t *slot = cnt + g.qcap;                                 // [S]
-    uint32_t *pool = slot + g.S;                                   // VT_POOL records of VT_MAXK indices
-    uint32_t *misc = pool + VT_POOL * VT_MAXK;                     // [1] records in use, [2] failure
-    uint32_t *qcount = a.qcount + (size_t)slot_id * g.P;
-    const uint2 *q = a.queue + ((size_t)slot_id * g.P + bk) * g.qcap;
-    uint32_t *word = a.word + (size_t)slot_id * g.lpad, *hkey = a.hkey + (size_t)slot_id * g.lpad;
-
+    // the queue entries and the count travel together (slots past the count hold stale entries: masked below)
     const uint32_t n = min(qcount[bk], g.qcap);
+    uint2 en[VT_EPT];
+#pragma unroll
+    for (int k = 0; k < VT_EPT; k++) {
+        const uint32_t e = tid + k * VT_BT;
+        en[k] = e < g.qcap ? q[e] : make_uint2(VT_NONE, 0u);
+    }
     if (n == 0) return;
     // table size for this bucket: load factor <= 2/3 when the maximum allows it
     uint32_t lgS = 6;
-    while ((1u << lgS) < n + (n >> 1) && lgS < g.lgS) lgS++;
+    while ((1u << lgS) < n + (n >> 1) && (1u << lgS) < (uint32_t)VT_SMAX) lgS++;
     const uint32_t S = 1u << lgS, smask = S - 1, hshift = 32u - lgS;
-    for (uint32_t s = tid; s < S; s += VT_THREADS) slot[s] = VT_NONE;
-    for (uint32_t e = tid; e < n; e += VT_THREADS) {
-        const uint2 x = q[e];
-        qs[e] = x; st[e] = vt_home(x.x, hshift); cnt[e] = 1u;
-    }
+    for (uint32_t s = tid; s < S; s += VT_BT) tab[s] = make_uint4(VT_NONE, VT_NONE, 0u, 0u);
     if (tid == 0) { misc[1] = 0; misc[2] = 0; }
+#pragma unroll
+    for (int k = 0; k < VT_EPT; k++)
+        if (tid + k * VT_BT >= n) en[k].x = VT_NONE;
     __syncthreads();
-    if (tid == 0) qcount[bk] = 0;   // everybody has read it: the counter is ready for the slot's next frame
-    if (n >= S) { if (tid == 0) *a.bail = 1u; return; }   // (cannot settle if every entry is its own voxel; n is CTA-uniform)
+    if (tid == 0) qcount[bk] = 0;   // everybody has read it: the counter is ready for the next chunk
+    if (n > S) { if (tid == 0) *a.bail = 1u; return; }   // (n is CTA-uniform)
 
-#pragma unroll 1
-    for (int r = 0; r < VT_ROUNDS; r++) {
-        for (uint32_t e = tid; e < n; e += VT_THREADS) {
-            const uint32_t s = st[e];
-            if (!(s >> 30) && slot[s] == VT_NONE) slot[s] = e;   // racy on purpose: any writer wins
-        }
-        __syncthreads();
-        for (uint32_t e = tid; e < n; e += VT_THREADS) {
-            const uint32_t s = st[e];
-            if (!(s >> 30)) {
-                const uint32_t wv = slot[s];
-                if (wv == e) st[e] = VT_E_WIN | qs[e].y;
-                else if (qs[wv].x == qs[e].x) st[e] = VT_E_JOIN | wv;
-                else st[e] = (s + 1) & smask;
-            }
-        }
-        __syncthreads();   // the next round's stores must not overtake this round's lookups
-    }
-    // stragglers: claim-or-join with compare-and-swap (no lock step needed: slots only ever fill)
-    for (uint32_t e = tid; e < n; e += VT_THREADS) {
-        uint32_t s = st[e];
-        if (!(s >> 30)) {
-            const uint32_t key = qs[e].x;
-            for (uint32_t it = 0;; it++) {
-                uint32_t wv = slot[s];
-                if (wv == VT_NONE) { const uint32_t old = atomicCAS(&slot[s], VT_NONE, e); wv = old == VT_NONE ? e : old; }
-                if (wv == e) { st[e] = VT_E_WIN | qs[e].y; break; }
-                if (qs[wv].x == key) { st[e] = VT_E_JOIN | wv; break; }
+    uint32_t sl[VT_EPT];
+#pragma unroll
+    for (int k = 0; k < VT_EPT; k++) {
+        sl[k] = 0;
+        if (en[k].x != VT_NONE) {
+            uint32_t s = vt_home(en[k].x, hshift);
+            for (uint32_t it = 0; it <= S; it++) {
+                const uint32_t old = atomicCAS(&tab[s].x, VT_NONE, en[k].x);
+                if (old == VT_NONE || old == en[k].x) break;
                 s = (s + 1) & smask;
-                if (it >= S) { misc[2] = 1u; st[e] = VT_E_WIN | qs[e].y; break; }   // cannot happen with n < S
             }
+            atomicMin(&tab[s].y, en[k].y);
+            atomicAdd(&tab[s].z, 1u);
+            sl[k] = s;
         }
     }
     __syncthreads();
-    // joiners: smallest index and point count of the voxel, on the winner's words
-    for (uint32_t e = tid; e < n; e += VT_THREADS) {
-        const uint32_t s = st[e];
-        if ((s >> 30) == 2u) { atomicMin(&st[s & VT_E_VAL], VT_E_WIN | qs[e].y); atomicAdd(&cnt[s & VT_E_VAL], 1u); }
-    }
-    __syncthreads();
-    if (misc[2]) { if (tid == 0) *a.bail = 1u; return; }
 
-    // voxels with more than K points: their K smallest indices by a min-cascade
+    // voxels with more than K points: their K smallest indices
     if (cthr != VT_NONE) {
         bool anyc = false;
-        for (uint32_t e = tid; e < n; e += VT_THREADS) {
-            const uint32_t s = st[e];
-            const uint32_t wv = (s >> 30) == 2u ? (s & VT_E_VAL) : e;
-            if ((cnt[wv] & 0xffffu) > cthr) {
-                anyc = true;
-                if ((st[wv] & VT_E_VAL) == qs[e].y) {   // the voxel's first point opens the record
-                    const uint32_t rec = atomicAdd(&misc[1], 1u);
-                    if (rec >= (uint32_t)VT_POOL) misc[2] = 1u;
-                    else {
-                        cnt[wv] |= (rec + 1u) << 16;   // the only writer of this word in this phase; readers look at the low half
-                        for (uint32_t j = 0; j < K; j++) pool[rec * VT_MAXK + j] = VT_NONE;
+#pragma unroll
+        for (int k = 0; k < VT_EPT; k++)
+            if (en[k].x != VT_NONE) {
+                const uint4 t = tab[sl[k]];
+                if (t.z > cthr) {
+                    anyc = true;
+                    if (t.y == en[k].y) {   // the voxel's first point opens the record
+                        const uint32_t r = atomicAdd(&misc[1], 1u);
+                        if (r >= (uint32_t)VT_POOL) misc[2] = 1u;
+                        else {
+                            tab[sl[k]].w = r;
+                            for (uint32_t j = 0; j < K; j++) pool[r * VT_MAXK + j] = VT_NONE;
+                        }
                     }
                 }
             }
-        }
         if (__syncthreads_or((int)anyc)) {
             if (misc[2]) { if (tid == 0) *a.bail = 1u; return; }
-            for (uint32_t e = tid; e < n; e += VT_THREADS) {
-                const uint32_t s = st[e];
-                const uint32_t wv = (s >> 30) == 2u ? (s & VT_E_VAL) : e;
-                const uint32_t c = cnt[wv];
-                if ((c & 0xffffu) > cthr) {
-                    uint32_t *rec = pool + ((c >> 16) - 1u) * VT_MAXK;
-                    uint32_t v = qs[e].y;
-                    for (uint32_t j = 0; j < K; j++) {
-                        const uint32_t old = atomicMin(&rec[j], v);
-                        v = max(old, v);              // the larger value moves on to the next level
-                        if (v == VT_NONE) break;
+#pragma unroll
+            for (int k = 0; k < VT_EPT; k++)
+                if (en[k].x != VT_NONE) {
+                    const uint4 t = tab[sl[k]];
+                    if (t.z > cthr) {
+                        uint32_t *rec = pool + t.w * VT_MAXK;
+                        uint32_t v = en[k].y;
+                        for (uint32_t j = 0; j < K; j++) {
+                            const uint32_t old = atomicMin(&rec[j], v);
+                            v = max(old, v);              // the larger value moves on to the next level
+                            if (v == VT_NONE) break;
+                        }
                     }
                 }
-            }
             __syncthreads();
         }
     }
 
     // a new word for every point that shares its voxel (a point that hears nothing is the only point of its voxel)
-    for (uint32_t e = tid; e < n; e += VT_THREADS) {
-        const uint32_t s = st[e];
-        const uint32_t wv = (s >> 30) == 2u ? (s & VT_E_VAL) : e;
-        const uint32_t c = cnt[wv], total = c & 0xffffu;
-        if (total == 1) continue;
-        const uint2 x = qs[e];
-        const uint32_t mn = st[wv] & VT_E_VAL;
-        uint32_t r;
-        if ((long long)total < (long long)a.min_points) r = VT_W_NONE;
-        else if (x.y == mn) { r = VT_W_HEAD | total; hkey[x.y] = x.x; }
-        else {
-            const bool kept = !(total > cthr) || x.y <= pool[((c >> 16) - 1u) * VT_MAXK + K - 1];
-            r = kept ? (VT_W_JOIN | mn) : VT_W_NONE;
+#pragma unroll
+    for (int k = 0; k < VT_EPT; k++)
+        if (en[k].x != VT_NONE) {
+            const uint4 t = tab[sl[k]];
+            if (t.z != 1u) {
+                uint32_t r;
+                if ((long long)t.z < (long long)a.min_points) r = VT_W_NONE;
+                else if (en[k].y == t.y) { r = VT_W_HEAD | min(t.z, VT_VAL); hkey[en[k].y] = en[k].x; }
+                else {
+                    const bool kept = !(t.z > cthr) || en[k].y <= pool[t.w * VT_MAXK + K - 1];
+                    r = kept ? (VT_W_JOIN | t.y) : VT_W_NONE;
+                }
+                word[en[k].y] = r;
+            }
         }
-        word[x.y] = r;
-    }
 }
 
 // ------------------------------------------------------------------------------------------------ scan
 // row table entry: .x first-of-voxel bits of the 32-point row, .y voxel rows before the row, .z keep bits, .w kept rows before the row
-__device__ __forceinline__ void vt_scan(const VtArgs &a, uint32_t chunk, unsigned char *dyn)
+__global__ void __launch_bounds__(VT_THREADS) vt_scan_kernel(const VtArgs a, uint32_t chunk)
 {
     const VtGeom &g = a.g;
     const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
-    unsigned long long *wsum = reinterpret_cast<unsigned long long *>(dyn);   // [8] warp sums, then exclusive warp bases
+    __shared__ unsigned long long wsum[VT_WARPS + 1];   // [8] warp sums, then exclusive warp bases; [8] the tile's exclusive prefix
+    __shared__ uint32_t s_misc[2];
     unsigned long long *s_excl = wsum + VT_WARPS;
-    uint32_t *s_misc = reinterpret_cast<uint32_t *>(s_excl + 1);
 
     if (tid == 0) s_misc[0] = atomicAdd(&a.tickets[chunk], 1u);
     __syncthreads();
     const uint32_t lt = s_misc[0];
     const uint32_t fl = lt / g.spf, t = lt - fl * g.spf;
     const int64_t f = (int64_t)chunk * g.CF + fl;
-    const uint32_t slot = (chunk % VT_STAGES) * g.CF + fl;
     const int64_t gt = f * (int64_t)g.spf + t;
     const uint32_t L = (uint32_t)min((long long)(a.offs[f + 1] - a.offs[f]), (long long)g.lmax);
     const uint32_t t0 = t * VT_STILE;
-    const uint32_t *word = a.word + (size_t)slot * g.lpad;
-    uint4 *ri_f = a.rowinfo + (size_t)slot * (g.lpad / 32);
+    const uint32_t *word = a.word + (size_t)fl * g.lpad;
+    uint4 *ri_f = a.rowinfo + (size_t)fl * (g.lpad / 32);
 
     // lane u of a warp keeps the bits of the warp's row u
     uint32_t myh = 0, myk = 0;
@@ -405,98 +367,75 @@ __device__ __forceinline__ void vt_scan(const VtArgs &a, uint32_t chunk, unsigne
 
 // ------------------------------------------------------------------------------------------------ write
 template <bool NF4>
-__device__ __forceinline__ void vt_write(const VtArgs &a, const VcDev &dv, uint32_t lt, uint32_t chunk)
+__global__ void __launch_bounds__(VT_THREADS, 4) vt_write_kernel(const VtArgs a, const VcDev dv, uint32_t chunk)
 {
     const VtGeom &g = a.g;
     const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
     const unsigned ltmask = lanemask_lt();
-    const uint32_t fl = lt / g.tpf, t = lt - fl * g.tpf;
+    const uint32_t fl = blockIdx.y, t = blockIdx.x;
     const int64_t f = (int64_t)chunk * g.CF + fl;
-    const uint32_t slot = (chunk % VT_STAGES) * g.CF + fl;
     const int64_t b = a.offs[f];
     const uint32_t L = (uint32_t)min((long long)(a.offs[f + 1] - b), (long long)g.lmax);
     const uint32_t t0 = t * VT_TILE;
     if (t0 >= L) return;
     const uint32_t vb = (uint32_t)a.counts[2 * f + 1];   // the frame's first voxel row
-    const uint32_t *word = a.word + (size_t)slot * g.lpad, *hkey = a.hkey + (size_t)slot * g.lpad;
-    const uint4 *ri_f = a.rowinfo + (size_t)slot * (g.lpad / 32);
+    const uint32_t *word = a.word + (size_t)fl * g.lpad, *hkey = a.hkey + (size_t)fl * g.lpad;
+    const uint4 *ri_f = a.rowinfo + (size_t)fl * (g.lpad / 32);
+    const uint32_t row0 = (t0 >> 5) + w * VT_PPT;
+    if (row0 * 32 >= L) return;
     const uint32_t mask_y = (1u << (dv.sh_x - dv.sh_y)) - 1u, mask_z = (1u << dv.sh_y) - 1u;
-    constexpr int U = 2;   // rows in flight per warp
-#pragma unroll 1
-    for (int r0 = 0; r0 < VT_PPT; r0 += U) {
-        const uint32_t row0 = (t0 >> 5) + w * VT_PPT + r0;
-        if (row0 * 32 >= L) break;
-        uint32_t wd[U];
-        uint4 ri[U];
+
+    // first round trip: words, row table entries (lane u holds row u's) and the points of the warp's four rows, unconditionally
+    uint32_t wd[VT_PPT];
+    float4 p4[VT_PPT];
+    const uint4 rme = ri_f[row0 + (lane & (VT_PPT - 1))];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t i = (row0 + u) * 32 + lane;
-            wd[u] = i < L ? word[i] : VT_W_NONE;
-            ri[u] = ri_f[row0 + u];
+    for (int u = 0; u < VT_PPT; u++) {
+        const uint32_t i = (row0 + u) * 32 + lane;
+        wd[u] = i < L ? word[i] : VT_W_NONE;
+        p4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (NF4 && i < L) p4[u] = __ldg(reinterpret_cast<const float4 *>(a.pts) + b + i);
+    }
+    // second round trip, few lanes: keys of first points of shared voxels, row table entries of the joiners' first points
+    uint32_t ckey[VT_PPT];
+    uint2 rj[VT_PPT];
+#pragma unroll
+    for (int u = 0; u < VT_PPT; u++) {
+        const uint32_t i = (row0 + u) * 32 + lane;
+        const uint32_t cat = wd[u] >> 30;
+        ckey[u] = wd[u]; rj[u] = make_uint2(0u, 0u);
+        if (cat == 3u) ckey[u] = hkey[i];
+        if (cat == 2u) rj[u] = *reinterpret_cast<const uint2 *>(ri_f + ((wd[u] & VT_VAL) >> 5));   // the id lives where the voxel's first point lives
+    }
+#pragma unroll
+    for (int u = 0; u < VT_PPT; u++) {
+        const uint32_t i = (row0 + u) * 32 + lane;
+        const uint32_t x = wd[u];
+        bool head, keep;
+        vt_decode(a, x, &head, &keep);
+        const uint32_t hb = __shfl_sync(0xffffffffu, rme.x, u), gh = __shfl_sync(0xffffffffu, rme.y, u);
+        const uint32_t kb = __shfl_sync(0xffffffffu, rme.z, u), gk = __shfl_sync(0xffffffffu, rme.w, u);
+        uint32_t vrow = 0;
+        if (head) {
+            vrow = gh + __popc(hb & ltmask);
+            const uint32_t c = (x >> 30) ? (x & VT_VAL) : 1u, key = ckey[u];
+            long long *co = reinterpret_cast<long long *>(a.out_coords) + (size_t)vrow * 3;
+            __stcs(co + 0, (long long)(key >> dv.sh_x) + dv.cadd[0]);
+            __stcs(co + 1, (long long)((key >> dv.sh_y) & mask_y) + dv.cadd[1]);
+            __stcs(co + 2, (long long)(key & mask_z) + dv.cadd[2]);
+            __stcs(a.out_npoints + vrow, (a.trim && c > a.K) ? (int32_t)a.K : (int32_t)c);
+        } else if (keep) {
+            const uint32_t m = x & VT_VAL;
+            vrow = rj[u].y + __popc(rj[u].x & ((1u << (m & 31u)) - 1u));
         }
-        // everything the rows need from memory in flight together
-        float4 p4[U];
-        uint32_t ckey[U];
-        uint2 rj[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t i = (row0 + u) * 32 + lane;
-            bool head, keep;
-            vt_decode(a, wd[u], &head, &keep);
-            p4[u] = make_float4(0.f, 0.f, 0.f, 0.f); ckey[u] = wd[u]; rj[u] = make_uint2(0u, 0u);
-            if (keep && NF4) p4[u] = __ldg(reinterpret_cast<const float4 *>(a.pts) + b + i);
-            if (head && (wd[u] >> 30)) ckey[u] = hkey[i];
-            if (keep && !head) rj[u] = *reinterpret_cast<const uint2 *>(ri_f + ((wd[u] & VT_VAL) >> 5));   // the id lives where the voxel's first point lives
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t i = (row0 + u) * 32 + lane;
-            const uint32_t x = wd[u];
-            bool head, keep;
-            vt_decode(a, x, &head, &keep);
-            uint32_t vrow = 0;
-            if (head) {
-                vrow = ri[u].y + __popc(ri[u].x & ltmask);
-                const uint32_t c = (x >> 30) ? (x & VT_VAL) : 1u, key = ckey[u];
-                long long *co = reinterpret_cast<long long *>(a.out_coords) + (size_t)vrow * 3;
-                __stcs(co + 0, (long long)(key >> dv.sh_x) + dv.cadd[0]);
-                __stcs(co + 1, (long long)((key >> dv.sh_y) & mask_y) + dv.cadd[1]);
-                __stcs(co + 2, (long long)(key & mask_z) + dv.cadd[2]);
-                __stcs(a.out_npoints + vrow, (a.trim && c > a.K) ? (int32_t)a.K : (int32_t)c);
-            } else if (keep) {
-                const uint32_t m = x & VT_VAL;
-                vrow = rj[u].y + __popc(rj[u].x & ((1u << (m & 31u)) - 1u));
-            }
-            if (keep) {
-                const size_t o = (size_t)ri[u].w + __popc(ri[u].z & ltmask);
-                if (NF4) __stcs(reinterpret_cast<float4 *>(a.out_points) + o, p4[u]);
-                else for (int q = 0; q < a.nfeat; q++) a.out_points[o * a.nfeat + q] = a.pts[(b + i) * a.nfeat + q];
-                __stcs(reinterpret_cast<long long *>(a.out_mask) + o, (long long)i);
-                __stcs(reinterpret_cast<long long *>(a.out_mapping) + o, (long long)(vrow - vb));
-            }
+        if (keep) {
+            const size_t o = (size_t)gk + __popc(kb & ltmask);
+            if (NF4) __stcs(reinterpret_cast<float4 *>(a.out_points) + o, p4[u]);
+            else for (int q = 0; q < a.nfeat; q++) a.out_points[o * a.nfeat + q] = a.pts[(b + i) * a.nfeat + q];
+            __stcs(reinterpret_cast<long long *>(a.out_mask) + o, (long long)i);
+            __stcs(reinterpret_cast<long long *>(a.out_mapping) + o, (long long)(vrow - vb));
         }
     }
-}
-
-// One tick of the pipeline.  The grid is cut into rounds of u.x write + u.y scan + u.z bucket + u.w split blocks so that
-// every wave of CTAs mixes the four stages (DRAM writes, a latency chain, shared-memory atomics, DRAM reads) instead
-// of running them one after the other; a block whose index passes its stage's count has nothing to do.
-struct VtTick { uint32_t chunk, n4, n3, n2, n1, u4, u3, u2, u1; };
-
-template <bool NF4>
-__global__ void __launch_bounds__(VT_THREADS, 5) vt_tick_kernel(const VtArgs a, const VcDev dv, const VtTick k)
-{
-    extern __shared__ __align__(16) unsigned char vt_dyn[];
-    const uint32_t U = k.u4 + k.u3 + k.u2 + k.u1;
-    const uint32_t m = blockIdx.x / U;
-    uint32_t j = blockIdx.x - m * U;
-    if (j < k.u4) { const uint32_t i = m * k.u4 + j; if (i < k.n4) vt_write<NF4>(a, dv, i, k.chunk - 3); return; }
-    j -= k.u4;
-    if (j < k.u3) { if (m * k.u3 + j < k.n3) vt_scan(a, k.chunk - 2, vt_dyn); return; }
-    j -= k.u3;
-    if (j < k.u2) { const uint32_t i = m * k.u2 + j; if (i < k.n2) vt_bucket_role(a, i, k.chunk - 1, vt_dyn); return; }
-    j -= k.u2;
-    { const uint32_t i = m * k.u1 + j; if (i < k.n1) vt_split<NF4>(a, dv, i, k.chunk, vt_dyn); }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -519,21 +458,18 @@ static int vt_env_roles()
 static bool vt_geom(int64_t max_frame_points, int64_t nframes, VtGeom *g)
 {
     if (max_frame_points < 1) max_frame_points = 1;
-    if (max_frame_points > (1ll << 21)) return false;            // 2048 buckets of 1024 points; 29-bit indices in the words
+    if (max_frame_points > (1ll << 21)) return false;            // 4096 buckets of 512 points
     g->lmax = (uint32_t)max_frame_points;
     g->tpf = (g->lmax + VT_TILE - 1) / VT_TILE;
     g->spf = (g->lmax + VT_STILE - 1) / VT_STILE;
     g->lpad = g->spf * VT_STILE;
-    g->lgP = vt_lg2_ceil(((uint64_t)g->lmax + 1023) / 1024);
+    g->lgP = vt_lg2_ceil(((uint64_t)g->lmax + 511) / 512);
     g->P = 1u << g->lgP;
-    const uint32_t per = (g->lmax + g->P - 1) / g->P;            // points per bucket if every point is kept and the hash is even
-    g->lgS = vt_lg2_ceil(2ull * per);
-    if (g->lgS < 6) g->lgS = 6;
-    if (g->lgS > 11) return false;                                // cannot happen with per <= 1024
-    g->S = 1u << g->lgS;
-    g->qcap = (per + per / 2 + 256 + 3) & ~3u;                   // the bucket's queue is staged in shared memory; more -> device flag
+    const uint32_t per = (g->lmax + g->P - 1) / g->P;            // points per bucket if every point is kept and the hash is even (<= 512)
+    g->qcap = (per + per / 2 + 128 + 3) & ~3u;                   // <= VT_QCAP: a bucket's queue lives in its CTA's registers; more -> device flag
+    if (g->qcap > (uint32_t)VT_QCAP) g->qcap = VT_QCAP;
     int cf = vt_env_cf();
-    if (cf <= 0) cf = 8;
+    if (cf <= 0) cf = 16;
     if ((int64_t)cf > nframes) cf = (int)(nframes > 0 ? nframes : 1);
     g->CF = (uint32_t)cf;
     g->nchunks = (uint32_t)((nframes + cf - 1) / cf);
@@ -546,7 +482,7 @@ struct VtLayout { size_t queue, word, hkey, rowinfo, zero, qcount, status, ticke
 static VtLayout vt_layout(const VtGeom &g, int64_t nframes)
 {
     VtLayout l;
-    const size_t slots = (size_t)VT_STAGES * g.CF;
+    const size_t slots = g.CF;
     size_t o = 0;
     l.queue = o;   o += align_up(slots * g.P * g.qcap * sizeof(uint2));
     l.word = o;    o += align_up(slots * g.lpad * 4);
@@ -610,42 +546,24 @@ int vox_tiles_sparse(const float *points, int64_t total, int nfeat, const int64_
     a.min_points = cfg.min_points;
     a.single_ok = cfg.min_points <= 1 ? 1 : 0;
 
-    static int smem_set[64];
-    const uint32_t dyn_bucket = 16u * g.qcap + 4u * g.S + VT_POOL * VT_MAXK * 4u + 64u;
-    const uint32_t dyn_split = 20u * g.P;
-    uint32_t dyn = dyn_bucket > dyn_split ? dyn_bucket : dyn_split;
-    if (dyn < 256u) dyn = 256u;
-    int dev = 0;
-    D3D_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && !smem_set[dev]) {
-        D3D_CUDA_TRY(cudaFuncSetAttribute(vt_tick_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        D3D_CUDA_TRY(cudaFuncSetAttribute(vt_tick_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        smem_set[dev] = 1;
-    }
     D3D_CUDA_TRY(cudaMemsetAsync(w + lay.zero, 0, lay.zero_end - lay.zero, st));
-    auto nf = [&](int64_t c) -> uint32_t {
-        if (c < 0 || c >= (int64_t)g.nchunks) return 0u;
-        const int64_t r = nframes - c * g.CF;
-        return (uint32_t)(r < (int64_t)g.CF ? r : g.CF);
-    };
-    for (int64_t k = 0; k < (int64_t)g.nchunks + VT_STAGES - 1; k++) {
-        VtTick tk;
-        tk.chunk = (uint32_t)k;
-        tk.n1 = nf(k) * g.tpf; tk.n2 = nf(k - 1) * g.P; tk.n3 = nf(k - 2) * g.spf; tk.n4 = nf(k - 3) * g.tpf;
-        const int roles = vt_env_roles();
-        if (!(roles & 1)) tk.n1 = 0;
-        if (!(roles & 2)) tk.n2 = 0;
-        if (!(roles & 4)) tk.n3 = 0;
-        if (!(roles & 8)) tk.n4 = 0;
-        const uint32_t total_blocks = tk.n1 + tk.n2 + tk.n3 + tk.n4;
-        if (total_blocks == 0) continue;
-        const uint32_t rounds = (total_blocks + 47) / 48;   // ~48 blocks per round
-        tk.u1 = (tk.n1 + rounds - 1) / rounds; tk.u2 = (tk.n2 + rounds - 1) / rounds;
-        tk.u3 = (tk.n3 + rounds - 1) / rounds; tk.u4 = (tk.n4 + rounds - 1) / rounds;
-        const uint32_t grid = rounds * (tk.u1 + tk.u2 + tk.u3 + tk.u4);
-        if (nfeat == 4) vt_tick_kernel<true><<<grid, VT_THREADS, dyn, st>>>(a, dv, tk);
-        else vt_tick_kernel<false><<<grid, VT_THREADS, dyn, st>>>(a, dv, tk);
-        D3D_LAUNCHED();
+    const int roles = vt_env_roles();
+    const uint32_t dyn_split = 8u * g.P;
+    for (uint32_t c = 0; c < g.nchunks; c++) {
+        const int64_t rem = nframes - (int64_t)c * g.CF;
+        const uint32_t nf = (uint32_t)(rem < (int64_t)g.CF ? rem : g.CF);
+        if (roles & 1) {
+            if (nfeat == 4) vt_split_kernel<true><<<dim3(g.tpf, nf), VT_THREADS, dyn_split, st>>>(a, dv, c);
+            else vt_split_kernel<false><<<dim3(g.tpf, nf), VT_THREADS, dyn_split, st>>>(a, dv, c);
+            D3D_LAUNCHED();
+        }
+        if (roles & 2) { vt_bucket_kernel<<<dim3(g.P, nf), VT_BT, 0, st>>>(a); D3D_LAUNCHED(); }
+        if (roles & 4) { vt_scan_kernel<<<nf * g.spf, VT_THREADS, 0, st>>>(a, c); D3D_LAUNCHED(); }
+        if (roles & 8) {
+            if (nfeat == 4) vt_write_kernel<true><<<dim3(g.tpf, nf), VT_THREADS, 0, st>>>(a, dv, c);
+            else vt_write_kernel<false><<<dim3(g.tpf, nf), VT_THREADS, 0, st>>>(a, dv, c);
+            D3D_LAUNCHED();
+        }
     }
     // the batch is redone by the cluster kernel when a queue, a table or a record pool overflowed (device flag)
     return vox_cluster_sparse(points, total, nfeat, offs, nframes, max_frame_points, cfg, out_points, out_mask, out_mapping, out_npoints, out_coords, counts,
@@ -653,11 +571,3 @@ int vox_tiles_sparse(const float *points, int64_t total, int nfeat, const int64_
 }
 
 }  // namespace d3d
-#ifdef VT_ROLE_PROBE
-namespace d3d {
-__global__ void __launch_bounds__(VT_THREADS) vt_probe_split(const VtArgs a, const VcDev dv) { extern __shared__ __align__(16) unsigned char d[]; vt_split<true>(a, dv, blockIdx.x, 0, d); }
-__global__ void __launch_bounds__(VT_THREADS) vt_probe_bucket(const VtArgs a, const VcDev dv) { extern __shared__ __align__(16) unsigned char d[]; vt_bucket_role(a, blockIdx.x, 0, d); }
-__global__ void __launch_bounds__(VT_THREADS) vt_probe_scan(const VtArgs a, const VcDev dv) { extern __shared__ __align__(16) unsigned char d[]; vt_scan(a, 0, d); }
-__global__ void __launch_bounds__(VT_THREADS) vt_probe_write(const VtArgs a, const VcDev dv) { vt_write<true>(a, dv, blockIdx.x, 0); }
-}
-#endif
