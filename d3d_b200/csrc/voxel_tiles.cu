@@ -26,9 +26,10 @@
 //                                frames (decoupled look-back): voxel ids in order of first appearance, packed rows.
 //   write   (1024 points / CTA)  voxel rows and kept point rows streamed out; no barrier, no waiting.
 //
-// A chunk is a few frames (16 by default), so the scratch of the chunk (queues, words, row tables: ~1.3 MB per
-// frame, plus the frame itself) lives in L2 between the kernels and HBM sees the algorithmic traffic only:
-// 16 B/point in, 32 B/kept point + 28 B/voxel out.
+// A batch is cut into chunks of frames (128 by default; D3D_B200_VOX_CF, read once, for tuning).  Small chunks keep the scratch
+// (queues, words, row tables: ~1.3 MB per frame, plus the frame itself) in L2 between the kernels, large chunks give fewer
+// and fuller launches; on B200 the large chunks win (C2 x 128 frames: 0.59 ms against 0.74 ms with chunks of 16) although
+// the scratch then travels through HBM (DRAM traffic ~1.9x the algorithmic 16 B/point in, 32 B/kept point + 28 B/voxel out).
 //
 // Determinism: every output is a function of the point set (smallest index, count, K smallest indices, prefix
 // sums in point order), never of the race order of the queues and tables.
@@ -46,10 +47,28 @@ constexpr int VT_PPT = 4;                         // points per thread (split, w
 constexpr int VT_TILE = VT_THREADS * VT_PPT;      // 1024 points per tile
 constexpr int VT_SPT = 32;                        // points per thread (scan): lane u of a warp keeps the warp's row u
 constexpr int VT_STILE = VT_THREADS * VT_SPT;     // 8192 points per scan tile
-constexpr int VT_BT = 128;                        // threads of a bucket CTA
-constexpr int VT_EPT = 8;                         // queue entries per bucket thread, all in registers
+#ifndef D3D_VT_BT
+#define D3D_VT_BT 128
+#endif
+#ifndef D3D_VT_EPT
+#define D3D_VT_EPT 8
+#endif
+#ifndef D3D_VT_BPTS
+#define D3D_VT_BPTS 512      // points per bucket the geometry aims at (if every point is kept)
+#endif
+#ifndef D3D_VT_BCTAS
+#define D3D_VT_BCTAS 12
+#endif
+#ifndef D3D_VT_WCTAS
+#define D3D_VT_WCTAS 4
+#endif
+#ifndef D3D_VT_SCTAS
+#define D3D_VT_SCTAS 6
+#endif
+constexpr int VT_BT = D3D_VT_BT;                  // threads of a bucket CTA
+constexpr int VT_EPT = D3D_VT_EPT;                // queue entries per bucket thread, all in registers
 constexpr int VT_QCAP = VT_BT * VT_EPT;           // largest queue a bucket CTA takes
-constexpr int VT_SMAX = 1024;                     // table slots per bucket (maximum)
+constexpr int VT_SMAX = VT_QCAP <= 512 ? 512 : (VT_QCAP <= 1024 ? 1024 : 2048);   // table slots per bucket (maximum)
 constexpr int VT_MAXK = 8;                        // deepest min-cascade (max_points of the TRIM filter)
 constexpr int VT_POOL = 64;                       // crowded-voxel records per bucket
 constexpr uint32_t VT_NONE = 0xffffffffu;         // empty table slot / queue entry
@@ -85,33 +104,76 @@ __device__ __forceinline__ void vt_st_release(unsigned long long *p, unsigned lo
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Decoupled look-back over the scan tiles of all frames (one warp).  Tiles take their numbers from a ticket counter, so
-// a tile only waits for tiles that are running or done.  flag 1: the tile's own sums; flag 2: inclusive prefix.
-__device__ __forceinline__ unsigned long long vt_lookback(unsigned long long *state, int64_t gt, unsigned long long mine)
+// L2 residency hints.  The scratch of a chunk (queues, point words, row tables) and the chunk's points are used again by the next
+// kernels: evict_last keeps them in L2 while the output rows, which nobody reads back, stream through with evict_first.
+__device__ __forceinline__ uint64_t vt_policy_keep() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint64_t vt_policy_stream() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint32_t vt_ld32(const void *p, uint64_t pol)
 {
-    const unsigned lane = threadIdx.x & 31u;
-    if (gt > 0 && lane == 0) vt_st_release(state + gt, (1ull << 62) | mine);
-    unsigned long long excl = 0;
-    for (int64_t j = gt - 1; j >= 0; j -= 32) {
-        const int64_t idx = j - (int64_t)lane;
-        unsigned long long v = 2ull << 62;   // before the first tile: an inclusive prefix of zero
-        unsigned first2, need;
-        for (;;) {
-            if (idx >= 0) v = vt_ld_acquire(state + idx);
-            const unsigned flag = (unsigned)(v >> 62);
-            const unsigned b2 = __ballot_sync(0xffffffffu, flag >= 2), b0 = __ballot_sync(0xffffffffu, flag == 0);
-            first2 = b2 ? (unsigned)__ffs((int)b2) - 1u : 32u;
-            need = first2 >= 31u ? 0xffffffffu : ((2u << first2) - 1u);
-            if (!(b0 & need)) break;
-            __nanosleep(40);
-        }
-        unsigned long long x = ((need >> lane) & 1u) ? (v & VT_PVAL) : 0ull;
-#pragma unroll
-        for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-        excl += x;
-        if (first2 < 32u) break;
+    uint32_t v;
+    asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint2 vt_ld64(const void *p, uint64_t pol)
+{
+    uint2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint4 vt_ld128(const void *p, uint64_t pol)
+{
+    uint4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float4 vt_ldpt(const void *p, uint64_t pol)   // read-only input
+{
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void vt_st32(void *p, uint32_t v, uint64_t pol) { asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory"); }
+__device__ __forceinline__ void vt_st64(void *p, uint32_t x, uint32_t y, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(x), "r"(y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void vt_st64ll(void *p, long long v, uint64_t pol) { asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory"); }
+__device__ __forceinline__ void vt_st128(void *p, uint4 v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+// programmatic dependent launch: the kernels of a call are chained in one stream; each lets the next one launch while it drains
+// and waits for its predecessor's results before it touches global memory
+__device__ __forceinline__ void vt_pdl_enter()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
+}
+
+// Prefix of a scan tile over the tiles of all frames.  Every tile of a chunk publishes its own sums (flag 1) and then adds up the
+// sums of the chunk's earlier tiles, one per thread -- a single round trip instead of a chain of look-back rounds; the chunk
+// starts from the inclusive prefix its predecessor's last tile left behind (flag 2, written by an earlier kernel).  Tiles take
+// their numbers from a ticket counter, so a tile only waits for tiles that are running or done.
+__device__ __forceinline__ unsigned long long vt_tile_prefix(unsigned long long *state, int64_t g0, int64_t gt, int64_t glast, unsigned long long mine,
+                                                             unsigned long long *red)
+{
+    const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+    if (tid == 0 && gt != glast) vt_st_release(state + gt, (1ull << 62) | mine);   // the chunk's last tile has no successor inside the chunk
+    unsigned long long x = 0;
+    for (int64_t j = g0 + tid; j < gt; j += VT_THREADS) {
+        unsigned long long v;
+        while (((v = vt_ld_acquire(state + j)) >> 62) == 0ull) __nanosleep(40);
+        x += v & VT_PVAL;
     }
-    if (lane == 0) vt_st_release(state + gt, (2ull << 62) | (excl + mine));
+    if (tid == 0 && g0 > 0) x += vt_ld_acquire(state + g0 - 1) & VT_PVAL;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+    if (lane == 0) red[w] = x;
+    __syncthreads();
+    unsigned long long excl = 0;
+#pragma unroll
+    for (int k = 0; k < VT_WARPS; k++) excl += red[k];
+    if (tid == 0 && gt == glast) vt_st_release(state + gt, (2ull << 62) | (excl + mine));
     return excl;
 }
 
@@ -128,9 +190,10 @@ __device__ __forceinline__ void vt_decode(const VtArgs &a, uint32_t w, bool *hea
 
 // ------------------------------------------------------------------------------------------------ split
 template <bool NF4>
-__global__ void __launch_bounds__(VT_THREADS, 6) vt_split_kernel(const VtArgs a, const VcDev dv, uint32_t chunk)
+__global__ void __launch_bounds__(VT_THREADS, D3D_VT_SCTAS) vt_split_kernel(const VtArgs a, const VcDev dv, uint32_t chunk)
 {
     extern __shared__ __align__(16) unsigned char vt_dyn[];
+    vt_pdl_enter();
     const VtGeom &g = a.g;
     const unsigned tid = threadIdx.x;
     const uint32_t fl = blockIdx.y, t = blockIdx.x;
@@ -139,6 +202,7 @@ __global__ void __launch_bounds__(VT_THREADS, 6) vt_split_kernel(const VtArgs a,
     const uint32_t L = (uint32_t)min((long long)(a.offs[f + 1] - b), (long long)g.lmax);
     const uint32_t t0 = t * VT_TILE;
     if (t0 >= L) return;
+    const uint64_t keep = vt_policy_keep();
 
     uint32_t *hist = reinterpret_cast<uint32_t *>(vt_dyn), *base = hist + g.P;
     uint32_t *word = a.word + (size_t)fl * g.lpad;
@@ -156,7 +220,7 @@ __global__ void __launch_bounds__(VT_THREADS, 6) vt_split_kernel(const VtArgs a,
         in[u] = i < L;
         p4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (in[u]) {
-            if (NF4) p4[u] = __ldg(reinterpret_cast<const float4 *>(a.pts) + b + i);
+            if (NF4) p4[u] = vt_ldpt(reinterpret_cast<const float4 *>(a.pts) + b + i, keep);   // read again by the write kernel
             else { const float *q = a.pts + (b + i) * a.nfeat; p4[u] = make_float4(q[0], q[1], q[2], 0.f); }
         }
     }
@@ -167,7 +231,7 @@ __global__ void __launch_bounds__(VT_THREADS, 6) vt_split_kernel(const VtArgs a,
         const bool ok = vc_cell<false>(dv, p4[u], &key) && in[u];
         keys[u] = ok ? key : VC_NOKEY;
         rank[u] = 0;
-        if (in[u]) word[t0 + u * VT_THREADS + tid] = (ok && a.single_ok) ? key : VT_W_NONE;   // min_points > 1: a lone point is dropped
+        if (in[u]) vt_st32(word + t0 + u * VT_THREADS + tid, (ok && a.single_ok) ? key : VT_W_NONE, keep);   // min_points > 1: a lone point is dropped
         if (ok) rank[u] = atomicAdd(&hist[vt_bucket(key, g.lgP)], 1u);
     }
     __syncthreads();
@@ -182,7 +246,7 @@ __global__ void __launch_bounds__(VT_THREADS, 6) vt_split_kernel(const VtArgs a,
         if (keys[u] != VC_NOKEY) {
             const uint32_t bk = vt_bucket(keys[u], g.lgP);
             const uint32_t pos = base[bk] + rank[u];
-            if (pos < g.qcap) queue[bk * g.qcap + pos] = make_uint2(keys[u], t0 + u * VT_THREADS + tid);
+            if (pos < g.qcap) vt_st64(queue + bk * g.qcap + pos, keys[u], t0 + u * VT_THREADS + tid, keep);
             else over = true;
         }
     }
@@ -191,7 +255,7 @@ __global__ void __launch_bounds__(VT_THREADS, 6) vt_split_kernel(const VtArgs a,
 
 // ------------------------------------------------------------------------------------------------ bucket
 // table slot: .x cell key, .y smallest point index, .z points, .w record of a crowded voxel
-__global__ void __launch_bounds__(VT_BT, 12) vt_bucket_kernel(const VtArgs a)
+__global__ void __launch_bounds__(VT_BT, D3D_VT_BCTAS) vt_bucket_kernel(const VtArgs a)
 {
     __shared__ uint4 tab[VT_SMAX];
     __shared__ uint32_t pool[VT_POOL * VT_MAXK];   // records of VT_MAXK indices
@@ -204,13 +268,15 @@ __global__ void __launch_bounds__(VT_BT, 12) vt_bucket_kernel(const VtArgs a)
     const uint2 *q = a.queue + ((size_t)fl * g.P + bk) * g.qcap;
     uint32_t *word = a.word + (size_t)fl * g.lpad, *hkey = a.hkey + (size_t)fl * g.lpad;
 
+    vt_pdl_enter();
+    const uint64_t keep = vt_policy_keep();
     // the queue entries and the count travel together (slots past the count hold stale entries: masked below)
     const uint32_t n = min(qcount[bk], g.qcap);
     uint2 en[VT_EPT];
 #pragma unroll
     for (int k = 0; k < VT_EPT; k++) {
         const uint32_t e = tid + k * VT_BT;
-        en[k] = e < g.qcap ? q[e] : make_uint2(VT_NONE, 0u);
+        en[k] = e < g.qcap ? vt_ld64(q + e, keep) : make_uint2(VT_NONE, 0u);
     }
     if (n == 0) return;
     // table size for this bucket: load factor <= 2/3 when the maximum allows it
@@ -219,18 +285,17 @@ __global__ void __launch_bounds__(VT_BT, 12) vt_bucket_kernel(const VtArgs a)
     const uint32_t S = 1u << lgS, smask = S - 1, hshift = 32u - lgS;
     for (uint32_t s = tid; s < S; s += VT_BT) tab[s] = make_uint4(VT_NONE, VT_NONE, 0u, 0u);
     if (tid == 0) { misc[1] = 0; misc[2] = 0; }
-#pragma unroll
-    for (int k = 0; k < VT_EPT; k++)
-        if (tid + k * VT_BT >= n) en[k].x = VT_NONE;
     __syncthreads();
     if (tid == 0) qcount[bk] = 0;   // everybody has read it: the counter is ready for the next chunk
     if (n > S) { if (tid == 0) *a.bail = 1u; return; }   // (n is CTA-uniform)
 
+    // every loop over the thread's entries stops at the bucket's count (CTA-uniform): an ordinary bucket holds ~2.6 per thread
     uint32_t sl[VT_EPT];
 #pragma unroll
     for (int k = 0; k < VT_EPT; k++) {
         sl[k] = 0;
-        if (en[k].x != VT_NONE) {
+        if (k * VT_BT >= n) break;
+        if (tid + k * VT_BT < n) {
             uint32_t s = vt_home(en[k].x, hshift);
             for (uint32_t it = 0; it <= S; it++) {
                 const uint32_t old = atomicCAS(&tab[s].x, VT_NONE, en[k].x);
@@ -248,8 +313,9 @@ __global__ void __launch_bounds__(VT_BT, 12) vt_bucket_kernel(const VtArgs a)
     if (cthr != VT_NONE) {
         bool anyc = false;
 #pragma unroll
-        for (int k = 0; k < VT_EPT; k++)
-            if (en[k].x != VT_NONE) {
+        for (int k = 0; k < VT_EPT; k++) {
+            if (k * VT_BT >= n) break;
+            if (tid + k * VT_BT < n) {
                 const uint4 t = tab[sl[k]];
                 if (t.z > cthr) {
                     anyc = true;
@@ -263,11 +329,13 @@ __global__ void __launch_bounds__(VT_BT, 12) vt_bucket_kernel(const VtArgs a)
                     }
                 }
             }
+        }
         if (__syncthreads_or((int)anyc)) {
             if (misc[2]) { if (tid == 0) *a.bail = 1u; return; }
 #pragma unroll
-            for (int k = 0; k < VT_EPT; k++)
-                if (en[k].x != VT_NONE) {
+            for (int k = 0; k < VT_EPT; k++) {
+                if (k * VT_BT >= n) break;
+                if (tid + k * VT_BT < n) {
                     const uint4 t = tab[sl[k]];
                     if (t.z > cthr) {
                         uint32_t *rec = pool + t.w * VT_MAXK;
@@ -279,26 +347,29 @@ __global__ void __launch_bounds__(VT_BT, 12) vt_bucket_kernel(const VtArgs a)
                         }
                     }
                 }
+            }
             __syncthreads();
         }
     }
 
     // a new word for every point that shares its voxel (a point that hears nothing is the only point of its voxel)
 #pragma unroll
-    for (int k = 0; k < VT_EPT; k++)
-        if (en[k].x != VT_NONE) {
+    for (int k = 0; k < VT_EPT; k++) {
+        if (k * VT_BT >= n) break;
+        if (tid + k * VT_BT < n) {
             const uint4 t = tab[sl[k]];
             if (t.z != 1u) {
                 uint32_t r;
                 if ((long long)t.z < (long long)a.min_points) r = VT_W_NONE;
-                else if (en[k].y == t.y) { r = VT_W_HEAD | min(t.z, VT_VAL); hkey[en[k].y] = en[k].x; }
+                else if (en[k].y == t.y) { r = VT_W_HEAD | min(t.z, VT_VAL); vt_st32(hkey + en[k].y, en[k].x, keep); }
                 else {
                     const bool kept = !(t.z > cthr) || en[k].y <= pool[t.w * VT_MAXK + K - 1];
                     r = kept ? (VT_W_JOIN | t.y) : VT_W_NONE;
                 }
-                word[en[k].y] = r;
+                vt_st32(word + en[k].y, r, keep);
             }
         }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ scan
@@ -307,9 +378,10 @@ __global__ void __launch_bounds__(VT_THREADS) vt_scan_kernel(const VtArgs a, uin
 {
     const VtGeom &g = a.g;
     const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
-    __shared__ unsigned long long wsum[VT_WARPS + 1];   // [8] warp sums, then exclusive warp bases; [8] the tile's exclusive prefix
+    __shared__ unsigned long long wsum[VT_WARPS], red[VT_WARPS];
     __shared__ uint32_t s_misc[2];
-    unsigned long long *s_excl = wsum + VT_WARPS;
+    vt_pdl_enter();
+    const uint64_t keepp = vt_policy_keep();
 
     if (tid == 0) s_misc[0] = atomicAdd(&a.tickets[chunk], 1u);
     __syncthreads();
@@ -327,7 +399,7 @@ __global__ void __launch_bounds__(VT_THREADS) vt_scan_kernel(const VtArgs a, uin
 #pragma unroll
     for (int u = 0; u < VT_SPT; u++) {
         const uint32_t i = t0 + (w * VT_SPT + u) * 32 + lane;
-        const uint32_t x = i < L ? word[i] : VT_W_NONE;
+        const uint32_t x = i < L ? vt_ld32(word + i, keepp) : VT_W_NONE;
         bool head, keep;
         vt_decode(a, x, &head, &keep);
         const uint32_t hb = __ballot_sync(0xffffffffu, head), kb = __ballot_sync(0xffffffffu, keep);
@@ -342,33 +414,29 @@ __global__ void __launch_bounds__(VT_THREADS) vt_scan_kernel(const VtArgs a, uin
     }
     if (lane == 31) wsum[w] = ((unsigned long long)ik << 31) | ih;
     __syncthreads();
-    if (w == 0) {
-        const unsigned long long v = lane < (unsigned)VT_WARPS ? wsum[lane] : 0ull;
-        unsigned long long inc = v;
+    unsigned long long total = 0, wex = 0;
 #pragma unroll
-        for (int d = 1; d < VT_WARPS; d <<= 1) { const unsigned long long x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (unsigned)d) inc += x; }
-        const unsigned long long total = __shfl_sync(0xffffffffu, inc, VT_WARPS - 1);
-        const unsigned long long ex = vt_lookback(a.status, gt, total);
-        if (lane < (unsigned)VT_WARPS) wsum[lane] = inc - v;
-        if (lane == 0) {
-            *s_excl = ex;
-            if (t == 0) { a.counts[2 * f] = (long long)((ex >> 31) & VT_F31); a.counts[2 * f + 1] = (long long)(ex & VT_F31); }
-            if (gt == a.nframes * (int64_t)g.spf - 1) {
-                const unsigned long long e2 = ex + total;
-                a.counts[2 * a.nframes] = (long long)((e2 >> 31) & VT_F31); a.counts[2 * a.nframes + 1] = (long long)(e2 & VT_F31);
-            }
+    for (int k = 0; k < VT_WARPS; k++) { if ((unsigned)k == w) wex = total; total += wsum[k]; }
+    const int64_t g0 = (int64_t)chunk * g.CF * g.spf;
+    const int64_t nfc = min((int64_t)g.CF, a.nframes - (int64_t)chunk * g.CF);
+    const unsigned long long ex = vt_tile_prefix(a.status, g0, gt, g0 + nfc * g.spf - 1, total, red);
+    if (tid == 0) {
+        if (t == 0) { a.counts[2 * f] = (long long)((ex >> 31) & VT_F31); a.counts[2 * f + 1] = (long long)(ex & VT_F31); }
+        if (gt == a.nframes * (int64_t)g.spf - 1) {
+            const unsigned long long e2 = ex + total;
+            a.counts[2 * a.nframes] = (long long)((e2 >> 31) & VT_F31); a.counts[2 * a.nframes + 1] = (long long)(e2 & VT_F31);
         }
     }
-    __syncthreads();
-    const unsigned long long run0 = *s_excl + wsum[w];
+    const unsigned long long run0 = ex + wex;
     const uint32_t Gh = ((uint32_t)run0 & VT_F31) + ih - __popc(myh), Gk = ((uint32_t)(run0 >> 31) & VT_F31) + ik - __popc(myk);
-    ri_f[t * (VT_STILE / 32) + w * VT_SPT + lane] = make_uint4(myh, Gh, myk, Gk);   // rows past the frame hold zero bits: harmless
+    vt_st128(ri_f + t * (VT_STILE / 32) + w * VT_SPT + lane, make_uint4(myh, Gh, myk, Gk), keepp);   // rows past the frame hold zero bits: harmless
 }
 
 // ------------------------------------------------------------------------------------------------ write
 template <bool NF4>
-__global__ void __launch_bounds__(VT_THREADS, 4) vt_write_kernel(const VtArgs a, const VcDev dv, uint32_t chunk)
+__global__ void __launch_bounds__(VT_THREADS, D3D_VT_WCTAS) vt_write_kernel(const VtArgs a, const VcDev dv, uint32_t chunk)
 {
+    vt_pdl_enter();
     const VtGeom &g = a.g;
     const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
     const unsigned ltmask = lanemask_lt();
@@ -378,6 +446,7 @@ __global__ void __launch_bounds__(VT_THREADS, 4) vt_write_kernel(const VtArgs a,
     const uint32_t L = (uint32_t)min((long long)(a.offs[f + 1] - b), (long long)g.lmax);
     const uint32_t t0 = t * VT_TILE;
     if (t0 >= L) return;
+    const uint64_t keepp = vt_policy_keep(), strm = vt_policy_stream();
     const uint32_t vb = (uint32_t)a.counts[2 * f + 1];   // the frame's first voxel row
     const uint32_t *word = a.word + (size_t)fl * g.lpad, *hkey = a.hkey + (size_t)fl * g.lpad;
     const uint4 *ri_f = a.rowinfo + (size_t)fl * (g.lpad / 32);
@@ -388,13 +457,13 @@ __global__ void __launch_bounds__(VT_THREADS, 4) vt_write_kernel(const VtArgs a,
     // first round trip: words, row table entries (lane u holds row u's) and the points of the warp's four rows, unconditionally
     uint32_t wd[VT_PPT];
     float4 p4[VT_PPT];
-    const uint4 rme = ri_f[row0 + (lane & (VT_PPT - 1))];
+    const uint4 rme = vt_ld128(ri_f + row0 + (lane & (VT_PPT - 1)), keepp);
 #pragma unroll
     for (int u = 0; u < VT_PPT; u++) {
         const uint32_t i = (row0 + u) * 32 + lane;
-        wd[u] = i < L ? word[i] : VT_W_NONE;
+        wd[u] = i < L ? vt_ld32(word + i, keepp) : VT_W_NONE;
         p4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (NF4 && i < L) p4[u] = __ldg(reinterpret_cast<const float4 *>(a.pts) + b + i);
+        if (NF4 && i < L) p4[u] = vt_ldpt(reinterpret_cast<const float4 *>(a.pts) + b + i, strm);   // last use
     }
     // second round trip, few lanes: keys of first points of shared voxels, row table entries of the joiners' first points
     uint32_t ckey[VT_PPT];
@@ -404,8 +473,8 @@ __global__ void __launch_bounds__(VT_THREADS, 4) vt_write_kernel(const VtArgs a,
         const uint32_t i = (row0 + u) * 32 + lane;
         const uint32_t cat = wd[u] >> 30;
         ckey[u] = wd[u]; rj[u] = make_uint2(0u, 0u);
-        if (cat == 3u) ckey[u] = hkey[i];
-        if (cat == 2u) rj[u] = *reinterpret_cast<const uint2 *>(ri_f + ((wd[u] & VT_VAL) >> 5));   // the id lives where the voxel's first point lives
+        if (cat == 3u) ckey[u] = vt_ld32(hkey + i, keepp);
+        if (cat == 2u) rj[u] = vt_ld64(ri_f + ((wd[u] & VT_VAL) >> 5), keepp);   // the id lives where the voxel's first point lives
     }
 #pragma unroll
     for (int u = 0; u < VT_PPT; u++) {
@@ -420,20 +489,20 @@ __global__ void __launch_bounds__(VT_THREADS, 4) vt_write_kernel(const VtArgs a,
             vrow = gh + __popc(hb & ltmask);
             const uint32_t c = (x >> 30) ? (x & VT_VAL) : 1u, key = ckey[u];
             long long *co = reinterpret_cast<long long *>(a.out_coords) + (size_t)vrow * 3;
-            __stcs(co + 0, (long long)(key >> dv.sh_x) + dv.cadd[0]);
-            __stcs(co + 1, (long long)((key >> dv.sh_y) & mask_y) + dv.cadd[1]);
-            __stcs(co + 2, (long long)(key & mask_z) + dv.cadd[2]);
-            __stcs(a.out_npoints + vrow, (a.trim && c > a.K) ? (int32_t)a.K : (int32_t)c);
+            vt_st64ll(co + 0, (long long)(key >> dv.sh_x) + dv.cadd[0], strm);
+            vt_st64ll(co + 1, (long long)((key >> dv.sh_y) & mask_y) + dv.cadd[1], strm);
+            vt_st64ll(co + 2, (long long)(key & mask_z) + dv.cadd[2], strm);
+            vt_st32(a.out_npoints + vrow, (a.trim && c > a.K) ? a.K : c, strm);
         } else if (keep) {
             const uint32_t m = x & VT_VAL;
             vrow = rj[u].y + __popc(rj[u].x & ((1u << (m & 31u)) - 1u));
         }
         if (keep) {
             const size_t o = (size_t)gk + __popc(kb & ltmask);
-            if (NF4) __stcs(reinterpret_cast<float4 *>(a.out_points) + o, p4[u]);
+            if (NF4) vt_st128(reinterpret_cast<float4 *>(a.out_points) + o, make_uint4(__float_as_uint(p4[u].x), __float_as_uint(p4[u].y), __float_as_uint(p4[u].z), __float_as_uint(p4[u].w)), strm);
             else for (int q = 0; q < a.nfeat; q++) a.out_points[o * a.nfeat + q] = a.pts[(b + i) * a.nfeat + q];
-            __stcs(reinterpret_cast<long long *>(a.out_mask) + o, (long long)i);
-            __stcs(reinterpret_cast<long long *>(a.out_mapping) + o, (long long)(vrow - vb));
+            vt_st64ll(reinterpret_cast<long long *>(a.out_mask) + o, (long long)i, strm);
+            vt_st64ll(reinterpret_cast<long long *>(a.out_mapping) + o, (long long)(vrow - vb), strm);
         }
     }
 }
@@ -463,13 +532,13 @@ static bool vt_geom(int64_t max_frame_points, int64_t nframes, VtGeom *g)
     g->tpf = (g->lmax + VT_TILE - 1) / VT_TILE;
     g->spf = (g->lmax + VT_STILE - 1) / VT_STILE;
     g->lpad = g->spf * VT_STILE;
-    g->lgP = vt_lg2_ceil(((uint64_t)g->lmax + 511) / 512);
+    g->lgP = vt_lg2_ceil(((uint64_t)g->lmax + D3D_VT_BPTS - 1) / D3D_VT_BPTS);
     g->P = 1u << g->lgP;
     const uint32_t per = (g->lmax + g->P - 1) / g->P;            // points per bucket if every point is kept and the hash is even (<= 512)
     g->qcap = (per + per / 2 + 128 + 3) & ~3u;                   // <= VT_QCAP: a bucket's queue lives in its CTA's registers; more -> device flag
     if (g->qcap > (uint32_t)VT_QCAP) g->qcap = VT_QCAP;
     int cf = vt_env_cf();
-    if (cf <= 0) cf = 16;
+    if (cf <= 0) cf = 128;   // measured on C2 x 128 frames: 0.74 ms with chunks of 16 (scratch mostly L2-resident), 0.59 ms with one chunk (fewer, fuller launches)
     if ((int64_t)cf > nframes) cf = (int)(nframes > 0 ? nframes : 1);
     g->CF = (uint32_t)cf;
     g->nchunks = (uint32_t)((nframes + cf - 1) / cf);
@@ -548,20 +617,33 @@ int vox_tiles_sparse(const float *points, int64_t total, int nfeat, const int64_
 
     D3D_CUDA_TRY(cudaMemsetAsync(w + lay.zero, 0, lay.zero_end - lay.zero, st));
     const int roles = vt_env_roles();
+    // the kernels of the call are chained with programmatic dependent launch: each one may be scheduled while its predecessor
+    // drains and waits (griddepcontrol.wait) for the predecessor's results
+    cudaLaunchAttribute pdl[1];
+    pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl[0].val.programmaticStreamSerializationAllowed = 1;
+    auto cfg_of = [&](dim3 grid, unsigned threads, size_t smem) {
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = grid; lc.blockDim = dim3(threads, 1, 1); lc.dynamicSmemBytes = smem; lc.stream = st;
+        lc.attrs = pdl; lc.numAttrs = 1;
+        return lc;
+    };
     const uint32_t dyn_split = 8u * g.P;
     for (uint32_t c = 0; c < g.nchunks; c++) {
         const int64_t rem = nframes - (int64_t)c * g.CF;
         const uint32_t nf = (uint32_t)(rem < (int64_t)g.CF ? rem : g.CF);
         if (roles & 1) {
-            if (nfeat == 4) vt_split_kernel<true><<<dim3(g.tpf, nf), VT_THREADS, dyn_split, st>>>(a, dv, c);
-            else vt_split_kernel<false><<<dim3(g.tpf, nf), VT_THREADS, dyn_split, st>>>(a, dv, c);
+            cudaLaunchConfig_t lc = cfg_of(dim3(g.tpf, nf), VT_THREADS, dyn_split);
+            if (nfeat == 4) D3D_CUDA_TRY(cudaLaunchKernelEx(&lc, vt_split_kernel<true>, a, dv, c));
+            else D3D_CUDA_TRY(cudaLaunchKernelEx(&lc, vt_split_kernel<false>, a, dv, c));
             D3D_LAUNCHED();
         }
-        if (roles & 2) { vt_bucket_kernel<<<dim3(g.P, nf), VT_BT, 0, st>>>(a); D3D_LAUNCHED(); }
-        if (roles & 4) { vt_scan_kernel<<<nf * g.spf, VT_THREADS, 0, st>>>(a, c); D3D_LAUNCHED(); }
+        if (roles & 2) { cudaLaunchConfig_t lc = cfg_of(dim3(g.P, nf), VT_BT, 0); D3D_CUDA_TRY(cudaLaunchKernelEx(&lc, vt_bucket_kernel, a)); D3D_LAUNCHED(); }
+        if (roles & 4) { cudaLaunchConfig_t lc = cfg_of(dim3(nf * g.spf), VT_THREADS, 0); D3D_CUDA_TRY(cudaLaunchKernelEx(&lc, vt_scan_kernel, a, c)); D3D_LAUNCHED(); }
         if (roles & 8) {
-            if (nfeat == 4) vt_write_kernel<true><<<dim3(g.tpf, nf), VT_THREADS, 0, st>>>(a, dv, c);
-            else vt_write_kernel<false><<<dim3(g.tpf, nf), VT_THREADS, 0, st>>>(a, dv, c);
+            cudaLaunchConfig_t lc = cfg_of(dim3(g.tpf, nf), VT_THREADS, 0);
+            if (nfeat == 4) D3D_CUDA_TRY(cudaLaunchKernelEx(&lc, vt_write_kernel<true>, a, dv, c));
+            else D3D_CUDA_TRY(cudaLaunchKernelEx(&lc, vt_write_kernel<false>, a, dv, c));
             D3D_LAUNCHED();
         }
     }
