@@ -49,6 +49,11 @@ iou3d_distance = _sig("d3d_iou3d_distance_f32", C.c_int, [_vp, _i64, _vp, _i64, 
 crop_workspace_bytes = _sig("d3d_crop2dr_workspace_bytes", _sz, [_i64, _i64, C.c_int])
 _crop_sig = [_vp, _i64, _vp, _i64, _vp, _vp, _sz, _vp]
 crop2dr = {F32: _sig("d3d_crop2dr_f32", C.c_int, _crop_sig), F64: _sig("d3d_crop2dr_f64", C.c_int, _crop_sig)}
+_pd_sig = [_vp, _i64, _vp, _i64, _vp, _vp, _vp]
+pdist2dr = {F32: _sig("d3d_pdist2dr_f32", C.c_int, _pd_sig), F64: _sig("d3d_pdist2dr_f64", C.c_int, _pd_sig)}
+_pdb_sig = [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]
+pdist2dr_backward = {F32: _sig("d3d_pdist2dr_backward_f32", C.c_int, _pdb_sig), F64: _sig("d3d_pdist2dr_backward_f64", C.c_int, _pdb_sig)}
+match_greedy = _sig("d3d_match_greedy_f32", C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp])
 iou_count_candidates = _sig("d3d_iou_count_candidates", C.c_int, [_vp, _i64, _vp, _i64, C.c_int, _vp, _vp, _sz, _vp])
 nms_workspace_bytes = _sig("d3d_nms2d_workspace_bytes", _sz, [_i64, C.c_int])
 _nms_sig = [_vp, _vp, _i64, C.c_int, C.c_int, _f, _f, _f, _vp, _vp, _sz, _vp]

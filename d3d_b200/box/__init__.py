@@ -156,6 +156,94 @@ def box3dp_crop(points, boxes, project_axis=2):
     return mask_2d & mask_p.to(mask_2d.device)
 
 
+class PDist2DR(torch.autograd.Function):
+    """Differentiable signed distance from points to rotated boxes (reference d3d/box/__init__.py:149-166 over pdist2dr_forward /
+    pdist2dr_backward[_cuda], d3d/box/dist.h:7-23).  Returns T[M boxes, N points], positive inside -- the layout of the native function
+    (and of box2dr_crop).  The reference's wrapper hands (boxes, points) to a native function declared (points, boxes) and cannot run."""
+    @staticmethod
+    def forward(ctx, points, boxes):
+        code = _c.dtype_code(points.dtype)
+        if boxes.dtype != points.dtype:
+            raise RuntimeError("points and boxes must have the same dtype")
+        n, m = points.shape[0], boxes.shape[0]
+        dist = torch.empty((m, n), dtype=points.dtype, device=points.device)
+        if n and m:
+            with torch.cuda.device(points.device):
+                st = _c.pdist2dr[code](_c.ptr(points), n, _c.ptr(boxes), m, _c.ptr(dist), None, _c.stream_ptr())
+            _c.check(st, "box2dr_pdist")
+        ctx.save_for_backward(points, boxes)
+        return dist
+
+    @staticmethod
+    def backward(ctx, grad):
+        points, boxes = ctx.saved_tensors
+        code = _c.dtype_code(points.dtype)
+        n, m = points.shape[0], boxes.shape[0]
+        grad = grad.contiguous()
+        grad_boxes, grad_points = torch.zeros_like(boxes), torch.zeros_like(points)
+        if n and m:
+            with torch.cuda.device(points.device):
+                st = _c.pdist2dr_backward[code](_c.ptr(points), n, _c.ptr(boxes), m, _c.ptr(grad), _c.ptr(grad_boxes), _c.ptr(grad_points), _c.stream_ptr())
+            _c.check(st, "box2dr_pdist backward")
+        return grad_points, grad_boxes
+
+
+def seg1d_pdist(points, segs):
+    """Signed distance from points [N] to 1-D segments [M, 2] (centre, width), positive inside: [M, N]
+    (reference d3d/box/__init__.py:316-328, in the [segments, points] layout of box2dr_pdist)."""
+    assert torch.all(segs[:, 1] > 0)
+    dsegs = (segs[:, 1] / 2)[:, None]
+    ctr = segs[:, 0][:, None]
+    return torch.where(points[None, :] > ctr, (ctr + dsegs) - points[None, :], points[None, :] - (ctr - dsegs))
+
+
+def box2dr_pdist(points, boxes, method="rbox"):
+    '''
+    Calculate signed distance from points to 2d boxes (surfaces), positive inside (reference d3d/box/__init__.py:330-346).
+    Differentiable in points and boxes.
+
+    :param points: target points, shape: N x 2
+    :param boxes: target boxes, shape: M x 5
+    :param method: 'rbox' - rotated box
+    :return: M x N
+    '''
+    if len(boxes.shape) != 2:
+        raise ValueError("Input boxes should be Nx2 tensors!")
+    if boxes.shape[1] != 5:
+        raise ValueError("Input boxes should have 5 fields: x, y, w, h, r")
+    if len(points.shape) != 2 or points.shape[1] != 2:
+        raise ValueError("Input points should be Nx2 tensors!")
+    if method != "rbox":
+        raise ValueError("Only supported rotated boxes by now!")
+    odev = points.device
+    r = PDist2DR.apply(_c.to_device(points).contiguous(), _c.to_device(boxes).contiguous())
+    return r if odev.type == "cuda" else r.cpu()
+
+
+def box3dr_pdist(points, boxes, project_axis=2):
+    '''
+    Calculate signed distance from points to 3d boxes (surfaces) (reference d3d/box/__init__.py:348-381)
+
+    :param points: target points, shape: N x 3
+    :param boxes: target boxes, shape: M x 7
+    :param project_axis: Axis for the box to be projected to. {0: x, 1: y, 2: z}
+    :return: M x N
+    '''
+    if project_axis == 0:
+        points_2d, boxes_2d = points[:, [1, 2]], boxes[:, [1, 2, 4, 5, 6]]
+    elif project_axis == 1:
+        points_2d, boxes_2d = points[:, [0, 2]], boxes[:, [0, 2, 3, 5, 6]]
+    elif project_axis == 2:
+        points_2d, boxes_2d = points[:, [0, 1]], boxes[:, [0, 1, 3, 4, 6]]
+    else:
+        raise ValueError("The projection axis can only be 0-x, 1-y and 2-z!")
+    dist_2d = box2dr_pdist(points_2d, boxes_2d)
+    dist_p = seg1d_pdist(points[:, project_axis], boxes[:, [project_axis, 3 + project_axis]]).to(dist_2d.device)
+    return torch.where(dist_p > 0,
+                       torch.where(dist_2d > 0, torch.min(dist_p, dist_2d), dist_2d),
+                       torch.where(dist_2d > 0, dist_p, -torch.sqrt(dist_2d.square() + dist_p.square())))
+
+
 def box3d_iou_distance(src_boxes, dst_boxes, metric="riou"):
     '''
     Distance matrix of the detection evaluator / tracking matcher: ``1 - iou2d * ziou`` in float32, the array
@@ -256,3 +344,49 @@ def box2d_nms(boxes, scores, iou_method="box", supression_method="hard",
     if convert_numpy:
         return mask.numpy()
     return mask
+
+
+def match_greedy(distance, src_scores, src_tags, dst_tags, thresholds):
+    '''
+    Greedy score-ordered matching on a distance matrix: ``ScoreMatcher.match`` of the reference (d3d/tracking/matcher.pyx:138-162 over
+    match_by_order :93-122) for one or many threshold sets at once -- the detection evaluator's loop over score thresholds
+    (d3d/benchmarks.pyx:220-238) is one launch.  Source boxes are visited from the best score down (ties: the later box first, like
+    ``np.flip(np.argsort(scores))``); each takes the closest free destination box of its category whose distance is <= the threshold.
+
+    :param distance: float32 N x M, e.g. the result of :func:`box3d_iou_distance`
+    :param src_scores: N scores of the source boxes
+    :param src_tags, dst_tags: integer category per source / destination box, values in [0, C)
+    :param thresholds: T x C (or C for a single set): maximum distance per category
+    :return: (src_assignment int32 T x N, dst_assignment int32 T x M) with -1 for unmatched boxes; the leading dimension is dropped
+        for a single threshold set.  numpy in -> numpy out.
+    '''
+    convert_numpy = isinstance(distance, np.ndarray)
+    as_t = lambda x, dt: (torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else torch.as_tensor(x)).to(dt)
+    distance = as_t(distance, torch.float32)
+    odev = distance.device
+    d = _c.to_device(distance).contiguous()
+    dev = d.device
+    if d.dim() != 2:
+        raise ValueError("distance should be an NxM matrix")
+    n, m = d.shape
+    thr = as_t(thresholds, torch.float32)
+    single = thr.dim() == 1
+    thr = thr.reshape(1, -1) if single else thr
+    scores = as_t(src_scores, torch.float64)
+    st, dt_ = as_t(src_tags, torch.int32).to(dev).contiguous(), as_t(dst_tags, torch.int32).to(dev).contiguous()
+    if len(scores) != n or len(st) != n or len(dt_) != m:
+        raise ValueError("scores / tags do not match the distance matrix")
+    order = torch.flip(torch.argsort(scores.cpu(), stable=True), dims=[0]).to(torch.int32).to(dev).contiguous()   # np.flip(np.argsort(scores))
+    thr = thr.to(dev).contiguous()
+    T, ncat = thr.shape
+    sa = torch.empty((T, n), dtype=torch.int32, device=dev)
+    da = torch.empty((T, m), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        stt = _c.match_greedy(_c.ptr(d), n, m, d.stride(0) if n else max(m, 1), _c.ptr(order), _c.ptr(st), _c.ptr(dt_), _c.ptr(thr), T, ncat, _c.ptr(sa), _c.ptr(da),
+                              _c.stream_ptr())
+    _c.check(stt, "match_greedy")
+    if single:
+        sa, da = sa[0], da[0]
+    if odev.type != "cuda" or convert_numpy:
+        sa, da = sa.cpu(), da.cpu()
+    return (sa.numpy(), da.numpy()) if convert_numpy else (sa, da)

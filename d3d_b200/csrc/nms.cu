@@ -566,6 +566,149 @@ nms_resolve_kernel(const uint64_t *__restrict__ mask, int64_t n, int64_t nwords,
     }
 }
 
+// ------------------------------------------------------------------------------------------------ soft-NMS
+// LINEAR / GAUSSIAN suppression (reference d3d/box/nms.cpp:33-94; its CUDA version, nms_cuda.cu:108-153, needs a dense N x N
+// coefficient matrix and indexes it with tile-local positions).  The rule is sequential in the boxes AND in the scores: after
+// box i has decayed the scores of everything behind it, the reference re-sorts the positions between i and the last suppressed
+// box with a stable insertion sort, so the next box is not known before the previous one is done.  One CTA walks that sequence:
+//   * the decay of the boxes behind position _i runs over all threads (one IoU each per round);
+//   * the re-sort is incremental: boxes whose score did not change since they were last sorted are still in order, so only the
+//     changed ones (a handful) are merged back -- rank among the unchanged ones by binary search, rank among the changed ones by
+//     counting -- which is the same permutation the insertion sort produces (both are THE stable sort by "not suppressed first,
+//     then score descending"); suppressed boxes keep their relative order, which the mask does not depend on.
+// Arrays are indexed by the box's position in the initial stable score order.
+constexpr int SOFT_THREADS = 1024;
+constexpr int SOFT_BCAP = 1024;   // changed boxes merged per step without falling back to counting all pairs
+
+template <typename T> struct SoftState {
+    T *sc;             // current scores
+    uint32_t *ord;     // ord[q] = box at position q of the emulated order
+    uint32_t *tmp;     // [n] unchanged boxes of the range, compacted
+    uint8_t *sup;      // suppressed
+    uint8_t *mk;       // score changed since the box was last sorted
+};
+
+// a before b in the order the reference's insertion sort produces
+template <typename T>
+__device__ __forceinline__ bool soft_before(const SoftState<T> &S, const uint32_t *pos, uint32_t a, uint32_t b)
+{
+    const bool sa = S.sup[a] != 0, sb = S.sup[b] != 0;
+    if (sa != sb) return sb;
+    if (!sa) { const T xa = S.sc[a], xb = S.sc[b]; if (xa != xb) return xa > xb; }
+    return pos[a] < pos[b];
+}
+
+template <typename T, bool AABB>
+__global__ void __launch_bounds__(SOFT_THREADS) nms_soft_kernel(const BoxRec<T> *__restrict__ recs, const AABBRec<T> *__restrict__ arecs, const T *__restrict__ scores,
+                                                                const uint32_t *__restrict__ order, int64_t n64, T thr, T sthr, T param, int sup_type,
+                                                                SoftState<T> S, uint32_t *__restrict__ pos, uint8_t *__restrict__ suppressed)
+{
+    const uint32_t n = (uint32_t)n64, tid = threadIdx.x, NT = SOFT_THREADS;
+    __shared__ uint32_t s_red[32], s_cnt, s_S, s_dirty;
+    __shared__ uint32_t Bp[SOFT_BCAP];
+    for (uint32_t p = tid; p < n; p += NT) {
+        const T v = scores[order[p]];
+        S.sc[p] = v; S.ord[p] = p; pos[p] = p; S.mk[p] = 0;
+        S.sup[p] = v > sthr ? 0 : 1;   // reference CUDA rule (nms_cuda.cu:223), as for hard NMS
+    }
+    __syncthreads();
+    uint32_t E = n;   // positions (_i, E) that are not marked are mutually sorted
+    for (uint32_t _i = 0; _i < n; _i++) {
+        __syncthreads();       // the previous step's reads of the shared words are done
+        const uint32_t i = S.ord[_i];
+        if (S.sup[i]) break;   // nms.cpp:37-42: everything behind a suppressed box is suppressed
+        if (tid == 0) { s_S = _i; s_cnt = 0; s_dirty = 0; }
+        __syncthreads();
+        // decay
+        {
+            BoxRec<T> A; AABBRec<T> AA;
+            if (AABB) AA = arecs[i]; else A = recs[i];
+            uint32_t smax = _i;
+            for (uint32_t q = _i + 1 + tid; q < n; q += NT) {
+                const uint32_t j = S.ord[q];
+                const T iou = AABB ? aabb_iou<T>(AA, arecs[j]) : rbox_iou<T>(A, recs[j]);
+                if (iou > thr) {
+                    const T coef = sup_type == D3D_SUP_LINEAR ? T(1) - pow(iou, param) : exp(-iou * iou / param);
+                    const T v = S.sc[j] * coef;
+                    S.sc[j] = v; S.sup[j] = v < sthr ? 1 : 0; S.mk[j] = 1;
+                }
+                if (S.sup[j]) smax = q;
+            }
+            // S = last position behind _i that holds a suppressed box (nms.cpp:77-78)
+#pragma unroll
+            for (int d = 16; d; d >>= 1) smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, d));
+            if ((tid & 31u) == 0) atomicMax(&s_S, smax);
+        }
+        __syncthreads();
+        const uint32_t Sp = s_S;
+        if (Sp <= _i + 2) continue;   // zero or one box in the range: nothing to sort (uniform); marks stay for a later sort
+        const uint32_t r0 = _i + 1, m = Sp - r0;   // range [r0, Sp)
+        // split the range into unchanged boxes (still mutually sorted) and the rest
+        const uint32_t per = (m + NT - 1) / NT, q0 = r0 + tid * per, q1 = min(q0 + per, Sp);
+        uint32_t na = 0;
+        for (uint32_t q = q0; q < q1; q++) { const uint32_t j = S.ord[q]; if (!(S.mk[j] || q >= E)) na++; }
+        // exclusive prefix of na over the threads
+        uint32_t inc = na;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d); if ((tid & 31u) >= (unsigned)d) inc += x; }
+        if ((tid & 31u) == 31u) s_red[tid >> 5] = inc;
+        __syncthreads();
+        if (tid < 32) {
+            uint32_t v = s_red[tid], iv = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, iv, d); if (tid >= (unsigned)d) iv += x; }
+            s_red[tid] = iv - v;
+            if (tid == 31) s_dirty = iv;   // unchanged boxes in the range
+        }
+        __syncthreads();
+        uint32_t abase = s_red[tid >> 5] + inc - na;
+        const uint32_t nA = s_dirty, nB = m - nA;
+        if (nB == 0) continue;        // nothing changed inside the range: it is still sorted
+        const bool brute = nB > (uint32_t)SOFT_BCAP;
+        for (uint32_t q = q0; q < q1; q++) {
+            const uint32_t j = S.ord[q];
+            if (!(S.mk[j] || q >= E)) S.tmp[abase++] = j;
+            else if (!brute) Bp[atomicAdd(&s_cnt, 1u)] = j;
+        }
+        __syncthreads();
+        if (!brute) {
+            // unchanged box a at compact index ia: new position = r0 + ia + (changed boxes before it)
+            for (uint32_t ia = tid; ia < nA; ia += NT) {
+                const uint32_t a = S.tmp[ia];
+                uint32_t c = 0;
+                for (uint32_t k = 0; k < nB; k++) c += soft_before<T>(S, pos, Bp[k], a) ? 1u : 0u;
+                S.ord[r0 + ia + c] = a;
+            }
+            // changed box b: unchanged boxes before it (binary search: they are sorted) + changed boxes before it
+            for (uint32_t kb = tid; kb < nB; kb += NT) {
+                const uint32_t b = Bp[kb];
+                uint32_t lo = 0, hi = nA;
+                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (soft_before<T>(S, pos, S.tmp[mid], b)) lo = mid + 1; else hi = mid; }
+                uint32_t c = lo;
+                for (uint32_t k = 0; k < nB; k++) c += (k != kb && soft_before<T>(S, pos, Bp[k], b)) ? 1u : 0u;
+                S.ord[r0 + c] = b;
+            }
+        } else {
+            // many changed boxes: count all pairs (tmp receives a copy of the range first)
+            __syncthreads();
+            for (uint32_t q = r0 + tid; q < Sp; q += NT) S.tmp[q - r0] = S.ord[q];
+            __syncthreads();
+            for (uint32_t x = tid; x < m; x += NT) {
+                const uint32_t a = S.tmp[x];
+                uint32_t c = 0;
+                for (uint32_t y = 0; y < m; y++) c += (y != x && soft_before<T>(S, pos, S.tmp[y], a)) ? 1u : 0u;
+                S.ord[r0 + c] = a;
+            }
+        }
+        __syncthreads();
+        for (uint32_t q = r0 + tid; q < Sp; q += NT) { const uint32_t j = S.ord[q]; pos[j] = q; S.mk[j] = 0; }
+        E = Sp;
+        __syncthreads();
+    }
+    __syncthreads();
+    for (uint32_t p = tid; p < n; p += NT) suppressed[order[p]] = S.sup[p];
+}
+
 constexpr int64_t NMS_SPARSE_MAX_WORDS = 8192;   // block counters + staging must fit shared memory next to the bitmap
 
 template <typename T> static size_t nms_ws_bytes(int64_t n)
@@ -576,17 +719,17 @@ template <typename T> static size_t nms_ws_bytes(int64_t n)
     return align_up((size_t)n * 8) + align_up((size_t)n * 4) + radix_sort_workspace_bytes(n) + align_up((size_t)npad * recs) +
            align_up((size_t)npad * 5 * sizeof(T)) + align_up((size_t)npad) + align_up((size_t)npad * nwords * 8) +
            align_up((size_t)(nwords + 1) * 4) + align_up((size_t)nwords * NMS_LIST_CAP * 4) + align_up((size_t)nwords * NMS_LIST_CAP * 8) +
-           align_up(sizeof(NmsGrid)) + 2 * align_up((size_t)2 * (NMS_GRID_CELLS + 1) * 4) + align_up((size_t)npad * sizeof(NmsCand<T>)) + scan_workspace_bytes(NMS_GRID_CELLS + 1) + 4096;
+           align_up(sizeof(NmsGrid)) + 2 * align_up((size_t)2 * (NMS_GRID_CELLS + 1) * 4) + align_up((size_t)npad * sizeof(NmsCand<T>)) + scan_workspace_bytes(NMS_GRID_CELLS + 1) + 4096 +
+           align_up((size_t)npad * sizeof(T)) + 3 * align_up((size_t)npad * 4) + 2 * align_up((size_t)npad);   // soft-NMS state
 }
 
 template <typename T>
-static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, int sup_type, float iou_thr, float score_thr, uint8_t *suppressed,
+static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, int sup_type, float iou_thr, float score_thr, float sup_param, uint8_t *suppressed,
                     void *ws, size_t ws_bytes, cudaStream_t st)
 {
     if (n < 0) return D3D_ERR_INVALID_ARGUMENT;
     if (iou_type != D3D_IOU_BOX && iou_type != D3D_IOU_RBOX) return D3D_ERR_INVALID_ARGUMENT;  // reference: "Unsupported iou type!"
     if (sup_type < D3D_SUP_HARD || sup_type > D3D_SUP_GAUSSIAN) return D3D_ERR_INVALID_ARGUMENT;
-    if (sup_type != D3D_SUP_HARD) return D3D_ERR_UNSUPPORTED;
     if (n == 0) return D3D_OK;
     if (!boxes || !scores || !suppressed) return D3D_ERR_INVALID_ARGUMENT;
     if (n >= (1ll << 31)) return D3D_ERR_INVALID_ARGUMENT;
@@ -612,6 +755,10 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
     uint32_t *cellptr = a.take<uint32_t>((size_t)2 * (NMS_GRID_CELLS + 1));
     NmsCand<T> *celllist = a.take<NmsCand<T>>((size_t)npad);
     void *cell_scan_ws = a.take<char>(scan_workspace_bytes(NMS_GRID_CELLS + 1));
+    SoftState<T> soft;
+    soft.sc = a.take<T>(npad); soft.ord = a.take<uint32_t>(npad); soft.tmp = a.take<uint32_t>(npad);
+    uint32_t *soft_pos = a.take<uint32_t>(npad);
+    soft.sup = a.take<uint8_t>(npad); soft.mk = a.take<uint8_t>(npad);
     if (!a.ok()) return D3D_ERR_WORKSPACE;
     // tuning / test override: D3D_B200_NMS_PATH=dense (dense matrix, dense resolve) | tiles (dense tiles + list resolve); default: spatial
     const char *path_env = getenv("D3D_B200_NMS_PATH");
@@ -631,6 +778,12 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
         nms_gather_kernel<T, false><<<(unsigned)cdiv(npad, 256), 256, 0, st>>>(boxes, scores, order, n, npad, score_thr, (BoxRec<T> *)recs, nullptr, recheck ? raw : nullptr, valid);
     D3D_LAUNCHED();
     const T thr = (T)iou_thr;   // (T)(float): SURVEY.md 8(c) T2
+    if (sup_type != D3D_SUP_HARD) {   // sequential in boxes and scores: one CTA emulates the reference's order
+        if (aabb) nms_soft_kernel<T, true><<<1, SOFT_THREADS, 0, st>>>(nullptr, (const AABBRec<T> *)recs, scores, order, n, thr, (T)score_thr, (T)sup_param, sup_type, soft, soft_pos, suppressed);
+        else nms_soft_kernel<T, false><<<1, SOFT_THREADS, 0, st>>>((const BoxRec<T> *)recs, nullptr, scores, order, n, thr, (T)score_thr, (T)sup_param, sup_type, soft, soft_pos, suppressed);
+        D3D_LAUNCHED();
+        return D3D_OK;
+    }
     if (nwords > 65535) return D3D_ERR_INVALID_ARGUMENT;
     // spatial candidate search: pairs with disjoint bounding circles have IoU 0, which never exceeds a threshold >= 0
     const bool spatial = !aabb && lists.blkcnt && thr >= T(0) && !force_tiles;
@@ -672,7 +825,7 @@ using namespace d3d;
 extern "C" size_t d3d_nms2d_workspace_bytes(int64_t n, int dtype) { return dtype == D3D_F64 ? nms_ws_bytes<double>(n) : nms_ws_bytes<float>(n); }
 extern "C" int d3d_nms2d_f32(const float *boxes, const float *scores, int64_t n, int iou_type, int sup_type, float iou_thr, float score_thr, float sup_param,
                              uint8_t *suppressed, void *ws, size_t wsb, void *stream)
-{ (void)sup_param; return nms_impl<float>(boxes, scores, n, iou_type, sup_type, iou_thr, score_thr, suppressed, ws, wsb, (cudaStream_t)stream); }
+{ return nms_impl<float>(boxes, scores, n, iou_type, sup_type, iou_thr, score_thr, sup_param, suppressed, ws, wsb, (cudaStream_t)stream); }
 extern "C" int d3d_nms2d_f64(const double *boxes, const double *scores, int64_t n, int iou_type, int sup_type, float iou_thr, float score_thr, float sup_param,
                              uint8_t *suppressed, void *ws, size_t wsb, void *stream)
-{ (void)sup_param; return nms_impl<double>(boxes, scores, n, iou_type, sup_type, iou_thr, score_thr, suppressed, ws, wsb, (cudaStream_t)stream); }
+{ return nms_impl<double>(boxes, scores, n, iou_type, sup_type, iou_thr, score_thr, sup_param, suppressed, ws, wsb, (cudaStream_t)stream); }

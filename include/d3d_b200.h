@@ -82,6 +82,16 @@ int d3d_iou2d_f64(const double *boxes1, int64_t n, const double *boxes2, int64_t
 size_t d3d_iou3d_distance_workspace_bytes(int64_t n, int64_t m);
 int d3d_iou3d_distance_f32(const float *boxes1, int64_t n, const float *boxes2, int64_t m, int rotated, float *dist,
                            int64_t ld, void *workspace, size_t workspace_bytes, void *stream);
+/* Greedy score-ordered matching over a distance matrix: replaces the pair walk of ScoreMatcher.match +
+ * BaseMatcher.match_by_order (reference d3d/tracking/matcher.pyx:93-122, 138-162) that the detection evaluator repeats for every score
+ * threshold (d3d/benchmarks.pyx:220-238).  dist f32[n, m] with leading dimension ld (the matrix d3d_iou3d_distance_f32 writes);
+ * src_order i32[n] = source indices from the best score down; src_tag i32[n], dst_tag i32[m] = category indices in [0, ncat);
+ * thresholds f32[nsets, ncat]: set t matches a pair when dist <= thresholds[t][category].  Outputs (device) src_assign i32[nsets, n],
+ * dst_assign i32[nsets, m]: the partner's index or -1.  Each source takes the closest free destination of its category within the
+ * threshold; equal distances go to the lower destination index.  One CTA per threshold set. */
+int d3d_match_greedy_f32(const float *dist, int64_t n, int64_t m, int64_t ld, const int32_t *src_order, const int32_t *src_tag,
+                         const int32_t *dst_tag, const float *thresholds, int32_t nsets, int32_t ncat, int32_t *src_assign,
+                         int32_t *dst_assign, void *stream);
 /* Point-in-rotated-box mask: mask u8[m boxes, n points] row-major, 1 where the point lies inside
  * the box.  points [n,2], boxes [m,5] (x, y, w, h, r).  Replaces crop_2dr (reference d3d/box/utils.h:45, utils.cpp:10-47,
  * bound at d3d/box/impl.cpp:26 and called by box2dr_crop / box3dp_crop, d3d/box/__init__.py:278-314); the reference
@@ -92,9 +102,19 @@ int d3d_crop2dr_f32(const float *points, int64_t n, const float *boxes, int64_t 
                     size_t workspace_bytes, void *stream);
 int d3d_crop2dr_f64(const double *points, int64_t n, const double *boxes, int64_t m, uint8_t *mask, void *workspace,
                     size_t workspace_bytes, void *stream);
-/* optional statistics of the last d3d_iou2dr_* call that used this workspace: counters[0] = candidate
- * pairs (bounding circles overlap) -- what roofline accounting needs.  Device i64[2]
- * at the start of the workspace; read it back after synchronising the stream. */
+/* Signed distance from points to rotated boxes: dist T[m boxes, n points] row-major, positive inside;
+ * iedge u8[m, n] (may be NULL) = edge of the box that realises the distance (edge k runs from vertex k to vertex k+1 of
+ * dgal::poly2_from_xywhr).  points [n,2], boxes [m,5].  Replaces pdist2dr_forward[_cuda] (reference d3d/box/dist.h:7-9,16-18,
+ * dist.cpp:11-47, dist_cuda.cu:9-50; dgal::distance geometry.hpp:453-497) behind box2dr_pdist / box3dr_pdist
+ * (d3d/box/__init__.py:149-166, 330-381).  The backward replaces pdist2dr_backward[_cuda] (dist.h:10-12,19-21, dist.cpp:49-110):
+ * grad T[m, n]; grad_boxes T[m,5] and grad_points T[n,2] are ACCUMULATED into (caller zero-fills them, like the reference's
+ * zeros_like). */
+int d3d_pdist2dr_f32(const float *points, int64_t n, const float *boxes, int64_t m, float *dist, uint8_t *iedge, void *stream);
+int d3d_pdist2dr_f64(const double *points, int64_t n, const double *boxes, int64_t m, double *dist, uint8_t *iedge, void *stream);
+int d3d_pdist2dr_backward_f32(const float *points, int64_t n, const float *boxes, int64_t m, const float *grad, float *grad_boxes,
+                              float *grad_points, void *stream);
+int d3d_pdist2dr_backward_f64(const double *points, int64_t n, const double *boxes, int64_t m, const double *grad, double *grad_boxes,
+                              double *grad_points, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * NMS, replaces nms2d[_cuda] (reference d3d/box/nms.h:6-10, nms.cpp:98-119, nms_cuda.cu:217-244).

@@ -27,6 +27,20 @@ MODULES = {
 }
 
 
+WRAP_SO = os.path.join(OUT, "libdgal_wrap.so")   # d3d/dgal_wrap.h behind a C ABI (oracle/dgal_wrap_shim.cpp), plain g++
+
+
+def build_wrap():
+    """g++ on the shim, which includes the reference's d3d/dgal_wrap.h where it lies. Idempotent."""
+    if os.path.exists(WRAP_SO) or not os.path.isdir(REF_ROOT):
+        return os.path.exists(WRAP_SO)
+    import subprocess
+    os.makedirs(OUT, exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-w", "-shared", "-fPIC", "-I", REF_ROOT, "-I", os.path.join(REF_ROOT, "thirdparty"),
+                           os.path.join(HERE, "dgal_wrap_shim.cpp"), "-o", WRAP_SO])
+    return True
+
+
 def so_path(name):
     return os.path.join(OUT, name, name + ".so")
 
@@ -39,6 +53,7 @@ def build(verbose=False):
     """Compile the three reference extensions if the reference tree is present. Idempotent."""
     if not os.path.isdir(REF_ROOT):
         return have_ref()
+    build_wrap()
     from torch.utils.cpp_extension import load
     for name, srcs in MODULES.items():
         if os.path.exists(so_path(name)):

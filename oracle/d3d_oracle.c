@@ -150,6 +150,49 @@ void orc_iou2d_f64(const double *b1, int64_t n, const double *b2, int64_t m, dou
 ORC_CROP_BODY(float, f32, sinf, cosf)
 ORC_CROP_BODY(double, f64, sin, cos)
 
+/* ---- signed point-to-rotated-box distance: d3d/box/dist.cpp:11-47 pdist2dr_forward.  dist is T[m boxes, n points]
+ * (positive inside), iedge u8[m, n] the edge (or vertex) that realises it.  Vertices as dgal::poly2_from_xywhr (geometry.hpp:417-429);
+ * distance(Poly2, Point2, idx) geometry.hpp:482-497 over distance(Segment2, Point2) :453-474 with the line of :331-336 and the
+ * projection parameter t_from_pxy :372-380 (three branches, kept as written). */
+#define ORC_PDIST_BODY(T, SFX, SIN, COS, HYPOT, ABS)                                                          \
+    static T orc_tpxy_##SFX(T a, T b, T c, T x, T y)                                                          \
+    {                                                                                                         \
+        if (b == 0) return (1 - y) / a;                                                                       \
+        else if (a == 0) return (x - 1) / b;                                                                  \
+        else return (b * x - a * y - a * (a + c) / b - b) / (a * a + b * b);                                  \
+    }                                                                                                         \
+    static T orc_segdist_##SFX(T x1, T y1, T x2, T y2, T px, T py)                                            \
+    {                                                                                                         \
+        const T a = y2 - y1, b = x1 - x2, c = x2 * y1 - x1 * y2;                                              \
+        const T t = orc_tpxy_##SFX(a, b, c, px, py);                                                          \
+        const T sign = a * px + b * py + c;                                                                   \
+        if (t < orc_tpxy_##SFX(a, b, c, x2, y2)) { const T d = HYPOT(px - x2, py - y2); return sign > 0 ? d : -d; } \
+        else if (t > orc_tpxy_##SFX(a, b, c, x1, y1)) { const T d = HYPOT(px - x1, py - y1); return sign > 0 ? d : -d; } \
+        else return sign / HYPOT(a, b);                                                                       \
+    }                                                                                                         \
+    void orc_pdist2dr_##SFX(const T *pts, int64_t n, const T *boxes, int64_t m, T *dist, uint8_t *iedge)      \
+    {                                                                                                         \
+        for (int64_t i = 0; i < m; i++) {                                                                     \
+            const T x = boxes[5 * i], y = boxes[5 * i + 1], w = boxes[5 * i + 2], h = boxes[5 * i + 3], r = boxes[5 * i + 4]; \
+            const T dxsin = w * SIN(r) / 2, dxcos = w * COS(r) / 2, dysin = h * SIN(r) / 2, dycos = h * COS(r) / 2; \
+            const T vx[4] = {x - dxcos + dysin, x + dxcos + dysin, x + dxcos - dysin, x - dxcos - dysin};       \
+            const T vy[4] = {y - dxsin - dycos, y + dxsin - dycos, y + dxsin + dycos, y - dxsin + dycos};       \
+            for (int64_t j = 0; j < n; j++) {                                                                 \
+                const T px = pts[2 * j], py = pts[2 * j + 1];                                                 \
+                T dmin = -orc_segdist_##SFX(vx[3], vy[3], vx[0], vy[0], px, py);                              \
+                uint8_t idx = 3;                                                                              \
+                for (int k = 1; k < 4; k++) {                                                                 \
+                    const T dl = -orc_segdist_##SFX(vx[k - 1], vy[k - 1], vx[k], vy[k], px, py);              \
+                    if (ABS(dl) < ABS(dmin)) { dmin = dl; idx = (uint8_t)(k - 1); }                           \
+                }                                                                                             \
+                dist[i * n + j] = dmin;                                                                       \
+                if (iedge) iedge[i * n + j] = idx;                                                            \
+            }                                                                                                 \
+        }                                                                                                     \
+    }
+ORC_PDIST_BODY(float, f32, sinf, cosf, hypotf, fabsf)
+ORC_PDIST_BODY(double, f64, sin, cos, hypot, fabs)
+
 /* ---- NMS: d3d/box/nms.cpp:9-96 nms2d_templated.
  * `order` (i64[n], descending score; computed by the caller exactly like nms.cpp:103) and `scores`
  * (copied by the caller like nms.cpp:104-105) are mutated by the soft variants.

@@ -99,6 +99,30 @@ def crop_2dr(points, boxes):
     return out.astype(bool)
 
 
+def pdist2dr(points, boxes, return_iedge=False):
+    """Signed point-to-rotated-box distance T[M boxes, N points] (positive inside) and the edge that realises it: reference
+    d3d/box/dist.cpp:11-47 pdist2dr_forward over dgal::distance (geometry.hpp:453-497)."""
+    dt = np.float32 if points.dtype == np.float32 else np.float64
+    pts = np.ascontiguousarray(points, dt)
+    bx = _boxes(boxes, dt)
+    dist = np.empty((len(bx), len(pts)), dt)
+    ie = np.empty((len(bx), len(pts)), np.uint8)
+    f = lib().orc_pdist2dr_f32 if dt == np.float32 else lib().orc_pdist2dr_f64
+    f(_p(pts), C.c_int64(len(pts)), _p(bx), C.c_int64(len(bx)), _p(dist), _p(ie))
+    return (dist, ie) if return_iedge else dist
+
+
+def box3dr_pdist(points, boxes, project_axis=2):
+    """d3d/box/__init__.py:344-381 with every term in the native [M boxes, N points] layout (the reference's wrapper hands
+    (boxes, points) to a native function declared (points, boxes), d3d/box/__init__.py:151-153 against dist.h:7-9, and cannot run)."""
+    ax2 = {0: ([1, 2], [1, 2, 4, 5, 6]), 1: ([0, 2], [0, 2, 3, 5, 6]), 2: ([0, 1], [0, 1, 3, 4, 6])}[project_axis]
+    d2 = pdist2dr(np.ascontiguousarray(points[:, ax2[0]]), np.ascontiguousarray(boxes[:, ax2[1]]))
+    pp = points[:, project_axis][None, :]
+    ctr, half = boxes[:, project_axis][:, None], boxes[:, 3 + project_axis][:, None] / 2
+    dp = np.where(pp > ctr, (ctr + half) - pp, pp - (ctr - half))
+    return np.where(dp > 0, np.where(d2 > 0, np.minimum(dp, d2), d2), np.where(d2 > 0, dp, -np.sqrt(d2 * d2 + dp * dp))).astype(d2.dtype)
+
+
 def box3dp_crop(points, boxes, project_axis=2):
     """d3d/box/__init__.py:289-314: 2-D crop of the projection & the open interval test along the projection axis."""
     ax2 = {0: ([1, 2], [1, 2, 4, 5, 6]), 1: ([0, 2], [0, 2, 3, 5, 6]), 2: ([0, 1], [0, 1, 3, 4, 6])}[project_axis]
@@ -112,8 +136,8 @@ def box3d_iou_distance(src, dst, metric="riou", alg=ALG_RC):
     (x, y, z, lx, ly, lz, rz): reference d3d/tracking/matcher.pyx:45-76 over box3dr_iou / box3d_iou,
     d3d/dgal_wrap.h:45-91.  The BEV IoU comes from the pinned fp32 restatement above (alg: the reference's RC, or
     ALG_TRUTH for geometric truth); the z factor follows dgal_wrap.h:50-66 operation by operation in float32.
-    PARITY NOTE: the reference's matcher is a Cython module that cannot be built here, so this function is pinned
-    through its 2-D part only (reference extension + golden vectors); the z arithmetic is a restatement."""
+    PINNED: equal bit for bit to the reference's own box3dr_iou / box3d_iou (d3d/dgal_wrap.h compiled by g++ into
+    oracle/_ref/libdgal_wrap.so through oracle/dgal_wrap_shim.cpp) live and on tests/golden/dist3d.npz."""
     f = np.float32
     a, b = np.array(src, dtype=f, copy=True), np.array(dst, dtype=f, copy=True)
     a[:, 3:6] = np.clip(a[:, 3:6], -1e3, 1e3)          # matcher.pyx:50-52
@@ -128,6 +152,27 @@ def box3d_iou_distance(src, dst, metric="riou", alg=ALG_RC):
     i = np.maximum(np.minimum(z1max, z2max) - np.maximum(z1min, z2min), f(0))
     u = np.maximum(np.maximum(z1max, z2max) - np.minimum(z1min, z2min), f(1e-6))
     return (f(1) - iou.astype(f) * (i / u).astype(f)).astype(f)
+
+
+def match_greedy(distance, src_scores, src_tags, dst_tags, thresholds):
+    """ScoreMatcher.match (d3d/tracking/matcher.pyx:138-162) over BaseMatcher.match_by_order (:93-122) for one threshold set
+    `thresholds[category]`: returns (src_assignment i32[N], dst_assignment i32[M]), -1 = unmatched.  The source order is
+    np.flip(np.argsort(scores)) as in :143; the destination order of a source is ascending distance with ties to the lower index
+    (the reference's unstable np.argsort leaves ties unspecified).  PARITY: restated, unpinned -- the matcher is a Cython module
+    that needs the reference's whole object model and cannot be built here."""
+    d = np.asarray(distance, np.float32)
+    n, m = d.shape
+    src_order = np.flip(np.argsort(np.asarray(src_scores, np.float64), kind="stable"))
+    sa, da = np.full(n, -1, np.int32), np.full(m, -1, np.int32)
+    for i in src_order:
+        for j in np.argsort(d[i], kind="stable"):          # :145, :152-156
+            if sa[i] >= 0:                                  # :104-105
+                break
+            if da[j] >= 0 or src_tags[i] != dst_tags[j]:    # :106-113
+                continue
+            if d[i, j] <= thresholds[dst_tags[j]]:          # :116-118
+                sa[i], da[j] = j, i
+    return sa, da
 
 
 def nms2d(boxes, scores, iou_type=IOU_BOX, sup_type=SUP_HARD, iou_threshold=0.0, score_threshold=0.0,

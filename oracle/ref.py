@@ -6,6 +6,8 @@ plumbing -- d3d/box/__init__.py:180-276, d3d/voxel/__init__.py:16-104, d3d/point
 call them with the reference's semantics.  It is used to (1) pin oracle/d3d_oracle.c, (2) generate
 tests/golden/*.npz, (3) serve as the `cpu_baseline.kind == "reference"` arm of bench.py.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -52,6 +54,57 @@ def box2d_iou(boxes1, boxes2, method="box", precise=True):
 def crop_2dr(points, boxes):
     """the reference's own crop_2dr (d3d/box/utils.cpp:36-47): bool[M, N]"""
     return _box().crop_2dr(_t(points), _t(boxes)).numpy()
+
+
+_WRAP = None
+
+
+def _wrap():
+    """the reference's d3d/dgal_wrap.h compiled by g++ behind oracle/dgal_wrap_shim.cpp"""
+    global _WRAP
+    if _WRAP is None:
+        import ctypes
+        from . import build_ref
+        if not os.path.exists(build_ref.WRAP_SO):
+            build_ref.build_wrap()
+        _WRAP = ctypes.CDLL(build_ref.WRAP_SO)
+    return _WRAP
+
+
+def box3d_iou_distance(src, dst, metric="riou"):
+    """the distance cache of ScoreMatcher.prepare_boxes (d3d/tracking/matcher.pyx:45-76) computed by the reference's own
+    box3dr_iou / box3d_iou (d3d/dgal_wrap.h:45-91): float32 [N, M]"""
+    import ctypes
+    a, b = np.array(src, dtype=np.float32, copy=True), np.array(dst, dtype=np.float32, copy=True)
+    a[:, 3:6] = np.clip(a[:, 3:6], -1e3, 1e3)
+    b[:, 3:6] = np.clip(b[:, 3:6], -1e3, 1e3)
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    out = np.empty((len(a), len(b)), np.float32)
+    _wrap().ref_iou3d_distance(a.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(len(a)), b.ctypes.data_as(ctypes.c_void_p),
+                               ctypes.c_int64(len(b)), ctypes.c_int(1 if metric == "riou" else 0), out.ctypes.data_as(ctypes.c_void_p))
+    return out
+
+
+def box3dr_pdist_scalar(box, points):
+    """d3d/dgal_wrap.h:21-43 box3dr_pdist for one box [7] and points [N,3]: float32 [N]"""
+    import ctypes
+    bx, pts = np.ascontiguousarray(box, np.float32), np.ascontiguousarray(points, np.float32)
+    out = np.empty(len(pts), np.float32)
+    _wrap().ref_box3dr_pdist(bx.ctypes.data_as(ctypes.c_void_p), pts.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(len(pts)),
+                             out.ctypes.data_as(ctypes.c_void_p))
+    return out
+
+
+def pdist2dr(points, boxes):
+    """the reference's own pdist2dr_forward (d3d/box/dist.cpp:36-47), called with its declared argument order: (T[M, N], u8[M, N])"""
+    d, ie = _box().pdist2dr_forward(_t(points), _t(boxes))
+    return d.numpy(), ie.numpy()
+
+
+def pdist2dr_backward(points, boxes, grad, iedge):
+    """the reference's own pdist2dr_backward (d3d/box/dist.cpp:90-110): (grad_boxes [M, 5], grad_points [N, 2])"""
+    gb, gp = _box().pdist2dr_backward(_t(points), _t(boxes), _t(grad), _t(iedge))
+    return gb.numpy(), gp.numpy()
 
 
 def box2d_nms(boxes, scores, iou_method="box", supression_method="hard", iou_threshold=0, score_threshold=0,

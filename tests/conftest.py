@@ -49,3 +49,20 @@ def proposals(rng, n, n_obj, extent=75.0):
     r = hd[k] + rng.normal(0, 0.05, n)
     scores = rng.permutation(n).astype(np.float64) / n + rng.random(n) * 0.1 / n
     return np.concatenate([xy, wh, r[:, None]], 1), scores
+
+
+SOFT_CASES = [  # tests/golden/make_golden.py SOFT_CASES: (tag, n, generator, method, iou_threshold, score_threshold, supression_param)
+    ("c1_lin", 1000, "boxes", "linear", 0.3, 0.2, 1.0), ("c1_gau", 1000, "boxes", "gaussian", 0.3, 0.2, 0.5),
+    ("c1_lin0", 1000, "boxes", "linear", 0.0, 0.0, 2.0), ("c1_gau_box", 1000, "boxes", "gaussian", 0.25, 0.3, 0.3),
+    ("p_lin", 4097, "proposals", "linear", 0.3, 0.1, 1.0), ("p_gau", 4097, "proposals", "gaussian", 0.5, 0.05, 0.5),
+]
+SOFT_TEST6 = (np.array([[1, 1, 2 - 1e-2, 2 - 1e-2, 0], [2, 2, 2 - 1e-2, 2 - 1e-2, 1e-3], [3, 3, 2 - 1e-2, 2 - 1e-2, 2e-3], [3, 1, 1, 2, 3e-3],
+                        [4, 2, 1, 2, 4e-3], [5, 3, 1, 2, 5e-3]], np.float64), np.array([0.5, 0.3, 0.4, 0.4, 0.2, 0.1], np.float64))
+
+
+def soft_inputs(n, gen):
+    """inputs of the soft-NMS fixtures (tests/golden/make_golden.py soft_inputs): regenerated from the seed"""
+    rng = np.random.default_rng(1234 + n)
+    if gen == "boxes":
+        return gen_boxes(rng, n), rng.random(n)
+    return proposals(rng, n, max(n // 25, 1))

@@ -59,6 +59,69 @@ def write_crop():
     np.savez_compressed(os.path.join(OUT, "crop.npz"), **out)
 
 
+SOFT_CASES = [  # (tag, n, generator, method, iou_threshold, score_threshold, supression_param)
+    ("c1_lin", 1000, "boxes", "linear", 0.3, 0.2, 1.0), ("c1_gau", 1000, "boxes", "gaussian", 0.3, 0.2, 0.5),
+    ("c1_lin0", 1000, "boxes", "linear", 0.0, 0.0, 2.0), ("c1_gau_box", 1000, "boxes", "gaussian", 0.25, 0.3, 0.3),
+    ("p_lin", 4097, "proposals", "linear", 0.3, 0.1, 1.0), ("p_gau", 4097, "proposals", "gaussian", 0.5, 0.05, 0.5),
+]
+
+
+def soft_inputs(n, gen):
+    """inputs of the soft-NMS fixtures: regenerated from the seed by the tests, only the masks are stored"""
+    rng = np.random.default_rng(1234 + n)
+    if gen == "boxes":
+        return gen_boxes(rng, n), rng.random(n)
+    return proposals(rng, n, max(n // 25, 1))
+
+
+def write_soft_nms():
+    """keep masks of the reference's own CPU nms2d (d3d/box/nms.cpp:9-119) for the LINEAR / GAUSSIAN rules, fp64, bits packed"""
+    nb = np.array([[1, 1, 2 - 1e-2, 2 - 1e-2, 0], [2, 2, 2 - 1e-2, 2 - 1e-2, 1e-3], [3, 3, 2 - 1e-2, 2 - 1e-2, 2e-3], [3, 1, 1, 2, 3e-3],
+                   [4, 2, 1, 2, 4e-3], [5, 3, 1, 2, 5e-3]], np.float64)
+    ns = np.array([0.5, 0.3, 0.4, 0.4, 0.2, 0.1], np.float64)
+    out = {}
+    for m, par in (("linear", 1.0), ("gaussian", 0.5)):
+        for im in ("box", "rbox"):
+            out[f"test6_{m}_{im}"] = R.box2d_nms(nb, ns, im, m, iou_threshold=0.1, score_threshold=0.15, supression_param=par)
+    for tag, n, gen, m, it, st, par in SOFT_CASES:
+        b, s = soft_inputs(n, gen)
+        im = "box" if tag.endswith("_box") else "rbox"
+        out[tag] = np.packbits(R.box2d_nms(b, s, im, m, iou_threshold=it, score_threshold=st, supression_param=par))
+    np.savez_compressed(os.path.join(OUT, "nms_soft.npz"), **out)
+
+
+def write_pdist():
+    """signed point-to-box distances and edge indices of the reference's own pdist2dr_forward (d3d/box/dist.cpp:11-47), and the point
+    gradients of its pdist2dr_backward for a fixed upstream gradient (its box gradients overwrite instead of accumulating,
+    utils.h make_box_grad, and are not a reference for anything)"""
+    rng = np.random.default_rng(11)
+    out = {}
+    for tag, dt in (("f32", np.float32), ("f64", np.float64)):
+        pts = ((rng.random((300, 2)) - .5) * 12).astype(dt)
+        bx = gen_boxes(rng, 24).astype(dt)
+        bx[:3] = np.array([[0, 0, 1, 1, 0], [0, 0, 2, 1, np.pi / 2], [1, 1, 2, 2, 100.0]], dt)   # axis-aligned edges hit the b == 0 / a == 0 branches of t_from_pxy
+        bx[:, 2:4] += 0.25
+        d, ie = R.pdist2dr(pts, bx)
+        g = rng.random(d.shape).astype(dt)
+        gb, gp = R.pdist2dr_backward(pts, bx, g, ie)
+        out[f"{tag}.points"], out[f"{tag}.boxes"], out[f"{tag}.dist"], out[f"{tag}.iedge"] = pts, bx, d, ie
+        out[f"{tag}.grad"], out[f"{tag}.grad_points"] = g, gp
+    np.savez_compressed(os.path.join(OUT, "pdist.npz"), **out)
+
+
+def write_dist3d():
+    """detection-evaluation distances 1 - iou2d * ziou of the reference's own box3dr_iou / box3d_iou (d3d/dgal_wrap.h:45-91, g++)"""
+    rng = np.random.default_rng(21)
+
+    def b3(n):
+        return np.concatenate([(rng.random((n, 2)) - .5) * 10, rng.normal(0, 0.5, (n, 1)), rng.random((n, 3)) * 4 + .3,
+                               (rng.random((n, 1)) - .5) * 10], 1).astype(np.float32)
+    a, b = b3(60), b3(45)
+    b[:5] = a[:5]                      # identical boxes
+    b[5, 2] += 50                      # no z overlap
+    np.savez_compressed(os.path.join(OUT, "dist3d.npz"), src=a, dst=b, riou=R.box3d_iou_distance(a, b, "riou"), iou=R.box3d_iou_distance(a, b, "iou"))
+
+
 def main():
     assert R.available(), "build oracle/_ref first"
     if "--only-crop" in sys.argv:
@@ -207,5 +270,8 @@ def main():
     print("golden fixtures written, total bytes:", tot)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) > 1:   # python make_golden.py soft_nms ...: only the named fixtures
+    for name in sys.argv[1:]:
+        globals()["write_" + name]()
+elif __name__ == "__main__":
     main()

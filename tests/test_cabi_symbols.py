@@ -41,11 +41,11 @@ def test_argument_validation_without_gpu():
     assert lib.d3d_iou2dr_f64(vp(0), i64(0), vp(0), i64(5), vp(0), i64(5), vp(0), C.c_size_t(0), vp(0)) == 0
     # workspace too small
     assert lib.d3d_iou2dr_f32(vp(8), i64(2), vp(8), i64(2), vp(8), i64(2), vp(8), C.c_size_t(16), vp(0)) == 3
-    # NMS: unsupported iou type (reference "Unsupported iou type!"), soft NMS unsupported in this ABI version
+    # NMS: unsupported iou type (reference "Unsupported iou type!"), unknown supression type
     nms = lib.d3d_nms2d_f32
     nms.argtypes = [vp, vp, i64, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, vp, vp, C.c_size_t, vp]
     assert nms(8, 8, 4, 4, 0, 0.5, 0, 0, 8, 8, 1 << 30, 0) == 1
-    assert nms(8, 8, 4, 2, 1, 0.5, 0, 0, 8, 8, 1 << 30, 0) == 4
+    assert nms(8, 8, 4, 2, 3, 0.5, 0, 0, 8, 8, 1 << 30, 0) == 1   # supression types are HARD / LINEAR / GAUSSIAN
     lib.d3d_iou_workspace_bytes.restype = C.c_size_t
     lib.d3d_iou_workspace_bytes.argtypes = [i64, i64, C.c_int]
     assert lib.d3d_iou_workspace_bytes(1000, 1000, 0) >= 2 * 1000 * 32

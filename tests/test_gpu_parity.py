@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden, gen_boxes, lidar, proposals
+from conftest import golden, gen_boxes, lidar, proposals, SOFT_CASES, SOFT_TEST6, soft_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -177,10 +177,41 @@ def test_box3d_iou_distance_vs_oracle(dev, oracle):
     flat = np.array([[0, 0, 0, 4, 2, 0, 0.3]], np.float32)
     assert np.allclose(box3d_iou_distance(flat, flat, "riou"), oracle.box3d_iou_distance(flat, flat, "riou", alg=oracle.ALG_TRUTH), atol=1e-6)
     assert box3d_iou_distance(torch.zeros((0, 7)), torch.zeros((5, 7))).shape == (0, 5)
+    g = golden("dist3d.npz")   # written by the reference's own box3dr_iou / box3d_iou (d3d/dgal_wrap.h, g++)
+    truth = oracle.box3d_iou_distance(g["src"], g["dst"], "riou", alg=oracle.ALG_TRUTH)
+    sane = np.abs(g["riou"] - truth) < 1e-4
+    assert np.abs(box3d_iou_distance(g["src"], g["dst"], "riou") - g["riou"])[sane].max() < 2e-4
+    assert np.abs(box3d_iou_distance(g["src"], g["dst"], "iou") - g["iou"]).max() < 2e-6
     with pytest.raises(ValueError):
         box3d_iou_distance(torch.zeros((3, 5)), torch.zeros((3, 7)))
     with pytest.raises(ValueError):
         box3d_iou_distance(torch.zeros((3, 7)), torch.zeros((3, 7)), metric="giou")
+
+
+def test_match_greedy_vs_oracle(dev, oracle):
+    """f1: greedy score-ordered matching of the detection evaluator (ScoreMatcher.match), 40 threshold sets in one launch, against the
+    restated walk; distances come from the distance-matrix kernel, so the pipeline prepare_boxes -> match runs on the device"""
+    from d3d_b200.box import box3d_iou_distance, match_greedy
+    rng = np.random.default_rng(41)
+    for n, m, ncat in ((1, 1, 1), (60, 45, 3), (400, 350, 4)):
+        A, B = _boxes3d(rng, n), _boxes3d(rng, m)
+        k = min(n, m) // 2
+        B[:k] = A[:k] + rng.normal(0, 0.2, (k, 7)).astype(np.float32)
+        st, dt = rng.integers(0, ncat, n), rng.integers(0, ncat, m)
+        dt[:k] = st[:k]
+        scores = rng.random(n)
+        d = box3d_iou_distance(_t(A, dev), _t(B, dev), "riou")
+        thr = np.stack([np.full(ncat, 1 - t) + rng.random(ncat) * 0.05 for t in np.linspace(0.1, 0.9, 40)]).astype(np.float32)
+        sa, da = match_greedy(d, _t(scores, dev), _t(st, dev), _t(dt, dev), _t(thr, dev))
+        assert sa.shape == (40, n) and da.shape == (40, m) and sa.dtype == torch.int32
+        dn = d.cpu().numpy()
+        for t in (0, 13, 39):
+            osa, oda = oracle.match_greedy(dn, scores, st, dt, thr[t])
+            assert np.array_equal(sa[t].cpu().numpy(), osa) and np.array_equal(da[t].cpu().numpy(), oda), (n, m, t)
+        s1, d1 = match_greedy(dn, scores, st, dt, thr[5])          # numpy in, numpy out, single threshold set
+        assert isinstance(s1, np.ndarray) and np.array_equal(s1, oracle.match_greedy(dn, scores, st, dt, thr[5])[0])
+    sa, da = match_greedy(torch.zeros((0, 4)), [], [], [0, 0, 0, 0], [0.5])
+    assert sa.shape == (0,) and da.tolist() == [-1, -1, -1, -1]
 
 
 def test_box_crop_vs_reference_and_oracle(dev, oracle, monkeypatch):
@@ -277,13 +308,40 @@ def test_nms_vs_oracle_sizes_and_thresholds(dev, oracle):
     assert box2d_nms(torch.zeros((0, 5), device=dev), torch.zeros(0, device=dev)).numel() == 0
     with pytest.raises(ValueError):
         box2d_nms(torch.zeros((3, 5), device=dev), torch.zeros(2, device=dev))
-    with pytest.raises(NotImplementedError):
-        box2d_nms(torch.rand((3, 5), device=dev), torch.rand(3, device=dev), supression_method="linear")
+    with pytest.raises(AttributeError):   # reference: getattr(SupressionType, "SOFT") fails the same way
+        box2d_nms(torch.rand((3, 5), device=dev), torch.rand(3, device=dev), supression_method="soft")
     # 2-D scores: max over classes (d3d/box/__init__.py:253-254)
     P, s = proposals(rng, 300, 12, extent=10.0)
     s2 = np.stack([s * 0.5, s, s * 0.1], 1)
     assert np.array_equal(box2d_nms(_t(P, dev), _t(s2, dev), "rbox", iou_threshold=0.4).cpu().numpy(),
                           oracle.box2d_nms(P, s, "rbox", iou_threshold=0.4, cuda_score_rule=True))
+
+
+def test_nms_soft_vs_reference_and_oracle(dev, oracle):
+    """f3: LINEAR / GAUSSIAN suppression.  Keep masks equal, bit for bit in fp64, to the fixtures written by the reference's own CPU
+    nms2d (n = 6, 1000, 4097) and to the oracle on fresh inputs; the fp32 path agrees with the fp64 one up to near-threshold pairs."""
+    from d3d_b200.box import box2d_nms
+    g = golden("nms_soft.npz")
+    nb, ns = SOFT_TEST6
+    for m, par in (("linear", 1.0), ("gaussian", 0.5)):
+        for im in ("box", "rbox"):
+            keep = box2d_nms(_t(nb, dev), _t(ns, dev), im, m, iou_threshold=0.1, score_threshold=0.15, supression_param=par)
+            assert keep.dtype == torch.bool and np.array_equal(keep.cpu().numpy(), g[f"test6_{m}_{im}"]), (m, im)
+    for tag, n, gen, m, it, st, par in SOFT_CASES:
+        b, s = soft_inputs(n, gen)
+        im = "box" if tag.endswith("_box") else "rbox"
+        keep = box2d_nms(_t(b, dev), _t(s, dev), im, m, iou_threshold=it, score_threshold=st, supression_param=par).cpu().numpy()
+        exp = _unpack(g[tag], n)
+        assert np.array_equal(keep, exp), (tag, int((keep != exp).sum()))
+        k32 = box2d_nms(_t(b.astype(np.float32), dev), _t(s.astype(np.float32), dev), im, m, iou_threshold=it, score_threshold=st,
+                        supression_param=par, precise=False).cpu().numpy()
+        assert (k32 != exp).mean() < 0.02, (tag, "fp32", int((k32 != exp).sum()))
+    rng = np.random.default_rng(77)
+    for n in (1, 2, 65, 300):
+        b, s = gen_boxes(rng, n, spread=4.0), rng.random(n)
+        for m, par in (("linear", 0.7), ("gaussian", 0.4)):
+            keep = box2d_nms(b, s, "rbox", m, iou_threshold=0.2, score_threshold=0.25, supression_param=par)   # numpy in, numpy out
+            assert np.array_equal(keep, oracle.box2d_nms(b, s, "rbox", m, 0.2, 0.25, par, cuda_score_rule=True)), (n, m)
 
 
 def test_nms_back_ends_agree(dev, monkeypatch):
@@ -545,6 +603,55 @@ def test_voxel_routed_and_l2_frames_in_one_launch(dev):
             assert set(a.keys()) == set(b.keys())
             for k in a:
                 assert torch.equal(a[k], b[k]), (kw, k)
+
+
+def test_box_pdist_vs_reference_and_oracle(dev, oracle):
+    """f4: signed point-to-rotated-box distance.  Forward against the fixture written by the reference's own pdist2dr_forward and the
+    oracle (fp64 to 1e-12: only hypot's rounding differs; edge index equal except on exact ties), backward against central
+    differences of the oracle and the reference's point gradients; 3-D wrapper against the oracle's."""
+    from d3d_b200.box import box2dr_pdist, box3dr_pdist
+    g = golden("pdist.npz")
+    for tag, tol in (("f32", 2e-5), ("f64", 1e-12)):
+        pts, bx = g[f"{tag}.points"], g[f"{tag}.boxes"]
+        d = box2dr_pdist(_t(pts, dev), _t(bx, dev))
+        assert d.shape == (len(bx), len(pts)) and d.dtype == _t(pts, dev).dtype
+        assert np.abs(d.cpu().numpy() - g[f"{tag}.dist"]).max() < tol, tag
+    pts, bx = _t(g["f64.points"], dev).requires_grad_(True), _t(g["f64.boxes"], dev).requires_grad_(True)
+    up = _t(g["f64.grad"], dev)
+    (box2dr_pdist(pts, bx) * up).sum().backward()
+    assert np.abs(pts.grad.cpu().numpy() - g["f64.grad_points"]).max() < 1e-9
+    # box gradients against central differences of the pinned forward, on the pairs whose closest feature is the inside of an edge: in
+    # the corner regions the reference's value takes its sign from whichever of two equal candidates wins a rounding tie
+    # (geometry.hpp:453-497), so it is not a differentiable function there (and the reference's own box gradients overwrite each other)
+    eps, bnp, pnp = 1e-6, g["f64.boxes"], g["f64.points"]
+    c, s_ = np.cos(bnp[:, 4])[:, None], np.sin(bnp[:, 4])[:, None]
+    dx, dy = pnp[None, :, 0] - bnp[:, 0:1], pnp[None, :, 1] - bnp[:, 1:2]
+    lx, ly = np.abs(dx * c + dy * s_), np.abs(-dx * s_ + dy * c)
+    hw, hh = np.abs(bnp[:, 2:3]) / 2, np.abs(bnp[:, 3:4]) / 2
+    smooth = ~((lx > hw - 1e-3) & (ly > hh - 1e-3)) & (np.abs((hw - lx) - (hh - ly)) > 1e-3)
+    smooth[:3] = False   # (nearly) axis-aligned boxes: t_from_pxy divides by a line coefficient of ~1e-16 (geometry.hpp:372-380) and the value jumps
+    upm = g["f64.grad"] * smooth
+    pts2, bx2 = _t(pnp, dev), _t(bnp, dev).requires_grad_(True)
+    (box2dr_pdist(pts2, bx2) * _t(upm, dev)).sum().backward()
+    num = np.zeros_like(bnp)
+    for i in range(len(bnp)):
+        for k in range(5):
+            hi, lo = bnp.copy(), bnp.copy()
+            hi[i, k] += eps; lo[i, k] -= eps
+            num[i, k] = ((oracle.pdist2dr(pnp, hi) - oracle.pdist2dr(pnp, lo)) * upm).sum() / (2 * eps)
+    assert smooth.mean() > 0.2 and np.abs(bx2.grad.cpu().numpy() - num).max() < 1e-5 * max(1.0, np.abs(num).max())
+    rng = np.random.default_rng(13)
+    for n, m in ((1, 1), (1000, 9), (257, 70)):
+        p, b = (rng.random((n, 2)) - .5) * 14, gen_boxes(rng, m)
+        od = oracle.pdist2dr(p, b)
+        assert np.abs(box2dr_pdist(torch.from_numpy(p), torch.from_numpy(b)).numpy() - od).max() < 1e-12   # host tensors in, host tensor out
+    p3 = (rng.random((400, 3)) - .5) * 10
+    b3 = np.concatenate([gen_boxes(rng, 15)[:, :2], rng.random((15, 1)), rng.random((15, 3)) * 4 + .2, rng.random((15, 1)) * 6], 1)
+    for ax in (0, 1, 2):
+        assert np.abs(box3dr_pdist(_t(p3, dev), _t(b3, dev), ax).cpu().numpy() - oracle.box3dr_pdist(p3, b3, ax)).max() < 1e-12
+    with pytest.raises(ValueError):
+        box2dr_pdist(_t(pnp, dev), _t(bnp, dev), method="box")
+    assert box2dr_pdist(torch.zeros((0, 2), dtype=torch.float64, device=dev), _t(bnp, dev)).shape == (len(bnp), 0)
 
 
 # ------------------------------------------------------------------ aligned scatter

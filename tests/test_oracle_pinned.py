@@ -4,7 +4,7 @@ and -- when oracle/_ref is present -- the reference extensions live.  CPU only."
 import numpy as np
 import pytest
 
-from conftest import golden, gen_boxes, lidar
+from conftest import golden, gen_boxes, lidar, SOFT_CASES, SOFT_TEST6, soft_inputs
 
 
 def _unpack(bits, n):
@@ -102,6 +102,24 @@ def test_nms_soft_smoke(oracle):
 
 
 # ------------------------------------------------------------------ voxelization
+def test_nms_soft_vs_reference_fixture(oracle):
+    """LINEAR / GAUSSIAN suppression (f3): the oracle's restatement of nms.cpp:33-94 reproduces the keep masks written by the
+    reference's own compiled CPU nms2d (tests/golden/make_golden.py write_soft_nms), fp64, bit for bit."""
+    g = golden("nms_soft.npz")
+    nb, ns = SOFT_TEST6
+    for m, par in (("linear", 1.0), ("gaussian", 0.5)):
+        for im in ("box", "rbox"):
+            keep = oracle.box2d_nms(nb, ns, im, m, iou_threshold=0.1, score_threshold=0.15, supression_param=par)
+            assert np.array_equal(keep, g[f"test6_{m}_{im}"]), (m, im)
+    for tag, n, gen, m, it, st, par in SOFT_CASES:
+        if n > 1000:
+            continue   # the 4097-box cases take ~10 s each in the scalar oracle: covered by the GPU suite against the fixture
+        b, s = soft_inputs(n, gen)
+        im = "box" if tag.endswith("_box") else "rbox"
+        keep = oracle.box2d_nms(b, s, im, m, iou_threshold=it, score_threshold=st, supression_param=par)
+        assert np.array_equal(keep, np.unpackbits(g[tag])[:n].astype(bool)), tag
+
+
 def test_voxel_spconv_golden(oracle):
     """test/test_voxel.py:80-88 + test/voxel_data.npz (spconv VoxelGeneratorV2 output)."""
     d = golden("voxel_spconv.npz")
@@ -239,6 +257,44 @@ def test_box3d_iou_distance_known_answers(oracle):
     assert np.allclose(oracle.box3d_iou_distance(big, ref, "iou"), 0, atol=1e-6)
 
 
+def test_box3d_iou_distance_pinned(oracle):
+    """f1: the restatement equals, bit for bit, the distances written by the reference's own box3dr_iou / box3d_iou (d3d/dgal_wrap.h
+    compiled by g++: tests/golden/dist3d.npz) and that library live where oracle/_ref holds it"""
+    g = golden("dist3d.npz")
+    for metric in ("riou", "iou"):
+        assert np.array_equal(oracle.box3d_iou_distance(g["src"], g["dst"], metric), g[metric]), metric
+    try:
+        from oracle import ref as R
+        R._wrap()
+    except Exception:
+        return
+    rng = np.random.default_rng(8)
+    mk = lambda n: np.concatenate([(rng.random((n, 2)) - .5) * 10, rng.normal(0, 0.5, (n, 1)), rng.random((n, 3)) * 4 + .3,
+                                   (rng.random((n, 1)) - .5) * 10], 1).astype(np.float32)
+    a, b = mk(150), mk(120)
+    for metric in ("riou", "iou"):
+        assert np.array_equal(oracle.box3d_iou_distance(a, b, metric), R.box3d_iou_distance(a, b, metric))
+    # box3dr_pdist (d3d/dgal_wrap.h:21-43) against the tensor form of d3d/box/__init__.py:348-381 (fp32: equal up to hypot/sqrt rounding)
+    p3 = ((rng.random((200, 3)) - .5) * 8).astype(np.float32)
+    for k in range(5):
+        sc = R.box3dr_pdist_scalar(a[k], p3)
+        assert np.abs(oracle.box3dr_pdist(p3, a[k:k + 1])[0] - sc).max() < 1e-5
+
+
+def test_match_greedy_known_answers(oracle):
+    """f1: ScoreMatcher.match restated (d3d/tracking/matcher.pyx:93-122, 138-162): best score first, closest free box of the same
+    category within the threshold"""
+    d = np.array([[0.2, 0.1, 0.9], [0.15, 0.3, 0.4], [0.5, 0.05, 0.1]], np.float32)
+    sa, da = oracle.match_greedy(d, [0.9, 0.8, 0.7], [0, 0, 0], [0, 0, 0], [0.45])
+    assert sa.tolist() == [1, 0, 2] and da.tolist() == [1, 0, 2]
+    sa, da = oracle.match_greedy(d, [0.1, 0.8, 0.7], [0, 0, 0], [0, 0, 0], [0.45])     # source 1 first, then 2, then 0 (only box 2 left: 0.9 > thr)
+    assert sa.tolist() == [-1, 0, 1] and da.tolist() == [1, 2, -1]
+    sa, da = oracle.match_greedy(d, [0.9, 0.8, 0.7], [0, 1, 0], [1, 0, 0], [0.45, 0.2])  # categories: source 1 may only take box 0 (0.15 <= 0.2)
+    assert sa.tolist() == [1, 0, 2] and da.tolist() == [1, 0, 2]
+    sa, da = oracle.match_greedy(d, [0.9, 0.8, 0.7], [0, 1, 0], [1, 0, 0], [0.45, 0.1])
+    assert sa.tolist() == [1, -1, 2]
+
+
 def test_crop_2dr_pinned(oracle):
     """point-in-rotated-box mask -- oracle == the reference's own crop_2dr (golden fixture, and the live
     extension when oracle/_ref exists) bit for bit, plus the known answers of reference test/test_box.py:191-205"""
@@ -258,3 +314,34 @@ def test_crop_2dr_pinned(oracle):
     b3 = np.array([[0, 0, 0.2, 1, 1, 1.5, 0.3]], np.float32)
     m3 = oracle.box3dp_crop(p3, b3)
     assert m3.shape == (1, 100) and np.array_equal(m3[0], oracle.crop_2dr(p3[:, :2], b3[:, [0, 1, 3, 4, 6]])[0] & (np.abs(p3[:, 2] - 0.2) < 0.75))
+
+
+def test_pdist2dr_pinned(oracle):
+    """f4: the oracle's signed point-to-box distance equals, bit for bit in fp32 and fp64, the fixture written by the reference's own
+    pdist2dr_forward (tests/golden/make_golden.py write_pdist) and the reference live when it is built; the point gradients of the
+    reference's backward agree with central differences of the pinned forward."""
+    g = golden("pdist.npz")
+    for tag in ("f32", "f64"):
+        d, ie = oracle.pdist2dr(g[f"{tag}.points"], g[f"{tag}.boxes"], return_iedge=True)
+        assert d.dtype == g[f"{tag}.dist"].dtype and np.array_equal(d, g[f"{tag}.dist"]) and np.array_equal(ie, g[f"{tag}.iedge"]), tag
+    pts, bx, up = g["f64.points"][:40], g["f64.boxes"], g["f64.grad"][:, :40]
+    eps, num = 1e-6, np.zeros((40, 2))
+    for j in range(40):
+        for k in range(2):
+            hi, lo = pts.copy(), pts.copy()
+            hi[j, k] += eps; lo[j, k] -= eps
+            num[j, k] = ((oracle.pdist2dr(hi, bx) - oracle.pdist2dr(lo, bx)) * up).sum() / (2 * eps)
+    # the fixture's gradient sums over all 24 boxes for the same upstream gradient
+    assert np.abs(num - g["f64.grad_points"][:40]).max() < 1e-6
+    try:
+        from oracle import ref as R
+        R._box()
+    except Exception:
+        return
+    rng = np.random.default_rng(3)
+    pts, bx = (rng.random((2000, 2)) - .5) * 14, gen_boxes(rng, 50)
+    rd, rie = R.pdist2dr(pts, bx)
+    d, ie = oracle.pdist2dr(pts, bx, return_iedge=True)
+    assert np.array_equal(d, rd) and np.array_equal(ie, rie)
+    p3, b3 = (rng.random((500, 3)) - .5) * 10, np.concatenate([gen_boxes(rng, 20)[:, :2], rng.random((20, 1)), rng.random((20, 3)) * 4 + .2, rng.random((20, 1)) * 6], 1)
+    assert oracle.box3dr_pdist(p3, b3).shape == (20, 500)
