@@ -53,6 +53,12 @@ _pd_sig = [_vp, _i64, _vp, _i64, _vp, _vp, _vp]
 pdist2dr = {F32: _sig("d3d_pdist2dr_f32", C.c_int, _pd_sig), F64: _sig("d3d_pdist2dr_f64", C.c_int, _pd_sig)}
 _pdb_sig = [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]
 pdist2dr_backward = {F32: _sig("d3d_pdist2dr_backward_f32", C.c_int, _pdb_sig), F64: _sig("d3d_pdist2dr_backward_f64", C.c_int, _pdb_sig)}
+_iex_sig = [_vp, _i64, _vp, _i64, _vp, _i64, _vp]
+giou2dr = {F32: _sig("d3d_giou2dr_f32", C.c_int, _iex_sig), F64: _sig("d3d_giou2dr_f64", C.c_int, _iex_sig)}
+diou2dr = {F32: _sig("d3d_diou2dr_f32", C.c_int, _iex_sig), F64: _sig("d3d_diou2dr_f64", C.c_int, _iex_sig)}
+_ibw_sig = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp]
+iou_backward = {name: {F32: _sig(f"d3d_{name}_backward_f32", C.c_int, _ibw_sig), F64: _sig(f"d3d_{name}_backward_f64", C.c_int, _ibw_sig)}
+                for name in ("iou2d", "iou2dr", "giou2dr", "diou2dr")}
 match_greedy = _sig("d3d_match_greedy_f32", C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp])
 iou_count_candidates = _sig("d3d_iou_count_candidates", C.c_int, [_vp, _i64, _vp, _i64, C.c_int, _vp, _vp, _sz, _vp])
 nms_workspace_bytes = _sig("d3d_nms2d_workspace_bytes", _sz, [_i64, C.c_int])

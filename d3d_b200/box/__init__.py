@@ -38,6 +38,36 @@ def iou2dr_forward_cuda(boxes1, boxes2):
     return _pairwise(boxes1, boxes2, _c.iou2dr)
 
 
+def giou2dr_forward_cuda(boxes1, boxes2):
+    """Rotated GIoU; CUDA tensors [N,5],[M,5] -> [N,M] (reference d3d/box/iou.h:24-26)"""
+    return _pairwise_ex(boxes1, boxes2, _c.giou2dr)
+
+
+def diou2dr_forward_cuda(boxes1, boxes2):
+    """Rotated DIoU; CUDA tensors [N,5],[M,5] -> [N,M] (reference d3d/box/iou.h:34-36)"""
+    return _pairwise_ex(boxes1, boxes2, _c.diou2dr)
+
+
+def iou2d_backward_cuda(boxes1, boxes2, grad):
+    """(grad_boxes1, grad_boxes2) of the AABB IoU (reference d3d/box/iou.h:10-12)"""
+    return _pairwise_backward("iou2d", boxes1, boxes2, grad)
+
+
+def iou2dr_backward_cuda(boxes1, boxes2, grad, nx=None, xflags=None):
+    """(grad_boxes1, grad_boxes2) of the rotated IoU (reference d3d/box/iou.h:17-20); nx / xflags are accepted and ignored"""
+    return _pairwise_backward("iou2dr", boxes1, boxes2, grad)
+
+
+def giou2dr_backward_cuda(boxes1, boxes2, grad, nxm=None, flags=None):
+    """(grad_boxes1, grad_boxes2) of the rotated GIoU (reference d3d/box/iou.h:27-30)"""
+    return _pairwise_backward("giou2dr", boxes1, boxes2, grad)
+
+
+def diou2dr_backward_cuda(boxes1, boxes2, grad, nxd=None, flags=None):
+    """(grad_boxes1, grad_boxes2) of the rotated DIoU (reference d3d/box/iou.h:37-40)"""
+    return _pairwise_backward("diou2dr", boxes1, boxes2, grad)
+
+
 def _pairwise(b1, b2, table, out=None):
     code = _c.dtype_code(b1.dtype)
     if b2.dtype != b1.dtype:
@@ -54,13 +84,69 @@ def _pairwise(b1, b2, table, out=None):
     return out
 
 
+def _pairwise_ex(b1, b2, table):
+    """GIoU / DIoU forward: no workspace"""
+    code = _c.dtype_code(b1.dtype)
+    if b2.dtype != b1.dtype:
+        raise RuntimeError("boxes1 and boxes2 must have the same dtype")
+    n, m = b1.shape[0], b2.shape[0]
+    out = torch.empty((n, m), dtype=b1.dtype, device=b1.device)
+    if n and m:
+        with torch.cuda.device(b1.device):
+            st = table[code](_c.ptr(b1), n, _c.ptr(b2), m, _c.ptr(out), out.stride(0), _c.stream_ptr())
+        _c.check(st, "box2d_iou")
+    return out
+
+
+def _pairwise_backward(name, b1, b2, grad):
+    code = _c.dtype_code(b1.dtype)
+    n, m = b1.shape[0], b2.shape[0]
+    grad = grad.contiguous()
+    g1, g2 = torch.empty_like(b1), torch.empty_like(b2)
+    with torch.cuda.device(b1.device):
+        st = _c.iou_backward[name][code](_c.ptr(b1), n, _c.ptr(b2), m, _c.ptr(grad), max(m, 1), _c.ptr(g1), _c.ptr(g2), _c.stream_ptr())
+    _c.check(st, "box2d_iou backward")
+    return g1, g2
+
+
+def _make_iou_function(name, doc, forward_impl):
+    class _F(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, boxes1, boxes2):
+            boxes1, boxes2 = boxes1.contiguous(), boxes2.contiguous()
+            ctx.save_for_backward(boxes1, boxes2)   # the reference also saves nx / xflags (9 B per pair); the backward here recomputes
+            return forward_impl(boxes1, boxes2)
+
+        @staticmethod
+        def backward(ctx, grad):
+            boxes1, boxes2 = ctx.saved_tensors
+            return _pairwise_backward(name, boxes1, boxes2, grad)
+    _F.__doc__ = doc
+    return _F
+
+
+Iou2D = _make_iou_function("iou2d", "Differentiable IoU function for 2D axis-aligned boxes (reference d3d/box/__init__.py:38-61)",
+                           lambda a, b: _pairwise(a, b, _c.iou2d))
+Iou2D.__name__ = Iou2D.__qualname__ = "Iou2D"
+Iou2DR = _make_iou_function("iou2dr", "Differentiable rotated IoU function for 2D boxes (reference d3d/box/__init__.py:63-84)",
+                            lambda a, b: _pairwise(a, b, _c.iou2dr))
+Iou2DR.__name__ = Iou2DR.__qualname__ = "Iou2DR"
+GIou2DR = _make_iou_function("giou2dr", "Differentiable rotated GIoU function for 2D boxes (reference d3d/box/__init__.py:86-107)",
+                             lambda a, b: _pairwise_ex(a, b, _c.giou2dr))
+GIou2DR.__name__ = GIou2DR.__qualname__ = "GIou2DR"
+DIou2DR = _make_iou_function("diou2dr", "Differentiable rotated DIoU function for 2D boxes (reference d3d/box/__init__.py:109-130)",
+                             lambda a, b: _pairwise_ex(a, b, _c.diou2dr))
+DIou2DR.__name__ = DIou2DR.__qualname__ = "DIou2DR"
+
+
 def box2d_iou(boxes1, boxes2, method="box", precise=True):
     '''
-    IoU on axis-aligned or rotated 2D boxes (reference d3d/box/__init__.py:180-224)
+    Differentiable IoU on axis-aligned or rotated 2D boxes (reference d3d/box/__init__.py:180-224)
 
     :param boxes1: Input boxes, shape is N x 5 (x,y,w,h,r)
     :param boxes2: Input boxes, shape is M x 5 (x,y,w,h,r)
-    :param method: 'box' - axis-aligned box, 'rbox' - rotated box
+    :param method: 'box' - axis-aligned box, 'rbox' - rotated box,
+        'grbox' - giou for rotated box, 'drbox' - diou for rotated box
     :param precise: force using double precision to calculate iou
     '''
     convert_numpy = False
@@ -79,24 +165,26 @@ def box2d_iou(boxes1, boxes2, method="box", precise=True):
 
     iou_type = getattr(IouType, method.upper())
     if iou_type == IouType.BOX:
-        table = _c.iou2d
+        impl = Iou2D
     elif iou_type == IouType.RBOX:
-        table = _c.iou2dr
-    elif iou_type in (IouType.GRBOX, IouType.DRBOX):
-        raise NotImplementedError("GIoU / DIoU are outside the hot path of this build (SURVEY.md 8(f) row f2)")
+        impl = Iou2DR
+    elif iou_type == IouType.GRBOX:
+        impl = GIou2DR
+    elif iou_type == IouType.DRBOX:
+        impl = DIou2DR
     else:
         raise ValueError("Unrecognized iou type!")
 
     b1, b2 = _c.to_device(boxes1), _c.to_device(boxes2)
     if precise:
         b1, b2 = b1.to(torch.float64), b2.to(torch.float64)
-    result = _pairwise(b1, b2, table)
+    result = impl.apply(b1, b2)
     if precise:
         result = result.to(otype)
     if not odev.type == "cuda":
         result = result.cpu()
     if convert_numpy:
-        return result.numpy()
+        return result.detach().numpy()
     return result
 
 

@@ -59,7 +59,7 @@ int64_t d3d_launch_count(void);
 /* ------------------------------------------------------------------------------------------------
  * Pairwise IoU.  ious is [n, m] row-major with leading dimension ld (elements, ld >= m).
  * d3d_iou2dr_*: rotated IoU, replaces iou2dr_forward[_cuda] (reference d3d/box/iou.h:14-16,
- *   iou.cpp:94-141, iou_cuda.cu:99-151).  The backward-only outputs nx/xflags are not produced.
+ *   iou.cpp:94-141, iou_cuda.cu:99-151).  The backward-only outputs nx/xflags are not produced (d3d_iou2dr_backward_* recomputes).
  * d3d_iou2d_*: IoU of the axis-aligned bounding boxes of the rotated boxes, replaces
  *   iou2d_forward[_cuda] (iou.h:7-9, iou.cpp:11-46, iou_cuda.cu:9-48).
  * Row-block sharding (multi-GPU): pass a slice of boxes1 and the matching slab of ious.
@@ -73,6 +73,31 @@ int d3d_iou2d_f32(const float *boxes1, int64_t n, const float *boxes2, int64_t m
                   void *workspace, size_t workspace_bytes, void *stream);
 int d3d_iou2d_f64(const double *boxes1, int64_t n, const double *boxes2, int64_t m, double *ious, int64_t ld,
                   void *workspace, size_t workspace_bytes, void *stream);
+/* Differentiable IoU family.
+ * d3d_giou2dr_* / d3d_diou2dr_*: rotated generalized / distance IoU, [n, m] with leading dimension ld; replace giou2dr_forward[_cuda] /
+ *   diou2dr_forward[_cuda] (reference d3d/box/iou.h:24-26, 34-36, iou.cpp:202-243, 311-352; dgal::giou / diou geometry.hpp:1232-1291:
+ *   GIoU = I/U + U/M - 1 with M the area of the convex hull of both boxes, DIoU = I/U - |c1 - c2|^2 / D^2 with D the largest vertex distance).
+ *   The backward-only outputs (nxm / nxd, flags) are not produced: the backward recomputes what it needs.
+ * d3d_*_backward_*: gradients of sum(grad * value) with respect to both box arrays; replace iou2d_backward, iou2dr_backward,
+ *   giou2dr_backward, diou2dr_backward [_cuda] (iou.h:10-12, 17-20, 27-30, 37-40, iou.cpp:48-92, 143-200, 245-309, 354-419; dgal::iou_grad /
+ *   giou_grad / diou_grad, geometry_grad.hpp:327-606).  grad [n, m] with leading dimension ld; grad_boxes1 [n,5] and grad_boxes2 [m,5] are
+ *   WRITTEN (not accumulated).  One warp owns one box and sums its row / column in a fixed order: results are deterministic, there is no
+ *   atomic and no race (the reference adds pair gradients into the box rows from all threads, iou_cuda.cu:184-185). */
+int d3d_giou2dr_f32(const float *boxes1, int64_t n, const float *boxes2, int64_t m, float *out, int64_t ld, void *stream);
+int d3d_giou2dr_f64(const double *boxes1, int64_t n, const double *boxes2, int64_t m, double *out, int64_t ld, void *stream);
+int d3d_diou2dr_f32(const float *boxes1, int64_t n, const float *boxes2, int64_t m, float *out, int64_t ld, void *stream);
+int d3d_diou2dr_f64(const double *boxes1, int64_t n, const double *boxes2, int64_t m, double *out, int64_t ld, void *stream);
+#define D3D_DECL_IOU_BACKWARD(NAME, T)                                                                                          \
+    int NAME(const T *boxes1, int64_t n, const T *boxes2, int64_t m, const T *grad, int64_t ld, T *grad_boxes1, T *grad_boxes2, \
+             void *stream);
+D3D_DECL_IOU_BACKWARD(d3d_iou2d_backward_f32, float)
+D3D_DECL_IOU_BACKWARD(d3d_iou2d_backward_f64, double)
+D3D_DECL_IOU_BACKWARD(d3d_iou2dr_backward_f32, float)
+D3D_DECL_IOU_BACKWARD(d3d_iou2dr_backward_f64, double)
+D3D_DECL_IOU_BACKWARD(d3d_giou2dr_backward_f32, float)
+D3D_DECL_IOU_BACKWARD(d3d_giou2dr_backward_f64, double)
+D3D_DECL_IOU_BACKWARD(d3d_diou2dr_backward_f32, float)
+D3D_DECL_IOU_BACKWARD(d3d_diou2dr_backward_f64, double)
 /* Detection-evaluation distance matrix: dist[i][j] = 1 - iou2d(BEV boxes) * ziou, fp32,
  * for 3-D boxes [n,7] / [m,7] with rows (x, y, z, lx, ly, lz, rz).  rotated != 0: rotated BEV IoU, replaces the pair
  * loop over box3dr_iou in ScoreMatcher.prepare_boxes (reference d3d/tracking/matcher.pyx:66-76, d3d/dgal_wrap.h:45-68);

@@ -154,6 +154,51 @@ def box3d_iou_distance(src, dst, metric="riou", alg=ALG_RC):
     return (f(1) - iou.astype(f) * (i / u).astype(f)).astype(f)
 
 
+def _hull_area_and_diameter(pts):
+    """area of the convex hull (Andrew's monotone chain) and largest pairwise distance of a few points, float64"""
+    p = sorted(map(tuple, pts))
+    def half(seq):
+        h = []
+        for q in seq:
+            while len(h) >= 2 and (h[-1][0] - h[-2][0]) * (q[1] - h[-2][1]) - (h[-1][1] - h[-2][1]) * (q[0] - h[-2][0]) <= 0:
+                h.pop()
+            h.append(q)
+        return h
+    hull = half(p)[:-1] + half(p[::-1])[:-1]
+    area = 0.5 * abs(sum(hull[i][0] * hull[(i + 1) % len(hull)][1] - hull[i][1] * hull[(i + 1) % len(hull)][0] for i in range(len(hull))))
+    pa = np.asarray(pts)
+    diam = np.sqrt(((pa[:, None, :] - pa[None, :, :]) ** 2).sum(-1)).max()
+    return area, diam
+
+
+def iou2dr_ex(boxes1, boxes2, method="grbox"):
+    """Rotated GIoU / DIoU [N, M] in float64 from their definitions (dgal::giou / diou, geometry.hpp:1241-1285):
+    GIoU = I/U + U/M - 1, DIoU = I/U - |c1 - c2|^2 / D^2, with I/U the pinned rotated IoU (geometric truth), M the area of the convex hull of
+    the eight vertices (dgal::merge :1021-1122 builds the same polygon with rotating calipers; here Andrew's monotone chain) and D their
+    largest distance (dgal::dimension :941-982).  Small inputs only (Python loops).  PINNED to the reference's own giou2dr_forward /
+    diou2dr_forward through tests/golden/iou_grad.npz (1e-12)."""
+    b1, b2 = np.asarray(boxes1, np.float64), np.asarray(boxes2, np.float64)
+    iou = iou2dr_truth(b1, b2)
+    out = np.empty((len(b1), len(b2)))
+    def verts(b):
+        x, y, w, h, r = b
+        c, s = np.cos(r), np.sin(r)
+        return np.array([[x - w * c / 2 + h * s / 2, y - w * s / 2 - h * c / 2], [x + w * c / 2 + h * s / 2, y + w * s / 2 - h * c / 2],
+                         [x + w * c / 2 - h * s / 2, y + w * s / 2 + h * c / 2], [x - w * c / 2 - h * s / 2, y - w * s / 2 + h * c / 2]])
+    v1, v2 = [verts(b) for b in b1], [verts(b) for b in b2]
+    for i in range(len(b1)):
+        for j in range(len(b2)):
+            m_area, diam = _hull_area_and_diameter(np.concatenate([v1[i], v2[j]]))
+            a1, a2 = b1[i, 2] * b1[i, 3], b2[j, 2] * b2[j, 3]
+            inter = iou[i, j] * (a1 + a2) / (1 + iou[i, j])
+            u = a1 + a2 - inter
+            if method == "grbox":
+                out[i, j] = inter / u + u / m_area - 1
+            else:
+                out[i, j] = inter / u - ((b1[i, 0] - b2[j, 0]) ** 2 + (b1[i, 1] - b2[j, 1]) ** 2) / diam ** 2
+    return out
+
+
 def match_greedy(distance, src_scores, src_tags, dst_tags, thresholds):
     """ScoreMatcher.match (d3d/tracking/matcher.pyx:138-162) over BaseMatcher.match_by_order (:93-122) for one threshold set
     `thresholds[category]`: returns (src_assignment i32[N], dst_assignment i32[M]), -1 = unmatched.  The source order is

@@ -56,6 +56,27 @@ def crop_2dr(points, boxes):
     return _box().crop_2dr(_t(points), _t(boxes)).numpy()
 
 
+def iou_forward_backward(boxes1, boxes2, grad, method="rbox"):
+    """the reference's own forward + backward of box2d_iou's four methods (d3d/box/iou.cpp), single-threaded so that its += into the box
+    rows does not race: (values [N, M], grad_boxes1 [N, 5], grad_boxes2 [M, 5])"""
+    m = _box()
+    b1, b2, g = _t(boxes1), _t(boxes2), _t(grad)
+    nt = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        if method == "box":
+            v = m.iou2d_forward(b1, b2)
+            g1, g2 = m.iou2d_backward(b1, b2, g)
+        else:
+            fw, bw = {"rbox": (m.iou2dr_forward, m.iou2dr_backward), "grbox": (m.giou2dr_forward, m.giou2dr_backward),
+                      "drbox": (m.diou2dr_forward, m.diou2dr_backward)}[method]
+            v, a, f = fw(b1, b2)
+            g1, g2 = bw(b1, b2, g, a, f)
+    finally:
+        torch.set_num_threads(nt)
+    return v.numpy(), g1.numpy(), g2.numpy()
+
+
 _WRAP = None
 
 

@@ -109,6 +109,20 @@ def write_pdist():
     np.savez_compressed(os.path.join(OUT, "pdist.npz"), **out)
 
 
+def write_iou_grad():
+    """values and gradients of the reference's own differentiable IoU family (d3d/box/iou.cpp:11-419, single-threaded), fp64"""
+    rng = np.random.default_rng(33)
+    A, B = gen_boxes(rng, 40), gen_boxes(rng, 30)
+    A[:, 2:4] += 0.3; B[:, 2:4] += 0.3
+    B[:6] = A[:6] + rng.normal(0, 0.2, (6, 5))       # strongly overlapping pairs
+    up = rng.random((40, 30))
+    out = dict(boxes1=A, boxes2=B, grad=up)
+    for m in ("box", "rbox", "grbox", "drbox"):
+        v, g1, g2 = R.iou_forward_backward(A, B, up, m)
+        out[m + ".value"], out[m + ".grad1"], out[m + ".grad2"] = v, g1, g2
+    np.savez_compressed(os.path.join(OUT, "iou_grad.npz"), **out)
+
+
 def write_dist3d():
     """detection-evaluation distances 1 - iou2d * ziou of the reference's own box3dr_iou / box3d_iou (d3d/dgal_wrap.h:45-91, g++)"""
     rng = np.random.default_rng(21)

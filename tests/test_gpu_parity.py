@@ -149,6 +149,46 @@ def _boxes3d(rng, n, extent=40.0):
                      3.5 + rng.random(n) * 2, 1.5 + rng.random(n), 1.4 + rng.random(n) * 0.6, (rng.random(n) - .5) * 7], 1).astype(np.float32)
 
 
+def test_iou_differentiable_family(dev, oracle):
+    """A2 / f2: box2d_iou is differentiable for its four methods.  Values of GIoU / DIoU and all gradients against the fixture written by
+    the reference's own forward / backward (fp64, single-threaded), torch.autograd.gradcheck on generic pairs, the fp32 path against
+    the fp64 one, identical boxes, numpy and host inputs."""
+    from d3d_b200.box import box2d_iou, Iou2DR, GIou2DR
+    g = golden("iou_grad.npz")
+    A, B, up = g["boxes1"], g["boxes2"], g["grad"]
+    for m, vtol in (("box", 1e-12), ("rbox", 1e-10), ("grbox", 1e-10), ("drbox", 1e-10)):
+        a, b = _t(A, dev).requires_grad_(True), _t(B, dev).requires_grad_(True)
+        v = box2d_iou(a, b, m)
+        assert v.requires_grad and np.abs(v.detach().cpu().numpy() - g[m + ".value"]).max() < vtol, m
+        (v * _t(up, dev)).sum().backward()
+        assert np.abs(a.grad.cpu().numpy() - g[m + ".grad1"]).max() < 1e-8, (m, float(np.abs(a.grad.cpu().numpy() - g[m + ".grad1"]).max()))
+        assert np.abs(b.grad.cpu().numpy() - g[m + ".grad2"]).max() < 1e-8, (m, float(np.abs(b.grad.cpu().numpy() - g[m + ".grad2"]).max()))
+        a32, b32 = _t(A.astype(np.float32), dev).requires_grad_(True), _t(B.astype(np.float32), dev).requires_grad_(True)
+        v32 = box2d_iou(a32, b32, m, precise=False)
+        assert v32.dtype == torch.float32 and np.abs(v32.detach().cpu().numpy() - g[m + ".value"]).max() < FP32_TOL
+        (v32 * _t(up.astype(np.float32), dev)).sum().backward()
+        assert np.abs(a32.grad.cpu().numpy() - g[m + ".grad1"]).max() < 5e-3 * max(1.0, np.abs(g[m + ".grad1"]).max())
+    rng = np.random.default_rng(5)
+    a = _t(gen_boxes(rng, 5, spread=4.0) + np.array([0, 0, .5, .5, 0]), dev).requires_grad_(True)
+    b = _t(gen_boxes(rng, 4, spread=4.0) + np.array([0, 0, .5, .5, 0]), dev).requires_grad_(True)
+    for m in ("box", "rbox", "grbox", "drbox"):
+        assert torch.autograd.gradcheck(lambda x, y: box2d_iou(x, y, m), (a, b), eps=1e-6, atol=1e-5, rtol=1e-4, nondet_tol=0.0), m
+    same = _t(A[:8], dev)
+    assert np.abs(box2d_iou(same, same, "grbox").diagonal().cpu().numpy() - 1).max() < 1e-12      # identical boxes: shared edges counted once
+    assert np.abs(box2d_iou(same, same, "drbox").diagonal().cpu().numpy() - 1).max() < 1e-12
+    assert np.abs(box2d_iou(A, B, "grbox") - g["grbox.value"]).max() < 1e-10                       # numpy in, numpy out
+    hv = box2d_iou(torch.from_numpy(A).requires_grad_(True), torch.from_numpy(B), "drbox")         # host tensors: differentiable through the copies
+    hv.sum().backward()
+    assert not hv.is_cuda
+    far = _t(A[:3] + np.array([1000, 0, 0, 0, 0]), dev).requires_grad_(True)                       # no overlap: zero IoU gradient, non-zero GIoU gradient
+    box2d_iou(far, _t(B, dev), "rbox").sum().backward()
+    assert float(far.grad.abs().max()) == 0.0
+    far.grad = None
+    box2d_iou(far, _t(B, dev), "grbox").sum().backward()
+    assert float(far.grad.abs().max()) > 0.0
+    assert Iou2DR.__name__ == "Iou2DR" and issubclass(GIou2DR, torch.autograd.Function)
+
+
 def test_box3d_iou_distance_vs_oracle(dev, oracle):
     """the evaluator's distance matrix 1 - iou2d * ziou (fp32).  Against geometric truth everywhere
     (tolerance 1e-4, north_star's fp32 bound), against the reference's own fp32 Rotating-Calipers path on the pairs where

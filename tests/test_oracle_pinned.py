@@ -345,3 +345,22 @@ def test_pdist2dr_pinned(oracle):
     assert np.array_equal(d, rd) and np.array_equal(ie, rie)
     p3, b3 = (rng.random((500, 3)) - .5) * 10, np.concatenate([gen_boxes(rng, 20)[:, :2], rng.random((20, 1)), rng.random((20, 3)) * 4 + .2, rng.random((20, 1)) * 6], 1)
     assert oracle.box3dr_pdist(p3, b3).shape == (20, 500)
+
+
+def test_iou_ex_pinned(oracle):
+    """f2: rotated GIoU / DIoU of the oracle (definitions over the pinned rotated IoU) against the values written by the reference's own
+    giou2dr_forward / diou2dr_forward (tests/golden/make_golden.py write_iou_grad), and the fixture's gradients against central
+    differences of the oracle on a few boxes: the fixture is a true gradient, so it can pin the CUDA backward"""
+    g = golden("iou_grad.npz")
+    A, B, up = g["boxes1"], g["boxes2"], g["grad"]
+    for m in ("grbox", "drbox"):
+        assert np.abs(oracle.iou2dr_ex(A, B, m) - g[m + ".value"]).max() < 1e-12, m
+    assert np.abs(oracle.iou2dr_truth(A, B) - g["rbox.value"]).max() < 1e-12
+    eps = 1e-6
+    for m in ("grbox", "drbox"):
+        for i in (0, 7):
+            for k in range(5):
+                hi, lo = A.copy(), A.copy()
+                hi[i, k] += eps; lo[i, k] -= eps
+                num = ((oracle.iou2dr_ex(hi[i:i + 1], B, m) - oracle.iou2dr_ex(lo[i:i + 1], B, m)) * up[i:i + 1]).sum() / (2 * eps)
+                assert abs(num - g[m + ".grad1"][i, k]) < 1e-6, (m, i, k)
