@@ -64,6 +64,9 @@ iou_count_candidates = _sig("d3d_iou_count_candidates", C.c_int, [_vp, _i64, _vp
 nms_workspace_bytes = _sig("d3d_nms2d_workspace_bytes", _sz, [_i64, C.c_int])
 _nms_sig = [_vp, _vp, _i64, C.c_int, C.c_int, _f, _f, _f, _vp, _vp, _sz, _vp]
 nms2d = {F32: _sig("d3d_nms2d_f32", C.c_int, _nms_sig), F64: _sig("d3d_nms2d_f64", C.c_int, _nms_sig)}
+nms_batch_workspace_bytes = _sig("d3d_nms2d_batch_workspace_bytes", _sz, [_i64, _i64, _i64, C.c_int])
+_nmsb_sig = [_vp, _vp, _i64, _vp, _i64, _i64, C.c_int, C.c_int, _f, _f, _vp, _vp, _sz, _vp]
+nms2d_batch = {F32: _sig("d3d_nms2d_batch_f32", C.c_int, _nmsb_sig), F64: _sig("d3d_nms2d_batch_f64", C.c_int, _nmsb_sig)}
 voxelize_workspace_bytes = _sig("d3d_voxelize_workspace_bytes", _sz, [_i64, _i64, _i64])
 voxelize_sparse = _sig("d3d_voxelize_sparse_f32", C.c_int,
                        [_vp, _i64, _i32, _vp, _i64, C.POINTER(VoxelParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp])
@@ -74,7 +77,7 @@ scatter_forward = _sig("d3d_aligned_scatter_forward", C.c_int, _sc_sig)
 scatter_backward = _sig("d3d_aligned_scatter_backward", C.c_int, _sc_sig)
 fma_peak_probe = _sig("d3d_fma_peak_probe", C.c_int, [C.c_int, _i64, _vp, C.POINTER(C.c_double), _vp])
 
-if abi_version() != 3:
+if abi_version() != 4:
     raise ImportError("libd3d_b200.so ABI version mismatch")
 
 

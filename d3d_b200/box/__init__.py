@@ -188,6 +188,75 @@ def box2d_iou(boxes1, boxes2, method="box", precise=True):
     return result
 
 
+def box2d_nms_batch(boxes, scores, offsets=None, iou_method="box", iou_threshold=0, score_threshold=0, precise=True, offsets_dev=None):
+    '''
+    Hard NMS on a batch of frames in one launch sequence (the reference has no batch form; per frame the result equals
+    :func:`box2d_nms`).  Two call forms: lists of per-frame ``boxes`` / ``scores`` (returns a list of keep masks), or the frames
+    packed back to back as ``boxes`` [total, 5] / ``scores`` [total] with ``offsets`` (int64 [nframes + 1], CPU tensor) (returns one
+    keep mask bool[total]).  Frames of more than 8192 boxes fall back to one :func:`box2d_nms` call per frame.
+
+    :param iou_method: 'box' - axis-aligned box, 'rbox' - rotated box
+    :param offsets_dev: the same offsets already on the device (saves the copy)
+    '''
+    as_list = isinstance(boxes, (list, tuple))
+    if as_list:
+        if len(boxes) != len(scores):
+            raise ValueError("Numbers of boxes and scores are inconsistent!")
+        if len(boxes) == 0:
+            return []
+        tt = lambda x: torch.from_numpy(x) if isinstance(x, np.ndarray) else x
+        numpy_in = isinstance(boxes[0], np.ndarray)
+        blist, slist = [tt(b) for b in boxes], [tt(s_) for s_ in scores]
+        odev = blist[0].device
+        lens = [int(b.shape[0]) for b in blist]
+        offsets = torch.zeros(len(lens) + 1, dtype=torch.int64)
+        offsets[1:] = torch.tensor(lens).cumsum(0)
+        boxes = torch.cat([_c.to_device(b).reshape(-1, 5) for b in blist], 0)
+        scores = torch.cat([_c.to_device(s_).reshape(-1) for s_ in slist], 0)
+    else:
+        numpy_in = isinstance(boxes, np.ndarray)
+        if numpy_in:
+            boxes, scores = torch.from_numpy(boxes), torch.from_numpy(scores)
+        odev = boxes.device
+        if offsets is None:
+            raise ValueError("packed boxes need the frame offsets")
+        offsets = torch.as_tensor(offsets).to(torch.int64).cpu()
+    if len(boxes) != len(scores) or int(offsets[-1]) != len(boxes):
+        raise ValueError("Numbers of boxes and scores are inconsistent!")
+    iou_type = getattr(IouType, iou_method.upper())
+    if iou_type not in (IouType.BOX, IouType.RBOX):
+        raise ValueError("Unsupported iou type!")
+    b, s_ = _c.to_device(boxes), _c.to_device(scores)
+    if precise:
+        b, s_ = b.to(torch.float64), s_.to(torch.float64)
+    elif s_.dtype != b.dtype:
+        s_ = s_.to(b.dtype)
+    b, s_ = b.contiguous(), s_.contiguous()
+    total, nframes = int(b.shape[0]), int(offsets.numel()) - 1
+    max_frame = int((offsets[1:] - offsets[:-1]).max()) if nframes > 0 else 0
+    suppressed = torch.zeros(total, dtype=torch.uint8, device=b.device)
+    if total > 0 and max_frame > 8192:
+        for f in range(nframes):
+            lo, hi = int(offsets[f]), int(offsets[f + 1])
+            if hi > lo:
+                suppressed[lo:hi] = nms2d_cuda(b[lo:hi], s_[lo:hi], iou_type, SupressionType.HARD, iou_threshold, score_threshold, 0).view(torch.uint8)
+    elif total > 0:
+        code = _c.dtype_code(b.dtype)
+        od = offsets.to(b.device, non_blocking=True) if offsets_dev is None else offsets_dev
+        ws = _c.workspace(_c.nms_batch_workspace_bytes(total, nframes, max_frame, code), b.device)
+        with torch.cuda.device(b.device):
+            st = _c.nms2d_batch[code](_c.ptr(b), _c.ptr(s_), total, _c.ptr(od), nframes, max_frame, int(iou_type), int(SupressionType.HARD),
+                                      float(iou_threshold), float(score_threshold), _c.ptr(suppressed), _c.ptr(ws), ws.numel(), _c.stream_ptr())
+        _c.check(st, "box2d_nms_batch")
+    keep = ~suppressed.view(torch.bool)
+    if odev.type != "cuda":
+        keep = keep.cpu()
+    if as_list:
+        out = [keep[int(offsets[f]):int(offsets[f + 1])] for f in range(nframes)]
+        return [k.cpu().numpy() for k in out] if numpy_in else out
+    return keep.cpu().numpy() if numpy_in else keep
+
+
 def crop_2dr_cuda(points, boxes):
     """bool[M, N] mask of the points [N,2] inside the rotated boxes [M,5] (reference crop_2dr, d3d/box/utils.h:45; CUDA tensors)"""
     code = _c.dtype_code(points.dtype)

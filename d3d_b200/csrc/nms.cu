@@ -290,15 +290,11 @@ __global__ void __launch_bounds__(NMS_PAIR_THREADS, D3D_NMS_PAIR_CTAS) nms_pairs
 }
 
 template <typename T>
-__global__ void __launch_bounds__(NMS_THREADS)
-nms_mask_rbox_kernel(const BoxRec<T> *__restrict__ recs, const T *__restrict__ raw, int64_t n, int64_t nwords, T thr, uint64_t *__restrict__ mask, const NmsLists lists,
-                     const NmsGrid *__restrict__ grid)
+__device__ __forceinline__ void nms_mask_rbox_body(const BoxRec<T> *__restrict__ recs, const T *__restrict__ raw, int64_t n, int64_t nwords, T thr, uint64_t *__restrict__ mask,
+                                                   const NmsLists lists, const int64_t cb, const int64_t rb_first, const int64_t rb_stride)
 {
-    // one CTA per column tile cb and per residue of the row tile: rb = blockIdx.y, blockIdx.y + gridDim.y, ... <= cb.  The short grid
-    // keeps the launch cheap when the spatial path has already produced the lists and every CTA leaves at once.
-    const int64_t cb = blockIdx.x;
-    if (cb < (int64_t)blockIdx.y) return;
-    if (grid && grid->ok && lists.blkcnt[nwords] == 0u) return;   // the spatial path produced the lists: nothing to do
+    // one CTA per column tile cb and per residue of the row tile: rb = rb_first, rb_first + rb_stride, ... <= cb
+    if (cb < rb_first) return;
     constexpr int RW = NMS_TILE / NMS_WARPS;  // 16 rows per warp
     constexpr int KC = NMS_TILE / 32;         // 2 column chunks
     __shared__ BoxRec<T> sA[NMS_TILE];
@@ -318,7 +314,7 @@ nms_mask_rbox_kernel(const BoxRec<T> *__restrict__ recs, const T *__restrict__ r
 #pragma unroll
     for (int k = 0; k < KC; k++) { bx[k] = sB[k * 32 + lane].cx; by[k] = sB[k * 32 + lane].cy; br[k] = sB[k * 32 + lane].rho; }
     uint16_t *q = queue[w];
-  for (int64_t rb = blockIdx.y; rb <= cb; rb += gridDim.y) {
+  for (int64_t rb = rb_first; rb <= cb; rb += rb_stride) {
     {
         const float4 *ga = reinterpret_cast<const float4 *>(recs + rb * NMS_TILE);
         float4 *da = reinterpret_cast<float4 *>(sA);
@@ -364,6 +360,17 @@ nms_mask_rbox_kernel(const BoxRec<T> *__restrict__ recs, const T *__restrict__ r
     nms_append_tile(lists, smask, rb, cb, n, nwords, &s_cnt, &s_base);
     __syncthreads();   // sA, smask and the counters are reused by the next row tile
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NMS_THREADS)
+nms_mask_rbox_kernel(const BoxRec<T> *__restrict__ recs, const T *__restrict__ raw, int64_t n, int64_t nwords, T thr, uint64_t *__restrict__ mask, const NmsLists lists,
+                     const NmsGrid *__restrict__ grid)
+{
+    // The short grid (gridDim.y row residues) keeps the launch cheap when the spatial path has already produced the lists and every
+    // CTA leaves at once.
+    if (grid && grid->ok && lists.blkcnt[nwords] == 0u) return;   // the spatial path produced the lists: nothing to do
+    nms_mask_rbox_body<T>(recs, raw, n, nwords, thr, mask, lists, blockIdx.x, blockIdx.y, gridDim.y);
 }
 
 // AABB variant: every pair is a handful of instructions, no queue needed
@@ -709,6 +716,210 @@ __global__ void __launch_bounds__(SOFT_THREADS) nms_soft_kernel(const BoxRec<T> 
     for (uint32_t p = tid; p < n; p += NT) suppressed[order[p]] = S.sup[p];
 }
 
+// ------------------------------------------------------------------------------------------------ batched hard NMS
+// Frame-batched NMS (BASELINE.json config 5): boxes of all frames packed back to back + device offsets, like the voxel
+// ABI.  The single-frame pipeline above spends ~50 launches on one frame and resolves it on ONE SM; here three launches cover the
+// batch and every stage has a frame dimension: (1) one CTA per frame sorts the frame's scores in shared memory (bitonic network on
+// (key, index) pairs: the same stable order as the radix sort) and writes the sorted records, (2) dense 64x64 tiles of every frame's
+// upper triangle (blockIdx.z = frame), (3) one resolve CTA per frame, so 64 frames occupy 64 SMs instead of 1.
+constexpr int NMSB_MAX = 8192;        // boxes per frame the shared-memory sort takes
+constexpr int NMSB_SORT_THREADS = 1024;
+
+template <typename T, bool AABB>
+__global__ void __launch_bounds__(NMSB_SORT_THREADS) nmsb_sort_kernel(const T *__restrict__ boxes, const T *__restrict__ scores, const int64_t *__restrict__ offs,
+                                                                    int64_t stride, float score_thr, uint32_t *__restrict__ order, BoxRec<T> *__restrict__ recs,
+                                                                    AABBRec<T> *__restrict__ arecs, T *__restrict__ raw, uint8_t *__restrict__ valid,
+                                                                    uint32_t *__restrict__ fail)
+{
+    extern __shared__ unsigned long long sk[];   // [npow] keys, then [npow] u32 indices
+    const int64_t f = blockIdx.x, b = offs[f];
+    int64_t n64 = offs[f + 1] - b;
+    if (n64 > stride) { if (threadIdx.x == 0) *fail = 1u; n64 = stride; }   // longer than max_frame_boxes: cut (documented hard bound)
+    const uint32_t n = (uint32_t)n64;
+    uint32_t npow = 64;
+    while (npow < n) npow <<= 1;
+    uint32_t *si = reinterpret_cast<uint32_t *>(sk + npow);
+    for (uint32_t p = threadIdx.x; p < npow; p += NMSB_SORT_THREADS) {
+        sk[p] = p < n ? desc_key(scores[b + p]) : ~0ull;
+        si[p] = p < n ? p : 0xffffffffu;
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= npow; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < npow / 2; t += NMSB_SORT_THREADS) {
+                const uint32_t lo = ((t / j) * 2 * j) + (t % j), hi = lo + j;
+                const bool up = (lo & k) == 0;
+                const unsigned long long ka = sk[lo], kb = sk[hi];
+                const uint32_t ia = si[lo], ib = si[hi];
+                const bool gt = ka > kb || (ka == kb && ia > ib);
+                if (gt == up) { sk[lo] = kb; sk[hi] = ka; si[lo] = ib; si[hi] = ia; }
+            }
+            __syncthreads();
+        }
+    const int64_t base = f * stride;
+    for (int64_t p = threadIdx.x; p < stride; p += NMSB_SORT_THREADS) {
+        if (p < n) {
+            const uint32_t i = si[p];
+            order[base + p] = i;
+            const T *bx = boxes + 5 * (b + i);
+            if (AABB) arecs[base + p] = make_aabb_rec<T>(bx[0], bx[1], bx[2], bx[3], bx[4]);
+            else {
+                recs[base + p] = make_box_rec<T>(bx[0], bx[1], bx[2], bx[3], bx[4]);
+                if (raw) { for (int q = 0; q < 5; q++) raw[5 * (base + p) + q] = bx[q]; }
+            }
+            valid[base + p] = scores[b + i] > score_thr ? 1 : 0;
+        } else {
+            if (AABB) { AABBRec<T> a; a.minx = a.maxx = a.miny = a.maxy = T(NAN); arecs[base + p] = a; }
+            else { BoxRec<T> r; r.cx = r.cy = r.c = r.s = r.hw = r.hh = r.area = T(0); r.rho = T(NAN); recs[base + p] = r; }
+            valid[base + p] = 0;
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NMS_THREADS)
+nmsb_mask_rbox_kernel(const BoxRec<T> *__restrict__ recs, const T *__restrict__ raw, const int64_t *__restrict__ offs, int64_t stride, int64_t nwords, T thr,
+                      uint64_t *__restrict__ mask)
+{
+    const int64_t f = blockIdx.z;
+    const int64_t n = min(offs[f + 1] - offs[f], stride);
+    if ((int64_t)blockIdx.x * NMS_TILE >= n) return;
+    const NmsLists none = {nullptr, nullptr, nullptr};
+    nms_mask_rbox_body<T>(recs + f * stride, raw ? raw + 5 * f * stride : nullptr, n, nwords, thr, mask + f * stride * nwords, none, blockIdx.x, blockIdx.y, gridDim.y);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NMS_TILE)
+nmsb_mask_aabb_kernel(const AABBRec<T> *__restrict__ recs_all, const int64_t *__restrict__ offs, int64_t stride, int64_t nwords, T thr, uint64_t *__restrict__ mask_all)
+{
+    const int64_t f = blockIdx.z, rb = blockIdx.y, cb = blockIdx.x;
+    const int64_t n = min(offs[f + 1] - offs[f], stride);
+    if (cb < rb || cb * NMS_TILE >= n) return;
+    const AABBRec<T> *recs = recs_all + f * stride;
+    uint64_t *mask = mask_all + f * stride * nwords;
+    __shared__ AABBRec<T> sB[NMS_TILE];
+    sB[threadIdx.x] = recs[cb * NMS_TILE + threadIdx.x];
+    __syncthreads();
+    const int64_t row = rb * NMS_TILE + threadIdx.x;
+    if (row < n) {
+        unsigned long long bits = 0;
+        const AABBRec<T> a = recs[row];
+        const int start = (rb == cb) ? threadIdx.x + 1 : 0;
+        for (int c = start; c < NMS_TILE; c++) {
+            if (cb * NMS_TILE + c >= n) break;
+            if (aabb_iou<T>(a, sB[c]) > thr) bits |= 1ull << c;
+        }
+        mask[row * nwords + cb] = bits;
+    }
+}
+
+// one CTA per frame: the dense walk over the frame's suppression matrix (same rule as nms_resolve_kernel's dense path)
+__global__ void __launch_bounds__(RESOLVE_THREADS)
+nmsb_resolve_kernel(const uint64_t *__restrict__ mask_all, const int64_t *__restrict__ offs, int64_t stride, int64_t nwords_max, const uint8_t *__restrict__ valid_all,
+                    const uint32_t *__restrict__ order_all, uint8_t *__restrict__ suppressed)
+{
+    extern __shared__ unsigned long long remv[];   // [nwords]
+    __shared__ unsigned long long diag0[64];
+    __shared__ unsigned long long keptbits;
+    const int64_t f = blockIdx.x, b = offs[f];
+    const int64_t n = min(offs[f + 1] - b, stride);
+    if (n == 0) return;
+    const int64_t nwords = (n + 63) / 64;
+    const uint64_t *mask = mask_all + f * stride * nwords_max;
+    const uint8_t *valid = valid_all + f * stride;
+    const uint32_t *order = order_all + f * stride;
+    uint8_t *sup = suppressed + b;
+    const int tid = threadIdx.x;
+    const uint32_t NT = blockDim.x;
+    for (int64_t w = tid; w < nwords; w += NT) {
+        unsigned long long bb = 0;
+        for (int t = 0; t < 64; t++) {
+            const int64_t p = w * 64 + t;
+            if (p >= n || !valid[p]) bb |= 1ull << t;
+        }
+        remv[w] = bb;
+    }
+    __syncthreads();
+    for (int64_t blk = 0; blk < nwords; blk++) {
+        if (tid < 64) {
+            const int64_t row = blk * 64 + tid;
+            diag0[tid] = row < n ? mask[row * nwords_max + blk] : 0ull;
+        }
+        __syncthreads();
+        if (tid == 0) keptbits = nms_resolve_diag(remv[blk], diag0);
+        __syncthreads();
+        const unsigned long long kept = keptbits;
+        if (tid < 64) {
+            const int64_t row = blk * 64 + tid;
+            if (row < n) sup[order[row]] = ((kept >> tid) & 1ull) ? 0 : 1;
+        }
+        if (kept) {
+            for (int64_t w = blk + 1 + tid; w < nwords; w += NT) {
+                unsigned long long acc = remv[w], k = kept;
+                const uint64_t *col = mask + (blk * 64) * nwords_max + w;
+                while (k) { const int t0 = __ffsll((long long)k) - 1; k &= k - 1; acc |= col[(int64_t)t0 * nwords_max]; }
+                remv[w] = acc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T> static size_t nmsb_ws_bytes(int64_t nframes, int64_t max_frame_boxes)
+{
+    if (nframes < 1) nframes = 1;
+    if (max_frame_boxes < 1) max_frame_boxes = 1;
+    const int64_t stride = cdiv(max_frame_boxes, NMS_TILE) * NMS_TILE, nwords = stride / 64;
+    const size_t rec = sizeof(BoxRec<T>) > sizeof(AABBRec<T>) ? sizeof(BoxRec<T>) : sizeof(AABBRec<T>);
+    const size_t per = align_up((size_t)stride * 4) + align_up((size_t)stride * rec) + align_up((size_t)stride * 5 * sizeof(T)) + align_up((size_t)stride) +
+                       align_up((size_t)stride * nwords * 8);
+    return per * (size_t)nframes + 4096;
+}
+
+template <typename T>
+static int nmsb_impl(const T *boxes, const T *scores, int64_t total, const int64_t *offs, int64_t nframes, int64_t max_frame_boxes, int iou_type, int sup_type,
+                     float iou_thr, float score_thr, uint8_t *suppressed, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    if (total < 0 || nframes < 0) return D3D_ERR_INVALID_ARGUMENT;
+    if (iou_type != D3D_IOU_BOX && iou_type != D3D_IOU_RBOX) return D3D_ERR_INVALID_ARGUMENT;
+    if (sup_type < D3D_SUP_HARD || sup_type > D3D_SUP_GAUSSIAN) return D3D_ERR_INVALID_ARGUMENT;
+    if (sup_type != D3D_SUP_HARD) return D3D_ERR_UNSUPPORTED;   // soft-NMS is sequential in the scores: one frame per call
+    if (nframes == 0 || total == 0) return D3D_OK;
+    if (!boxes || !scores || !offs || !suppressed) return D3D_ERR_INVALID_ARGUMENT;
+    if (max_frame_boxes <= 0 || max_frame_boxes > total) max_frame_boxes = total;
+    if (max_frame_boxes > NMSB_MAX) return D3D_ERR_UNSUPPORTED;   // the per-frame sort lives in shared memory: use d3d_nms2d_* per frame
+    if (nframes > 65535) return D3D_ERR_INVALID_ARGUMENT;
+    if (!ws || ws_bytes < nmsb_ws_bytes<T>(nframes, max_frame_boxes)) return D3D_ERR_WORKSPACE;
+    const int64_t stride = cdiv(max_frame_boxes, NMS_TILE) * NMS_TILE, nwords = stride / 64;
+    const bool aabb = iou_type == D3D_IOU_BOX, recheck = sizeof(T) == 4 && !aabb;
+    Arena a(ws, ws_bytes);
+    uint32_t *order = a.take<uint32_t>((size_t)nframes * stride);
+    void *recs = a.take<char>((size_t)nframes * stride * (sizeof(BoxRec<T>) > sizeof(AABBRec<T>) ? sizeof(BoxRec<T>) : sizeof(AABBRec<T>)));
+    T *raw = a.take<T>((size_t)nframes * stride * 5);
+    uint8_t *valid = a.take<uint8_t>((size_t)nframes * stride);
+    uint64_t *mask = a.take<uint64_t>((size_t)nframes * stride * nwords);
+    uint32_t *fail = a.take<uint32_t>(64);
+    if (!a.ok()) return D3D_ERR_WORKSPACE;
+    uint32_t npow = 64;
+    while (npow < (uint32_t)stride) npow <<= 1;
+    const size_t sort_smem = (size_t)npow * 12;
+    if (aabb) {
+        if (sort_smem > 40 * 1024) D3D_CUDA_TRY(cudaFuncSetAttribute(nmsb_sort_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+        nmsb_sort_kernel<T, true><<<(unsigned)nframes, NMSB_SORT_THREADS, sort_smem, st>>>(boxes, scores, offs, stride, score_thr, order, nullptr, (AABBRec<T> *)recs, nullptr, valid, fail);
+    } else {
+        if (sort_smem > 40 * 1024) D3D_CUDA_TRY(cudaFuncSetAttribute(nmsb_sort_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+        nmsb_sort_kernel<T, false><<<(unsigned)nframes, NMSB_SORT_THREADS, sort_smem, st>>>(boxes, scores, offs, stride, score_thr, order, (BoxRec<T> *)recs, nullptr, recheck ? raw : nullptr, valid, fail);
+    }
+    D3D_LAUNCHED();
+    const T thr = (T)iou_thr;
+    if (aabb) nmsb_mask_aabb_kernel<T><<<dim3((unsigned)nwords, (unsigned)nwords, (unsigned)nframes), NMS_TILE, 0, st>>>((const AABBRec<T> *)recs, offs, stride, nwords, thr, mask);
+    else nmsb_mask_rbox_kernel<T><<<dim3((unsigned)nwords, (unsigned)(nwords < 8 ? nwords : 8), (unsigned)nframes), NMS_THREADS, 0, st>>>((const BoxRec<T> *)recs, recheck ? raw : nullptr, offs, stride, nwords, thr, mask);
+    D3D_LAUNCHED();
+    nmsb_resolve_kernel<<<(unsigned)nframes, 256, (size_t)nwords * 8, st>>>(mask, offs, stride, nwords, valid, order, suppressed);
+    D3D_LAUNCHED();
+    return D3D_OK;
+}
+
 constexpr int64_t NMS_SPARSE_MAX_WORDS = 8192;   // block counters + staging must fit shared memory next to the bitmap
 
 template <typename T> static size_t nms_ws_bytes(int64_t n)
@@ -829,3 +1040,14 @@ extern "C" int d3d_nms2d_f32(const float *boxes, const float *scores, int64_t n,
 extern "C" int d3d_nms2d_f64(const double *boxes, const double *scores, int64_t n, int iou_type, int sup_type, float iou_thr, float score_thr, float sup_param,
                              uint8_t *suppressed, void *ws, size_t wsb, void *stream)
 { return nms_impl<double>(boxes, scores, n, iou_type, sup_type, iou_thr, score_thr, sup_param, suppressed, ws, wsb, (cudaStream_t)stream); }
+extern "C" size_t d3d_nms2d_batch_workspace_bytes(int64_t total, int64_t nframes, int64_t max_frame_boxes, int dtype)
+{
+    if (max_frame_boxes <= 0 || max_frame_boxes > total) max_frame_boxes = total;
+    return dtype == D3D_F64 ? nmsb_ws_bytes<double>(nframes, max_frame_boxes) : nmsb_ws_bytes<float>(nframes, max_frame_boxes);
+}
+extern "C" int d3d_nms2d_batch_f32(const float *boxes, const float *scores, int64_t total, const int64_t *frame_offsets, int64_t nframes, int64_t max_frame_boxes,
+                                   int iou_type, int sup_type, float iou_thr, float score_thr, uint8_t *suppressed, void *ws, size_t wsb, void *stream)
+{ return nmsb_impl<float>(boxes, scores, total, frame_offsets, nframes, max_frame_boxes, iou_type, sup_type, iou_thr, score_thr, suppressed, ws, wsb, (cudaStream_t)stream); }
+extern "C" int d3d_nms2d_batch_f64(const double *boxes, const double *scores, int64_t total, const int64_t *frame_offsets, int64_t nframes, int64_t max_frame_boxes,
+                                   int iou_type, int sup_type, float iou_thr, float score_thr, uint8_t *suppressed, void *ws, size_t wsb, void *stream)
+{ return nmsb_impl<double>(boxes, scores, total, frame_offsets, nframes, max_frame_boxes, iou_type, sup_type, iou_thr, score_thr, suppressed, ws, wsb, (cudaStream_t)stream); }

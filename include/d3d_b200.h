@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define D3D_B200_ABI_VERSION 3   /* 3: + d3d_iou3d_distance_*, d3d_crop2dr_* */
+#define D3D_B200_ABI_VERSION 4   /* 4: + differentiable IoU family, soft-NMS, d3d_nms2d_batch_*, d3d_pdist2dr_*, d3d_match_greedy_f32, voxel algo TILES */
 
 enum d3d_status {
     D3D_OK = 0,
@@ -87,17 +87,22 @@ int d3d_giou2dr_f32(const float *boxes1, int64_t n, const float *boxes2, int64_t
 int d3d_giou2dr_f64(const double *boxes1, int64_t n, const double *boxes2, int64_t m, double *out, int64_t ld, void *stream);
 int d3d_diou2dr_f32(const float *boxes1, int64_t n, const float *boxes2, int64_t m, float *out, int64_t ld, void *stream);
 int d3d_diou2dr_f64(const double *boxes1, int64_t n, const double *boxes2, int64_t m, double *out, int64_t ld, void *stream);
-#define D3D_DECL_IOU_BACKWARD(NAME, T)                                                                                          \
-    int NAME(const T *boxes1, int64_t n, const T *boxes2, int64_t m, const T *grad, int64_t ld, T *grad_boxes1, T *grad_boxes2, \
-             void *stream);
-D3D_DECL_IOU_BACKWARD(d3d_iou2d_backward_f32, float)
-D3D_DECL_IOU_BACKWARD(d3d_iou2d_backward_f64, double)
-D3D_DECL_IOU_BACKWARD(d3d_iou2dr_backward_f32, float)
-D3D_DECL_IOU_BACKWARD(d3d_iou2dr_backward_f64, double)
-D3D_DECL_IOU_BACKWARD(d3d_giou2dr_backward_f32, float)
-D3D_DECL_IOU_BACKWARD(d3d_giou2dr_backward_f64, double)
-D3D_DECL_IOU_BACKWARD(d3d_diou2dr_backward_f32, float)
-D3D_DECL_IOU_BACKWARD(d3d_diou2dr_backward_f64, double)
+int d3d_iou2d_backward_f32(const float *boxes1, int64_t n, const float *boxes2, int64_t m, const float *grad, int64_t ld, float *grad_boxes1,
+                           float *grad_boxes2, void *stream);
+int d3d_iou2d_backward_f64(const double *boxes1, int64_t n, const double *boxes2, int64_t m, const double *grad, int64_t ld, double *grad_boxes1,
+                           double *grad_boxes2, void *stream);
+int d3d_iou2dr_backward_f32(const float *boxes1, int64_t n, const float *boxes2, int64_t m, const float *grad, int64_t ld, float *grad_boxes1,
+                            float *grad_boxes2, void *stream);
+int d3d_iou2dr_backward_f64(const double *boxes1, int64_t n, const double *boxes2, int64_t m, const double *grad, int64_t ld, double *grad_boxes1,
+                            double *grad_boxes2, void *stream);
+int d3d_giou2dr_backward_f32(const float *boxes1, int64_t n, const float *boxes2, int64_t m, const float *grad, int64_t ld, float *grad_boxes1,
+                             float *grad_boxes2, void *stream);
+int d3d_giou2dr_backward_f64(const double *boxes1, int64_t n, const double *boxes2, int64_t m, const double *grad, int64_t ld, double *grad_boxes1,
+                             double *grad_boxes2, void *stream);
+int d3d_diou2dr_backward_f32(const float *boxes1, int64_t n, const float *boxes2, int64_t m, const float *grad, int64_t ld, float *grad_boxes1,
+                             float *grad_boxes2, void *stream);
+int d3d_diou2dr_backward_f64(const double *boxes1, int64_t n, const double *boxes2, int64_t m, const double *grad, int64_t ld, double *grad_boxes1,
+                             double *grad_boxes2, void *stream);
 /* Detection-evaluation distance matrix: dist[i][j] = 1 - iou2d(BEV boxes) * ziou, fp32,
  * for 3-D boxes [n,7] / [m,7] with rows (x, y, z, lx, ly, lz, rz).  rotated != 0: rotated BEV IoU, replaces the pair
  * loop over box3dr_iou in ScoreMatcher.prepare_boxes (reference d3d/tracking/matcher.pyx:66-76, d3d/dgal_wrap.h:45-68);
@@ -147,8 +152,10 @@ int d3d_pdist2dr_backward_f64(const double *points, int64_t n, const double *box
  * front door returns ~suppressed (d3d/box/__init__.py:272).  Order = stable descending sort of
  * scores (ties keep the lower original index first).  iou > (T)(float)iou_threshold, strict.
  * Score rule: every box with score <= score_threshold is suppressed (reference CUDA rule,
- * nms_cuda.cu:223).  iou_type: D3D_IOU_BOX or D3D_IOU_RBOX; supression_type: D3D_SUP_HARD only
- * (LINEAR / GAUSSIAN return D3D_ERR_UNSUPPORTED in this ABI version).
+ * nms_cuda.cu:223).  iou_type: D3D_IOU_BOX or D3D_IOU_RBOX; supression_type: D3D_SUP_HARD, or D3D_SUP_LINEAR / D3D_SUP_GAUSSIAN
+ * (soft-NMS, nms.cpp:33-94: a suppressed box's score is multiplied by 1 - iou^supression_param / exp(-iou^2 / supression_param) and
+ * the box is dropped once its score falls below score_threshold; the order is re-established after every box exactly like the
+ * reference's insertion sort, so the walk is sequential: one CTA, no dense N x N coefficient matrix).
  * ---------------------------------------------------------------------------------------------- */
 size_t d3d_nms2d_workspace_bytes(int64_t n, int dtype);
 int d3d_nms2d_f32(const float *boxes, const float *scores, int64_t n, int iou_type, int supression_type,
@@ -157,6 +164,20 @@ int d3d_nms2d_f32(const float *boxes, const float *scores, int64_t n, int iou_ty
 int d3d_nms2d_f64(const double *boxes, const double *scores, int64_t n, int iou_type, int supression_type,
                   float iou_threshold, float score_threshold, float supression_param, uint8_t *suppressed,
                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* Frame-batched hard NMS (BASELINE.json config 5; the reference has no batch form): boxes [total,5] / scores [total] of all frames
+ * back to back, frame_offsets DEVICE i64[nframes+1] as in the voxel ABI, suppressed u8[total] in the ORIGINAL order of every frame;
+ * per frame exactly the result of d3d_nms2d_* (same order, thresholds and score rule).  max_frame_boxes: HARD UPPER BOUND of the frame
+ * sizes (0 = unknown, assume `total`); frames of up to 8192 boxes are supported (more: D3D_ERR_UNSUPPORTED, use d3d_nms2d_* per frame);
+ * supression_type: D3D_SUP_HARD only (soft-NMS is sequential in the scores).  Three launches for the whole batch: per-frame sort in shared
+ * memory, dense 64x64 tiles of every frame's upper triangle, one resolve CTA per frame. */
+size_t d3d_nms2d_batch_workspace_bytes(int64_t total, int64_t nframes, int64_t max_frame_boxes, int dtype);
+int d3d_nms2d_batch_f32(const float *boxes, const float *scores, int64_t total, const int64_t *frame_offsets, int64_t nframes,
+                        int64_t max_frame_boxes, int iou_type, int supression_type, float iou_threshold, float score_threshold,
+                        uint8_t *suppressed, void *workspace, size_t workspace_bytes, void *stream);
+int d3d_nms2d_batch_f64(const double *boxes, const double *scores, int64_t total, const int64_t *frame_offsets, int64_t nframes,
+                        int64_t max_frame_boxes, int iou_type, int supression_type, float iou_threshold, float score_threshold,
+                        uint8_t *suppressed, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Voxelization of a BATCH of frames (one frame = one reference VoxelGenerator.__call__).

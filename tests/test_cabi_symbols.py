@@ -21,11 +21,11 @@ def test_library_exports_every_declared_symbol():
     assert os.path.exists(LIB), "run __graft_entry__.build() first"
     lib = C.CDLL(LIB)
     names = _declared()
-    assert len(names) >= 18
+    assert len(names) >= 40
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/d3d_b200.h but not exported"
     lib.d3d_abi_version.restype = C.c_int
-    assert lib.d3d_abi_version() == 3
+    assert lib.d3d_abi_version() == 4
     lib.d3d_error_string.restype = C.c_char_p
     assert lib.d3d_error_string(3) == b"workspace too small"
 

@@ -384,6 +384,39 @@ def test_nms_soft_vs_reference_and_oracle(dev, oracle):
             assert np.array_equal(keep, oracle.box2d_nms(b, s, "rbox", m, 0.2, 0.25, par, cuda_score_rule=True)), (n, m)
 
 
+def test_nms_batch_equals_per_frame(dev, oracle):
+    """J1 (BASELINE.json config 5): frame-batched hard NMS == one box2d_nms call per frame == oracle, for ragged frames (empty, one box,
+    exactly 64, 4096 proposals), both IoU methods, fp64 and fp32, list and packed call forms"""
+    from d3d_b200.box import box2d_nms, box2d_nms_batch
+    rng = np.random.default_rng(17)
+    sizes = (700, 0, 1, 64, 4096, 65, 1500, 333)
+    frames = [proposals(rng, n, max(n // 20, 1), extent=30.0) if n else (np.zeros((0, 5)), np.zeros(0)) for n in sizes]
+    for im, thr, sthr in (("rbox", 0.5, 0.0), ("rbox", 0.3, 0.2), ("box", 0.5, 0.1)):
+        keeps = box2d_nms_batch([_t(b, dev) for b, _ in frames], [_t(s, dev) for _, s in frames], iou_method=im, iou_threshold=thr, score_threshold=sthr)
+        assert len(keeps) == len(frames)
+        for (b, s), k in zip(frames, keeps):
+            assert k.dtype == torch.bool and k.shape == (len(b),)
+            if len(b):
+                single = box2d_nms(_t(b, dev), _t(s, dev), im, iou_threshold=thr, score_threshold=sthr)
+                assert torch.equal(k, single), (im, len(b))
+                if len(b) <= 1500:
+                    assert np.array_equal(k.cpu().numpy(), oracle.box2d_nms(b, s, im, iou_threshold=thr, score_threshold=sthr, cuda_score_rule=True)), (im, len(b))
+    packed_b = np.concatenate([b for b, _ in frames]).astype(np.float32)
+    packed_s = np.concatenate([s for _, s in frames]).astype(np.float32)
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    k32 = box2d_nms_batch(packed_b, packed_s, offs, iou_method="rbox", iou_threshold=0.5, precise=False)     # numpy, packed, fp32
+    assert isinstance(k32, np.ndarray) and k32.shape == (sum(sizes),)
+    lo = 0
+    for (b, s), n in zip(frames, sizes):
+        if n:
+            assert np.array_equal(k32[lo:lo + n], box2d_nms(b.astype(np.float32), s.astype(np.float32), "rbox", iou_threshold=0.5, precise=False)), n
+        lo += n
+    big = [proposals(rng, 9000, 300, extent=60.0), proposals(rng, 100, 5, extent=10.0)]                          # a frame beyond 8192 boxes: per-frame fallback
+    kb = box2d_nms_batch([_t(b, dev) for b, _ in big], [_t(s, dev) for _, s in big], iou_method="rbox", iou_threshold=0.5)
+    assert torch.equal(kb[0], box2d_nms(_t(big[0][0], dev), _t(big[0][1], dev), "rbox", iou_threshold=0.5))
+    assert box2d_nms_batch([], []) == []
+
+
 def test_nms_back_ends_agree(dev, monkeypatch):
     """the three NMS back ends (spatial candidate grid, dense tiles + list resolve, dense matrix + dense resolve) give the
     same keep mask; D3D_B200_NMS_PATH is read per call"""
