@@ -108,6 +108,40 @@ def _cpu_iou_block(args):
     return time.perf_counter() - t0, (hi - lo) * 4000
 
 
+def _cpu_iou64_block(args):
+    import torch
+    torch.set_num_threads(1)
+    seed, lo, hi = args
+    rng = np.random.default_rng(seed)
+    A, B = gen_boxes(rng, hi)[lo:hi], gen_boxes(rng, 4000)
+    t0 = time.perf_counter()
+    if _CPU_KIND == "reference":
+        from oracle import ref as R
+        R.box2d_iou(A, B, "rbox", precise=True)
+    else:
+        from oracle import oracle as O
+        O.iou2dr(A, B)
+    return time.perf_counter() - t0, (hi - lo) * 4000
+
+
+def _cpu_c5_frame(seed):
+    """one C5 frame on the CPU: voxelize a C2 cloud, then rotated NMS of 4096 proposals"""
+    import torch
+    torch.set_num_threads(1)
+    pts = lidar(500 + seed)
+    P, s = proposals(900 + seed, 4096, 160)
+    t0 = time.perf_counter()
+    if _CPU_KIND == "reference":
+        from oracle import ref as R
+        R.VoxelGenerator(C2_BOUNDS, C2_SHAPE, **C2_KW)(pts)
+        R.box2d_nms(P, s, "rbox", iou_threshold=0.5)
+    else:
+        from oracle import oracle as O
+        O.VoxelGenerator(C2_BOUNDS, C2_SHAPE, **C2_KW)(pts)
+        O.box2d_nms(P, s, "rbox", iou_threshold=0.5)
+    return time.perf_counter() - t0
+
+
 def gen_boxes3d(rng, n):
     b = gen_boxes(rng, n)
     return np.stack([b[:, 0], b[:, 1], rng.normal(-1.0, 0.5, n), b[:, 2], b[:, 3], 1.4 + rng.random(n) * 0.6, b[:, 4]], 1)
@@ -246,6 +280,17 @@ def cpu_baseline(op, cores, rounds=2):
                     sample=f"{len(res)} row-blocks of {rows} x 4000 fp32 boxes (C4 distribution, precise=False), one block per "
                            f"process on {cores} cores; {len(res) - len(ok)} block(s) aborted inside the reference "
                            f"(dgal fp32 Rotating-Calipers overflows its Poly2<T,8> buffer: 'stack smashing detected') and are not counted")
+    if op == "iou_f64":
+        rows = 256
+        res, wall = cpu_pool(_cpu_iou64_block, [(3, i * rows, (i + 1) * rows) for i in range(cores * rounds)], cores)
+        ok = [r for r in res if r is not None]
+        return dict(value=sum(r[1] for r in ok) / wall, unit="pairs/s", cores=cores, kind=_CPU_KIND, crashed_blocks=len(res) - len(ok),
+                    sample=f"{len(res)} row-blocks of {rows} x 4000 fp64 boxes (C1 distribution, precise=True), one block per process on {cores} cores")
+    if op == "c5":
+        res, wall = cpu_pool(_cpu_c5_frame, list(range(cores * rounds)), cores)
+        ok = [r for r in res if r is not None]
+        return dict(value=len(ok) / wall, unit="frames/s", cores=cores, kind=_CPU_KIND,
+                    sample=f"{len(ok)} C5 frames (C2 cloud + 4096 proposals), one frame per process on {cores} cores; single-frame latency {np.median(ok) * 1e3:.0f} ms")
     if op == "dist3d":
         rows = 256
         res, wall = cpu_pool(_cpu_dist3d_block, [(3, i * rows, (i + 1) * rows) for i in range(cores * rounds)], cores)
@@ -420,6 +465,20 @@ def fma_peak(dtype_code):
     return best
 
 
+def alu_roofline(dtype_code, achieved_tflops, clocks):
+    """roofline entry of an ALU-bound operator: against the measured FMA peak of this run (FFMA2 / DFMA probe), the nominal peak at the
+    maximum clock and the nominal peak at the clock sampled under the operator's load"""
+    lanes = 128 if dtype_code == 0 else 64
+    peak = fma_peak(dtype_code)
+    nominal = 148 * lanes * 2 * 1.965e9 / 1e12
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    at_clock = 148 * lanes * 2 * mhz * 1e6 / 1e12
+    return dict(bound="fp32_alu" if dtype_code == 0 else "fp64_alu", achieved=achieved_tflops, peak=peak, unit="TFLOP/s", frac=achieved_tflops / peak, traffic=None,
+                peak_source="measured in this run: d3d_fma_peak_probe, 16 chains/thread of " + ("FFMA2" if dtype_code == 0 else "DFMA"),
+                peak_nominal=nominal, frac_nominal=achieved_tflops / nominal, peak_at_sampled_clock=at_clock, frac_at_sampled_clock=achieved_tflops / at_clock,
+                probe_frac_of_nominal_at_sampled_clock=peak / at_clock)
+
+
 # ------------------------------------------------------------------ operators
 def bench_voxel(args, rank, world, barrier):
     import torch
@@ -448,11 +507,15 @@ def bench_voxel(args, rank, world, barrier):
     ms = max_over_ranks(ms, world)
     e2e_steps = max(2, min(args.steps, 4))
     ms_e2e = max_over_ranks(timed(lambda: gen.batch(host), e2e_steps, 1, barrier), world)
+    # one frame per call (the reference API): device-timed and end to end
+    one_dev, one_offs = dev_pts[:C2_POINTS], offs[:2].clone()
+    ms_one = max_over_ranks(timed(lambda: gen.batch_packed(one_dev, one_offs), max(args.steps, 20), 3, barrier), world)
+    ms_one_e2e = max_over_ranks(timed(lambda: gen(host[0]), 10, 2, barrier), world)
     hbm, how = peaks()
     ach = alg_bytes / (ms * 1e-3) / 1e9
     traffic = None   # DRAM bytes per launch from the committed ncu capture, when it was taken on this workload
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as fh:
             t = json.load(fh)["voxel"]
         if t["frames"] == F and t["points_per_frame"] == C2_POINTS:
             traffic = float(t["bytes"])
@@ -468,27 +531,30 @@ def bench_voxel(args, rank, world, barrier):
                          d2h_bytes_per_step=int(32 * K + 28 * V + (F + 8) * 16), ms_per_step=ms_e2e,
                          api="VoxelGenerator.batch(list of pinned host tensors) -> host tensors"),
                 roofline=dict(bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm, traffic=traffic, peak_source=how,
-                              traffic_source="profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch)",
-                              kernel="vox_cluster_kernel<sparse>: one persistent launch per step, shared-memory routed path; algorithmic bytes 16N+32K+28V'",
+                              traffic_source="profiles/r2_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the step's four kernels)",
+                              kernel="vt_split / vt_bucket / vt_scan / vt_write (voxel_tiles.cu): four launches per chunk of frames; algorithmic bytes 16N+32K+28V'",
                               algorithmic_bytes_per_step=alg_bytes),
+                single_frame=dict(ms_device=ms_one, points_per_s=C2_POINTS / (ms_one * 1e-3), ms_e2e=ms_one_e2e, e2e_points_per_s=C2_POINTS / (ms_one_e2e * 1e-3),
+                                  note="one 120k-point frame per call (the reference's call shape); bound by launch latency of the call's 7 launches"),
                 clocks=cs.summary())
 
 
-def bench_iou(args, rank, world, barrier):
+def bench_iou(args, rank, world, barrier, f64=False):
     import torch
     from d3d_b200 import _cabi as c
     from d3d_b200.box import box2d_iou, _pairwise
     from d3d_b200.parallel import row_block
-    n = m = args.iou_n
+    n = m = args.iou_f64_n if f64 else args.iou_n
+    code, npdt, tdt, esz = (1, np.float64, torch.float64, 8) if f64 else (0, np.float32, torch.float32, 4)
     rng = np.random.default_rng(3)
-    A, B = gen_boxes(rng, n).astype(np.float32), gen_boxes(rng, m).astype(np.float32)
+    A, B = gen_boxes(rng, n).astype(npdt), gen_boxes(rng, m).astype(npdt)
     lo, hi = row_block(n, rank, world)                 # strong scaling: row-blocks of the same N x M matrix
     tA, tB = torch.from_numpy(A[lo:hi]).cuda(), torch.from_numpy(B).cuda()
-    out = torch.empty((hi - lo, m), dtype=torch.float32, device="cuda")
+    out = torch.empty((hi - lo, m), dtype=tdt, device="cuda")
     # candidate pairs of this rank's slab (roofline accounting only, outside the timed region)
     cnt = torch.zeros(64, dtype=torch.int64, device="cuda")
-    ws = c.workspace(c.iou_workspace_bytes(hi - lo, m, 0), tA.device)
-    c.check(c.iou_count_candidates(c.ptr(tA), hi - lo, c.ptr(tB), m, 0, c.ptr(cnt), c.ptr(ws), ws.numel(), c.stream_ptr()), "count")
+    ws = c.workspace(c.iou_workspace_bytes(hi - lo, m, code), tA.device)
+    c.check(c.iou_count_candidates(c.ptr(tA), hi - lo, c.ptr(tB), m, code, c.ptr(cnt), c.ptr(ws), ws.numel(), c.stream_ptr()), "count")
     ncand = float(cnt.sum().item())
     pairs = float(hi - lo) * m
     l0 = c.launch_count()
@@ -499,34 +565,33 @@ def bench_iou(args, rank, world, barrier):
     launches = (l1 - l0) // (args.steps + args.warmup) * args.steps
     ms = max_over_ranks(ms, world)
     tot_pairs, tot_cand = sum_over_ranks(pairs, world), sum_over_ranks(ncand, world)
-    peak32 = fma_peak(0)
     flops = tot_cand * W_CAND + (tot_pairs - tot_cand) * W_REJ
     ach = flops / (ms * 1e-3) / 1e12 / world
     # e2e: host boxes in, a row-block slab of the matrix back on the host
     er = min(hi - lo, args.iou_e2e_rows)
     hA, hB = torch.from_numpy(A[lo:lo + er]).pin_memory(), torch.from_numpy(B).pin_memory()
-    hout = torch.empty((er, m), dtype=torch.float32).pin_memory()
+    hout = torch.empty((er, m), dtype=tdt).pin_memory()
 
     def e2e_step():
-        r = box2d_iou(hA.cuda(non_blocking=True), hB.cuda(non_blocking=True), "rbox", precise=False)
+        r = box2d_iou(hA.cuda(non_blocking=True), hB.cuda(non_blocking=True), "rbox", precise=f64)
         hout.copy_(r, non_blocking=True)
         torch.cuda.current_stream().synchronize()
     ms_e2e = max_over_ranks(timed(e2e_step, 3, 1, barrier), world)
     hbm, _ = peaks()
-    return dict(metric="rotated-IoU pairs/sec", unit="pairs/s", value=tot_pairs / (ms * 1e-3), ms_per_step=ms, dtype="f32", scaling="strong",
+    clk = cs.summary()
+    roof = alu_roofline(code, ach, clk)
+    roof.update(algorithmic_flops=f"{W_CAND:.0f} per candidate pair + {W_REJ:.0f} per rejected pair (SURVEY.md 8(d))",
+                store_gbs=tot_pairs * esz / (ms * 1e-3) / 1e9 / world, store_frac_of_hbm=tot_pairs * esz / (ms * 1e-3) / 1e9 / world / hbm)
+    return dict(metric="rotated-IoU pairs/sec", unit="pairs/s", value=tot_pairs / (ms * 1e-3), ms_per_step=ms, dtype="f64" if f64 else "f32", scaling="strong",
                 gpu_launches=int(launches),
-                config=dict(workload=f"C4 detection-eval rotated IoU {n}x{m} fp32 (precise=False), dense-overlap C1 distribution, "
-                                     f"row-block sharded over {world} GPU(s)", candidate_fraction=tot_cand / tot_pairs,
-                            l2_policy=f"output slab {pairs * 4 / 1e9:.1f} GB per GPU streams through HBM, far larger than L2"),
-                e2e=dict(value=er * m * world / (ms_e2e * 1e-3), unit="pairs/s", h2d_bytes_per_step=int((er + m) * 20),
-                         d2h_bytes_per_step=int(er * m * 4), ms_per_step=ms_e2e,
+                config=dict(workload=(f"rotated IoU {n}x{m} fp64 (precise=True), C1 distribution" if f64 else
+                                      f"C4 detection-eval rotated IoU {n}x{m} fp32 (precise=False), C1 distribution") + f", row-block sharded over {world} GPU(s)",
+                            candidate_fraction=tot_cand / tot_pairs,
+                            l2_policy=f"output slab {pairs * esz / 1e9:.1f} GB per GPU streams through HBM, far larger than L2"),
+                e2e=dict(value=er * m * world / (ms_e2e * 1e-3), unit="pairs/s", h2d_bytes_per_step=int((er + m) * 5 * esz),
+                         d2h_bytes_per_step=int(er * m * esz), ms_per_step=ms_e2e,
                          api=f"box2d_iou(pinned host boxes [{er},5],[{m},5]) -> host [{er},{m}] slab"),
-                roofline=dict(bound="fp32_alu", achieved=ach, peak=peak32, unit="TFLOP/s", frac=ach / peak32, traffic=None,
-                              peak_source="measured with d3d_fma_peak_probe (8 FMA chains/thread, 2048 threads/SM) in this run",
-                              peak_nominal_tflops=148 * 128 * 2 * 1.965e9 / 1e12,
-                              algorithmic_flops=f"{W_CAND:.0f} per candidate pair + {W_REJ:.0f} per rejected pair (SURVEY.md 8(d))",
-                              store_gbs=tot_pairs * 4 / (ms * 1e-3) / 1e9 / world, store_frac_of_hbm=tot_pairs * 4 / (ms * 1e-3) / 1e9 / world / hbm),
-                clocks=cs.summary())
+                roofline=roof, clocks=clk)
 
 
 def bench_dist3d(args, rank, world, barrier):
@@ -669,7 +734,7 @@ def bench_scatter(args, rank, world, barrier):
     ach = alg / (ms * 1e-3) / 1e9
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as fh:
             t = json.load(fh)["scatter"]
         if t["points"] == n:
             traffic = float(t["bytes"])
@@ -708,7 +773,23 @@ def bench_nms(args, rank, world, barrier):
     ms = max_over_ranks(ms, world)
     hP, hs = torch.from_numpy(P).pin_memory(), torch.from_numpy(s).pin_memory()
     ms_e2e = max_over_ranks(timed(lambda: box2d_nms(hP, hs, "rbox", iou_threshold=0.5), 3, 1, barrier), world)
-    peak64 = fma_peak(1)
+    # phase times: the same call truncated after sort + gather (knob 1) and after the candidate phase (knob 2)
+    phase = {}
+    for knob in (1, 2):
+        c.tuning_set("D3D_B200_NMS_STOP", knob)
+        phase[knob] = timed_flushed(lambda: box2d_nms(tP, ts, "rbox", iou_threshold=0.5), max(3, args.steps // 2), 2, barrier)
+    c.tuning_set("D3D_B200_NMS_STOP", None)
+    ms_sort, ms_pairs, ms_resolve = phase[1], max(phase[2] - phase[1], 1e-6), max(ms - phase[2], 1e-6)
+    # clips of the candidate phase: pairs i < j in score order whose bounding circles overlap
+    cnt = torch.zeros(64, dtype=torch.int64, device="cuda")
+    ws = c.workspace(c.iou_workspace_bytes(n, n, 1), tP.device)
+    c.check(c.iou_count_candidates(c.ptr(tP), n, c.ptr(tP), n, 1, c.ptr(cnt), c.ptr(ws), ws.numel(), c.stream_ptr()), "count")
+    clips = max((float(cnt.sum().item()) - n) / 2.0, 0.0)
+    clk = cs.summary()
+    roof = alu_roofline(1, clips * W_CAND / (ms_pairs * 1e-3) / 1e12, clk)
+    roof.update(phase="candidate phase (nms_pairs_kernel): clips x 230 flop over its own time", clips=clips, ms_sort_gather=ms_sort, ms_candidates=ms_pairs,
+                ms_resolve=ms_resolve, resolve_us_per_64_box_block=ms_resolve * 1e3 / ((n + 63) // 64),
+                note="the resolve is one dependent chain over the 64-box blocks on one SM (latency, no roofline); frame-batched NMS (ops.c5) runs one resolve per frame")
     return dict(metric="NMS boxes/sec", unit="boxes/s", value=n * world / (ms * 1e-3), ms_per_step=ms, dtype="f64", scaling="weak",
                 gpu_launches=int(launches),
                 config=dict(workload=f"C3 BEV rotated NMS: {n} clustered proposals/frame (2000 objects), rbox thr 0.5, precise=True (fp64), "
@@ -717,9 +798,78 @@ def bench_nms(args, rank, world, barrier):
                                       "timed steps, each step timed by its own event pair"),
                 e2e=dict(value=n * world / (ms_e2e * 1e-3), unit="boxes/s", h2d_bytes_per_step=int(n * 48), d2h_bytes_per_step=int(n),
                          ms_per_step=ms_e2e, api="box2d_nms(pinned host boxes, scores) -> host keep mask"),
-                roofline=dict(bound="fp64_alu", achieved=None, peak=peak64, unit="TFLOP/s", frac=None, traffic=None,
-                              note="candidate phase (3x3 grid cells per box, fp64 clips) is load-latency bound, resolve phase is one dependent chain over the "
-                                   "64-box blocks; see profiles/r1_nms_v5_ncu.txt and DESIGN.md 3.2"),
+                roofline=roof, clocks=clk)
+
+
+def bench_c5(args, rank, world, barrier):
+    """BASELINE.json config 5: a batch of 64 frames, each a C2 cloud + 4096 BEV proposals, voxelize -> NMS, frames sharded over the GPUs
+    (strong scaling), keep masks and voxel counts gathered over NCCL at the end; the gather is timed separately"""
+    import torch
+    from d3d_b200 import _cabi as c
+    from d3d_b200.voxel import VoxelGenerator
+    from d3d_b200.box import box2d_nms_batch
+    from d3d_b200.parallel import frame_shard, gather_frames
+    F, NP = args.c5_frames, 4096
+    mine = frame_shard(F, rank, world)
+    clouds = [lidar(500 + f) for f in mine]
+    props = [proposals(900 + f, NP, 160) for f in mine]
+    nf = len(mine)
+    dev_pts = torch.cat([torch.from_numpy(x) for x in clouds], 0).cuda() if nf else torch.zeros((0, 4), device="cuda")
+    offs = torch.zeros(nf + 1, dtype=torch.int64)
+    offs[1:] = torch.tensor([len(x) for x in clouds], dtype=torch.int64).cumsum(0) if nf else 0
+    offs_dev = offs.cuda()
+    pb = torch.cat([torch.from_numpy(b) for b, _ in props], 0).cuda() if nf else torch.zeros((0, 5), dtype=torch.float64, device="cuda")
+    ps = torch.cat([torch.from_numpy(s_) for _, s_ in props], 0).cuda() if nf else torch.zeros(0, dtype=torch.float64, device="cuda")
+    poffs = torch.arange(nf + 1, dtype=torch.int64) * NP
+    poffs_dev = poffs.cuda()
+    gen = VoxelGenerator(C2_BOUNDS, C2_SHAPE, **C2_KW)
+    state = {}
+
+    def step():
+        if nf:
+            state["vox"] = gen.batch_packed(dev_pts, offs, offs_dev)
+            state["keep"] = box2d_nms_batch(pb, ps, poffs, iou_method="rbox", iou_threshold=0.5, offsets_dev=poffs_dev)
+    l0 = c.launch_count()
+    with ClockSampler(torch.cuda.current_device()) as cs:
+        ms = timed(step, args.steps, args.warmup, barrier)
+        l1 = c.launch_count()
+        cs.hold(step)
+    launches = (l1 - l0) // (args.steps + args.warmup) * args.steps
+    ms = max_over_ranks(ms, world)
+
+    def gather():
+        keeps = [state["keep"][k * NP:(k + 1) * NP] for k in range(nf)]
+        rows = state["vox"].rows if nf else torch.zeros((1, 2), dtype=torch.int64, device="cuda")
+        nvox = [(rows[k + 1, 1] - rows[k, 1]).reshape(1) for k in range(nf)]
+        gk = gather_frames(keeps, F, dtype=torch.bool, device=torch.device("cuda", torch.cuda.current_device()))
+        gv = gather_frames(nvox, F, dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
+        return gk, gv
+    step()
+    ms_gather = max_over_ranks(timed(gather, 3, 1, barrier), world)
+    gk, gv = gather()
+    kept = int(sum(int(k.sum()) for k in gk))
+    voxels = int(sum(int(v.item()) for v in gv))
+    # end to end: pinned host clouds and proposals in, host keep masks and per-frame voxel results out
+    hclouds = [torch.from_numpy(x).pin_memory() for x in clouds]
+    hb = [torch.from_numpy(b).pin_memory() for b, _ in props]
+    hs = [torch.from_numpy(s_).pin_memory() for _, s_ in props]
+
+    def e2e_step():
+        if nf:
+            gen.batch(hclouds)
+            box2d_nms_batch(hb, hs, iou_method="rbox", iou_threshold=0.5)
+    ms_e2e = max_over_ranks(timed(e2e_step, 2, 1, barrier), world)
+    return dict(metric="voxelize->NMS pipeline frames/sec", unit="frames/s", value=F / (ms * 1e-3), ms_per_step=ms, dtype="f32 voxels, f64 NMS", scaling="strong",
+                gpu_launches=int(launches),
+                config=dict(workload=f"C5: batch of {F} frames x (C2 cloud of {C2_POINTS} points + {NP} BEV proposals), voxelize -> rotated NMS thr 0.5, "
+                                     f"frames sharded over {world} GPU(s)", frames=F, frames_this_rank=nf, kept_boxes=kept, voxels=voxels,
+                            l2_policy=f"{nf * C2_POINTS * 16 / 1e6:.0f} MB of points per step on this rank"),
+                e2e=dict(value=F / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=int(nf * (C2_POINTS * 16 + NP * 48)),
+                         d2h_bytes_per_step=int(nf * NP + voxels / max(world, 1) * 28), ms_per_step=ms_e2e,
+                         api="VoxelGenerator.batch(pinned host clouds) + box2d_nms_batch(pinned host boxes, scores) -> host results"),
+                gather=dict(ms=ms_gather, what=f"keep masks ({F} x {NP} bool) + voxel counts of all frames, gather_frames over " + ("NCCL" if world > 1 else "one rank (no collective)")),
+                roofline=dict(bound="hbm", achieved=None, peak=None, unit="GB/s", frac=None, traffic=None,
+                              note="pipeline of the voxel and NMS operators; their rooflines are the top-level line and ops.nms"),
                 clocks=cs.summary())
 
 
@@ -736,13 +886,15 @@ def run_reference(args):
     vals = vals[args.warmup:] or vals
     v = float(np.median([x["value"] for x in vals]))
     cb = dict(vals[-1]); cb["value"] = v
-    metric = {"voxel": "voxelized points/sec", "iou": "rotated-IoU pairs/sec", "nms": "NMS boxes/sec", "dist3d": "evaluator distance-matrix pairs/sec", "crop": "point-in-box pairs/sec", "scatter": "aligned_scatter points/sec (forward)"}[op]
+    metric = {"voxel": "voxelized points/sec", "iou": "rotated-IoU pairs/sec", "iou_f64": "rotated-IoU pairs/sec", "c5": "voxelize->NMS pipeline frames/sec", "nms": "NMS boxes/sec", "dist3d": "evaluator distance-matrix pairs/sec", "crop": "point-in-box pairs/sec", "scatter": "aligned_scatter points/sec (forward)"}[op]
     unit = cb["unit"]
     line = dict(impl="reference", metric=metric, value=v, unit=unit, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=None, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype={"voxel": "f32", "iou": "f32", "nms": "f64", "dist3d": "f32", "crop": "f32", "scatter": "f32"}[op], data="synthetic",
+                dtype={"voxel": "f32", "iou": "f32", "iou_f64": "f64", "c5": "f32 voxels, f64 NMS", "nms": "f64", "dist3d": "f32", "crop": "f32", "scatter": "f32"}[op], data="synthetic",
                 config=dict(workload={"voxel": "C2 KITTI-shaped voxelization 120k pts/frame, 0.05x0.05x0.1 m voxels, max 5 pts/voxel (reference CPU path)",
                                       "iou": "C4 rotated IoU fp32, C1 distribution (reference CPU path, row-block sample)",
+                                      "iou_f64": "rotated IoU fp64, C1 distribution (reference CPU path, row-block sample)",
+                                      "c5": "C5 frames: C2 cloud voxelization + rotated NMS of 4096 proposals (reference CPU path)",
                                       "nms": "C3-style rotated NMS fp64, 5000-proposal frames (reference CPU path)",
                                       "scatter": "C2s aligned_scatter forward, method linear (reference CPU path)",
                                       "crop": "box2dr_crop 180k points x 256-box blocks fp32 (reference CPU path)",
@@ -758,7 +910,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--op", default="all", choices=["all", "voxel", "iou", "nms", "scatter", "dist3d", "crop"])
+    ap.add_argument("--op", default="all", choices=["all", "voxel", "iou", "iou_f64", "nms", "c5", "scatter", "dist3d", "crop"])
+    ap.add_argument("--iou-f64-n", type=int, default=30_000)
+    ap.add_argument("--c5-frames", type=int, default=64)
     ap.add_argument("--frames", type=int, default=128, help="C2 frames per GPU per voxelization step")
     ap.add_argument("--iou-n", type=int, default=100_000)
     ap.add_argument("--iou-e2e-rows", type=int, default=8192)
@@ -771,7 +925,7 @@ def main():
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    ops = ["voxel", "iou", "nms", "scatter", "dist3d", "crop"] if args.op == "all" else [args.op]
+    ops = ["voxel", "iou", "nms", "iou_f64", "c5", "scatter", "dist3d", "crop"] if args.op == "all" else [args.op]
 
     # CPU baseline first: the fork-based pool must run before this process touches CUDA
     cpu = {}
@@ -793,7 +947,8 @@ def main():
         barrier = lambda: None
     import d3d_b200  # noqa: F401  (raises if the CUDA extension is missing: no fallback)
 
-    fns = dict(voxel=bench_voxel, iou=bench_iou, nms=bench_nms, dist3d=bench_dist3d, crop=bench_crop, scatter=bench_scatter)
+    fns = dict(voxel=bench_voxel, iou=bench_iou, iou_f64=lambda *a: bench_iou(*a, f64=True), nms=bench_nms, c5=bench_c5, dist3d=bench_dist3d, crop=bench_crop,
+               scatter=bench_scatter)
     res = {}
     for op in ops:
         res[op] = fns[op](args, rank, world, barrier)
@@ -812,6 +967,13 @@ def main():
                     dtype=top.pop("dtype"), data="synthetic (seeded generators of SURVEY.md 8(d))")
         line.update(top)
         line.setdefault("cpu_baseline", None)
+        # the three north_star metrics as top-level keys (the other operators keep their full records under "ops")
+        for op, keys in (("iou", ("iou_pairs_per_s", "iou_frac_of_fp32_peak")), ("nms", ("nms_boxes_per_s", "nms_candidate_frac_of_fp64_peak")),
+                         ("iou_f64", ("iou_f64_pairs_per_s", "iou_f64_frac_of_fp64_peak")), ("c5", ("c5_frames_per_s", None))):
+            if op in res:
+                line[keys[0]] = res[op]["value"]
+                if keys[1]:
+                    line[keys[1]] = res[op]["roofline"].get("frac")
         if len(ops) > 1:
             line["ops"] = {op: res[op] for op in ops[1:]}
         print(json.dumps(line))

@@ -40,6 +40,13 @@ abi_version = _sig("d3d_abi_version", C.c_int, [])
 error_string = _sig("d3d_error_string", C.c_char_p, [C.c_int])
 last_cuda_error = _sig("d3d_last_cuda_error", C.c_char_p, [])
 launch_count = _sig("d3d_launch_count", _i64, [])
+_tuning_set = _sig("d3d_tuning_set", C.c_int, [C.c_char_p, C.c_int, C.c_int])
+
+
+def tuning_set(name, value=None):
+    """override (value) or clear (None) a tuning knob of the library, e.g. tuning_set("D3D_B200_NMS_PATH", 2)"""
+    if _tuning_set(name.encode(), 0 if value is None else int(value), 0 if value is None else 1) != 0:
+        raise ValueError(f"unknown tuning knob {name}")
 iou_workspace_bytes = _sig("d3d_iou_workspace_bytes", _sz, [_i64, _i64, C.c_int])
 _iou_sig = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _sz, _vp]
 iou2dr = {F32: _sig("d3d_iou2dr_f32", C.c_int, _iou_sig), F64: _sig("d3d_iou2dr_f64", C.c_int, _iou_sig)}

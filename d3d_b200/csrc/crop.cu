@@ -237,7 +237,7 @@ static int crop_impl(const T *pts, int64_t n, const T *boxes, int64_t m, uint8_t
     CropBox<T> *recs = a.take<CropBox<T>>(m);
     crop_prep_kernel<T><<<(unsigned)cdiv(m, 256), 256, 0, st>>>(boxes, m, recs); D3D_LAUNCHED();
     int mode = 0;   // tuning / test override: D3D_B200_CROP_PATH=brute | grid
-    if (const char *e = getenv("D3D_B200_CROP_PATH")) mode = e[0] == 'b' ? 1 : (e[0] == 'g' ? 2 : 0);
+    if (const int t = tuning(D3D_TUNE_CROP_PATH, 0)) mode = t;   // 1 brute force, 2 grid
     const bool grid = mode == 2 || (mode == 0 && m * n >= CROP_GRID_MIN_PAIRS);
     if (!grid) {
         crop2dr_kernel<T><<<dim3((unsigned)gx, (unsigned)gy), CROP_THREADS, 0, st>>>(pts, n, recs, m, mask, nullptr); D3D_LAUNCHED();

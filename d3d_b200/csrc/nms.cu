@@ -99,7 +99,7 @@ __device__ __forceinline__ bool over_threshold(T v, T thr, const T *raw, unsigne
 template <>
 __device__ __forceinline__ bool over_threshold<float>(float v, float thr, const float *raw, unsigned gi, unsigned gj)
 {
-    if (raw && fabsf(v - thr) < NMS_F32_RECHECK) {
+    if (raw && v != 0.0f && fabsf(v - thr) < NMS_F32_RECHECK) {   // an exact 0 is a pair the clip found disjoint: nothing to re-evaluate
         const float *a = raw + 5 * (int64_t)gi, *b = raw + 5 * (int64_t)gj;
         BoxRec<double> A = make_box_rec<double>(a[0], a[1], a[2], a[3], a[4]);
         BoxRec<double> B = make_box_rec<double>(b[0], b[1], b[2], b[3], b[4]);
@@ -333,7 +333,7 @@ __device__ __forceinline__ void nms_mask_rbox_body(const BoxRec<T> *__restrict__
 #pragma unroll
             for (int k = 0; k < KC; k++) {
                 T dx = ax - bx[k], dy = ay - by[k], rs = ar + br[k];
-                bool cand = (dx * dx + dy * dy <= rs * rs) && (!diag || (unsigned)(k * 32 + lane) > rl);
+                bool cand = ((dx * dx + dy * dy <= rs * rs) || thr < T(0)) && (!diag || (unsigned)(k * 32 + lane) > rl);   // thr < 0: disjoint pairs (IoU 0) suppress too, like the reference
                 unsigned bal = __ballot_sync(0xffffffffu, cand);
                 if (cand) q[(tail + __popc(bal & lanemask_lt())) & 127] = (uint16_t)((rl << 8) | (k * 32 + lane));
                 tail += __popc(bal);
@@ -972,8 +972,8 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
     soft.sup = a.take<uint8_t>(npad); soft.mk = a.take<uint8_t>(npad);
     if (!a.ok()) return D3D_ERR_WORKSPACE;
     // tuning / test override: D3D_B200_NMS_PATH=dense (dense matrix, dense resolve) | tiles (dense tiles + list resolve); default: spatial
-    const char *path_env = getenv("D3D_B200_NMS_PATH");
-    const bool force_dense = path_env && path_env[0] == 'd', force_tiles = path_env && path_env[0] == 't';
+    const int path_knob = tuning(D3D_TUNE_NMS_PATH, 0);
+    const bool force_dense = path_knob == 2, force_tiles = path_knob == 1;
     if (nwords <= NMS_SPARSE_MAX_WORDS && !force_dense) {
         lists.blkcnt = blkcnt; lists.ent_w = ent_w; lists.ent_bits = ent_bits;
         D3D_CUDA_TRY(cudaMemsetAsync(blkcnt, 0, (size_t)(nwords + 1) * 4, st));
@@ -989,6 +989,8 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
         nms_gather_kernel<T, false><<<(unsigned)cdiv(npad, 256), 256, 0, st>>>(boxes, scores, order, n, npad, score_thr, (BoxRec<T> *)recs, nullptr, recheck ? raw : nullptr, valid);
     D3D_LAUNCHED();
     const T thr = (T)iou_thr;   // (T)(float): SURVEY.md 8(c) T2
+    const int stop = tuning(D3D_TUNE_NMS_STOP, 0);   // measurement only (bench.py phase times): 1 = stop after sort + gather, 2 = after the candidate phase
+    if (stop == 1) return D3D_OK;
     if (sup_type != D3D_SUP_HARD) {   // sequential in boxes and scores: one CTA emulates the reference's order
         if (aabb) nms_soft_kernel<T, true><<<1, SOFT_THREADS, 0, st>>>(nullptr, (const AABBRec<T> *)recs, scores, order, n, thr, (T)score_thr, (T)sup_param, sup_type, soft, soft_pos, suppressed);
         else nms_soft_kernel<T, false><<<1, SOFT_THREADS, 0, st>>>((const BoxRec<T> *)recs, nullptr, scores, order, n, thr, (T)score_thr, (T)sup_param, sup_type, soft, soft_pos, suppressed);
@@ -1013,6 +1015,7 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
     if (aabb) nms_mask_aabb_kernel<T><<<tiles, NMS_TILE, 0, st>>>((const AABBRec<T> *)recs, n, nwords, thr, mask, lists);
     else nms_mask_rbox_kernel<T><<<dim3((unsigned)nwords, (unsigned)(nwords < 24 ? nwords : 24)), NMS_THREADS, 0, st>>>((const BoxRec<T> *)recs, recheck ? raw : nullptr, n, nwords, thr, mask, lists, spatial ? grid : nullptr);
     D3D_LAUNCHED();
+    if (stop == 2) return D3D_OK;
     size_t smem = (size_t)nwords * 8;
     uint32_t stage_cap = 0;
     if (lists.blkcnt) {   // bitmap + keep words + block counts, the rest of ~200 KB goes to the list stages
@@ -1020,12 +1023,12 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
         size_t sc = (200 * 1024 - fixed) / ((size_t)RS_STAGES * 12);
         if (sc > NMS_LIST_CAP) sc = NMS_LIST_CAP;
         stage_cap = (uint32_t)(sc & ~(size_t)1);   // even: the 64-bit stage arrays stay 8-byte aligned
-        if (const char *e = getenv("D3D_B200_NMS_STAGE")) { const long v = atol(e); if (v >= 0 && v < (long)stage_cap) stage_cap = (uint32_t)(v & ~1l); }   // tuning override
+        { const long v = tuning(D3D_TUNE_NMS_STAGE, -1); if (v >= 0 && v < (long)stage_cap) stage_cap = (uint32_t)(v & ~1l); }   // tuning override
         smem = fixed + (size_t)RS_STAGES * stage_cap * 12;
     }
     if (smem > 40 * 1024) D3D_CUDA_TRY(cudaFuncSetAttribute(nms_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int resolve_nt = lists.blkcnt ? 512 : RESOLVE_THREADS;   // list walk: 64 1.9x slower, 256 +10 %, 512 = 1024 (tools/nms_stage_probe.sh)
-    if (const char *e = getenv("D3D_B200_NMS_NT")) { const int v = atoi(e); if (v >= 128 && v <= 1024 && v % 32 == 0) resolve_nt = v; }   // tuning override
+    { const int v = tuning(D3D_TUNE_NMS_NT, 0); if (v >= 128 && v <= 1024 && v % 32 == 0) resolve_nt = v; }   // tuning override
     nms_resolve_kernel<<<1, resolve_nt, smem, st>>>(mask, n, nwords, valid, order, suppressed, lists, stage_cap); D3D_LAUNCHED();
     return D3D_OK;
 }

@@ -1249,8 +1249,8 @@ static int vc_shape(VcShape *out, int64_t max_frame_points)
         return occ[cs];
     };
     int forced = 0, route = DENSE ? 0 : 1;
-    if (const char *e = getenv("D3D_B200_VOX_CLUSTER")) forced = atoi(e);   // tuning overrides
-    if (const char *e = getenv("D3D_B200_VOX_ROUTE")) route = DENSE ? 0 : atoi(e);
+    forced = tuning(D3D_TUNE_VOX_CLUSTER, 0);   // tuning overrides
+    route = DENSE ? 0 : tuning(D3D_TUNE_VOX_ROUTE, route);
     if (forced < 0 || forced > VC_MAX_CSIZE) forced = 0;
     VcShape best = {0, 0, dyn, 0};
     if (route) {
@@ -1295,7 +1295,7 @@ static int vc_launch(VcArgs &args, int64_t nframes, int64_t max_frame_points, si
     at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     lc.attrs = at; lc.numAttrs = 1;
     int64_t ncl = shape.max_clusters;
-    if (const char *e = getenv("D3D_B200_VOX_MAXCL")) { int m = atoi(e); if (m > 0 && m < ncl) ncl = m; }   // tuning override
+    { const int m = tuning(D3D_TUNE_VOX_MAXCL, 0); if (m > 0 && m < ncl) ncl = m; }   // tuning override
     if (ncl > nframes) ncl = nframes;
     if (ncl > VC_MAX_CLUSTERS) ncl = VC_MAX_CLUSTERS;
     const size_t state_bytes = 256 + align_up((size_t)nframes * 16);

@@ -510,19 +510,9 @@ __global__ void __launch_bounds__(VT_THREADS, D3D_VT_WCTAS) vt_write_kernel(cons
 // ------------------------------------------------------------------------------------------------ host side
 static uint32_t vt_lg2_ceil(uint64_t x) { uint32_t l = 0; while ((1ull << l) < x) l++; return l; }
 
-static int vt_env_cf()
-{
-    static int cf = -1;   // read once: the environment is a tuning aid, not part of the call
-    if (cf < 0) { const char *e = getenv("D3D_B200_VOX_CF"); int v = e ? atoi(e) : 0; cf = v > 0 ? v : 0; }
-    return cf;
-}
-
-static int vt_env_roles()
-{
-    static int r = -1;   // tuning only: bit 0 split, 1 bucket, 2 scan, 3 write (later stages may only be dropped together with everything behind them)
-    if (r < 0) { const char *e = getenv("D3D_B200_VOX_ROLES"); r = e ? atoi(e) : 15; }
-    return r;
-}
+static int vt_env_cf() { const int v = tuning(D3D_TUNE_VOX_CF, 0); return v > 0 ? v : 0; }
+// tuning only: bit 0 split, 1 bucket, 2 scan, 3 write (later stages may only be dropped together with everything behind them)
+static int vt_env_roles() { return tuning(D3D_TUNE_VOX_ROLES, 15); }
 
 static bool vt_geom(int64_t max_frame_points, int64_t nframes, VtGeom *g)
 {

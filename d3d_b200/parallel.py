@@ -63,13 +63,21 @@ def gather_ragged(t, dst=None):
     return out
 
 
-def gather_frames(per_frame, nframes):
-    """Reassemble per-frame 1-D results computed under `frame_shard` into frame order on every rank."""
+def gather_frames(per_frame, nframes, dtype=None, device=None):
+    """Reassemble per-frame 1-D results computed under `frame_shard` into frame order on every rank.
+
+    `dtype` / `device` of the payload must be the same on every rank; a rank whose shard is empty (more ranks than frames) cannot read
+    them off its tensors, so pass them whenever that can happen (default: those of the rank's first tensor, else float32 on the
+    current CUDA device under NCCL / the CPU under gloo)."""
     rank, w = world()
     if w == 1:
         return list(per_frame)
-    lens = torch.tensor([x.numel() for x in per_frame], dtype=torch.int64, device=per_frame[0].device if per_frame else "cpu")
-    flat = torch.cat([x.reshape(-1) for x in per_frame]) if per_frame else lens.new_zeros(0)
+    if device is None:
+        device = per_frame[0].device if per_frame else (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu"))
+    if dtype is None:
+        dtype = per_frame[0].dtype if per_frame else torch.float32
+    lens = torch.tensor([x.numel() for x in per_frame], dtype=torch.int64, device=device)
+    flat = torch.cat([x.reshape(-1) for x in per_frame]).to(device=device, dtype=dtype) if per_frame else torch.zeros(0, dtype=dtype, device=device)
     all_lens = gather_ragged(lens)
     all_flat = gather_ragged(flat)
     out = [None] * nframes

@@ -53,6 +53,11 @@ enum d3d_voxel_algo { D3D_VOXEL_AUTO = 0, D3D_VOXEL_SORT = 1, D3D_VOXEL_CLUSTER 
 int d3d_abi_version(void);
 const char *d3d_error_string(int status);
 const char *d3d_last_cuda_error(void);
+/* Tuning knobs select between back ends that produce identical results (names = the environment variables D3D_B200_NMS_PATH,
+ * D3D_B200_NMS_STAGE, D3D_B200_NMS_NT, D3D_B200_CROP_PATH, D3D_B200_VOX_CLUSTER, D3D_B200_VOX_ROUTE, D3D_B200_VOX_MAXCL, D3D_B200_VOX_CF,
+ * D3D_B200_VOX_ROLES, and D3D_B200_NMS_STOP, which truncates d3d_nms2d_* after a phase for phase timing).  The environment is read once, at the first use of a knob; this call overrides (set != 0) or clears (set == 0) a
+ * knob afterwards -- tests and tuning tools use it instead of changing the environment of a running process. */
+int d3d_tuning_set(const char *name, int value, int set);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 int64_t d3d_launch_count(void);
 
@@ -247,8 +252,9 @@ int d3d_aligned_scatter_backward(const void *coord, int64_t n, int32_t dim, cons
 
 /* ------------------------------------------------------------------------------------------------
  * Measurement helper: FMA-chain microbenchmark used as the measured FP32/FP64 ALU peak for the IoU
- * roofline.  Runs `iters` dependent FMAs x 8 independent chains per thread on a full
- * grid; writes the number of FLOPs executed to *flops_host.  Time it with CUDA events on `stream`.
+ * roofline.  Runs `iters` dependent FMAs x 16 independent chains per thread on a full
+ * grid (fp32: packed FFMA2, the instruction the IoU clip uses; fp64: DFMA); writes the number of FLOPs
+ * executed to *flops_host.  Time it with CUDA events on `stream`.
  * ---------------------------------------------------------------------------------------------- */
 int d3d_fma_peak_probe(int dtype, int64_t iters, float *sink, double *flops_host, void *stream);
 

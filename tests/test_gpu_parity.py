@@ -6,6 +6,7 @@ import pytest
 import torch
 
 from conftest import golden, gen_boxes, lidar, proposals, SOFT_CASES, SOFT_TEST6, soft_inputs
+from d3d_b200 import _cabi
 
 pytestmark = pytest.mark.gpu
 
@@ -254,7 +255,7 @@ def test_match_greedy_vs_oracle(dev, oracle):
     assert sa.shape == (0,) and da.tolist() == [-1, -1, -1, -1]
 
 
-def test_box_crop_vs_reference_and_oracle(dev, oracle, monkeypatch):
+def test_box_crop_vs_reference_and_oracle(dev, oracle):
     """box2dr_crop / box3dp_crop.  Masks are compared bit for bit with the golden fixture written by the
     reference's own crop_2dr and with the oracle on ragged sizes; points closer than a few ulps to an edge could flip with
     the last-ulp difference between CUDA's and glibc's sin/cos (none do on these inputs)."""
@@ -273,20 +274,20 @@ def test_box_crop_vs_reference_and_oracle(dev, oracle, monkeypatch):
             bx = gen_boxes(rng, m).astype(dt)
             exp = oracle.crop_2dr(pts, bx)
             for path in ("brute", "grid"):   # both back ends (the grid over the points is the default from 64 M pairs on)
-                monkeypatch.setenv("D3D_B200_CROP_PATH", path)
+                _cabi.tuning_set("D3D_B200_CROP_PATH", {"brute": 1, "grid": 2}[path])
                 got = box2dr_crop(_t(pts, dev), _t(bx, dev)).cpu().numpy()
                 assert np.array_equal(got, exp), (n, m, dt, path)
-            monkeypatch.delenv("D3D_B200_CROP_PATH")
+            _cabi.tuning_set("D3D_B200_CROP_PATH", None)
     # grid path corner cases: boxes far outside the cloud, a degenerate (flat) box, clustered points, a NaN point (falls back to brute force)
     pts = np.concatenate([rng.normal(0, 0.01, (5000, 2)), (rng.random((5000, 2)) - .5) * 200]).astype(np.float32)
     bx = np.array([[0, 0, 0.05, 0.05, 0.4], [1e6, 1e6, 5, 5, 0], [0, 0, 0, 3, 1], [0, 0, 400, 400, 0.1], [-90, 95, 30, 2, 2.0]], np.float32)
-    monkeypatch.setenv("D3D_B200_CROP_PATH", "grid")
+    _cabi.tuning_set("D3D_B200_CROP_PATH", 2)
     assert np.array_equal(box2dr_crop(_t(pts, dev), _t(bx, dev)).cpu().numpy(), oracle.crop_2dr(pts, bx))
     pts[17] = np.nan
     assert np.array_equal(box2dr_crop(_t(pts, dev), _t(bx, dev)).cpu().numpy(), oracle.crop_2dr(pts, bx))
     one = np.zeros((300, 2), np.float32)
     assert np.array_equal(box2dr_crop(_t(one, dev), _t(bx, dev)).cpu().numpy(), oracle.crop_2dr(one, bx))
-    monkeypatch.delenv("D3D_B200_CROP_PATH")
+    _cabi.tuning_set("D3D_B200_CROP_PATH", None)
     # reference test/test_box.py:191-205
     cloud = (rng.random((100, 2)) * 2 - 1).astype(np.float32)
     boxes = np.array([[0, 0, 1, 1, 0], [0, 0, 1, 1, np.pi / 4]], np.float32)
@@ -417,9 +418,9 @@ def test_nms_batch_equals_per_frame(dev, oracle):
     assert box2d_nms_batch([], []) == []
 
 
-def test_nms_back_ends_agree(dev, monkeypatch):
+def test_nms_back_ends_agree(dev):
     """the three NMS back ends (spatial candidate grid, dense tiles + list resolve, dense matrix + dense resolve) give the
-    same keep mask; D3D_B200_NMS_PATH is read per call"""
+    same keep mask (the knob is set through d3d_tuning_set: the environment is read once)"""
     from d3d_b200.box import box2d_nms
     rng = np.random.default_rng(5)
     for n, nobj, extent in ((20000, 800, 75.0), (3000, 40, 30.0), (700, 700, 400.0)):
@@ -427,11 +428,18 @@ def test_nms_back_ends_agree(dev, monkeypatch):
         for dt in (np.float64, np.float32):
             out = {}
             for path in ("", "tiles", "dense"):
-                monkeypatch.setenv("D3D_B200_NMS_PATH", path)
+                _cabi.tuning_set("D3D_B200_NMS_PATH", {"": None, "dense": 2, "tiles": 1}[path])
                 out[path] = box2d_nms(_t(P.astype(dt), dev), _t(s.astype(dt), dev), "rbox", iou_threshold=0.45, precise=dt == np.float64).cpu().numpy()
-            monkeypatch.delenv("D3D_B200_NMS_PATH")
+            _cabi.tuning_set("D3D_B200_NMS_PATH", None)
             assert np.array_equal(out[""], out["dense"]) and np.array_equal(out["tiles"], out["dense"]), (n, dt)
             assert 0 < out[""].sum() < n
+    # a negative threshold suppresses disjoint pairs too (IoU 0 > thr), like the reference: only the best box survives
+    P, s = proposals(rng, 500, 50, extent=100.0)
+    for path in (None, 2):
+        _cabi.tuning_set("D3D_B200_NMS_PATH", path)
+        k = box2d_nms(_t(P, dev), _t(s, dev), "rbox", iou_threshold=-0.5).cpu().numpy()
+        assert k.sum() == 1 and k[np.argmax(s)]
+    _cabi.tuning_set("D3D_B200_NMS_PATH", None)
 
 
 def test_nms_c3_scale_properties(dev, oracle):

@@ -61,8 +61,10 @@ def _worker(rank, world, port, q):
         for f, c in enumerate(clouds):
             assert np.array_equal(allm[f].numpy(), gen(c)["points_mapping"]), f
         # ---- dst-only gather and the empty-shard case (more ranks than frames)
-        one = P.gather_frames([torch.arange(3)] if rank == 0 else [], 1)
-        assert len(one) == 1 and one[0].tolist() == [0, 1, 2]
+        one = P.gather_frames([torch.arange(3)] if rank == 0 else [], 1, dtype=torch.int64)
+        assert len(one) == 1 and one[0].tolist() == [0, 1, 2] and one[0].dtype == torch.int64
+        kb = P.gather_frames([torch.tensor([True, False, True])] if rank == 0 else [], 1, dtype=torch.bool)   # payload dtype agreed across ranks
+        assert kb[0].dtype == torch.bool and kb[0].tolist() == [True, False, True]
         r = P.gather_ragged(torch.arange(rank + 1), dst=0)
         assert (r is None) == (rank != 0)
         if rank == 0:
