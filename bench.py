@@ -465,6 +465,49 @@ def fma_peak(dtype_code):
     return best
 
 
+def ref_cuda_baseline(op):
+    """Secondary GPU baseline: the reference's OWN CUDA kernels (d3d/box/iou_cuda.cu, nms_cuda.cu), compiled unmodified for sm_100a into
+    oracle/_ref/box_impl_cuda (oracle/build_ref.py --cuda), on sizes their 32-bit pair index allows, next to this build on the same
+    inputs.  Returns None when the module is not there."""
+    import torch
+    try:
+        from oracle import build_ref
+        m = build_ref.load_ref(build_ref.CUDA_MODULE)
+    except Exception:
+        return None
+    from d3d_b200.box import box2d_iou, box2d_nms
+    rng = np.random.default_rng(3)
+
+    def ev(fn, reps=3):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    if op == "iou":
+        n = 16000   # the reference keeps u8[N, M, 8] flags for its backward: 16000^2 x 8 is the largest square below its int32 element limit
+        A, B = torch.from_numpy(gen_boxes(rng, n).astype(np.float32)).cuda(), torch.from_numpy(gen_boxes(rng, n).astype(np.float32)).cuda()
+        ms_ref = ev(lambda: m.iou2dr_forward_cuda(A, B), 2)
+        ms_own = ev(lambda: box2d_iou(A, B, "rbox", precise=False))
+        ref = m.iou2dr_forward_cuda(A[:2000], B[:2000])[0]
+        own = box2d_iou(A[:2000], B[:2000], "rbox", precise=False)
+        return dict(workload=f"rotated IoU {n}x{n} fp32, C1 distribution", ref_cuda_ms=ms_ref, this_build_ms=ms_own, speedup=ms_ref / ms_own,
+                    ref_cuda_pairs_per_s=n * n / (ms_ref * 1e-3), max_abs_diff_2000x2000=float((ref - own).abs().max()))
+    if op == "nms":
+        n = 20000
+        P, sc = proposals(2, n, 800)
+        tP, ts = torch.from_numpy(P).cuda(), torch.from_numpy(sc).cuda()
+        it, st = m.IouType.RBOX, m.SupressionType.HARD
+        ms_ref = ev(lambda: m.nms2d_cuda(tP, ts, it, st, 0.5, 0.0, 0.0), 2)
+        ms_own = ev(lambda: box2d_nms(tP, ts, "rbox", iou_threshold=0.5))
+        same = bool(torch.equal(~m.nms2d_cuda(tP, ts, it, st, 0.5, 0.0, 0.0), box2d_nms(tP, ts, "rbox", iou_threshold=0.5)))
+        return dict(workload=f"rotated NMS {n} clustered proposals fp64, thr 0.5", ref_cuda_ms=ms_ref, this_build_ms=ms_own, speedup=ms_ref / ms_own,
+                    ref_cuda_boxes_per_s=n / (ms_ref * 1e-3), same_keep_mask=same)
+    return None
+
+
 def alu_roofline(dtype_code, achieved_tflops, clocks):
     """roofline entry of an ALU-bound operator: against the measured FMA peak of this run (FFMA2 / DFMA probe), the nominal peak at the
     maximum clock and the nominal peak at the clock sampled under the operator's load"""
@@ -954,6 +997,13 @@ def main():
         res[op] = fns[op](args, rank, world, barrier)
         if op in cpu:
             res[op]["cpu_baseline"] = cpu[op]
+        if world == 1 and op in ("iou", "nms"):
+            try:
+                rc = ref_cuda_baseline(op)
+            except Exception as e:   # a baseline, never required
+                rc = dict(unavailable=repr(e)[:200])
+            if rc:
+                res[op]["ref_cuda"] = rc
         torch.cuda.empty_cache()
     if world > 1:
         # the only collective of the pipeline: small per-rank results are gathered at the end (outside the timed regions)

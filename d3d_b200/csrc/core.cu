@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(256) fma_probe_kernel(int64_t iters, T seed, f
 #pragma unroll
     for (int k = 0; k < PROBE_CHAINS; k++) a[k] = Op::init(seed + (T)(threadIdx.x + k));
     const typename Op::V m = Op::init(T(0.999)), c = Op::init(T(0.001));
+#pragma unroll 8   // the loop's own instructions (counter, compare, branch) must not compete with the FMAs for issue slots
     for (int64_t i = 0; i < iters; i++) {
 #pragma unroll
         for (int k = 0; k < PROBE_CHAINS; k++) a[k] = Op::fma(a[k], m, c);

@@ -270,18 +270,21 @@ __global__ void __launch_bounds__(VT_BT, D3D_VT_BCTAS) vt_bucket_kernel(const Vt
 
     vt_pdl_enter();
     const uint64_t keep = vt_policy_keep();
-    // the queue entries and the count travel together (slots past the count hold stale entries: masked below)
     const uint32_t n = min(qcount[bk], g.qcap);
+    if (n == 0) return;
+    // the thread's entries e = tid, tid + 128, ... < n stay in registers; every loop over them stops at the bucket's count (CTA-uniform):
+    // an ordinary bucket holds ~2.6 per thread
     uint2 en[VT_EPT];
 #pragma unroll
     for (int k = 0; k < VT_EPT; k++) {
-        const uint32_t e = tid + k * VT_BT;
-        en[k] = e < g.qcap ? vt_ld64(q + e, keep) : make_uint2(VT_NONE, 0u);
+        en[k] = make_uint2(VT_NONE, 0u);
+        if (k * VT_BT >= n) break;
+        if (tid + k * VT_BT < n) en[k] = vt_ld64(q + tid + k * VT_BT, keep);
     }
-    if (n == 0) return;
     // table size for this bucket: load factor <= 2/3 when the maximum allows it
-    uint32_t lgS = 6;
-    while ((1u << lgS) < n + (n >> 1) && (1u << lgS) < (uint32_t)VT_SMAX) lgS++;
+    uint32_t lgS = 32u - (uint32_t)__clz((int)(n + (n >> 1)));
+    lgS = lgS < 6u ? 6u : lgS;
+    if ((1u << lgS) > (uint32_t)VT_SMAX) lgS = 31u - (uint32_t)__clz(VT_SMAX);
     const uint32_t S = 1u << lgS, smask = S - 1, hshift = 32u - lgS;
     for (uint32_t s = tid; s < S; s += VT_BT) tab[s] = make_uint4(VT_NONE, VT_NONE, 0u, 0u);
     if (tid == 0) { misc[1] = 0; misc[2] = 0; }
@@ -289,7 +292,6 @@ __global__ void __launch_bounds__(VT_BT, D3D_VT_BCTAS) vt_bucket_kernel(const Vt
     if (tid == 0) qcount[bk] = 0;   // everybody has read it: the counter is ready for the next chunk
     if (n > S) { if (tid == 0) *a.bail = 1u; return; }   // (n is CTA-uniform)
 
-    // every loop over the thread's entries stops at the bucket's count (CTA-uniform): an ordinary bucket holds ~2.6 per thread
     uint32_t sl[VT_EPT];
 #pragma unroll
     for (int k = 0; k < VT_EPT; k++) {

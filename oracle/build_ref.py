@@ -41,6 +41,27 @@ def build_wrap():
     return True
 
 
+CUDA_MODULE = "box_impl_cuda"   # the reference's OWN CUDA kernels (iou_cuda.cu, nms_cuda.cu, dist_cuda.cu), unmodified, built for sm_100a:
+CUDA_SOURCES = ["d3d/box/impl.cpp", "d3d/box/utils.cpp", "d3d/box/iou.cpp", "d3d/box/nms.cpp", "d3d/box/dist.cpp",   # the secondary GPU baseline of bench.py
+                "d3d/box/iou_cuda.cu", "d3d/box/nms_cuda.cu", "d3d/box/dist_cuda.cu"]
+
+
+def build_cuda(verbose=False):
+    """Compile the reference's box extension WITH its CUDA kernels (a few minutes).  Idempotent; optional."""
+    if os.path.exists(so_path(CUDA_MODULE)) or not os.path.isdir(REF_ROOT):
+        return os.path.exists(so_path(CUDA_MODULE))
+    from torch.utils.cpp_extension import load
+    bdir = os.path.join(OUT, CUDA_MODULE)
+    os.makedirs(bdir, exist_ok=True)
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+    load(name=CUDA_MODULE, sources=[os.path.join(REF_ROOT, s) for s in CUDA_SOURCES],
+         extra_include_paths=[REF_ROOT, os.path.join(REF_ROOT, "thirdparty")],
+         extra_cflags=["-O2", "-DNDEBUG", "-w", "-DBUILD_WITH_CUDA"],
+         extra_cuda_cflags=["-O2", "-DNDEBUG", "-w", "-DBUILD_WITH_CUDA", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr"],
+         build_directory=bdir, verbose=verbose)
+    return os.path.exists(so_path(CUDA_MODULE))
+
+
 def so_path(name):
     return os.path.join(OUT, name, name + ".so")
 
@@ -89,3 +110,5 @@ def load_ref(name):
 if __name__ == "__main__":
     ok = build(verbose="-v" in sys.argv)
     print("reference extensions available:", ok)
+    if "--cuda" in sys.argv:
+        print("reference CUDA extension available:", build_cuda(verbose="-v" in sys.argv))

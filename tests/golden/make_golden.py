@@ -123,6 +123,12 @@ def write_iou_grad():
     np.savez_compressed(os.path.join(OUT, "iou_grad.npz"), **out)
 
 
+def write_nms_c3():
+    """keep mask of the reference's own CPU nms2d on the full C3 frame (50 000 clustered proposals, rbox, thr 0.5, fp64; ~25 s), bits packed"""
+    P, ps = proposals(np.random.default_rng(2), 50000, 2000)
+    np.savez_compressed(os.path.join(OUT, "nms_c3.npz"), keep=np.packbits(R.box2d_nms(P, ps, "rbox", iou_threshold=0.5)))
+
+
 def write_dist3d():
     """detection-evaluation distances 1 - iou2d * ziou of the reference's own box3dr_iou / box3d_iou (d3d/dgal_wrap.h:45-91, g++)"""
     rng = np.random.default_rng(21)

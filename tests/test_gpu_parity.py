@@ -443,8 +443,8 @@ def test_nms_back_ends_agree(dev):
 
 
 def test_nms_c3_scale_properties(dev, oracle):
-    """config C3: 50k clustered proposals, rbox thr 0.5, fp64.  The oracle needs ~25 s for this, so the
-    full mask is checked through NMS invariants plus an oracle run on a prefix in score order."""
+    """config C3: 50k clustered proposals, rbox thr 0.5, fp64: the full keep mask against the fixture written by the reference's own
+    CPU nms2d (one ~25 s run, committed as 6 KB of bits), NMS invariants, and a live oracle run on a prefix in score order."""
     from d3d_b200.box import box2d_nms, box2d_iou
     rng = np.random.default_rng(2)
     P, s = proposals(rng, 50000, 2000)
@@ -467,6 +467,8 @@ def test_nms_c3_scale_properties(dev, oracle):
     # oracle on the 6000 best-scoring proposals (greedy NMS on a score prefix equals the prefix of the full run)
     top = np.argsort(-s, kind="stable")[:6000]
     assert np.array_equal(k[top], oracle.box2d_nms(P[top], s[top], "rbox", iou_threshold=0.5))
+    # the full 50k mask, bit for bit, against the one written by the reference's own CPU nms2d (tests/golden/make_golden.py write_nms_c3)
+    assert np.array_equal(k, _unpack(golden("nms_c3.npz")["keep"], 50000))
 
 
 # ------------------------------------------------------------------ voxelization
