@@ -59,16 +59,21 @@ template <bool DENSE>
 __device__ __forceinline__ bool vc_cell(const VcDev &c, const float4 &p, uint32_t *key)
 {
     float v0, v1, v2;
+    int i0, i1, i2;
     if (DENSE) {
         v0 = __fdiv_rn(__fsub_rn(p.x, c.lo[0]), c.size[0]);
         v1 = __fdiv_rn(__fsub_rn(p.y, c.lo[1]), c.size[1]);
         v2 = __fdiv_rn(__fsub_rn(p.z, c.lo[2]), c.size[2]);
+        i0 = (int)v0; i1 = (int)v1; i2 = (int)v2;                       // truncation toward zero, voxelize.cpp:100
     } else {
-        v0 = floorf(__fdiv_rn(p.x, c.size[0]));
-        v1 = floorf(__fdiv_rn(p.y, c.size[1]));
-        v2 = floorf(__fdiv_rn(p.z, c.size[2]));
+        v0 = __fdiv_rn(p.x, c.size[0]);
+        v1 = __fdiv_rn(p.y, c.size[1]);
+        v2 = __fdiv_rn(p.z, c.size[2]);
+        // (int)floorf(v) in one conversion (F2I.FLOOR): same value for every finite v, same saturation beyond the int range; NaN is
+        // rejected below.  One trip through the conversion unit per coordinate instead of two (the split kernel is bound by it)
+        i0 = __float2int_rd(v0); i1 = __float2int_rd(v1); i2 = __float2int_rd(v2);
     }
-    const uint32_t c0 = (uint32_t)((int)v0 - c.vlo[0]), c1 = (uint32_t)((int)v1 - c.vlo[1]), c2 = (uint32_t)((int)v2 - c.vlo[2]);
+    const uint32_t c0 = (uint32_t)(i0 - c.vlo[0]), c1 = (uint32_t)(i1 - c.vlo[1]), c2 = (uint32_t)(i2 - c.vlo[2]);
     *key = (c0 << c.sh_x) | (c1 << c.sh_y) | c2;
     return v0 == v0 && v1 == v1 && v2 == v2 && c0 < c.ext[0] && c1 < c.ext[1] && c2 < c.ext[2];
 }

@@ -38,6 +38,7 @@
 // device flag; the cluster kernel is launched behind the pipeline on that flag and redoes the batch.
 #include "voxel.cuh"
 #include <stdlib.h>
+#include <mutex>
 
 namespace d3d {
 
@@ -51,7 +52,7 @@ constexpr int VT_STILE = VT_THREADS * VT_SPT;     // 8192 points per scan tile
 #define D3D_VT_BT 128
 #endif
 #ifndef D3D_VT_EPT
-#define D3D_VT_EPT 8
+#define D3D_VT_EPT 4
 #endif
 #ifndef D3D_VT_BPTS
 #define D3D_VT_BPTS 512      // points per bucket the geometry aims at (if every point is kept)
@@ -66,8 +67,8 @@ constexpr int VT_STILE = VT_THREADS * VT_SPT;     // 8192 points per scan tile
 #define D3D_VT_SCTAS 6
 #endif
 constexpr int VT_BT = D3D_VT_BT;                  // threads of a bucket CTA
-constexpr int VT_EPT = D3D_VT_EPT;                // queue entries per bucket thread, all in registers
-constexpr int VT_QCAP = VT_BT * VT_EPT;           // largest queue a bucket CTA takes
+constexpr int VT_EPT = D3D_VT_EPT;                // queue entries per bucket thread kept in registers (longer queues: the rest is re-read)
+constexpr int VT_QCAP = 1024;                     // largest queue a bucket CTA takes
 constexpr int VT_SMAX = VT_QCAP <= 512 ? 512 : (VT_QCAP <= 1024 ? 1024 : 2048);   // table slots per bucket (maximum)
 constexpr int VT_MAXK = 8;                        // deepest min-cascade (max_points of the TRIM filter)
 constexpr int VT_POOL = 64;                       // crowded-voxel records per bucket
@@ -292,64 +293,108 @@ __global__ void __launch_bounds__(VT_BT, D3D_VT_BCTAS) vt_bucket_kernel(const Vt
     if (tid == 0) qcount[bk] = 0;   // everybody has read it: the counter is ready for the next chunk
     if (n > S) { if (tid == 0) *a.bail = 1u; return; }   // (n is CTA-uniform)
 
-    uint32_t sl[VT_EPT];
+    // per-entry steps; the first VT_EPT entries of a thread live in registers with their slot, the rest of a long queue (rare) is read
+    // again from the queue and finds its slot by probing
+    auto insert = [&](const uint2 x) -> uint32_t {
+        uint32_t s = vt_home(x.x, hshift);
+        for (uint32_t it = 0; it <= S; it++) {
+            const uint32_t old = atomicCAS(&tab[s].x, VT_NONE, x.x);
+            if (old == VT_NONE || old == x.x) break;
+            s = (s + 1) & smask;
+        }
+        atomicMin(&tab[s].y, x.y);
+        atomicAdd(&tab[s].z, 1u);
+        return s;
+    };
+    auto find = [&](const uint32_t key) -> uint32_t {
+        uint32_t s = vt_home(key, hshift);
+        while (tab[s].x != key) s = (s + 1) & smask;
+        return s;
+    };
+    bool anyc = false;
+    auto open_rec = [&](const uint2 x, const uint32_t s) {
+        const uint4 t = tab[s];
+        if (t.z > cthr) {
+            anyc = true;
+            if (t.y == x.y) {   // the voxel's first point opens the record
+                const uint32_t r = atomicAdd(&misc[1], 1u);
+                if (r >= (uint32_t)VT_POOL) misc[2] = 1u;
+                else {
+                    tab[s].w = r;
+                    for (uint32_t j = 0; j < K; j++) pool[r * VT_MAXK + j] = VT_NONE;
+                }
+            }
+        }
+    };
+    auto cascade = [&](const uint2 x, const uint32_t s) {
+        const uint4 t = tab[s];
+        if (t.z > cthr) {
+            uint32_t *rec = pool + t.w * VT_MAXK;
+            uint32_t v = x.y;
+            for (uint32_t j = 0; j < K; j++) {
+                const uint32_t old = atomicMin(&rec[j], v);
+                v = max(old, v);              // the larger value moves on to the next level
+                if (v == VT_NONE) break;
+            }
+        }
+    };
+    auto reply = [&](const uint2 x, const uint32_t s) {
+        const uint4 t = tab[s];
+        if (t.z != 1u) {
+            uint32_t r;
+            if ((long long)t.z < (long long)a.min_points) r = VT_W_NONE;
+            else if (x.y == t.y) { r = VT_W_HEAD | min(t.z, VT_VAL); vt_st32(hkey + x.y, x.x, keep); }
+            else {
+                const bool kept = !(t.z > cthr) || x.y <= pool[t.w * VT_MAXK + K - 1];
+                r = kept ? (VT_W_JOIN | t.y) : VT_W_NONE;
+            }
+            vt_st32(word + x.y, r, keep);
+        }
+    };
+    const uint32_t rest = tid + VT_EPT * VT_BT;   // this thread's first entry beyond the registers
+
+    // the home-slot claims of the thread's register entries are issued back to back (independent atomics in flight), then the few that
+    // met another voxel's key walk on
+    uint32_t sl[VT_EPT], first[VT_EPT];
 #pragma unroll
     for (int k = 0; k < VT_EPT; k++) {
-        sl[k] = 0;
+        sl[k] = 0; first[k] = VT_NONE;
+        if (k * VT_BT >= n) break;
+        if (tid + k * VT_BT < n) { sl[k] = vt_home(en[k].x, hshift); first[k] = atomicCAS(&tab[sl[k]].x, VT_NONE, en[k].x); }
+    }
+#pragma unroll
+    for (int k = 0; k < VT_EPT; k++) {
         if (k * VT_BT >= n) break;
         if (tid + k * VT_BT < n) {
-            uint32_t s = vt_home(en[k].x, hshift);
-            for (uint32_t it = 0; it <= S; it++) {
-                const uint32_t old = atomicCAS(&tab[s].x, VT_NONE, en[k].x);
-                if (old == VT_NONE || old == en[k].x) break;
+            uint32_t s = sl[k], old = first[k];
+            for (uint32_t it = 0; it <= S && !(old == VT_NONE || old == en[k].x); it++) {
                 s = (s + 1) & smask;
+                old = atomicCAS(&tab[s].x, VT_NONE, en[k].x);
             }
             atomicMin(&tab[s].y, en[k].y);
             atomicAdd(&tab[s].z, 1u);
             sl[k] = s;
         }
     }
+    for (uint32_t e = rest; e < n; e += VT_BT) insert(vt_ld64(q + e, keep));
     __syncthreads();
 
     // voxels with more than K points: their K smallest indices
     if (cthr != VT_NONE) {
-        bool anyc = false;
 #pragma unroll
         for (int k = 0; k < VT_EPT; k++) {
             if (k * VT_BT >= n) break;
-            if (tid + k * VT_BT < n) {
-                const uint4 t = tab[sl[k]];
-                if (t.z > cthr) {
-                    anyc = true;
-                    if (t.y == en[k].y) {   // the voxel's first point opens the record
-                        const uint32_t r = atomicAdd(&misc[1], 1u);
-                        if (r >= (uint32_t)VT_POOL) misc[2] = 1u;
-                        else {
-                            tab[sl[k]].w = r;
-                            for (uint32_t j = 0; j < K; j++) pool[r * VT_MAXK + j] = VT_NONE;
-                        }
-                    }
-                }
-            }
+            if (tid + k * VT_BT < n) open_rec(en[k], sl[k]);
         }
+        for (uint32_t e = rest; e < n; e += VT_BT) { const uint2 x = vt_ld64(q + e, keep); open_rec(x, find(x.x)); }
         if (__syncthreads_or((int)anyc)) {
             if (misc[2]) { if (tid == 0) *a.bail = 1u; return; }
 #pragma unroll
             for (int k = 0; k < VT_EPT; k++) {
                 if (k * VT_BT >= n) break;
-                if (tid + k * VT_BT < n) {
-                    const uint4 t = tab[sl[k]];
-                    if (t.z > cthr) {
-                        uint32_t *rec = pool + t.w * VT_MAXK;
-                        uint32_t v = en[k].y;
-                        for (uint32_t j = 0; j < K; j++) {
-                            const uint32_t old = atomicMin(&rec[j], v);
-                            v = max(old, v);              // the larger value moves on to the next level
-                            if (v == VT_NONE) break;
-                        }
-                    }
-                }
+                if (tid + k * VT_BT < n) cascade(en[k], sl[k]);
             }
+            for (uint32_t e = rest; e < n; e += VT_BT) { const uint2 x = vt_ld64(q + e, keep); cascade(x, find(x.x)); }
             __syncthreads();
         }
     }
@@ -358,20 +403,9 @@ __global__ void __launch_bounds__(VT_BT, D3D_VT_BCTAS) vt_bucket_kernel(const Vt
 #pragma unroll
     for (int k = 0; k < VT_EPT; k++) {
         if (k * VT_BT >= n) break;
-        if (tid + k * VT_BT < n) {
-            const uint4 t = tab[sl[k]];
-            if (t.z != 1u) {
-                uint32_t r;
-                if ((long long)t.z < (long long)a.min_points) r = VT_W_NONE;
-                else if (en[k].y == t.y) { r = VT_W_HEAD | min(t.z, VT_VAL); vt_st32(hkey + en[k].y, en[k].x, keep); }
-                else {
-                    const bool kept = !(t.z > cthr) || en[k].y <= pool[t.w * VT_MAXK + K - 1];
-                    r = kept ? (VT_W_JOIN | t.y) : VT_W_NONE;
-                }
-                vt_st32(word + en[k].y, r, keep);
-            }
-        }
+        if (tid + k * VT_BT < n) reply(en[k], sl[k]);
     }
+    for (uint32_t e = rest; e < n; e += VT_BT) { const uint2 x = vt_ld64(q + e, keep); reply(x, find(x.x)); }
 }
 
 // ------------------------------------------------------------------------------------------------ scan
@@ -527,10 +561,10 @@ static bool vt_geom(int64_t max_frame_points, int64_t nframes, VtGeom *g)
     g->lgP = vt_lg2_ceil(((uint64_t)g->lmax + D3D_VT_BPTS - 1) / D3D_VT_BPTS);
     g->P = 1u << g->lgP;
     const uint32_t per = (g->lmax + g->P - 1) / g->P;            // points per bucket if every point is kept and the hash is even (<= 512)
-    g->qcap = (per + per / 2 + 128 + 3) & ~3u;                   // <= VT_QCAP: a bucket's queue lives in its CTA's registers; more -> device flag
+    g->qcap = (per + per / 2 + 128 + 3) & ~3u;                   // <= VT_QCAP = table slots of a bucket CTA; more -> device flag
     if (g->qcap > (uint32_t)VT_QCAP) g->qcap = VT_QCAP;
     int cf = vt_env_cf();
-    if (cf <= 0) cf = 128;   // measured on C2 x 128 frames: 0.74 ms with chunks of 16 (scratch mostly L2-resident), 0.59 ms with one chunk (fewer, fuller launches)
+    if (cf <= 0) cf = 64;    // measured on C2 x 128 frames (one stream): 0.74 ms with chunks of 16 (scratch mostly L2-resident), 0.59 ms with one chunk of 128 (fewer, fuller launches)
     if ((int64_t)cf > nframes) cf = (int)(nframes > 0 ? nframes : 1);
     g->CF = (uint32_t)cf;
     g->nchunks = (uint32_t)((nframes + cf - 1) / cf);
@@ -543,7 +577,7 @@ struct VtLayout { size_t queue, word, hkey, rowinfo, zero, qcount, status, ticke
 static VtLayout vt_layout(const VtGeom &g, int64_t nframes)
 {
     VtLayout l;
-    const size_t slots = g.CF;
+    const size_t slots = (size_t)g.CF * (g.nchunks > 1 ? 2 : 1);   // two chunks in flight on two internal streams
     size_t o = 0;
     l.queue = o;   o += align_up(slots * g.P * g.qcap * sizeof(uint2));
     l.word = o;    o += align_up(slots * g.lpad * 4);
@@ -557,6 +591,31 @@ static VtLayout vt_layout(const VtGeom &g, int64_t nframes)
     l.zero_end = o;
     l.total = o;
     return l;
+}
+
+// two internal streams + events per device (created once; the library's only long-lived CUDA objects)
+struct VtLanes { cudaStream_t s[2]; cudaEvent_t fork, scan_done[2], join[2]; std::mutex mu; bool ok; };
+static VtLanes *vt_lanes()
+{
+    static VtLanes pool[64];
+    static std::mutex init_mu;
+    static bool made[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return nullptr; }
+    std::lock_guard<std::mutex> gd(init_mu);
+    VtLanes &L = pool[dev];
+    if (!made[dev]) {
+        made[dev] = true;
+        L.ok = true;
+        for (int i = 0; i < 2; i++) {
+            L.ok = L.ok && cudaStreamCreateWithFlags(&L.s[i], cudaStreamNonBlocking) == cudaSuccess;
+            L.ok = L.ok && cudaEventCreateWithFlags(&L.scan_done[i], cudaEventDisableTiming) == cudaSuccess;
+            L.ok = L.ok && cudaEventCreateWithFlags(&L.join[i], cudaEventDisableTiming) == cudaSuccess;
+        }
+        L.ok = L.ok && cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming) == cudaSuccess;
+        if (!L.ok) cudaGetLastError();
+    }
+    return L.ok ? &L : nullptr;
 }
 
 bool vox_tiles_supported(const VoxCfg &cfg, int64_t total, int64_t nframes, int64_t max_frame_points)
@@ -609,35 +668,63 @@ int vox_tiles_sparse(const float *points, int64_t total, int nfeat, const int64_
 
     D3D_CUDA_TRY(cudaMemsetAsync(w + lay.zero, 0, lay.zero_end - lay.zero, st));
     const int roles = vt_env_roles();
-    // the kernels of the call are chained with programmatic dependent launch: each one may be scheduled while its predecessor
-    // drains and waits (griddepcontrol.wait) for the predecessor's results
+    // Two chunks are in flight at a time, each on its own internal stream with its own scratch: the four kernels of a chunk have
+    // different bottlenecks (issue slots, shared-memory latency, a short dependent chain, DRAM stores) and fill each other's tails.
+    // Inside a stream the kernels are chained with programmatic dependent launch (each may be scheduled while its predecessor
+    // drains and waits, griddepcontrol.wait, for the predecessor's results); the scan of chunk c waits for the scan of chunk c-1
+    // (packed output rows) through an event.  The caller's stream forks into the two lanes and joins them again: the call stays
+    // asynchronous and ordered on the caller's stream.
+    VtLanes *lanes = g.nchunks > 1 ? vt_lanes() : nullptr;
+    std::unique_lock<std::mutex> lock;
+    cudaStream_t lane_stream[2] = {st, st};
+    if (lanes) {
+        lock = std::unique_lock<std::mutex>(lanes->mu);
+        D3D_CUDA_TRY(cudaEventRecord(lanes->fork, st));
+        for (int i = 0; i < 2; i++) { lane_stream[i] = lanes->s[i]; D3D_CUDA_TRY(cudaStreamWaitEvent(lanes->s[i], lanes->fork, 0)); }
+    }
     cudaLaunchAttribute pdl[1];
     pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     pdl[0].val.programmaticStreamSerializationAllowed = 1;
-    auto cfg_of = [&](dim3 grid, unsigned threads, size_t smem) {
-        cudaLaunchConfig_t lc = {};
-        lc.gridDim = grid; lc.blockDim = dim3(threads, 1, 1); lc.dynamicSmemBytes = smem; lc.stream = st;
-        lc.attrs = pdl; lc.numAttrs = 1;
-        return lc;
-    };
     const uint32_t dyn_split = 8u * g.P;
     for (uint32_t c = 0; c < g.nchunks; c++) {
         const int64_t rem = nframes - (int64_t)c * g.CF;
         const uint32_t nf = (uint32_t)(rem < (int64_t)g.CF ? rem : g.CF);
+        const int ln = lanes ? (int)(c & 1u) : 0;
+        cudaStream_t cs = lane_stream[ln];
+        VtArgs al = a;   // this lane's scratch
+        al.queue += (size_t)ln * g.CF * g.P * g.qcap; al.word += (size_t)ln * g.CF * g.lpad; al.hkey += (size_t)ln * g.CF * g.lpad;
+        al.rowinfo += (size_t)ln * g.CF * (g.lpad / 32); al.qcount += (size_t)ln * g.CF * g.P;
+        auto cfg_of = [&](dim3 grid, unsigned threads, size_t smem) {
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = grid; lc.blockDim = dim3(threads, 1, 1); lc.dynamicSmemBytes = smem; lc.stream = cs;
+            lc.attrs = pdl; lc.numAttrs = 1;
+            return lc;
+        };
         if (roles & 1) {
             cudaLaunchConfig_t lc = cfg_of(dim3(g.tpf, nf), VT_THREADS, dyn_split);
-            if (nfeat == 4) D3D_CUDA_TRY(cudaLaunchKernelEx(&lc, vt_split_kernel<true>, a, dv, c));
-            else D3D_CUDA_TRY(cudaLaunchKernelEx(&lc, vt_split_kernel<false>, a, dv, c));
+            if (nfeat == 4) D3D_CUDA_TRY(cudaLaunchKernelEx(&lc, vt_split_kernel<true>, al, dv, c));
+            else D3D_CUDA_TRY(cudaLaunchKernelEx(&lc, vt_split_kernel<false>, al, dv, c));
             D3D_LAUNCHED();
         }
-        if (roles & 2) { cudaLaunchConfig_t lc = cfg_of(dim3(g.P, nf), VT_BT, 0); D3D_CUDA_TRY(cudaLaunchKernelEx(&lc, vt_bucket_kernel, a)); D3D_LAUNCHED(); }
-        if (roles & 4) { cudaLaunchConfig_t lc = cfg_of(dim3(nf * g.spf), VT_THREADS, 0); D3D_CUDA_TRY(cudaLaunchKernelEx(&lc, vt_scan_kernel, a, c)); D3D_LAUNCHED(); }
+        if (roles & 2) { cudaLaunchConfig_t lc = cfg_of(dim3(g.P, nf), VT_BT, 0); D3D_CUDA_TRY(cudaLaunchKernelEx(&lc, vt_bucket_kernel, al)); D3D_LAUNCHED(); }
+        if (lanes && c > 0) D3D_CUDA_TRY(cudaStreamWaitEvent(cs, lanes->scan_done[(c - 1) & 1u], 0));
+        if (roles & 4) {
+            cudaLaunchConfig_t lc = cfg_of(dim3(nf * g.spf), VT_THREADS, 0);
+            if (lanes && c > 0) lc.numAttrs = 0;   // its predecessor in the other lane is a full dependency (event), not a programmatic one
+            D3D_CUDA_TRY(cudaLaunchKernelEx(&lc, vt_scan_kernel, al, c)); D3D_LAUNCHED();
+        }
+        if (lanes) D3D_CUDA_TRY(cudaEventRecord(lanes->scan_done[c & 1u], cs));
         if (roles & 8) {
             cudaLaunchConfig_t lc = cfg_of(dim3(g.tpf, nf), VT_THREADS, 0);
-            if (nfeat == 4) D3D_CUDA_TRY(cudaLaunchKernelEx(&lc, vt_write_kernel<true>, a, dv, c));
-            else D3D_CUDA_TRY(cudaLaunchKernelEx(&lc, vt_write_kernel<false>, a, dv, c));
+            if (lanes) lc.numAttrs = 0;            // an event record sits between the scan and this launch
+            if (nfeat == 4) D3D_CUDA_TRY(cudaLaunchKernelEx(&lc, vt_write_kernel<true>, al, dv, c));
+            else D3D_CUDA_TRY(cudaLaunchKernelEx(&lc, vt_write_kernel<false>, al, dv, c));
             D3D_LAUNCHED();
         }
+    }
+    if (lanes) {
+        for (int i = 0; i < 2; i++) { D3D_CUDA_TRY(cudaEventRecord(lanes->join[i], lanes->s[i])); D3D_CUDA_TRY(cudaStreamWaitEvent(st, lanes->join[i], 0)); }
+        lock.unlock();
     }
     // the batch is redone by the cluster kernel when a queue, a table or a record pool overflowed (device flag)
     return vox_cluster_sparse(points, total, nfeat, offs, nframes, max_frame_points, cfg, out_points, out_mask, out_mapping, out_npoints, out_coords, counts,
