@@ -418,6 +418,28 @@ def timed_flushed(fn, steps, warmup, barrier):
     return sum(a.elapsed_time(b) for a, b in evs) / steps
 
 
+def bind_to_gpu_numa(local):
+    """Run this rank (and place the pinned staging memory it allocates afterwards: first touch) on the NUMA node of its GPU.  Without it
+    every rank of a torchrun launch inherits the same affinity and all PCIe traffic of an 8-GPU box crosses one socket."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        addr = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{addr}/numa_node").read())
+        if node < 0:
+            return dict(node=None, pci=addr)
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = (cpus & allowed) or cpus
+        os.sched_setaffinity(0, use)
+        return dict(node=node, pci=addr, cpus=len(use))
+    except Exception as e:   # affinity is an optimisation, never required
+        return dict(node=None, error=repr(e)[:120])
+
+
 def max_over_ranks(x, world):
     import torch
     if world == 1:
@@ -571,8 +593,8 @@ def bench_voxel(args, rank, world, barrier):
                             frames_per_gpu=F, points_per_frame=C2_POINTS, kept_points=K, voxels=V,
                             l2_policy=f"inputs larger than L2 ({N * 16 / 1e6:.0f} MB of points per step vs 126 MB L2)"),
                 e2e=dict(value=N * world / (ms_e2e * 1e-3), unit="points/s", h2d_bytes_per_step=int(N * 16 + offs.numel() * 8),
-                         d2h_bytes_per_step=int(32 * K + 28 * V + (F + 8) * 16), ms_per_step=ms_e2e,
-                         api="VoxelGenerator.batch(list of pinned host tensors) -> host tensors"),
+                         d2h_bytes_per_step=int(16 * K + 28 * V + (F + 8) * 16), ms_per_step=ms_e2e,
+                         api="VoxelGenerator.batch(list of pinned host tensors) -> host tensors (points = input[points_mask] is gathered on the host on first read)"),
                 roofline=dict(bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm, traffic=traffic, peak_source=how,
                               traffic_source="profiles/r2_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the step's four kernels)",
                               kernel="vt_split / vt_bucket / vt_scan / vt_write (voxel_tiles.cu): four launches per chunk of frames; algorithmic bytes 16N+32K+28V'",
@@ -982,6 +1004,7 @@ def main():
 
     import torch
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -1017,6 +1040,7 @@ def main():
                     dtype=top.pop("dtype"), data="synthetic (seeded generators of SURVEY.md 8(d))")
         line.update(top)
         line.setdefault("cpu_baseline", None)
+        line["numa"] = numa
         # the three north_star metrics as top-level keys (the other operators keep their full records under "ops")
         for op, keys in (("iou", ("iou_pairs_per_s", "iou_frac_of_fp32_peak")), ("nms", ("nms_boxes_per_s", "nms_candidate_frac_of_fp64_peak")),
                          ("iou_f64", ("iou_f64_pairs_per_s", "iou_f64_frac_of_fp64_peak")), ("c5", ("c5_frames_per_s", None))):

@@ -30,16 +30,41 @@ class MaxVoxelsFilterType(enum.IntEnum):
     DESCENDING = 2
 
 
+class _Lazy:
+    """a dict value that is computed the first time it is read (d3d_b200.voxel.Dict)"""
+    __slots__ = ("fn",)
+
+    def __init__(self, fn):
+        self.fn = fn
+
+
 class Dict(dict):
-    """attribute-access dict, standing in for addict.Dict (reference d3d/voxel/__init__.py:1)"""
-    __getattr__ = dict.__getitem__
+    """attribute-access dict, standing in for addict.Dict (reference d3d/voxel/__init__.py:1).  A value may be a `_Lazy` thunk: it is
+    evaluated, and replaced by its result, the first time the key is read (used for the `points` of host-streamed batches, which
+    are `input[points_mask]` and need not cross the PCIe link twice)."""
     __setattr__ = dict.__setitem__
+
+    def __getitem__(self, k):
+        v = dict.__getitem__(self, k)
+        if isinstance(v, _Lazy):
+            v = v.fn()
+            dict.__setitem__(self, k, v)
+        return v
 
     def __getattr__(self, k):
         try:
             return self[k]
         except KeyError:
             raise AttributeError(k)
+
+    def get(self, k, default=None):
+        return self[k] if k in self else default
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
 
 
 class VoxelGenerator:
@@ -217,9 +242,10 @@ class VoxelBatch:
     (`.rows`) and are read back -- the only synchronisation -- the first time a frame is indexed."""
     POINT_KEYS = ("points", "points_mask", "points_mapping")
 
-    def __init__(self, bufs, rows, nframes, dense, rows_host=None):
+    def __init__(self, bufs, rows, nframes, dense, rows_host=None, lazy_points=None):
         self.packed, self.rows, self.nframes, self.dense = bufs, rows, nframes, dense
         self._rows_host = rows_host
+        self._lazy_points = lazy_points   # frame -> input tensor: `points` of a frame is input[points_mask], built on first read
         self._cache = {}
 
     def __len__(self):
@@ -247,6 +273,9 @@ class VoxelBatch:
             else:
                 k0, k1, v0, v1 = int(rh[f, 0]), int(rh[f + 1, 0]), int(rh[f, 1]), int(rh[f + 1, 1])
                 r = Dict((k, v[k0:k1] if k in self.POINT_KEYS else v[v0:v1]) for k, v in self.packed.items())
+                if self._lazy_points is not None and "points" not in r:
+                    src, mask = self._lazy_points(f), r["points_mask"]
+                    dict.__setitem__(r, "points", _Lazy(lambda src=src, mask=mask: src.index_select(0, mask)))
             self._cache[f] = r
         return r
 

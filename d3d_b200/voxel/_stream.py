@@ -13,6 +13,7 @@ from . import Dict, VoxelBatch
 
 CHUNK_POINTS = 2_000_000   # ~16 KITTI frames: enough frames per launch to fill the GPU, small enough to pipeline
 NSTREAMS = 2
+LAZY_POINTS = True        # host batches: `points` of a frame is gathered from the caller's input on first read instead of being copied back
 TIMELINE = None   # tuning: set to a list to collect (label, chunk, event) marks of one call
 
 
@@ -181,12 +182,16 @@ def host_batch(gen, frames, offs_host):
             host = {}
             _mark("d2h0", ci, s)
             for k, v in res.packed.items():
+                if k == "points" and LAZY_POINTS:
+                    continue   # points = input[points_mask]: 16 of the ~58 B per point that would cross the link a second time
                 m = nk if k in VoxelBatch.POINT_KEYS else nv
                 t = arena.take((m,) + tuple(v.shape[1:]), v.dtype)
                 t.copy_(v[:m], non_blocking=True)
                 host[k] = t
             _mark("d2h1", ci, s)
-            results[ci] = ("sparse", VoxelBatch(host, None, res.nframes, dense=False, rows_host=rows_h))
+            f0 = chunks[ci][0]
+            results[ci] = ("sparse", VoxelBatch(host, None, res.nframes, dense=False, rows_host=rows_h,
+                                                lazy_points=(lambda j, f0=f0: frames[f0 + j]) if LAZY_POINTS else None))
 
     for ci in range(len(chunks)):
         if len(pending) == nstreams:
