@@ -851,6 +851,13 @@ def bench_nms(args, rank, world, barrier):
     c.check(c.iou_count_candidates(c.ptr(tP), n, c.ptr(tP), n, 1, c.ptr(cnt), c.ptr(ws), ws.numel(), c.stream_ptr()), "count")
     clips = max((float(cnt.sum().item()) - n) / 2.0, 0.0)
     clk = cs.summary()
+    # soft-NMS (gaussian) of the reference's default shape: sequential in the kept boxes, a latency path; reported, not a roofline line
+    soft = {}
+    if rank == 0:
+        for m in (1000, 4096):
+            sP, ss = tP[:m].contiguous(), ts[:m].contiguous()
+            f = lambda: box2d_nms(sP, ss, "rbox", "gaussian", iou_threshold=0.3, score_threshold=0.2, supression_param=0.5)  # noqa: E731
+            soft[str(m)] = dict(ms=timed(f, 3, 1, lambda: None), kept=int(f().sum().item()))
     roof = alu_roofline(1, clips * W_CAND / (ms_pairs * 1e-3) / 1e12, clk)
     roof.update(phase="candidate phase (nms_pairs_kernel): clips x 230 flop over its own time", clips=clips, ms_sort_gather=ms_sort, ms_candidates=ms_pairs,
                 ms_resolve=ms_resolve, resolve_us_per_64_box_block=ms_resolve * 1e3 / ((n + 63) // 64),
@@ -863,7 +870,7 @@ def bench_nms(args, rank, world, barrier):
                                       "timed steps, each step timed by its own event pair"),
                 e2e=dict(value=n * world / (ms_e2e * 1e-3), unit="boxes/s", h2d_bytes_per_step=int(n * 48), d2h_bytes_per_step=int(n),
                          ms_per_step=ms_e2e, api="box2d_nms(pinned host boxes, scores) -> host keep mask"),
-                roofline=roof, clocks=clk)
+                roofline=roof, clocks=clk, soft=soft)
 
 
 def bench_c5(args, rank, world, barrier):
