@@ -215,6 +215,55 @@ __global__ void __launch_bounds__(256) crop_grid_boxes_kernel(const CropPt<T> *_
     }
 }
 
+// One pass over the mask: a CTA owns one (box, segment of the point index range), builds that piece of the mask row in shared
+// memory -- zero it, set a byte for every candidate of the box's grid cells that lies inside and in the segment -- and streams it
+// out once with full 16-byte lines.  The mask (1 byte per pair, the only large object) is written exactly once and never read;
+// the candidates of a box are visited once per segment, which is negligible next to the row bytes.  The row piece sits in shared
+// memory at the same 16-byte phase as in global memory, so that aligned global lines are aligned shared lines.
+constexpr int CROP_SEG = 61440;   // bytes of a row piece (+16 for the phase): three CTAs per SM
+template <typename T>
+__global__ void __launch_bounds__(256) crop_rows_kernel(const CropPt<T> *__restrict__ sorted, int64_t n, const CropBox<T> *__restrict__ recs, int64_t m,
+                                                        const CropGrid *__restrict__ g, const uint32_t *__restrict__ cellptr, uint8_t *__restrict__ mask, uint32_t seg)
+{
+    extern __shared__ uint4 crop_row4[];
+    if (!g->ok) return;   // no grid: the brute-force kernel that follows writes the whole mask
+    uint8_t *rowb = reinterpret_cast<uint8_t *>(crop_row4);
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int64_t i = blockIdx.x, s0 = (int64_t)blockIdx.y * seg;
+    const uint32_t len = (uint32_t)(n - s0 < (int64_t)seg ? n - s0 : (int64_t)seg);
+    uint8_t *out = mask + i * n + s0;
+    const uint32_t ph = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15);
+    const uint32_t n4 = (ph + len + 15) >> 4;
+    for (uint32_t k = threadIdx.x; k < n4; k += blockDim.x) crop_row4[k] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    const CropBox<T> B = recs[i];
+    if (B.minx < B.maxx && B.miny < B.maxy) {   // otherwise empty or NaN box: no point passes the open AABB test
+        const CropGrid G = *g;
+        // float bounds rounded outwards, so that the cell range covers the exact AABB of the fp64 instantiation as well
+        const float lx = sizeof(T) == 8 ? __double2float_rd((double)B.minx) : (float)B.minx, hx = sizeof(T) == 8 ? __double2float_ru((double)B.maxx) : (float)B.maxx;
+        const float ly = sizeof(T) == 8 ? __double2float_rd((double)B.miny) : (float)B.miny, hy = sizeof(T) == 8 ? __double2float_ru((double)B.maxy) : (float)B.maxy;
+        const int x0 = crop_cell(lx, G.minx, G.invx), x1 = crop_cell(hx, G.minx, G.invx);
+        const int y0 = crop_cell(ly, G.miny, G.invy), y1 = crop_cell(hy, G.miny, G.invy);
+        for (int cy = y0 + (int)warp; cy <= y1; cy += (int)nwarps) {
+            const uint32_t beg = cellptr[cy * CG + x0], end = cellptr[cy * CG + x1 + 1];
+            for (uint32_t k = beg + lane; k < end; k += 32) {
+                const CropPt<T> p = sorted[k];
+                const uint32_t rel = p.idx - (uint32_t)s0;   // wraps for points before the segment
+                if (rel < len && crop_inside<T>(B, p.x, p.y)) rowb[ph + rel] = 1;
+            }
+        }
+    }
+    __syncthreads();
+    // head and tail bytes that share a 16-byte line with a neighbouring row piece are stored one by one
+    const uint32_t head = ph ? (16u - ph < len ? 16u - ph : len) : 0u;
+    const uint32_t body = (len - head) >> 4, tail = (len - head) & 15u;
+    if (threadIdx.x < head) out[threadIdx.x] = rowb[ph + threadIdx.x];
+    uint4 *out4 = reinterpret_cast<uint4 *>(out + head);
+    const uint32_t k0 = (ph + head) >> 4;
+    for (uint32_t k = threadIdx.x; k < body; k += blockDim.x) __stcs(out4 + k, crop_row4[k0 + k]);
+    if (threadIdx.x < tail) out[head + body * 16 + threadIdx.x] = rowb[ph + head + body * 16 + threadIdx.x];
+}
+
 template <typename T> static size_t crop_grid_ws_bytes(int64_t n)
 {
     return align_up(64) + align_up(sizeof(CropGrid)) + 2 * align_up((size_t)2 * (CG_CELLS + 1) * 4) + align_up((size_t)(n > 0 ? n : 1) * sizeof(CropPt<T>)) +
@@ -238,7 +287,7 @@ static int crop_impl(const T *pts, int64_t n, const T *boxes, int64_t m, uint8_t
     crop_prep_kernel<T><<<(unsigned)cdiv(m, 256), 256, 0, st>>>(boxes, m, recs); D3D_LAUNCHED();
     int mode = 0;   // tuning / test override: D3D_B200_CROP_PATH=brute | grid
     if (const int t = tuning(D3D_TUNE_CROP_PATH, 0)) mode = t;   // 1 brute force, 2 grid
-    const bool grid = mode == 2 || (mode == 0 && m * n >= CROP_GRID_MIN_PAIRS);
+    const bool grid = mode >= 2 || (mode == 0 && m * n >= CROP_GRID_MIN_PAIRS);   // 3: the round-1 two-pass grid path (zero-fill, then scattered hits)
     if (!grid) {
         crop2dr_kernel<T><<<dim3((unsigned)gx, (unsigned)gy), CROP_THREADS, 0, st>>>(pts, n, recs, m, mask, nullptr); D3D_LAUNCHED();
         return D3D_OK;
@@ -253,7 +302,7 @@ static int crop_impl(const T *pts, int64_t n, const T *boxes, int64_t m, uint8_t
     const uint32_t init[5] = {0xffffffffu, 0u, 0xffffffffu, 0u, 0u};
     D3D_CUDA_TRY(cudaMemcpyAsync(acc, init, sizeof(init), cudaMemcpyHostToDevice, st));
     D3D_CUDA_TRY(cudaMemsetAsync(cellcnt, 0, (size_t)2 * (CG_CELLS + 1) * 4, st));
-    D3D_CUDA_TRY(cudaMemsetAsync(mask, 0, (size_t)m * n, st));
+    if (mode == 3) D3D_CUDA_TRY(cudaMemsetAsync(mask, 0, (size_t)m * n, st));
     const unsigned gb = (unsigned)cdiv(n, 256);
     crop_bounds_kernel<T><<<gb < 592 ? gb : 592, 256, 0, st>>>(pts, n, acc); D3D_LAUNCHED();
     crop_grid_kernel<<<1, 1, 0, st>>>(acc, g); D3D_LAUNCHED();
@@ -261,7 +310,18 @@ static int crop_impl(const T *pts, int64_t n, const T *boxes, int64_t m, uint8_t
     int rc = exclusive_scan_u32(cellcnt, cellptr, CG_CELLS + 1, nullptr, scan_ws, st);
     if (rc) return rc;
     crop_bin_kernel<T, 1><<<gb, 256, 0, st>>>(pts, n, g, cellcnt + CG_CELLS + 1, cellptr, sorted); D3D_LAUNCHED();
-    crop_grid_boxes_kernel<T><<<(unsigned)m, 256, 0, st>>>(sorted, n, recs, m, g, cellptr, mask); D3D_LAUNCHED();
+    if (mode == 3) {
+        crop_grid_boxes_kernel<T><<<(unsigned)m, 256, 0, st>>>(sorted, n, recs, m, g, cellptr, mask); D3D_LAUNCHED();
+    } else {
+        // row pieces of at most CROP_SEG bytes, equal in size and a multiple of 16 so that only a row's ends are unaligned
+        const int64_t nseg = cdiv(n, (int64_t)CROP_SEG);
+        const uint32_t seg = (uint32_t)(cdiv(cdiv(n, nseg), (int64_t)16) * 16);
+        if (nseg > 65535) return D3D_ERR_INVALID_ARGUMENT;
+        const size_t smem = (size_t)seg + 32;
+        static bool attr_set = false;   // the same value every time: a benign race
+        if (!attr_set) { D3D_CUDA_TRY(cudaFuncSetAttribute(crop_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, CROP_SEG + 32)); attr_set = true; }
+        crop_rows_kernel<T><<<dim3((unsigned)m, (unsigned)nseg), 256, smem, st>>>(sorted, n, recs, m, g, cellptr, mask, seg); D3D_LAUNCHED();
+    }
     // geometry that admits no grid (non-finite points, all points identical): the brute-force pass runs instead (it leaves at once otherwise)
     crop2dr_kernel<T><<<dim3((unsigned)gx, (unsigned)gy), CROP_THREADS, 0, st>>>(pts, n, recs, m, mask, g); D3D_LAUNCHED();
     return D3D_OK;
