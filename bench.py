@@ -755,8 +755,9 @@ def bench_crop(args, rank, world, barrier):
                 e2e=dict(value=float(m) * n * world / (ms_e2e * 1e-3), unit="pairs/s", h2d_bytes_per_step=int(8 * n + 20 * m), d2h_bytes_per_step=int(m * n),
                          ms_per_step=ms_e2e, api="box2dr_crop(pinned host points, boxes) -> host bool mask"),
                 roofline=dict(bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm, traffic=None, peak_source=how,
-                              algorithmic_bytes_per_step=alg, note="1 mask byte per pair: the mask is zero-filled at memset speed and a grid over the points limits the "
-                                                                    "per-box work to the cells its AABB touches (brute force: D3D_B200_CROP_PATH=brute)"),
+                              algorithmic_bytes_per_step=alg, note="1 mask byte per pair, written once: a pure store stream zero-fills the mask (7 TB/s, tools/write_bw_probe.cu) "
+                                                                    "while the points are binned into a grid on a high-priority internal stream; the hit kernels then set the few "
+                                                                    "bytes of the candidates inside their box (brute force: D3D_B200_CROP_PATH=brute)"),
                 clocks=cs.summary())
 
 
