@@ -772,12 +772,15 @@ def bench_scatter(args, rank, world, barrier):
     grad = torch.ones((n, ch), dtype=torch.float32, device="cuda")
     image_grad = torch.zeros_like(fm)
 
-    def fwd():
-        return aligned_scatter_forward_cuda(coords, fm, AlignType.LINEAR)
+    from d3d_b200.point import ScatterPlan, _dims
+
+    def fwd(plan=None):
+        return aligned_scatter_forward_cuda(coords, fm, AlignType.LINEAR, plan)
 
     def step():
-        fwd()
-        aligned_scatter_backward_cuda(coords, grad, AlignType.LINEAR, image_grad)   # accumulates in place (the caller zeroes once, d3d/point/__init__.py:32)
+        plan = ScatterPlan(n, 2, fm.shape[0], _dims(fm.shape), fm.device)   # what AlignedScatter does: the backward reuses the forward's binning
+        fwd(plan)
+        aligned_scatter_backward_cuda(coords, grad, AlignType.LINEAR, image_grad, plan)   # accumulates in place (the caller zeroes once, d3d/point/__init__.py:32)
     anchor = float(fwd().double().sum().item())
     l0 = c.launch_count()
     with ClockSampler(torch.cuda.current_device()) as cs:
@@ -815,9 +818,10 @@ def bench_scatter(args, rank, world, barrier):
                          ms_per_step=ms_e2e, api="aligned_scatter(pinned host coordinates, device feature map, 'linear') -> host [N,64]"),
                 roofline=dict(bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm, traffic=traffic, peak_source=how,
                               algorithmic_bytes_per_step=alg, forward_gbs=alg_f / (ms_fwd * 1e-3) / 1e9,
-                              note="N*C*(2^Dim+1)*4 + N*(1+Dim)*4 bytes per pass (SURVEY 8(d)).  Every 4-byte neighbour of a random point costs a 32-byte "
-                                   "sector, so the DRAM traffic (ncu, profiles/r1_scatter_ncu.txt) is 3x the algorithmic bytes: the forward kernel moves "
-                                   "352 MB in 95 us = 57 % of the measured HBM peak, the backward (RED.ADD per neighbour) 328 MB in 206 us"),
+                              note="N*C*(2^Dim+1)*4 + N*(1+Dim)*4 bytes per pass (SURVEY 8(d)).  Tile path (scatter.cu): the points are binned by 8x64-cell tile, "
+                                   "every tile is staged once in shared memory by a 3-D TMA tensor copy and the backward sends it back with a TMA reduce-add; "
+                                   "DRAM traffic per pass = the 144 MB map + halo (ncu: forward 146 MB read + 13 MB written; profiles/r2_scatter_launches.txt). "
+                                   "The gather path (D3D_B200_SCATTER_PATH=gather) pays a 32-byte sector per 4-byte neighbour: 352 MB forward, 0.31 ms per step"),
                 clocks=cs.summary())
 
 

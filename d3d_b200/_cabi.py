@@ -82,9 +82,13 @@ voxelize_dense = _sig("d3d_voxelize_dense_f32", C.c_int,
 _sc_sig = [_vp, _i64, _i32, _vp, _i64, _i64, C.POINTER(C.c_int64), C.c_int, C.c_int, _vp, _vp]
 scatter_forward = _sig("d3d_aligned_scatter_forward", C.c_int, _sc_sig)
 scatter_backward = _sig("d3d_aligned_scatter_backward", C.c_int, _sc_sig)
+_scw_sig = _sc_sig[:-1] + [_vp, _sz, C.c_int, _vp]
+scatter_workspace_bytes = _sig("d3d_aligned_scatter_workspace_bytes", _sz, [_i64, _i32, _i64, C.POINTER(C.c_int64)])
+scatter_forward_ws = _sig("d3d_aligned_scatter_forward_ws", C.c_int, _scw_sig)
+scatter_backward_ws = _sig("d3d_aligned_scatter_backward_ws", C.c_int, _scw_sig)
 fma_peak_probe = _sig("d3d_fma_peak_probe", C.c_int, [C.c_int, _i64, _vp, C.POINTER(C.c_double), _vp])
 
-if abi_version() != 4:
+if abi_version() != 5:
     raise ImportError("libd3d_b200.so ABI version mismatch")
 
 

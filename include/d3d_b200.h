@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define D3D_B200_ABI_VERSION 4   /* 4: + differentiable IoU family, soft-NMS, d3d_nms2d_batch_*, d3d_pdist2dr_*, d3d_match_greedy_f32, voxel algo TILES */
+#define D3D_B200_ABI_VERSION 5   /* 5: + d3d_aligned_scatter_*_ws (tile path); 4: + differentiable IoU family, soft-NMS, d3d_nms2d_batch_*, d3d_pdist2dr_*, d3d_match_greedy_f32, voxel algo TILES */
 
 enum d3d_status {
     D3D_OK = 0,
@@ -55,7 +55,7 @@ const char *d3d_error_string(int status);
 const char *d3d_last_cuda_error(void);
 /* Tuning knobs select between back ends that produce identical results (names = the environment variables D3D_B200_NMS_PATH,
  * D3D_B200_NMS_STAGE, D3D_B200_NMS_NT, D3D_B200_CROP_PATH, D3D_B200_VOX_CLUSTER, D3D_B200_VOX_ROUTE, D3D_B200_VOX_MAXCL, D3D_B200_VOX_CF,
- * D3D_B200_VOX_ROLES, and D3D_B200_NMS_STOP, which truncates d3d_nms2d_* after a phase for phase timing).  The environment is read once, at the first use of a knob; this call overrides (set != 0) or clears (set == 0) a
+ * D3D_B200_VOX_ROLES, D3D_B200_SCATTER_PATH (gather | tiles), and D3D_B200_NMS_STOP, which truncates d3d_nms2d_* after a phase for phase timing).  The environment is read once, at the first use of a knob; this call overrides (set != 0) or clears (set == 0) a
  * knob afterwards -- tests and tuning tools use it instead of changing the environment of a running process. */
 int d3d_tuning_set(const char *name, int value, int set);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
@@ -249,6 +249,21 @@ int d3d_aligned_scatter_forward(const void *coord, int64_t n, int32_t dim, const
 int d3d_aligned_scatter_backward(const void *coord, int64_t n, int32_t dim, const void *grad, int64_t nbatch,
                                  int64_t nchan, const int64_t *dims_host, int align, int dtype, void *image_grad,
                                  void *stream);
+/* The same two operators with a caller-provided workspace (d3d_aligned_scatter_workspace_bytes; 0 = none needed).  With a workspace,
+ * 2-D fp32 maps whose points are dense (n >= cells / 16) take the tile path: the points are binned by 8 x 64-cell tile and every tile is
+ * staged once in shared memory, instead of one 32-byte sector per neighbour row and channel plane.  Forward outputs are bit-identical to
+ * the gather path; backward sums in a different (still unspecified) order.  A point whose batch index lies outside [0, nbatch) -- for
+ * which the gather path, like the reference, reads outside the map -- is skipped by the tile path (its output row is not written).
+ * reuse_plan != 0: the workspace still holds the binning of an earlier call with the same coord / n / nbatch / dims (the backward pass
+ * after its forward pass: the autograd function keeps the workspace) and the three binning launches are skipped.
+ * The entry points without workspace always gather. */
+size_t d3d_aligned_scatter_workspace_bytes(int64_t n, int32_t dim, int64_t nbatch, const int64_t *dims_host);
+int d3d_aligned_scatter_forward_ws(const void *coord, int64_t n, int32_t dim, const void *image, int64_t nbatch,
+                                   int64_t nchan, const int64_t *dims_host, int align, int dtype, void *out,
+                                   void *workspace, size_t workspace_bytes, int reuse_plan, void *stream);
+int d3d_aligned_scatter_backward_ws(const void *coord, int64_t n, int32_t dim, const void *grad, int64_t nbatch,
+                                    int64_t nchan, const int64_t *dims_host, int align, int dtype, void *image_grad,
+                                    void *workspace, size_t workspace_bytes, int reuse_plan, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Measurement helper: FMA-chain microbenchmark used as the measured FP32/FP64 ALU peak for the IoU

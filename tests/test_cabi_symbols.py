@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/d3d_b200.h but not exported"
     lib.d3d_abi_version.restype = C.c_int
-    assert lib.d3d_abi_version() == 4
+    assert lib.d3d_abi_version() == 5
     lib.d3d_error_string.restype = C.c_char_p
     assert lib.d3d_error_string(3) == b"workspace too small"
 

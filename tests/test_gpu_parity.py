@@ -816,6 +816,40 @@ def test_scatter_c2s_anchor(dev, oracle):
     assert np.array_equal(ol.cpu().numpy()[idx], oracle.scatter_forward(crd[idx], fmn, 2))
 
 
+def test_scatter_tile_path_equals_gather_and_oracle(dev, oracle):
+    """the tile path (2-D fp32 maps staged tile by tile in shared memory) against the gather path and the oracle: forward bit for bit, backward
+    to rounding; ragged map sizes (tiles cut by the border, widths that are no multiple of 4), several batch images, channel counts that
+    are no multiple of the 32-channel chunk, coordinates outside the map and on integers, a tile holding thousands of points (slices)"""
+    from d3d_b200.point import aligned_scatter
+    rng = np.random.default_rng(5)
+    for (nb, ch, H, W, n) in ((1, 64, 64, 128, 6000), (2, 40, 37, 131, 5000), (1, 3, 9, 65, 900), (3, 33, 8, 64, 2000), (1, 32, 70, 200, 20000)):
+        img = rng.random((nb, ch, H, W), dtype=np.float32)
+        crd = np.stack([rng.integers(0, nb, n).astype(np.float32), rng.random(n, dtype=np.float32) * (H + 2) - 1, rng.random(n, dtype=np.float32) * (W + 2) - 1], 1)
+        crd[: n // 10, 1:] = np.round(crd[: n // 10, 1:])                      # integral coordinates: the 2x weight quirk
+        crd[n // 10: n // 5, 1:] = crd[n // 10: n // 5, 1:] * 0.05 + 3.0        # a crowd inside one tile
+        for meth, at in (("mean", 1), ("linear", 2)):
+            res = {}
+            for path in (1, 2):
+                _cabi.tuning_set("D3D_B200_SCATTER_PATH", path)
+                ti = _t(img, dev).requires_grad_(True)
+                o = aligned_scatter(_t(crd, dev), ti, meth)
+                gr = np.random.default_rng(n).random(o.shape).astype(np.float32)
+                o.backward(_t(gr, dev))
+                res[path] = (o.detach().cpu().numpy(), ti.grad.cpu().numpy())
+            _cabi.tuning_set("D3D_B200_SCATTER_PATH", None)
+            assert np.array_equal(res[1][0], res[2][0]), (nb, ch, H, W, meth)
+            sel = rng.integers(0, n, 300)
+            assert np.array_equal(res[2][0][sel], oracle.scatter_forward(crd[sel], img, at)), (nb, ch, H, W, meth)
+            exp = oracle.scatter_backward(crd, gr, at, img.shape)
+            scale = max(1.0, float(np.abs(exp).max()))
+            assert np.abs(res[2][1] - exp).max() < 2e-5 * scale and np.abs(res[1][1] - exp).max() < 2e-5 * scale, (nb, ch, H, W, meth)
+    # the default rule picks the tile path for a dense cloud and the gather path for a sparse one; both give the oracle's rows
+    img = rng.random((1, 8, 64, 64), dtype=np.float32)
+    for n in (10, 4000):
+        crd = np.stack([np.zeros(n, np.float32), rng.random(n, dtype=np.float32) * 63, rng.random(n, dtype=np.float32) * 63], 1)
+        assert np.array_equal(aligned_scatter(_t(crd, dev), _t(img, dev), "linear").cpu().numpy(), oracle.scatter_forward(crd, img, 2))
+
+
 @pytest.mark.gpu
 def test_voxel_rank_paths_stress(dev, oracle):
     """the three rank regimes of the cluster back end (voxels with <= max_points points, up to 32, beyond 32) in
