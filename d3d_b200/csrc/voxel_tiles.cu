@@ -561,7 +561,7 @@ static bool vt_geom(int64_t max_frame_points, int64_t nframes, VtGeom *g)
     g->lgP = vt_lg2_ceil(((uint64_t)g->lmax + D3D_VT_BPTS - 1) / D3D_VT_BPTS);
     g->P = 1u << g->lgP;
     const uint32_t per = (g->lmax + g->P - 1) / g->P;            // points per bucket if every point is kept and the hash is even (<= 512)
-    g->qcap = (per + per / 2 + 128 + 3) & ~3u;                   // <= VT_QCAP = table slots of a bucket CTA; more -> device flag
+    g->qcap = (per + per / 2 + 128 + 15) & ~15u;                 // multiple of 16 entries: every bucket's queue starts on a 128-byte line
     if (g->qcap > (uint32_t)VT_QCAP) g->qcap = VT_QCAP;
     int cf = vt_env_cf();
     if (cf <= 0) cf = 64;    // measured on C2 x 128 frames (one stream): 0.74 ms with chunks of 16 (scratch mostly L2-resident), 0.59 ms with one chunk of 128 (fewer, fuller launches)

@@ -5,7 +5,7 @@ set -e
 name=$1; shift
 cd "$(dirname "$0")/../d3d_b200/csrc"
 d=$(mktemp -d)
-for f in core prims iou nms voxel voxel_cluster voxel_tiles scatter crop; do
+for f in core prims iou nms voxel voxel_cluster voxel_tiles scatter crop dist match iou_grad; do
   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC --expt-relaxed-constexpr "$@" -c $f.cu -o $d/$f.o &
 done
 wait
