@@ -103,18 +103,21 @@ __global__ void __launch_bounds__(256) scatter_bwd_kernel(const T *__restrict__ 
 // ------------------------------------------------------------------ tile path (2-D maps, fp32)
 // The gather above costs one 32-byte sector per 4-byte neighbour and channel plane (lanes of a warp are 32 channels: 32 planes, 2.25 MB
 // apart on the C2s map), 3x the algorithmic bytes.  When the points are dense enough that this exceeds the map itself, the map is
-// streamed instead: the points are binned by the 8 x 64-cell tile of their lower neighbour, and one CTA per (tile, 32-channel chunk,
-// slice of <= 256 points) stages the tile's 9 x 65 cells (one halo row and column for the upper neighbours) of its 32 channel planes
+// streamed instead: the points are binned by the 6 x 64-cell tile of their lower neighbour, and one CTA per (tile, 32-channel chunk,
+// slice of <= 256 points) stages the tile's 7 x 65 cells (one halo row and column for the upper neighbours) of its 32 channel planes
 // in shared memory with 4-byte cp.async -- row segments of 65 consecutive floats, full sectors -- and serves its points from there:
-// a warp per point, a lane per channel, plane pitch 585 words (odd: the 32 lanes hit 32 banks), output rows written as 128-byte
+// a warp per point, a lane per channel, plane pitch 455 words (odd: the 32 lanes hit 32 banks; 476 with the 68-cell rows of a TMA box: four lanes per bank), output rows written as 128-byte
 // lines.  Tiles with few points skip the staging and gather from global memory.  The backward pass accumulates the tile in shared
 // memory (atomicAdd on shared memory) and sends each non-zero cell to the map gradient once, as a RED on consecutive addresses.
 // Arithmetic per (point, channel) is the gather kernel's, operation by operation: forward outputs are bit-identical on both paths.
-constexpr int ST_H = 8, ST_W = 64, ST_CH = 32, ST_ROWS = ST_H + 1, ST_COLS = ST_W + 1;
+#ifndef D3D_ST_H
+#define D3D_ST_H 6
+#endif
+constexpr int ST_H = D3D_ST_H, ST_W = 64, ST_CH = 32, ST_ROWS = ST_H + 1, ST_COLS = ST_W + 1;
 constexpr int ST_TMA_COLS = 68;   // TMA boxes are multiples of 16 bytes wide: 65 cells + 3
-template <bool TMA> struct StLayout { static constexpr int PITCH = TMA ? ST_TMA_COLS : ST_COLS, PLANE = ST_ROWS * PITCH; };   // 612 / 585 words per channel plane
+template <bool TMA> struct StLayout { static constexpr int PITCH = TMA ? ST_TMA_COLS : ST_COLS, PLANE = ST_ROWS * PITCH; };   // 476 / 455 words per channel plane
 constexpr int ST_SLICE = 256;      // points per work item
-constexpr int ST_DIRECT = 12;      // tiles with fewer points gather from global memory (12 points x 2 rows x 32 B < the 9 x 288 B of a staged plane)
+constexpr int ST_DIRECT = 12;      // tiles with fewer points gather from global memory (12 points x 2 rows x 32 B < the 7 x 288 B of a staged plane)
 constexpr int ST_THREADS = 256;
 constexpr int64_t ST_MAX_TILES = 1 << 16;
 
@@ -413,152 +416,6 @@ __global__ void __launch_bounds__(ST_THREADS) st_tile_kernel(const T *__restrict
     }
 }
 
-// The same work as st_tile_kernel<.., TMA = true> with one persistent CTA per SM and TWO tile buffers: the tensor copy of work item k+1
-// (forward) runs under the points of item k, the reduce-add of item k (backward) under the accumulation of item k+1, and the item
-// descriptor and point records of item k+1 are fetched one iteration ahead -- a CTA's phases overlap each other instead of relying on
-// a second resident CTA (78 KB per tile admit only two).  Work item w = (item w / chunks, channel chunk w % chunks).
-template <typename T, bool LINEAR, bool FWD>
-__global__ void __launch_bounds__(ST_THREADS, 1) st_pipe_kernel(const T *__restrict__ src, int64_t nchan, StGeom g, const float4 *__restrict__ sorted,
-                                                                const uint4 *__restrict__ items, const uint32_t *__restrict__ nitems, uint32_t chunks, T *__restrict__ dst,
-                                                                const __grid_constant__ CUtensorMap tmap)
-{
-    constexpr int PITCH = StLayout<true>::PITCH, PLANE = StLayout<true>::PLANE;
-    constexpr uint32_t TILE_BYTES = ST_CH * PLANE * sizeof(T), NW = ST_THREADS / 32;
-    extern __shared__ float st_smem_raw[];
-    __shared__ __align__(8) uint64_t st_bar[2];
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t total = *nitems * chunks;
-    if (blockIdx.x >= total) return;
-    const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(st_smem_raw), tile_s0 = (raw_s + 127u) & ~127u;   // TMA alignment
-    T *tile0 = reinterpret_cast<T *>(reinterpret_cast<char *>(st_smem_raw) + (tile_s0 - raw_s));                  // two buffers [ST_CH][ST_ROWS][PITCH]
-    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&st_bar[0]);
-    const int64_t plane = (int64_t)g.H * g.W;
-    const int64_t tiles_per_image = (int64_t)g.ntx * g.nty;
-    if (FWD && threadIdx.x == 0) { st_mbar_init(bar_s, 1); st_mbar_init(bar_s + 8, 1); }
-    uint32_t phase[2] = {0u, 0u};
-
-    // descriptor of a work item; the tensor copy of a staged forward item is issued by thread 0 as soon as the descriptor is known
-    struct Work { uint4 it; int tx, ty, c0, zplane; int64_t b; bool direct; };
-    auto describe = [&](uint32_t w, const uint4 it) {
-        Work k;
-        k.it = it;
-        const int64_t t = it.x;
-        k.tx = (int)(t % g.ntx); k.ty = (int)((t / g.ntx) % g.nty); k.b = t / tiles_per_image;
-        k.c0 = (int)(w % chunks) * ST_CH;
-        k.zplane = (int)(k.b * nchan + k.c0);
-        k.direct = it.w < (uint32_t)ST_DIRECT;
-        return k;
-    };
-    auto record = [&](const Work &k) {   // lane l's point of this warp's share (the points of an item are dealt round robin to the warps)
-        const uint32_t q = k.it.y + warp + lane * NW;
-        return q < k.it.z ? sorted[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    uint32_t w = blockIdx.x;
-    Work cur = describe(w, items[w / chunks]);
-    float4 rec = record(cur);
-    __syncthreads();   // the barriers are initialised
-    if (FWD && !cur.direct && threadIdx.x == 0) { st_mbar_expect(bar_s, TILE_BYTES); st_tma_load(tile_s0, &tmap, cur.tx * ST_W, cur.ty * ST_H, cur.zplane, bar_s); }
-    for (uint32_t stage = 0; w < total; w += gridDim.x, stage ^= 1u) {
-        const uint32_t wn = w + gridDim.x;
-        const bool more = wn < total;
-        Work nxt = cur;
-        if (more) nxt = describe(wn, items[wn / chunks]);
-        T *tile = tile0 + stage * (ST_CH * PLANE);
-        const uint32_t tile_s = tile_s0 + stage * TILE_BYTES;
-        if (FWD) {
-            // the other buffer was released by the barrier that ended the previous iteration: refill it now
-            if (more && !nxt.direct && threadIdx.x == 0) {
-                st_mbar_expect(bar_s + 8 * (stage ^ 1u), TILE_BYTES);
-                st_tma_load(tile_s0 + (stage ^ 1u) * TILE_BYTES, &tmap, nxt.tx * ST_W, nxt.ty * ST_H, nxt.zplane, bar_s + 8 * (stage ^ 1u));
-            }
-        } else if (!cur.direct) {
-            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the reduce-add that last used this buffer has read it
-            __syncthreads();
-            float4 *t4 = reinterpret_cast<float4 *>(tile);
-            for (int e = threadIdx.x; e < ST_CH * PLANE / 4; e += ST_THREADS) t4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        // this item's points
-        const int y0 = cur.ty * ST_H, x0 = cur.tx * ST_W;
-        const int nc = (int)min((int64_t)ST_CH, nchan - cur.c0), c = cur.c0 + (int)lane;
-        const bool chan_ok = (int)lane < nc, direct = cur.direct;
-        const int64_t b = cur.b;
-        const uint32_t q0 = cur.it.y + warp, p1 = cur.it.z;
-        const uint32_t myi = __float_as_uint(rec.x);
-        int lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
-        T wy0 = T(0), wy1 = T(0), wx0 = T(0), wx1 = T(0);
-        axis_neighbours<T>((T)rec.y, g.H - 1, &lo0, &hi0, &wy0, &wy1);
-        axis_neighbours<T>((T)rec.z, g.W - 1, &lo1, &hi1, &wx0, &wx1);
-        float4 rec_next = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (more) rec_next = record(nxt);   // in flight under this item's points
-        if (!direct) {
-            if (FWD) { st_mbar_wait(bar_s + 8 * stage, phase[stage]); phase[stage] ^= 1u; }
-            else __syncthreads();   // the buffer is zeroed
-        }
-        const int np = q0 < p1 ? (int)min(32u, (p1 - q0 + NW - 1) / NW) : 0;
-        for (int k0 = 0; k0 < np; k0 += 4) {   // four points per round: their gradient rows (backward) are in flight together
-            uint32_t pi[4];
-            T gr[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                pi[u] = __shfl_sync(0xffffffffu, myi, min(k0 + u, np - 1));
-                gr[u] = T(0);
-                if (!FWD && chan_ok && k0 + u < np) gr[u] = src[(int64_t)pi[u] * nchan + c];
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int k = min(k0 + u, np - 1);   // np is the same in every lane: the shuffles are converged
-                const int a0 = __shfl_sync(0xffffffffu, lo0, k), a1 = __shfl_sync(0xffffffffu, hi0, k);
-                const int b0 = __shfl_sync(0xffffffffu, lo1, k), b1 = __shfl_sync(0xffffffffu, hi1, k);
-                const T u0 = __shfl_sync(0xffffffffu, wy0, k), u1 = __shfl_sync(0xffffffffu, wy1, k);
-                const T v0 = __shfl_sync(0xffffffffu, wx0, k), v1 = __shfl_sync(0xffffffffu, wx1, k);
-                if (!chan_ok || k0 + u >= np) continue;
-                T wt[4];   // neighbour j: bit 0 of j = upper neighbour along the first axis, bit 1 = along the second (the order of neighbours())
-                if (LINEAR) { wt[0] = mul_rn<T>(mul_rn<T>(T(1), u0), v0); wt[1] = mul_rn<T>(mul_rn<T>(T(1), u1), v0); wt[2] = mul_rn<T>(mul_rn<T>(T(1), u0), v1); wt[3] = mul_rn<T>(mul_rn<T>(T(1), u1), v1); }
-                if (FWD) {
-                    T v[4];
-                    if (direct) {
-                        const T *pl = src + ((int64_t)b * nchan + c) * plane;
-                        v[0] = __ldg(pl + (int64_t)a0 * g.W + b0); v[1] = __ldg(pl + (int64_t)a1 * g.W + b0);
-                        v[2] = __ldg(pl + (int64_t)a0 * g.W + b1); v[3] = __ldg(pl + (int64_t)a1 * g.W + b1);
-                    } else {
-                        const T *pl = tile + (int)lane * PLANE;
-                        v[0] = pl[(a0 - y0) * PITCH + (b0 - x0)]; v[1] = pl[(a1 - y0) * PITCH + (b0 - x0)];
-                        v[2] = pl[(a0 - y0) * PITCH + (b1 - x0)]; v[3] = pl[(a1 - y0) * PITCH + (b1 - x0)];
-                    }
-                    T sum = T(0);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) sum = add_rn<T>(sum, LINEAR ? mul_rn<T>(v[j], wt[j]) : v[j]);
-                    dst[(int64_t)pi[u] * nchan + c] = LINEAR ? sum : sum / T(4);
-                } else {
-                    T a[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) a[j] = LINEAR ? mul_rn<T>(gr[u], wt[j]) : gr[u] / T(4);
-                    if (direct) {
-                        T *pl = dst + ((int64_t)b * nchan + c) * plane;
-                        atomicAdd(pl + (int64_t)a0 * g.W + b0, a[0]); atomicAdd(pl + (int64_t)a1 * g.W + b0, a[1]);
-                        atomicAdd(pl + (int64_t)a0 * g.W + b1, a[2]); atomicAdd(pl + (int64_t)a1 * g.W + b1, a[3]);
-                    } else {
-                        T *pl = tile + (int)lane * PLANE;
-                        atomicAdd(pl + (a0 - y0) * PITCH + (b0 - x0), a[0]); atomicAdd(pl + (a1 - y0) * PITCH + (b0 - x0), a[1]);
-                        atomicAdd(pl + (a0 - y0) * PITCH + (b1 - x0), a[2]); atomicAdd(pl + (a1 - y0) * PITCH + (b1 - x0), a[3]);
-                    }
-                }
-            }
-        }
-        if (!FWD && !direct) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the accumulation becomes visible to the copy engine
-        __syncthreads();   // every thread is done with this buffer (forward: it may be refilled; backward: it may be sent)
-        if (!FWD && threadIdx.x == 0) {
-            if (!direct)
-                asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
-                             ::"l"(reinterpret_cast<uint64_t>(&tmap)), "r"(tile_s), "r"(x0), "r"(y0), "r"(cur.zplane) : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // one group per iteration (empty for a direct item): "all but the latest group" above always means this buffer's last use
-        }
-        cur = nxt;
-        rec = rec_next;
-    }
-    if (!FWD && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory is read before the CTA leaves
-}
-
 // cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
 typedef CUresult (*StEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -626,10 +483,6 @@ static int scatter_tiles(bool fwd, const T *coord, int64_t n, const T *src, int6
     memset(&tmap, 0, sizeof(tmap));
     const bool tma = sizeof(T) == 4 && st_tensor_map(fwd ? (const void *)src : (const void *)dst, nbatch * nchan, g, &tmap);
     const dim3 grid((unsigned)max_items, (unsigned)chunks);
-    const bool pipe = tuning(D3D_TUNE_SCATTER_PIPE, 1) != 0 && max_items * chunks < (1ll << 31);   // 0: one CTA per work item (st_tile_kernel) also where TMA applies
-    int dev = 0, nsm_i = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm_i, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t nsm = nsm_i;
 #define D3D_ST_LAUNCH(LIN, FWD, TMA)                                                                                                         \
     do {                                                                                                                                     \
         const size_t smem = (size_t)ST_CH * StLayout<TMA>::PLANE * sizeof(T) + 128;                                                          \
@@ -637,15 +490,7 @@ static int scatter_tiles(bool fwd, const T *coord, int64_t n, const T *src, int6
         if (!attr) { D3D_CUDA_TRY(cudaFuncSetAttribute(st_tile_kernel<T, LIN, FWD, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; } \
         st_tile_kernel<T, LIN, FWD, TMA><<<grid, ST_THREADS, smem, st>>>(src, nchan, g, sorted, items, nitems, dst, tmap);      \
     } while (0)
-#define D3D_ST_PIPE(LIN, FWD)                                                                                                                \
-    do {                                                                                                                                     \
-        const size_t smem = 2 * (size_t)ST_CH * StLayout<true>::PLANE * sizeof(T) + 128;                                                     \
-        static bool attr = false;                                                                                                            \
-        if (!attr) { D3D_CUDA_TRY(cudaFuncSetAttribute(st_pipe_kernel<T, LIN, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; } \
-        const int64_t work = max_items * chunks;                                                                                             \
-        st_pipe_kernel<T, LIN, FWD><<<(unsigned)(work < nsm ? work : nsm), ST_THREADS, smem, st>>>(src, nchan, g, sorted, items, nitems, (uint32_t)chunks, dst, tmap); \
-    } while (0)
-#define D3D_ST_LAUNCH2(LIN, FWD) do { if (tma && pipe) D3D_ST_PIPE(LIN, FWD); else if (tma) D3D_ST_LAUNCH(LIN, FWD, true); else D3D_ST_LAUNCH(LIN, FWD, false); } while (0)
+#define D3D_ST_LAUNCH2(LIN, FWD) do { if (tma) D3D_ST_LAUNCH(LIN, FWD, true); else D3D_ST_LAUNCH(LIN, FWD, false); } while (0)
     if (fwd) {
         // points with a batch index outside the map are skipped (the gather path, like the reference, would read outside the map): their rows stay unwritten
         if (align == D3D_ALIGN_LINEAR) D3D_ST_LAUNCH2(true, true); else D3D_ST_LAUNCH2(false, true);
@@ -653,7 +498,6 @@ static int scatter_tiles(bool fwd, const T *coord, int64_t n, const T *src, int6
         if (align == D3D_ALIGN_LINEAR) D3D_ST_LAUNCH2(true, false); else D3D_ST_LAUNCH2(false, false);
     }
 #undef D3D_ST_LAUNCH2
-#undef D3D_ST_PIPE
 #undef D3D_ST_LAUNCH
     D3D_LAUNCHED();
     return D3D_OK;

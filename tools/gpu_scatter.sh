@@ -1,6 +1,6 @@
 #!/bin/bash
 timeout 300 python -m pytest tests -m gpu -x -q -k "scatter" 2>&1 | tail -5
-for cfg in "gather 1" "tiles 0" "tiles 1"; do set -- $cfg
+for cfg in "gather 1" "tiles 1"; do set -- $cfg
 D3D_B200_SCATTER_PATH=$1 D3D_B200_SCATTER_PIPE=$2 timeout 300 python bench.py --op scatter --no-cpu-baseline --steps 10 > gpurun_out/bench_scatter.json 2> gpurun_out/bench_scatter.err; tail -2 gpurun_out/bench_scatter.err
 python -c "
 import json
