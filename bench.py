@@ -509,13 +509,16 @@ def ref_cuda_baseline(op):
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
     if op == "iou":
-        n = 16000   # the reference keeps u8[N, M, 8] flags for its backward: 16000^2 x 8 is the largest square below its int32 element limit
-        A, B = torch.from_numpy(gen_boxes(rng, n).astype(np.float32)).cuda(), torch.from_numpy(gen_boxes(rng, n).astype(np.float32)).cuda()
+        # fp64, the reference's default dtype: its fp32 Rotating-Calipers path overruns a fixed-size vertex buffer on ~15 % of generic blocks
+        # (CPU: "stack smashing detected"; GPU: illegal address).  The reference keeps u8[N, M, 8] flags for its backward and indexes pairs
+        # with int32, so the square stays well below 16000.
+        n = 8192
+        A, B = torch.from_numpy(gen_boxes(rng, n)).cuda(), torch.from_numpy(gen_boxes(rng, n)).cuda()
         ms_ref = ev(lambda: m.iou2dr_forward_cuda(A, B), 2)
-        ms_own = ev(lambda: box2d_iou(A, B, "rbox", precise=False))
+        ms_own = ev(lambda: box2d_iou(A, B, "rbox"))
         ref = m.iou2dr_forward_cuda(A[:2000], B[:2000])[0]
-        own = box2d_iou(A[:2000], B[:2000], "rbox", precise=False)
-        return dict(workload=f"rotated IoU {n}x{n} fp32, C1 distribution", ref_cuda_ms=ms_ref, this_build_ms=ms_own, speedup=ms_ref / ms_own,
+        own = box2d_iou(A[:2000], B[:2000], "rbox")
+        return dict(workload=f"rotated IoU {n}x{n} fp64, C1 distribution", ref_cuda_ms=ms_ref, this_build_ms=ms_own, speedup=ms_ref / ms_own,
                     ref_cuda_pairs_per_s=n * n / (ms_ref * 1e-3), max_abs_diff_2000x2000=float((ref - own).abs().max()))
     if op == "nms":
         n = 20000
