@@ -288,6 +288,20 @@ def test_box_crop_vs_reference_and_oracle(dev, oracle):
     one = np.zeros((300, 2), np.float32)
     assert np.array_equal(box2dr_crop(_t(one, dev), _t(bx, dev)).cpu().numpy(), oracle.crop_2dr(one, bx))
     _cabi.tuning_set("D3D_B200_CROP_PATH", None)
+    # bench size (180k lidar-like points x 4096 proposals: boxes on the dense first metres have tens of thousands of candidates):
+    # the grid path against the brute-force path over the whole mask, and against the oracle on sampled rows
+    from bench import lidar as bench_lidar, proposals as bench_proposals
+    pts = bench_lidar(300, 180_000)[:, :2].copy()
+    bx = bench_proposals(300, 4096, 2048)[0].astype(np.float32)
+    tp, tb = _t(pts, dev), _t(bx, dev)
+    _cabi.tuning_set("D3D_B200_CROP_PATH", 1)
+    brute = box2dr_crop(tp, tb)
+    _cabi.tuning_set("D3D_B200_CROP_PATH", 2)
+    grid = box2dr_crop(tp, tb)
+    _cabi.tuning_set("D3D_B200_CROP_PATH", None)
+    assert torch.equal(brute, grid) and int(grid.sum()) > 0
+    rows = rng.integers(0, 4096, 24)
+    assert np.array_equal(grid[torch.from_numpy(rows).to(dev)].cpu().numpy(), oracle.crop_2dr(pts, bx[rows]))
     # reference test/test_box.py:191-205
     cloud = (rng.random((100, 2)) * 2 - 1).astype(np.float32)
     boxes = np.array([[0, 0, 1, 1, 0], [0, 0, 1, 1, np.pi / 4]], np.float32)
@@ -814,6 +828,19 @@ def test_scatter_c2s_anchor(dev, oracle):
     fmn = fm.numpy()
     assert np.array_equal(om.cpu().numpy()[idx], oracle.scatter_forward(crd[idx], fmn, 1))
     assert np.array_equal(ol.cpu().numpy()[idx], oracle.scatter_forward(crd[idx], fmn, 2))
+    # full size, both back ends: the default above is the tile path (TMA); the gather path must give the same bits, and the two
+    # backward passes the same map gradient up to the order of their sums
+    grads = {}
+    for path in (1, 2):
+        _cabi.tuning_set("D3D_B200_SCATTER_PATH", path)
+        tfg = tf.clone().requires_grad_(True)
+        o = aligned_scatter(tc, tfg, "linear")
+        assert torch.equal(o.detach(), ol), path
+        o.backward(torch.ones_like(o))
+        grads[path] = tfg.grad
+    _cabi.tuning_set("D3D_B200_SCATTER_PATH", None)
+    assert float((grads[1] - grads[2]).abs().max()) < 1e-3 * max(1.0, float(grads[1].abs().max()))
+    assert abs(float(grads[2].double().sum()) - 64.0 * len(p)) < 1e-3 * 64.0 * len(p)   # every point spreads weight 1 per channel (up to the 2x quirk on integral coordinates: none here)
 
 
 def test_scatter_tile_path_equals_gather_and_oracle(dev, oracle):
