@@ -869,7 +869,8 @@ def bench_nms(args, rank, world, barrier):
     roof = alu_roofline(1, clips * W_CAND / (ms_pairs * 1e-3) / 1e12, clk)
     roof.update(phase="candidate phase (nms_pairs_kernel): clips x 230 flop over its own time", clips=clips, ms_sort_gather=ms_sort, ms_candidates=ms_pairs,
                 ms_resolve=ms_resolve, resolve_us_per_64_box_block=ms_resolve * 1e3 / ((n + 63) // 64),
-                note="the resolve is one dependent chain over the 64-box blocks on one SM (latency, no roofline); frame-batched NMS (ops.c5) runs one resolve per frame")
+                note="the resolve is a fixpoint of keep / suppress decisions reached in parallel rounds on a cooperative grid (two grid barriers per round, latency: "
+                     "no roofline; D3D_B200_NMS_FIX=0: the block-by-block walk in score order on one SM, 0.97 ms); frame-batched NMS (ops.c5) runs one walk per frame")
     return dict(metric="NMS boxes/sec", unit="boxes/s", value=n * world / (ms * 1e-3), ms_per_step=ms, dtype="f64", scaling="weak",
                 gpu_launches=int(launches),
                 config=dict(workload=f"C3 BEV rotated NMS: {n} clustered proposals/frame (2000 objects), rbox thr 0.5, precise=True (fp64), "

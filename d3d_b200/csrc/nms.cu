@@ -22,6 +22,7 @@
 #include "geom.cuh"
 #include "prims.cuh"
 #include <cuda_pipeline.h>
+#include <cooperative_groups.h>
 #include <stdlib.h>
 #include <stdio.h>
 
@@ -444,11 +445,13 @@ __device__ __forceinline__ unsigned long long nms_resolve_diag(unsigned long lon
 
 __global__ void __launch_bounds__(RESOLVE_THREADS)
 nms_resolve_kernel(const uint64_t *__restrict__ mask, int64_t n, int64_t nwords, const uint8_t *__restrict__ valid,
-                   const uint32_t *__restrict__ order, uint8_t *__restrict__ suppressed, const NmsLists lists, const uint32_t stage_cap)
+                   const uint32_t *__restrict__ order, uint8_t *__restrict__ suppressed, const NmsLists lists, const uint32_t stage_cap,
+                   const uint32_t *__restrict__ skip_if)
 {
     extern __shared__ unsigned long long remv[];   // [nwords] removal bitmap in sorted order (+ the sparse path's arrays behind it)
     __shared__ unsigned long long diag[2][64];
     __shared__ unsigned long long keptbits;
+    if (skip_if && *skip_if) return;   // the parallel resolve produced the keep mask (CTA-uniform)
     const int tid = threadIdx.x;
     const uint32_t NT = blockDim.x;   // >= 128
     // boxes at or below the score threshold (and the padding past n) start out removed
@@ -571,6 +574,78 @@ nms_resolve_kernel(const uint64_t *__restrict__ mask, int64_t n, int64_t nwords,
         }
         __syncthreads();
     }
+}
+
+// ------------------------------------------------------------------------------------------------ parallel resolve
+// Greedy NMS keeps a box iff no KEPT box of higher score overlaps it.  The list walk above follows the score order block by block on
+// one SM (782 dependent steps of ~1.2 us for 50 000 boxes).  The same fixpoint is reached in parallel: in a round every undecided box
+// whose higher-scored overlapping boxes are all suppressed becomes kept, and every box overlapped by a kept box becomes suppressed.
+// The highest-scored undecided box is always decided, so the rounds terminate, and the number of rounds is the longest chain of
+// alternating decisions -- the depth of a cluster of proposals around one object, not the number of boxes.  One cooperative grid, two
+// grid barriers per round; the edges are the per-block hit lists the candidate kernels wrote (row -> column bits, row < column in score
+// order).  A list overflow or more than NMS_FIX_ROUNDS rounds (a long chain of pairwise overlapping boxes) leaves `done` at 0 and the
+// list walk runs; the result is the same keep mask either way.
+constexpr int NMS_FIX_THREADS = 1024, NMS_FIX_ROUNDS = 96;
+constexpr uint8_t NMS_UNDECIDED = 0, NMS_KEPT = 1, NMS_SUPPRESSED = 2;
+
+__global__ void __launch_bounds__(NMS_FIX_THREADS, 1)
+nms_fixpoint_kernel(int64_t n, int64_t nwords, const uint8_t *__restrict__ valid, const uint32_t *__restrict__ order, uint8_t *__restrict__ suppressed, const NmsLists lists,
+                    uint8_t *state, uint32_t *blocked, uint32_t *ctl /* [0], [1]: undecided boxes of even / odd rounds; [2] done; [3] rounds */)
+{
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsize = (int64_t)gridDim.x * blockDim.x;
+    if (lists.blkcnt[nwords] != 0u) return;   // a list overflowed (grid-uniform): the dense walk decides
+    for (int64_t j = gtid; j < nwords * 64; j += gsize) {
+        __stcg(state + j, (j < n && valid[j]) ? NMS_UNDECIDED : NMS_SUPPRESSED);   // boxes at or below the score threshold (and the padding) never keep anything
+        __stcg(blocked + j, 0u);
+    }
+    if (gtid < 2) __stcg(ctl + gtid, 0u);
+    grid.sync();
+    // a quarter CTA per 64-row block: its list is ~1500 entries on a 50 000-box frame
+    const int64_t quarter = gtid >> 8, nquarters = gsize >> 8;
+    const unsigned qt = threadIdx.x & 255u;
+    __shared__ uint32_t s_left;
+    uint32_t round = 1;
+    for (; round <= (uint32_t)NMS_FIX_ROUNDS; round++) {
+        for (int64_t b = quarter; b < nwords; b += nquarters) {
+            const uint32_t c = min(lists.blkcnt[b], NMS_LIST_CAP);
+            const uint32_t *gw = lists.ent_w + b * NMS_LIST_CAP;
+            const uint64_t *gb = lists.ent_bits + b * NMS_LIST_CAP;
+            for (uint32_t e = qt; e < c; e += 256u) {
+                const uint32_t we = gw[e];
+                const uint8_t si = __ldcg(state + b * 64 + (we >> 16));   // L2: other CTAs change it between the barriers
+                if (si == NMS_SUPPRESSED) continue;
+                unsigned long long bits = gb[e];
+                const int64_t col0 = (int64_t)(we & 0xffffu) * 64;
+                while (bits) {
+                    const int t = __ffsll((long long)bits) - 1;
+                    bits &= bits - 1;
+                    if (si == NMS_KEPT) __stcg(state + col0 + t, NMS_SUPPRESSED);
+                    else __stcg(blocked + col0 + t, round);   // a higher-scored overlapping box is still undecided
+                }
+            }
+        }
+        grid.sync();
+        uint32_t left = 0;
+        for (int64_t j = gtid; j < n; j += gsize) {
+            if (__ldcg(state + j) == NMS_UNDECIDED) {
+                if (__ldcg(blocked + j) != round) __stcg(state + j, NMS_KEPT);
+                else left++;
+            }
+        }
+        if (threadIdx.x == 0) s_left = 0;
+        __syncthreads();
+        left = __reduce_add_sync(0xffffffffu, left);
+        if ((threadIdx.x & 31) == 0 && left) atomicAdd(&s_left, left);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_left) atomicAdd(ctl + (round & 1u), s_left);
+        if (gtid == 0) __stcg(ctl + ((round + 1) & 1u), 0u);   // the other counter: last read before the previous barrier, next used in the next round
+        grid.sync();
+        if (__ldcg(ctl + (round & 1u)) == 0u) break;           // grid-uniform
+    }
+    if (round > (uint32_t)NMS_FIX_ROUNDS) return;              // too deep: the list walk decides (done stays 0)
+    for (int64_t row = gtid; row < n; row += gsize) suppressed[order[row]] = __ldcg(state + row) == NMS_KEPT ? 0 : 1;
+    if (gtid == 0) { ctl[2] = 1u; ctl[3] = round; }
 }
 
 // ------------------------------------------------------------------------------------------------ soft-NMS
@@ -931,7 +1006,8 @@ template <typename T> static size_t nms_ws_bytes(int64_t n)
            align_up((size_t)npad * 5 * sizeof(T)) + align_up((size_t)npad) + align_up((size_t)npad * nwords * 8) +
            align_up((size_t)(nwords + 1) * 4) + align_up((size_t)nwords * NMS_LIST_CAP * 4) + align_up((size_t)nwords * NMS_LIST_CAP * 8) +
            align_up(sizeof(NmsGrid)) + 2 * align_up((size_t)2 * (NMS_GRID_CELLS + 1) * 4) + align_up((size_t)npad * sizeof(NmsCand<T>)) + scan_workspace_bytes(NMS_GRID_CELLS + 1) + 4096 +
-           align_up((size_t)npad * sizeof(T)) + 3 * align_up((size_t)npad * 4) + 2 * align_up((size_t)npad);   // soft-NMS state
+           align_up((size_t)npad * sizeof(T)) + 3 * align_up((size_t)npad * 4) + 2 * align_up((size_t)npad) +   // soft-NMS state
+           align_up((size_t)npad) + align_up((size_t)npad * 4) + align_up(64);   // parallel resolve: state, blocked, control words
 }
 
 template <typename T>
@@ -970,6 +1046,8 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
     soft.sc = a.take<T>(npad); soft.ord = a.take<uint32_t>(npad); soft.tmp = a.take<uint32_t>(npad);
     uint32_t *soft_pos = a.take<uint32_t>(npad);
     soft.sup = a.take<uint8_t>(npad); soft.mk = a.take<uint8_t>(npad);
+    uint8_t *fix_state = a.take<uint8_t>(npad);
+    uint32_t *fix_blocked = a.take<uint32_t>(npad), *fix_ctl = a.take<uint32_t>(16);
     if (!a.ok()) return D3D_ERR_WORKSPACE;
     // tuning / test override: D3D_B200_NMS_PATH=dense (dense matrix, dense resolve) | tiles (dense tiles + list resolve); default: spatial
     const int path_knob = tuning(D3D_TUNE_NMS_PATH, 0);
@@ -1029,7 +1107,24 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
     if (smem > 40 * 1024) D3D_CUDA_TRY(cudaFuncSetAttribute(nms_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int resolve_nt = lists.blkcnt ? 512 : RESOLVE_THREADS;   // list walk: 64 1.9x slower, 256 +10 %, 512 = 1024 (tools/nms_stage_probe.sh)
     { const int v = tuning(D3D_TUNE_NMS_NT, 0); if (v >= 128 && v <= 1024 && v % 32 == 0) resolve_nt = v; }   // tuning override
-    nms_resolve_kernel<<<1, resolve_nt, smem, st>>>(mask, n, nwords, valid, order, suppressed, lists, stage_cap); D3D_LAUNCHED();
+    // parallel resolve for frames where the block-by-block walk is long; it leaves fix_ctl[2] = 1 when it produced the mask
+    const uint32_t *skip_if = nullptr;
+    const int fix_knob = tuning(D3D_TUNE_NMS_FIX, -1);   // 0: never, 1: always (where lists exist); default: from 128 blocks (8192 boxes) on
+    if (lists.blkcnt && (fix_knob == 1 || (fix_knob < 0 && nwords >= 128))) {
+        int dev = 0, nsm = 0, per_sm = 0;
+        D3D_CUDA_TRY(cudaGetDevice(&dev));
+        D3D_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+        D3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nms_fixpoint_kernel, NMS_FIX_THREADS, 0));
+        if (nsm > 0 && per_sm > 0) {
+            D3D_CUDA_TRY(cudaMemsetAsync(fix_ctl, 0, 64, st));
+            int64_t n_ = n, nwords_ = nwords;
+            const uint8_t *valid_ = valid; const uint32_t *order_ = order; uint8_t *sup_ = suppressed;
+            void *args[] = {&n_, &nwords_, &valid_, &order_, &sup_, &lists, &fix_state, &fix_blocked, &fix_ctl};
+            D3D_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)nms_fixpoint_kernel, dim3((unsigned)nsm), dim3(NMS_FIX_THREADS), args, 0, st)); D3D_LAUNCHED();
+            skip_if = fix_ctl + 2;
+        }
+    }
+    nms_resolve_kernel<<<1, resolve_nt, smem, st>>>(mask, n, nwords, valid, order, suppressed, lists, stage_cap, skip_if); D3D_LAUNCHED();
     return D3D_OK;
 }
 

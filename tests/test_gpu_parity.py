@@ -432,6 +432,31 @@ def test_nms_batch_equals_per_frame(dev, oracle):
     assert box2d_nms_batch([], []) == []
 
 
+def test_nms_parallel_resolve_equals_list_walk(dev, oracle):
+    """the resolve phase has two forms -- the block-by-block walk in score order on one SM and the parallel fixpoint (rounds of
+    keep / suppress decisions over the whole frame, default from 8192 boxes on) -- with the same keep mask: sizes on both sides of the
+    switch, both candidate back ends, score thresholds, and a chain of pairwise overlapping boxes whose depth exceeds the round limit
+    (the fixpoint gives up and the walk decides)"""
+    from d3d_b200.box import box2d_nms
+    rng = np.random.default_rng(11)
+    cases = [proposals(rng, n, nobj, extent=ext) for n, nobj, ext in ((64, 4, 10.0), (1000, 30, 30.0), (4097, 150, 60.0), (12000, 500, 75.0))]
+    m = 400   # unit squares 0.2 apart, each turned by 0.37 rad against the last: neighbours overlap with IoU 0.61, second neighbours with 0.39
+    chain = np.stack([0.2 * np.arange(m), np.zeros(m), np.ones(m), np.ones(m), 0.37 * np.arange(m)], 1)   # -> keep, suppress, keep, ... 200 decisions deep
+    cases.append((chain, np.linspace(1.0, 0.1, m)))
+    cases.append((np.concatenate([chain, cases[1][0]]), np.concatenate([np.linspace(1.0, 0.1, m), cases[1][1]])))
+    for P, sc in cases:
+        for thr, sthr in ((0.5, 0.0), (0.3, 0.4)):
+            exp = oracle.box2d_nms(P, sc, "rbox", iou_threshold=thr, score_threshold=sthr, cuda_score_rule=True)
+            for path in (None, 1):          # spatial candidates | dense tiles
+                for fix in (0, 1):          # list walk | parallel fixpoint
+                    _cabi.tuning_set("D3D_B200_NMS_PATH", path)
+                    _cabi.tuning_set("D3D_B200_NMS_FIX", fix)
+                    got = box2d_nms(_t(P, dev), _t(sc, dev), "rbox", iou_threshold=thr, score_threshold=sthr).cpu().numpy()
+                    assert np.array_equal(got, exp), (len(P), thr, sthr, path, fix, int((got != exp).sum()))
+    _cabi.tuning_set("D3D_B200_NMS_PATH", None)
+    _cabi.tuning_set("D3D_B200_NMS_FIX", None)
+
+
 def test_nms_back_ends_agree(dev):
     """the three NMS back ends (spatial candidate grid, dense tiles + list resolve, dense matrix + dense resolve) give the
     same keep mask (the knob is set through d3d_tuning_set: the environment is read once)"""
