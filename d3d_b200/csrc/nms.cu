@@ -804,9 +804,10 @@ template <typename T, bool AABB>
 __global__ void __launch_bounds__(NMSB_SORT_THREADS) nmsb_sort_kernel(const T *__restrict__ boxes, const T *__restrict__ scores, const int64_t *__restrict__ offs,
                                                                     int64_t stride, float score_thr, uint32_t *__restrict__ order, BoxRec<T> *__restrict__ recs,
                                                                     AABBRec<T> *__restrict__ arecs, T *__restrict__ raw, uint8_t *__restrict__ valid,
-                                                                    uint32_t *__restrict__ fail)
+                                                                    uint32_t *__restrict__ fail, const uint32_t *__restrict__ run_if)
 {
     extern __shared__ unsigned long long sk[];   // [npow] keys, then [npow] u32 indices
+    if (run_if && !*run_if) return;   // the edge-list path produced the keep masks
     const int64_t f = blockIdx.x, b = offs[f];
     int64_t n64 = offs[f + 1] - b;
     if (n64 > stride) { if (threadIdx.x == 0) *fail = 1u; n64 = stride; }   // longer than max_frame_boxes: cut (documented hard bound)
@@ -854,8 +855,9 @@ __global__ void __launch_bounds__(NMSB_SORT_THREADS) nmsb_sort_kernel(const T *_
 template <typename T>
 __global__ void __launch_bounds__(NMS_THREADS)
 nmsb_mask_rbox_kernel(const BoxRec<T> *__restrict__ recs, const T *__restrict__ raw, const int64_t *__restrict__ offs, int64_t stride, int64_t nwords, T thr,
-                      uint64_t *__restrict__ mask)
+                      uint64_t *__restrict__ mask, const uint32_t *__restrict__ run_if)
 {
+    if (run_if && !*run_if) return;   // the edge-list path produced the keep masks
     const int64_t f = blockIdx.z;
     const int64_t n = min(offs[f + 1] - offs[f], stride);
     if ((int64_t)blockIdx.x * NMS_TILE >= n) return;
@@ -891,11 +893,12 @@ nmsb_mask_aabb_kernel(const AABBRec<T> *__restrict__ recs_all, const int64_t *__
 // one CTA per frame: the dense walk over the frame's suppression matrix (same rule as nms_resolve_kernel's dense path)
 __global__ void __launch_bounds__(RESOLVE_THREADS)
 nmsb_resolve_kernel(const uint64_t *__restrict__ mask_all, const int64_t *__restrict__ offs, int64_t stride, int64_t nwords_max, const uint8_t *__restrict__ valid_all,
-                    const uint32_t *__restrict__ order_all, uint8_t *__restrict__ suppressed)
+                    const uint32_t *__restrict__ order_all, uint8_t *__restrict__ suppressed, const uint32_t *__restrict__ run_if)
 {
     extern __shared__ unsigned long long remv[];   // [nwords]
     __shared__ unsigned long long diag0[64];
     __shared__ unsigned long long keptbits;
+    if (run_if && !*run_if) return;   // the edge-list path produced the keep masks
     const int64_t f = blockIdx.x, b = offs[f];
     const int64_t n = min(offs[f + 1] - b, stride);
     if (n == 0) return;
@@ -940,6 +943,283 @@ nmsb_resolve_kernel(const uint64_t *__restrict__ mask_all, const int64_t *__rest
     }
 }
 
+// ------------------------------------------------------------------ batched rotated NMS over an edge list (threshold >= 0)
+// The dense path above tests every pair of a frame (64 frames x 4096 proposals: 545 M circle tests, 1.08 ms) because boxes that are
+// neighbours in score order are anywhere in the scene.  Greedy NMS does not need the score order as a memory order, only as a relation:
+// box a suppresses box b iff a is kept, overlaps b and comes first in (score descending, index ascending).  So a frame is sorted along
+// a Morton curve through the box centres instead, 64 consecutive boxes cover a small patch of the scene, a tile of two blocks whose
+// bounding rectangles do not meet is skipped without looking at its pairs, every surviving pair above the threshold becomes one
+// directed edge (first box -> later box; circle test per tile, clips over the flat candidate list), and the keep mask is the fixpoint of nms_fixpoint_kernel's rounds over that edge list -- one
+// CTA per frame, box states in shared memory.  An edge list that overflows its capacity (frames of near-identical boxes) raises a
+// device flag and the dense kernels, launched behind it, redo the batch.
+constexpr int NMSB_ECAP_PER_BOX = 32;   // edge capacity per frame = 32 x max_frame_boxes
+
+__device__ __forceinline__ uint32_t morton_part(uint32_t x) { x &= 0x3ffu; x = (x | (x << 8)) & 0x00ff00ffu; x = (x | (x << 4)) & 0x0f0f0f0fu; x = (x | (x << 2)) & 0x33333333u; return (x | (x << 1)) & 0x55555555u; }
+
+template <typename T>
+__global__ void __launch_bounds__(NMSB_SORT_THREADS) nmsb_morton_kernel(const T *__restrict__ boxes, const T *__restrict__ scores, const int64_t *__restrict__ offs,
+                                                                      int64_t stride, float score_thr, uint32_t *__restrict__ order, BoxRec<T> *__restrict__ recs,
+                                                                      T *__restrict__ raw, uint8_t *__restrict__ valid, uint64_t *__restrict__ skey,
+                                                                      float4 *__restrict__ bounds, uint32_t *__restrict__ fail)
+{
+    extern __shared__ unsigned long long sk[];   // [npow] keys, then [npow] u32 indices
+    __shared__ float red[4][32];
+    const int64_t f = blockIdx.x, b = offs[f];
+    int64_t n64 = offs[f + 1] - b;
+    if (n64 > stride) { if (threadIdx.x == 0) fail[0] = 1u; n64 = stride; }   // longer than max_frame_boxes: cut (documented hard bound)
+    const uint32_t n = (uint32_t)n64;
+    uint32_t npow = 64;
+    while (npow < n) npow <<= 1;
+    uint32_t *si = reinterpret_cast<uint32_t *>(sk + npow);
+    // extent of the finite box centres
+    float mnx = 3e38f, mxx = -3e38f, mny = 3e38f, mxy = -3e38f;
+    for (uint32_t p = threadIdx.x; p < n; p += NMSB_SORT_THREADS) {
+        const float x = (float)boxes[5 * (b + p)], y = (float)boxes[5 * (b + p) + 1];
+        if (fabsf(x) < 1e30f && fabsf(y) < 1e30f) { mnx = fminf(mnx, x); mxx = fmaxf(mxx, x); mny = fminf(mny, y); mxy = fmaxf(mxy, y); }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, d)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, d)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = mnx; red[1][threadIdx.x >> 5] = mxx; red[2][threadIdx.x >> 5] = mny; red[3][threadIdx.x >> 5] = mxy; }
+    __syncthreads();
+    for (int w = 0; w < NMSB_SORT_THREADS / 32; w++) { mnx = fminf(mnx, red[0][w]); mxx = fmaxf(mxx, red[1][w]); mny = fminf(mny, red[2][w]); mxy = fmaxf(mxy, red[3][w]); }
+    const float ivx = mxx > mnx ? 1023.f / (mxx - mnx) : 0.f, ivy = mxy > mny ? 1023.f / (mxy - mny) : 0.f;
+    for (uint32_t p = threadIdx.x; p < npow; p += NMSB_SORT_THREADS) {
+        unsigned long long key = ~0ull;
+        if (p < n) {   // the order only decides which tiles can be skipped, never a result: any value is a valid key (NaN -> cell 0)
+            const float x = (float)boxes[5 * (b + p)], y = (float)boxes[5 * (b + p) + 1];
+            const uint32_t qx = (uint32_t)fminf(fmaxf((x - mnx) * ivx, 0.f), 1023.f), qy = (uint32_t)fminf(fmaxf((y - mny) * ivy, 0.f), 1023.f);
+            key = morton_part(qx) | (morton_part(qy) << 1);
+        }
+        sk[p] = key;
+        si[p] = p < n ? p : 0xffffffffu;
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= npow; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < npow / 2; t += NMSB_SORT_THREADS) {
+                const uint32_t lo = ((t / j) * 2 * j) + (t % j), hi = lo + j;
+                const bool up = (lo & k) == 0;
+                const unsigned long long ka = sk[lo], kb = sk[hi];
+                const uint32_t ia = si[lo], ib = si[hi];
+                const bool gt = ka > kb || (ka == kb && ia > ib);
+                if (gt == up) { sk[lo] = kb; sk[hi] = ka; si[lo] = ib; si[hi] = ia; }
+            }
+            __syncthreads();
+        }
+    const int64_t base = f * stride;
+    for (int64_t p = threadIdx.x; p < stride; p += NMSB_SORT_THREADS) {
+        if (p < n) {
+            const uint32_t i = si[p];
+            order[base + p] = i;
+            const T *bx = boxes + 5 * (b + i);
+            recs[base + p] = make_box_rec<T>(bx[0], bx[1], bx[2], bx[3], bx[4]);
+            if (raw) { for (int q = 0; q < 5; q++) raw[5 * (base + p) + q] = bx[q]; }
+            valid[base + p] = scores[b + i] > score_thr ? 1 : 0;
+            skey[base + p] = desc_key(scores[b + i]);
+        } else {
+            BoxRec<T> r; r.cx = r.cy = r.c = r.s = r.hw = r.hh = r.area = T(0); r.rho = T(NAN); recs[base + p] = r;
+            valid[base + p] = 0;
+            skey[base + p] = ~0ull;
+        }
+    }
+    __syncthreads();   // this CTA's records are visible to its own threads
+    // bounding rectangle of every 64-box block's circles, rounded outwards (a block without a finite box gets an empty rectangle)
+    const int64_t nwords = stride / 64;
+    for (int64_t blk = threadIdx.x >> 5; blk < nwords; blk += NMSB_SORT_THREADS / 32) {
+        float lox = 3e38f, hix = -3e38f, loy = 3e38f, hiy = -3e38f;
+        for (int t = threadIdx.x & 31; t < 64; t += 32) {
+            const BoxRec<T> r = recs[base + blk * 64 + t];
+            const double cx = (double)r.cx, cy = (double)r.cy, rho = (double)r.rho;
+            if (fabs(cx) < 1e30 && fabs(cy) < 1e30 && rho < 1e30) {   // false for the NaN padding
+                lox = fminf(lox, __double2float_rd(cx - rho)); hix = fmaxf(hix, __double2float_ru(cx + rho));
+                loy = fminf(loy, __double2float_rd(cy - rho)); hiy = fmaxf(hiy, __double2float_ru(cy + rho));
+            }
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, d)); hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, d));
+            loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, d)); hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, d));
+        }
+        if ((threadIdx.x & 31) == 0) bounds[f * nwords + blk] = make_float4(lox, hix, loy, hiy);
+    }
+}
+
+// one CTA per (row block, frame): the column blocks cb >= rb whose rectangle meets the row block's are tested pair by pair with the
+// bounding-circle test; every surviving pair goes to the frame's candidate list as (first box | later box << 16), first = the one that
+// comes first in (score descending, index ascending).  The clips run in a second kernel over the flat list: the candidates of a frame
+// sit in a few diagonal tiles (the proposals around one object), and a kernel that clipped its own tiles would wait for those CTAs.
+template <typename T>
+__global__ void __launch_bounds__(NMS_THREADS)
+nmsb_cand_kernel(const BoxRec<T> *__restrict__ recs_all, const uint64_t *__restrict__ skey_all, const uint32_t *__restrict__ order_all,
+                 const float4 *__restrict__ bounds_all, const int64_t *__restrict__ offs, int64_t stride, int64_t nwords, uint32_t *__restrict__ cands_all,
+                 uint32_t *__restrict__ ccount, uint32_t ccap, size_t cand_stride, uint32_t *__restrict__ fail)
+{
+    constexpr int RW = NMS_TILE / NMS_WARPS;  // 16 rows per warp
+    constexpr int KC = NMS_TILE / 32;         // 2 column chunks
+    const int64_t f = blockIdx.y, rb = blockIdx.x;
+    const int64_t n = min(offs[f + 1] - offs[f], stride);
+    if (rb * NMS_TILE >= n) return;
+    const int64_t nb = (n + NMS_TILE - 1) / NMS_TILE;
+    const BoxRec<T> *recs = recs_all + f * stride;
+    const uint64_t *skey = skey_all + f * stride;
+    const uint32_t *order = order_all + f * stride;
+    const float4 *bounds = bounds_all + f * nwords;
+    uint32_t *cands = cands_all + (size_t)f * cand_stride;
+    __shared__ T ax_[NMS_TILE], ay_[NMS_TILE], ar_[NMS_TILE];
+    __shared__ unsigned long long kA[NMS_TILE], kB[NMS_TILE];
+    __shared__ uint32_t oA[NMS_TILE], oB[NMS_TILE];
+    __shared__ uint32_t queue[NMS_WARPS][64];
+    const unsigned lane = lane_id(), w = threadIdx.x >> 5;
+    if (threadIdx.x < NMS_TILE) {
+        const BoxRec<T> a = recs[rb * NMS_TILE + threadIdx.x];
+        ax_[threadIdx.x] = a.cx; ay_[threadIdx.x] = a.cy; ar_[threadIdx.x] = a.rho;
+        kA[threadIdx.x] = skey[rb * NMS_TILE + threadIdx.x]; oA[threadIdx.x] = order[rb * NMS_TILE + threadIdx.x];
+    }
+    // the column blocks whose rectangle meets this row block's, compacted by the first warps (one global round trip for all of them)
+    __shared__ uint16_t cbs[NMSB_MAX / NMS_TILE];
+    __shared__ uint32_t ncbs;
+    if (threadIdx.x == 0) ncbs = 0;
+    __syncthreads();
+    {
+        const float4 mine = bounds[rb];
+        for (int64_t cb0 = rb; cb0 < nb; cb0 += NMS_THREADS) {
+            const int64_t cb = cb0 + threadIdx.x;
+            bool meet = false;
+            if (cb < nb) { const float4 other = bounds[cb]; meet = mine.x <= other.y && other.x <= mine.y && mine.z <= other.w && other.z <= mine.w; }
+            const unsigned bal = __ballot_sync(0xffffffffu, meet);
+            uint32_t at = 0;
+            if (lane == 0 && bal) at = atomicAdd(&ncbs, (uint32_t)__popc(bal));
+            at = __shfl_sync(0xffffffffu, at, 0) + __popc(bal & lanemask_lt());
+            if (meet) cbs[at] = (uint16_t)cb;   // any order: every tile is independent
+        }
+    }
+    __syncthreads();
+    const uint32_t ntiles = ncbs;
+    uint32_t *q = queue[w];
+    unsigned head = 0, tail = 0;
+    auto flush = [&](bool all) {   // full groups of 32 candidates (at the end: the rest) leave for the frame's list with one reservation
+        while (tail - head >= 32u || (all && tail != head)) {
+            __syncwarp();
+            const unsigned cnt = min(tail - head, 32u);
+            uint32_t at = 0;
+            if (lane == 0) at = atomicAdd(ccount + f, cnt);
+            at = __shfl_sync(0xffffffffu, at, 0);
+            if (lane < cnt) {
+                if (at + lane < ccap) cands[at + lane] = q[(head + lane) & 63];
+                else fail[1] = 1u;
+            }
+            head += cnt;
+            __syncwarp();
+        }
+    };
+    for (uint32_t ti = blockIdx.z; ti < ntiles; ti += gridDim.z) {   // the row block's tiles are dealt to gridDim.z CTAs
+        const int64_t cb = cbs[ti];
+        __syncthreads();   // the previous tile's readers are done with the column arrays
+        T bx[KC], by[KC], br[KC];
+#pragma unroll
+        for (int k = 0; k < KC; k++) { const BoxRec<T> bb = recs[cb * NMS_TILE + k * 32 + lane]; bx[k] = bb.cx; by[k] = bb.cy; br[k] = bb.rho; }
+        if (threadIdx.x < NMS_TILE) { kB[threadIdx.x] = skey[cb * NMS_TILE + threadIdx.x]; oB[threadIdx.x] = order[cb * NMS_TILE + threadIdx.x]; }
+        __syncthreads();
+        const bool diag = (rb == cb);
+#pragma unroll 1
+        for (int r = 0; r < RW; r++) {
+            const unsigned rl = w * RW + r;
+            const T ax = ax_[rl], ay = ay_[rl], ar = ar_[rl];
+#pragma unroll
+            for (int k = 0; k < KC; k++) {
+                const unsigned cl = k * 32 + lane;
+                T dx = ax - bx[k], dy = ay - by[k], rs = ar + br[k];
+                const bool cand = (dx * dx + dy * dy <= rs * rs) && (!diag || cl > rl);   // every unordered pair once
+                const unsigned bal = __ballot_sync(0xffffffffu, cand);
+                if (cand) {
+                    const bool a_first = kA[rl] < kB[cl] || (kA[rl] == kB[cl] && oA[rl] < oB[cl]);
+                    const uint32_t pa = (uint32_t)(rb * NMS_TILE + rl), pb = (uint32_t)(cb * NMS_TILE + cl);
+                    q[(tail + __popc(bal & lanemask_lt())) & 63] = a_first ? (pa | (pb << 16)) : (pb | (pa << 16));
+                }
+                tail += __popc(bal);
+                flush(false);
+            }
+        }
+    }
+    flush(true);
+}
+
+// the clips of a frame's candidate list, 32 per warp step: candidate (first | later << 16) -> edge first -> later when iou(first, later) > threshold (nms.cpp:50)
+template <typename T>
+__global__ void __launch_bounds__(NMS_THREADS)
+nmsb_clip_kernel(const BoxRec<T> *__restrict__ recs_all, const T *__restrict__ raw_all, int64_t stride, T thr, const uint32_t *__restrict__ cands_all,
+                 const uint32_t *__restrict__ ccount, uint32_t ccap, size_t cand_stride, uint32_t *__restrict__ edges_all, uint32_t *__restrict__ ecount, uint32_t ecap,
+                 uint32_t *__restrict__ fail)
+{
+    const int64_t f = blockIdx.y;
+    const uint32_t nc = min(ccount[f], ccap);
+    const BoxRec<T> *recs = recs_all + f * stride;
+    const T *raw = raw_all ? raw_all + 5 * f * stride : nullptr;
+    const uint32_t *cands = cands_all + (size_t)f * cand_stride;
+    uint32_t *edges = edges_all + (size_t)f * ecap;
+    const unsigned lane = lane_id(), w = threadIdx.x >> 5;
+    for (uint32_t base = (blockIdx.x * NMS_WARPS + w) * 32u; base < nc; base += gridDim.x * NMS_WARPS * 32u) {
+        const bool live = base + lane < nc;
+        const uint32_t c = cands[live ? base + lane : nc - 1];
+        const uint32_t pa = c & 0xffffu, pb = c >> 16;
+        const BoxRec<T> A = recs[pa], B = recs[pb];
+        const T v = rbox_iou<T>(A, B);
+        const bool hit = live && over_threshold<T>(v, thr, raw, pa, pb);
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (bal) {
+            uint32_t at = 0;
+            if (lane == 0) at = atomicAdd(ecount + f, (uint32_t)__popc(bal));
+            at = __shfl_sync(0xffffffffu, at, 0) + __popc(bal & lanemask_lt());
+            if (hit) {
+                if (at < ecap) edges[at] = c;   // source | destination << 16
+                else fail[1] = 1u;
+            }
+        }
+    }
+}
+
+// one CTA per frame: rounds of keep / suppress decisions over the frame's edge list (see nms_fixpoint_kernel), states in shared memory
+__global__ void __launch_bounds__(1024)
+nmsb_fix_kernel(const uint32_t *__restrict__ edges_all, const uint32_t *__restrict__ ecount, uint32_t ecap, const int64_t *__restrict__ offs, int64_t stride,
+                const uint8_t *__restrict__ valid_all, const uint32_t *__restrict__ order_all, uint8_t *__restrict__ suppressed, const uint32_t *__restrict__ fail)
+{
+    __shared__ uint8_t state[NMSB_MAX];
+    __shared__ uint16_t blocked[NMSB_MAX];
+    if (fail[1]) return;   // an edge list overflowed: the dense kernels behind this one redo the batch (CTA-uniform)
+    const int64_t f = blockIdx.x, b = offs[f];
+    const uint32_t n = (uint32_t)min(offs[f + 1] - b, stride);
+    if (n == 0) return;
+    const uint32_t ne = min(ecount[f], ecap);
+    const uint32_t *edges = edges_all + (size_t)f * ecap;
+    const uint8_t *valid = valid_all + f * stride;
+    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) { state[j] = valid[j] ? NMS_UNDECIDED : NMS_SUPPRESSED; blocked[j] = 0; }
+    __syncthreads();
+    for (uint32_t round = 1;; round++) {
+        const uint16_t stamp = (uint16_t)(1u + (round - 1u) % 65535u);   // never 0; a stamp is only compared within its own round
+        if (stamp == 1u && round > 1u) { for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) blocked[j] = 0; __syncthreads(); }
+        for (uint32_t e = threadIdx.x; e < ne; e += blockDim.x) {
+            const uint32_t ed = edges[e], src = ed & 0xffffu, dst = ed >> 16;
+            const uint8_t ss = state[src];
+            if (ss == NMS_KEPT) state[dst] = NMS_SUPPRESSED;
+            else if (ss == NMS_UNDECIDED) blocked[dst] = stamp;   // a box that comes first and overlaps is still undecided
+        }
+        __syncthreads();
+        int left = 0;
+        for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+            if (state[j] == NMS_UNDECIDED) {
+                if (blocked[j] != stamp) state[j] = NMS_KEPT;
+                else left = 1;
+            }
+        }
+        if (!__syncthreads_or(left)) break;
+    }
+    const uint32_t *order = order_all + f * stride;
+    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) suppressed[b + order[j]] = state[j] == NMS_KEPT ? 0 : 1;
+}
+
 template <typename T> static size_t nmsb_ws_bytes(int64_t nframes, int64_t max_frame_boxes)
 {
     if (nframes < 1) nframes = 1;
@@ -947,8 +1227,9 @@ template <typename T> static size_t nmsb_ws_bytes(int64_t nframes, int64_t max_f
     const int64_t stride = cdiv(max_frame_boxes, NMS_TILE) * NMS_TILE, nwords = stride / 64;
     const size_t rec = sizeof(BoxRec<T>) > sizeof(AABBRec<T>) ? sizeof(BoxRec<T>) : sizeof(AABBRec<T>);
     const size_t per = align_up((size_t)stride * 4) + align_up((size_t)stride * rec) + align_up((size_t)stride * 5 * sizeof(T)) + align_up((size_t)stride) +
-                       align_up((size_t)stride * nwords * 8);
-    return per * (size_t)nframes + 4096;
+                       align_up((size_t)stride * nwords * 8) +
+                       align_up((size_t)stride * 8) + align_up((size_t)nwords * 16) + align_up((size_t)stride * NMSB_ECAP_PER_BOX * 4);   // edge-list path: score keys, block rectangles, edges
+    return per * (size_t)nframes + align_up((size_t)nframes * 8) + 4096;
 }
 
 template <typename T>
@@ -973,24 +1254,52 @@ static int nmsb_impl(const T *boxes, const T *scores, int64_t total, const int64
     T *raw = a.take<T>((size_t)nframes * stride * 5);
     uint8_t *valid = a.take<uint8_t>((size_t)nframes * stride);
     uint64_t *mask = a.take<uint64_t>((size_t)nframes * stride * nwords);
-    uint32_t *fail = a.take<uint32_t>(64);
+    uint32_t *fail = a.take<uint32_t>(64);   // [0] a frame was longer than max_frame_boxes (cut), [1] an edge list overflowed
+    uint64_t *skey = a.take<uint64_t>((size_t)nframes * stride);
+    float4 *bounds = a.take<float4>((size_t)nframes * nwords);
+    const uint32_t ecap = (uint32_t)(stride * NMSB_ECAP_PER_BOX);
+    uint32_t *edges = a.take<uint32_t>((size_t)nframes * ecap);
+    uint32_t *ecount = a.take<uint32_t>(2 * nframes), *ccount = ecount + nframes;
     if (!a.ok()) return D3D_ERR_WORKSPACE;
     uint32_t npow = 64;
     while (npow < (uint32_t)stride) npow <<= 1;
     const size_t sort_smem = (size_t)npow * 12;
+    const T thr = (T)iou_thr;
+    D3D_CUDA_TRY(cudaMemsetAsync(fail, 0, 256, st));
+    // rotated boxes, threshold >= 0 (pairs with disjoint bounding circles have IoU 0 and never exceed it): Morton order + edge list + fixpoint;
+    // D3D_B200_NMS_BATCH_PATH=dense forces the score-ordered dense path
+    const bool edge_path = !aabb && thr >= T(0) && tuning(D3D_TUNE_NMS_BATCH_PATH, 0) != 1;
+    const uint32_t *run_if = nullptr;
+    if (edge_path) {
+        D3D_CUDA_TRY(cudaMemsetAsync(ecount, 0, (size_t)nframes * 8, st));
+        if (sort_smem > 40 * 1024) D3D_CUDA_TRY(cudaFuncSetAttribute(nmsb_morton_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+        nmsb_morton_kernel<T><<<(unsigned)nframes, NMSB_SORT_THREADS, sort_smem, st>>>(boxes, scores, offs, stride, score_thr, order, (BoxRec<T> *)recs, recheck ? raw : nullptr, valid,
+                                                                                     skey, bounds, fail);
+        D3D_LAUNCHED();
+        // the candidate lists live in the frames' dense-matrix slabs (only the fallback behind the flag uses them as matrices)
+        const size_t cand_stride = (size_t)stride * nwords * 2;
+        const uint32_t ccap = (uint32_t)(cand_stride < 0xffffffffull ? cand_stride : 0xffffffffull);
+        nmsb_cand_kernel<T><<<dim3((unsigned)nwords, (unsigned)nframes, 4), NMS_THREADS, 0, st>>>((const BoxRec<T> *)recs, skey, order, bounds, offs, stride, nwords,
+                                                                                           reinterpret_cast<uint32_t *>(mask), ccount, ccap, cand_stride, fail);
+        D3D_LAUNCHED();
+        nmsb_clip_kernel<T><<<dim3(32, (unsigned)nframes), NMS_THREADS, 0, st>>>((const BoxRec<T> *)recs, recheck ? raw : nullptr, stride, thr, reinterpret_cast<const uint32_t *>(mask),
+                                                                              ccount, ccap, cand_stride, edges, ecount, ecap, fail);
+        D3D_LAUNCHED();
+        nmsb_fix_kernel<<<(unsigned)nframes, 1024, 0, st>>>(edges, ecount, ecap, offs, stride, valid, order, suppressed, fail); D3D_LAUNCHED();
+        run_if = fail + 1;   // the dense kernels below leave at once unless an edge list overflowed
+    }
     if (aabb) {
         if (sort_smem > 40 * 1024) D3D_CUDA_TRY(cudaFuncSetAttribute(nmsb_sort_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
-        nmsb_sort_kernel<T, true><<<(unsigned)nframes, NMSB_SORT_THREADS, sort_smem, st>>>(boxes, scores, offs, stride, score_thr, order, nullptr, (AABBRec<T> *)recs, nullptr, valid, fail);
+        nmsb_sort_kernel<T, true><<<(unsigned)nframes, NMSB_SORT_THREADS, sort_smem, st>>>(boxes, scores, offs, stride, score_thr, order, nullptr, (AABBRec<T> *)recs, nullptr, valid, fail, run_if);
     } else {
         if (sort_smem > 40 * 1024) D3D_CUDA_TRY(cudaFuncSetAttribute(nmsb_sort_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
-        nmsb_sort_kernel<T, false><<<(unsigned)nframes, NMSB_SORT_THREADS, sort_smem, st>>>(boxes, scores, offs, stride, score_thr, order, (BoxRec<T> *)recs, nullptr, recheck ? raw : nullptr, valid, fail);
+        nmsb_sort_kernel<T, false><<<(unsigned)nframes, NMSB_SORT_THREADS, sort_smem, st>>>(boxes, scores, offs, stride, score_thr, order, (BoxRec<T> *)recs, nullptr, recheck ? raw : nullptr, valid, fail, run_if);
     }
     D3D_LAUNCHED();
-    const T thr = (T)iou_thr;
     if (aabb) nmsb_mask_aabb_kernel<T><<<dim3((unsigned)nwords, (unsigned)nwords, (unsigned)nframes), NMS_TILE, 0, st>>>((const AABBRec<T> *)recs, offs, stride, nwords, thr, mask);
-    else nmsb_mask_rbox_kernel<T><<<dim3((unsigned)nwords, (unsigned)(nwords < 8 ? nwords : 8), (unsigned)nframes), NMS_THREADS, 0, st>>>((const BoxRec<T> *)recs, recheck ? raw : nullptr, offs, stride, nwords, thr, mask);
+    else nmsb_mask_rbox_kernel<T><<<dim3((unsigned)nwords, (unsigned)(edge_path ? 1 : (nwords < 8 ? nwords : 8)), (unsigned)nframes), NMS_THREADS, 0, st>>>((const BoxRec<T> *)recs, recheck ? raw : nullptr, offs, stride, nwords, thr, mask, run_if);
     D3D_LAUNCHED();
-    nmsb_resolve_kernel<<<(unsigned)nframes, 256, (size_t)nwords * 8, st>>>(mask, offs, stride, nwords, valid, order, suppressed);
+    nmsb_resolve_kernel<<<(unsigned)nframes, 256, (size_t)nwords * 8, st>>>(mask, offs, stride, nwords, valid, order, suppressed, run_if);
     D3D_LAUNCHED();
     return D3D_OK;
 }

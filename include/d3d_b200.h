@@ -55,7 +55,7 @@ const char *d3d_error_string(int status);
 const char *d3d_last_cuda_error(void);
 /* Tuning knobs select between back ends that produce identical results (names = the environment variables D3D_B200_NMS_PATH,
  * D3D_B200_NMS_STAGE, D3D_B200_NMS_NT, D3D_B200_CROP_PATH, D3D_B200_VOX_CLUSTER, D3D_B200_VOX_ROUTE, D3D_B200_VOX_MAXCL, D3D_B200_VOX_CF,
- * D3D_B200_VOX_ROLES, D3D_B200_SCATTER_PATH (gather | tiles), D3D_B200_NMS_FIX (0 | 1: resolve by the block walk | the parallel fixpoint), and D3D_B200_NMS_STOP, which truncates d3d_nms2d_* after a phase for phase timing).  The environment is read once, at the first use of a knob; this call overrides (set != 0) or clears (set == 0) a
+ * D3D_B200_VOX_ROLES, D3D_B200_SCATTER_PATH (gather | tiles), D3D_B200_NMS_FIX (0 | 1: resolve by the block walk | the parallel fixpoint), D3D_B200_NMS_BATCH_PATH (dense), and D3D_B200_NMS_STOP, which truncates d3d_nms2d_* after a phase for phase timing).  The environment is read once, at the first use of a knob; this call overrides (set != 0) or clears (set == 0) a
  * knob afterwards -- tests and tuning tools use it instead of changing the environment of a running process. */
 int d3d_tuning_set(const char *name, int value, int set);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
@@ -174,8 +174,12 @@ int d3d_nms2d_f64(const double *boxes, const double *scores, int64_t n, int iou_
  * back to back, frame_offsets DEVICE i64[nframes+1] as in the voxel ABI, suppressed u8[total] in the ORIGINAL order of every frame;
  * per frame exactly the result of d3d_nms2d_* (same order, thresholds and score rule).  max_frame_boxes: HARD UPPER BOUND of the frame
  * sizes (0 = unknown, assume `total`); frames of up to 8192 boxes are supported (more: D3D_ERR_UNSUPPORTED, use d3d_nms2d_* per frame);
- * supression_type: D3D_SUP_HARD only (soft-NMS is sequential in the scores).  Three launches for the whole batch: per-frame sort in shared
- * memory, dense 64x64 tiles of every frame's upper triangle, one resolve CTA per frame. */
+ * supression_type: D3D_SUP_HARD only (soft-NMS is sequential in the scores).  Rotated boxes with a threshold >= 0: every frame is sorted
+ * along a Morton curve through its box centres, tiles of two 64-box blocks whose bounding rectangles do not meet are skipped, the
+ * surviving pairs are clipped from one flat candidate list, and the keep mask is the fixpoint of keep / suppress rounds over the
+ * resulting edge list (one CTA per frame).  Axis-aligned boxes, negative thresholds and frames whose edge list overflows (device flag)
+ * take the dense form: per-frame sort by score in shared memory, 64x64 tiles of the upper triangle, one resolve CTA per frame.  Both
+ * forms give the keep mask of d3d_nms2d_* called per frame (D3D_B200_NMS_BATCH_PATH=dense forces the second). */
 size_t d3d_nms2d_batch_workspace_bytes(int64_t total, int64_t nframes, int64_t max_frame_boxes, int dtype);
 int d3d_nms2d_batch_f32(const float *boxes, const float *scores, int64_t total, const int64_t *frame_offsets, int64_t nframes,
                         int64_t max_frame_boxes, int iou_type, int supression_type, float iou_threshold, float score_threshold,

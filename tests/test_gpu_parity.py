@@ -430,6 +430,21 @@ def test_nms_batch_equals_per_frame(dev, oracle):
     kb = box2d_nms_batch([_t(b, dev) for b, _ in big], [_t(s, dev) for _, s in big], iou_method="rbox", iou_threshold=0.5)
     assert torch.equal(kb[0], box2d_nms(_t(big[0][0], dev), _t(big[0][1], dev), "rbox", iou_threshold=0.5))
     assert box2d_nms_batch([], []) == []
+    # the two batched back ends for rotated boxes (Morton order + edge list + fixpoint | score order + dense matrix + walk) agree; a frame of
+    # near-identical boxes overflows its edge list (n^2 / 2 edges) and the dense kernels behind the device flag redo the batch; equal scores
+    # (ties go to the lower index) and a negative threshold (always the dense path: disjoint boxes suppress too)
+    crowd = (np.tile(np.array([[1.0, 2.0, 3.0, 2.0, 0.3]]), (2500, 1)) + rng.normal(0, 1e-3, (2500, 5)), rng.random(2500))
+    ties = (frames[0][0], np.round(frames[0][1] * 4) / 4)
+    mixed = [frames[4], crowd, frames[6], ties]
+    for thr in (0.5, -1.0):
+        out = {}
+        for path in (None, 1):
+            _cabi.tuning_set("D3D_B200_NMS_BATCH_PATH", path)
+            out[path] = box2d_nms_batch([_t(b, dev) for b, _ in mixed], [_t(s, dev) for _, s in mixed], iou_method="rbox", iou_threshold=thr)
+        _cabi.tuning_set("D3D_B200_NMS_BATCH_PATH", None)
+        for (b, s), k0, k1 in zip(mixed, out[None], out[1]):
+            assert torch.equal(k0, k1), (thr, len(b))
+            assert torch.equal(k0, box2d_nms(_t(b, dev), _t(s, dev), "rbox", iou_threshold=thr)), (thr, len(b))
 
 
 def test_nms_parallel_resolve_equals_list_walk(dev, oracle):
