@@ -128,30 +128,39 @@ iou2dr_tile_kernel(const BoxRec<T> *__restrict__ recA, int64_t n, const BoxRec<T
     }
     __syncthreads();
 
-    // ---- scan: bounding-circle test of this warp's RW x TC pairs: 6 flops, a compare, a ballot and a select per pair
-    // (no popc, no shared-memory traffic on the per-pair path).
-    // The six flops of the circle test run on pairs of column chunks (FADD2 / FMUL2 / FFMA2 on sm_100a: two pairs per issue slot).
+    // ---- scan: reject test of this warp's RW x TC pairs: 8 flops, two compares, a ballot and a select per pair (no popc, no
+    // shared-memory traffic on the per-pair path).  A pair survives when the centre of box B, seen in box A's frame, lies inside A's
+    // rectangle grown by B's bounding radius (the separating-axis test on A's two axes with B replaced by its bounding circle):
+    // 28.6 % of the pairs of the C1 distribution against 32.8 % for the bounding-circle test it replaces (21 % truly overlap), and
+    // what it rejects has an empty intersection, stored as exactly +0.  The thresholds carry a relative slack of 2^-16 so that
+    // rounding in the frame change never rejects a pair whose IoU would exceed the tolerance.
+    // The flops run on pairs of column chunks (FADD2 / FMUL2 / FFMA2 on sm_100a: two pairs per issue slot).
     using PV = typename Vec2<T>::type;
     static_assert(KC % 2 == 0, "column chunks are tested two at a time");
     PV bx2[KC / 2], by2[KC / 2], br2[KC / 2];
+    const T slack = T(1) + T(1.52587890625e-5);
 #pragma unroll
     for (int k = 0; k < KC / 2; k++) {
         bx2[k] = P2<T>::mk(sm.sB[0][(2 * k) * 32 + lane], sm.sB[0][(2 * k + 1) * 32 + lane]);
         by2[k] = P2<T>::mk(sm.sB[1][(2 * k) * 32 + lane], sm.sB[1][(2 * k + 1) * 32 + lane]);
-        br2[k] = P2<T>::mk(sm.sB[6][(2 * k) * 32 + lane], sm.sB[6][(2 * k + 1) * 32 + lane]);
+        br2[k] = P2<T>::mk(sm.sB[6][(2 * k) * 32 + lane] * slack, sm.sB[6][(2 * k + 1) * 32 + lane] * slack);   // NaN for padding
     }
     static_assert(RW * KC <= 32, "one lane per tested (row, column chunk)");
     unsigned mybal = 0;     // lane r*KC+k keeps the ballot of (row r, columns k*32 .. k*32+31)
 #pragma unroll
     for (int r = 0; r < RW; r++) {
         const BoxRec<T> &a = sm.sA[w * RW + r];
-        const PV ax2 = P2<T>::mk(a.cx, a.cx), ay2 = P2<T>::mk(a.cy, a.cy), ar2 = P2<T>::mk(a.rho, a.rho);
+        const T grow = (a.hw + a.hh) * T(1.52587890625e-5) + (a.rho - a.rho);   // NaN for a padding row: every test fails
+        const PV ax2 = P2<T>::mk(a.cx, a.cx), ay2 = P2<T>::mk(a.cy, a.cy);
+        const PV ac2 = P2<T>::mk(a.c, a.c), as2 = P2<T>::mk(a.s, a.s), nas2 = P2<T>::mk(-a.s, -a.s);
+        const PV aw2 = P2<T>::mk(a.hw + grow, a.hw + grow), ah2 = P2<T>::mk(a.hh + grow, a.hh + grow);
 #pragma unroll
         for (int k = 0; k < KC / 2; k++) {
-            const PV dx = P2<T>::sub(ax2, bx2[k]), dy = P2<T>::sub(ay2, by2[k]), rs = P2<T>::add(ar2, br2[k]);
-            const PV d2 = P2<T>::fma(dy, dy, P2<T>::mul(dx, dx)), r2 = P2<T>::mul(rs, rs);
-            const unsigned bal0 = __ballot_sync(0xffffffffu, d2.x <= r2.x);   // false for NaN padding
-            const unsigned bal1 = __ballot_sync(0xffffffffu, d2.y <= r2.y);
+            const PV dx = P2<T>::sub(bx2[k], ax2), dy = P2<T>::sub(by2[k], ay2);
+            const PV xl = P2<T>::fma(dy, as2, P2<T>::mul(dx, ac2)), yl = P2<T>::fma(dx, nas2, P2<T>::mul(dy, ac2));
+            const PV tx = P2<T>::add(aw2, br2[k]), ty = P2<T>::add(ah2, br2[k]);
+            const unsigned bal0 = __ballot_sync(0xffffffffu, Num<T>::abs_(xl.x) <= tx.x && Num<T>::abs_(yl.x) <= ty.x);   // false for NaN padding
+            const unsigned bal1 = __ballot_sync(0xffffffffu, Num<T>::abs_(xl.y) <= tx.y && Num<T>::abs_(yl.y) <= ty.y);
             if (lane == (unsigned)(r * KC + 2 * k)) mybal = bal0;
             if (lane == (unsigned)(r * KC + 2 * k + 1)) mybal = bal1;
         }
