@@ -1078,11 +1078,13 @@ nmsb_cand_kernel(const BoxRec<T> *__restrict__ recs_all, const uint64_t *__restr
         ax_[threadIdx.x] = a.cx; ay_[threadIdx.x] = a.cy; ar_[threadIdx.x] = a.rho;
         kA[threadIdx.x] = skey[rb * NMS_TILE + threadIdx.x]; oA[threadIdx.x] = order[rb * NMS_TILE + threadIdx.x];
     }
-    // the column blocks whose rectangle meets this row block's, compacted by the first warps (one global round trip for all of them)
+    // the column blocks whose rectangle meets this row block's, compacted in ascending order (one global round trip for all of them).
+    // The order matters: the gridDim.z CTAs of a row block each build this list for themselves and take every gridDim.z-th entry of
+    // it, so all of them must arrive at the SAME list (positions handed out by an atomic counter differ from CTA to CTA: tiles were
+    // then clipped twice or never)
     __shared__ uint16_t cbs[NMSB_MAX / NMS_TILE];
-    __shared__ uint32_t ncbs;
-    if (threadIdx.x == 0) ncbs = 0;
-    __syncthreads();
+    __shared__ uint32_t wbal[NMS_WARPS];
+    uint32_t ncbs = 0;
     {
         const float4 mine = bounds[rb];
         for (int64_t cb0 = rb; cb0 < nb; cb0 += NMS_THREADS) {
@@ -1090,10 +1092,13 @@ nmsb_cand_kernel(const BoxRec<T> *__restrict__ recs_all, const uint64_t *__restr
             bool meet = false;
             if (cb < nb) { const float4 other = bounds[cb]; meet = mine.x <= other.y && other.x <= mine.y && mine.z <= other.w && other.z <= mine.w; }
             const unsigned bal = __ballot_sync(0xffffffffu, meet);
-            uint32_t at = 0;
-            if (lane == 0 && bal) at = atomicAdd(&ncbs, (uint32_t)__popc(bal));
-            at = __shfl_sync(0xffffffffu, at, 0) + __popc(bal & lanemask_lt());
-            if (meet) cbs[at] = (uint16_t)cb;   // any order: every tile is independent
+            __syncthreads();   // the previous pass is done with wbal
+            if (lane == 0) wbal[w] = bal;
+            __syncthreads();
+            uint32_t at = ncbs;
+#pragma unroll
+            for (int ww = 0; ww < NMS_WARPS; ww++) { const uint32_t c = (uint32_t)__popc(wbal[ww]); if (ww < (int)w) at += c; ncbs += c; }
+            if (meet) cbs[at + __popc(bal & lanemask_lt())] = (uint16_t)cb;
         }
     }
     __syncthreads();

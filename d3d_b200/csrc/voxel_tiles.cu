@@ -68,7 +68,10 @@ constexpr int VT_STILE = VT_THREADS * VT_SPT;     // 8192 points per scan tile
 #endif
 constexpr int VT_BT = D3D_VT_BT;                  // threads of a bucket CTA
 constexpr int VT_EPT = D3D_VT_EPT;                // queue entries per bucket thread kept in registers (longer queues: the rest is re-read)
-constexpr int VT_QCAP = 1024;                     // largest queue a bucket CTA takes
+#ifndef D3D_VT_QCAP
+#define D3D_VT_QCAP 1024
+#endif
+constexpr int VT_QCAP = D3D_VT_QCAP;              // largest queue a bucket CTA takes
 constexpr int VT_SMAX = VT_QCAP <= 512 ? 512 : (VT_QCAP <= 1024 ? 1024 : 2048);   // table slots per bucket (maximum)
 constexpr int VT_MAXK = 8;                        // deepest min-cascade (max_points of the TRIM filter)
 constexpr int VT_POOL = 64;                       // crowded-voxel records per bucket

@@ -472,6 +472,34 @@ def test_nms_parallel_resolve_equals_list_walk(dev, oracle):
     _cabi.tuning_set("D3D_B200_NMS_FIX", None)
 
 
+def test_sort_forms_agree(dev):
+    """the stable radix sort has two forms -- five launches per pass (any size) and, up to 131 072 keys, every pass inside one
+    cooperative launch (the NMS score sort) -- with the same order: NMS keep masks with tied scores (ties go to the lower index: the
+    sort must be stable) and the sort back end of the voxelizer, at sizes around the tile (2048) and the switch"""
+    from d3d_b200.box import box2d_nms
+    from d3d_b200.voxel import VoxelGenerator
+    rng = np.random.default_rng(21)
+    for n in (1, 33, 2048, 2049, 20000, 131072, 131073):
+        P, sc = proposals(rng, n, max(1, n // 25), extent=75.0)
+        sc = np.round(sc * 64) / 64          # many equal scores
+        out = []
+        for coop in (0, 1):
+            _cabi.tuning_set("D3D_B200_SORT_COOP", coop)
+            out.append(box2d_nms(_t(P, dev), _t(sc, dev), "rbox", iou_threshold=0.5).cpu().numpy())
+        _cabi.tuning_set("D3D_B200_SORT_COOP", None)
+        assert np.array_equal(out[0], out[1]), n
+    pts = lidar(rng, 60000)
+    res = []
+    for coop in (0, 1):
+        _cabi.tuning_set("D3D_B200_SORT_COOP", coop)
+        gen = VoxelGenerator([0, 70.4, -40, 40, -3, 1], [1408, 1600, 40], max_points=5, max_points_filter="trim")
+        gen.algo = "sort"
+        res.append({k: v.cpu().numpy() for k, v in gen(_t(pts, dev)).items()})
+    _cabi.tuning_set("D3D_B200_SORT_COOP", None)
+    for k in res[0]:
+        assert np.array_equal(res[0][k], res[1][k]), k
+
+
 def test_nms_back_ends_agree(dev):
     """the three NMS back ends (spatial candidate grid, dense tiles + list resolve, dense matrix + dense resolve) give the
     same keep mask (the knob is set through d3d_tuning_set: the environment is read once)"""

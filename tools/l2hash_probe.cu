@@ -97,6 +97,55 @@ __global__ void __launch_bounds__(256, CTAS) k_lookup(uint32_t L, const unsigned
     if ((tid & 31) == 0) { atomicAdd(stats + 0, (unsigned long long)heads); atomicAdd(stats + 1, (unsigned long long)joins); atomicAdd(stats + 2, (unsigned long long)probes); }
 }
 
+
+// ---- second experiment: two bitmaps per frame (seen once / seen twice) as an exact singleton filter in front of the bucket path
+__global__ void __launch_bounds__(256, 8) k_mark(const float4 *pts, uint32_t L, uint32_t *seen1, uint32_t *seen2, uint32_t lgbits, uint32_t *word, Geo g)
+{
+    const uint32_t f = blockIdx.y, t0 = blockIdx.x * 1024u, tid = threadIdx.x;
+    const float4 *p = pts + (size_t)f * L;
+    uint32_t *s1 = seen1 + ((size_t)f << (lgbits - 5)), *s2 = seen2 + ((size_t)f << (lgbits - 5));
+    uint32_t *w = word + (size_t)f * L;
+    float4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const uint32_t i = t0 + u * 256 + tid; q[u] = i < L ? __ldg(p + i) : make_float4(1e9f, 0, 0, 0); }
+    uint32_t old[4], bit[4], wd[4]; bool act[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const uint32_t i = t0 + u * 256 + tid;
+        uint32_t key;
+        act[u] = cell(g, q[u], &key) && i < L;
+        if (i < L) w[i] = act[u] ? key : 0x40000000u;
+        const uint32_t h = (key * 0x9E3779B1u) >> (32 - lgbits);
+        wd[u] = h >> 5; bit[u] = 1u << (h & 31);
+        if (act[u]) old[u] = atomicOr(s1 + wd[u], bit[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (act[u] && (old[u] & bit[u])) atomicOr(s2 + wd[u], bit[u]);
+}
+__global__ void __launch_bounds__(256, 8) k_filter(uint32_t L, const uint32_t *seen2, uint32_t lgbits, const uint32_t *word, unsigned long long *stats)
+{
+    const uint32_t f = blockIdx.y, t0 = blockIdx.x * 1024u, tid = threadIdx.x;
+    const uint32_t *s2 = seen2 + ((size_t)f << (lgbits - 5));
+    const uint32_t *w = word + (size_t)f * L;
+    uint32_t shared_pts = 0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const uint32_t i = t0 + u * 256 + tid;
+        const uint32_t key = i < L ? w[i] : 0x40000000u;
+        if ((key >> 30) == 0) {
+            const uint32_t h = (key * 0x9E3779B1u) >> (32 - lgbits);
+            shared_pts += (__ldcg(s2 + (h >> 5)) >> (h & 31)) & 1u;
+        }
+    }
+    __shared__ uint32_t tot;
+    if (tid == 0) tot = 0;
+    __syncthreads();
+    for (int d = 16; d; d >>= 1) shared_pts += __shfl_xor_sync(~0u, shared_pts, d);
+    if ((tid & 31) == 0 && shared_pts) atomicAdd(&tot, shared_pts);
+    __syncthreads();
+    if (tid == 0) atomicAdd(stats + (blockIdx.x & 7), (unsigned long long)tot);
+}
+
 static float frand(uint64_t &s) { s = s * 6364136223846793005ull + 1442695040888963407ull; return (float)((s >> 40) & 0xffffff) / 16777216.0f; }
 
 int main(int argc, char **argv)
@@ -136,7 +185,7 @@ int main(int argc, char **argv)
     cudaMalloc(&tab, (size_t)NF * maxslots * 8);
     cudaEvent_t e[4]; for (auto &x : e) cudaEventCreate(&x);
     const float factors[] = {1.25f, 1.5f, 2.2f, 3.0f};
-    for (int ctas = 6; ctas <= 8; ctas += 2)
+    for (int ctas = 6; ctas <= 8 && argc <= 2; ctas += 2)
     for (float fac : factors) {
         const uint32_t nslots = (uint32_t)(L * fac);
         float best[3] = {1e9f, 1e9f, 1e9f};
@@ -160,6 +209,30 @@ int main(int argc, char **argv)
         printf("ctas/SM %d slots %.2f L (%.1f MB per %d frames): memset %.1f us, build %.1f us, lookup %.1f us | heads %llu joiners %llu lookup probes %llu  %s  [%s]\n",
                ctas, fac, (double)NF * nslots * 8 / 1e6, NF, best[0] * 1e3, best[1] * 1e3, best[2] * 1e3, st[0], st[1], st[2],
                (st[0] == tv && st[1] == tj) ? "MATCH" : "MISMATCH", cudaGetErrorString(cudaGetLastError()));
+    }
+    {
+        uint32_t *s1, *s2;
+        cudaMalloc(&s1, (size_t)NF << 19); cudaMalloc(&s2, (size_t)NF << 19);
+        for (uint32_t lgbits = 19; lgbits <= 22; lgbits++) {
+            float best[3] = {1e9f, 1e9f, 1e9f};
+            unsigned long long st[8];
+            for (int rep = 0; rep < 5; rep++) {
+                cudaMemsetAsync(stats, 0, 64);
+                cudaEventRecord(e[0]);
+                cudaMemsetAsync(s1, 0, (size_t)NF << (lgbits - 3)); cudaMemsetAsync(s2, 0, (size_t)NF << (lgbits - 3));
+                cudaEventRecord(e[1]);
+                k_mark<<<dim3((L + 1023) / 1024, NF), 256>>>(pts, L, s1, s2, lgbits, word, g);
+                cudaEventRecord(e[2]);
+                k_filter<<<dim3((L + 1023) / 1024, NF), 256>>>(L, s2, lgbits, word, stats);
+                cudaEventRecord(e[3]);
+                cudaEventSynchronize(e[3]);
+                for (int k = 0; k < 3; k++) { float ms; cudaEventElapsedTime(&ms, e[k], e[k + 1]); if (ms < best[k]) best[k] = ms; }
+                cudaMemcpy(st, stats, 64, cudaMemcpyDeviceToHost);
+            }
+            unsigned long long sh = 0; for (int k = 0; k < 8; k++) sh += st[k];
+            printf("bitmaps of 2^%u bits per frame: memset %.1f us, mark %.1f us, filter %.1f us | points sent to the bucket path %llu of %llu in range (%.1f %%; truly shared %.1f %%)  [%s]\n",
+                   lgbits, best[0] * 1e3, best[1] * 1e3, best[2] * 1e3, sh, tv + tj, 100.0 * sh / (tv + tj), 100.0 * (tj + (tv - (tv + tj - 2 * tj > 0 ? 0 : 0))) / (tv + tj), cudaGetErrorString(cudaGetLastError()));
+        }
     }
     return 0;
 }
