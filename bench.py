@@ -648,7 +648,8 @@ def bench_iou(args, rank, world, barrier, f64=False):
     hbm, _ = peaks()
     clk = cs.summary()
     roof = alu_roofline(code, ach, clk)
-    roof.update(algorithmic_flops=f"{W_CAND:.0f} per candidate pair + {W_REJ:.0f} per rejected pair (SURVEY.md 8(d))",
+    roof.update(algorithmic_flops=f"{W_CAND:.0f} per candidate pair + {W_REJ:.0f} per rejected pair (SURVEY.md 8(d): a candidate is a pair whose bounding circles "
+                                  "overlap, counted by count_candidates_kernel; the tile kernel's own reject test passes fewer pairs to the clip)",
                 store_gbs=tot_pairs * esz / (ms * 1e-3) / 1e9 / world, store_frac_of_hbm=tot_pairs * esz / (ms * 1e-3) / 1e9 / world / hbm)
     return dict(metric="rotated-IoU pairs/sec", unit="pairs/s", value=tot_pairs / (ms * 1e-3), ms_per_step=ms, dtype="f64" if f64 else "f32", scaling="strong",
                 gpu_launches=int(launches),
