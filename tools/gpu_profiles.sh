@@ -14,3 +14,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 tail -1 gpurun_out/launches_bench.csv | cut -c1-200
 ncu --set full --clock-control none --import-source on -k regex:iou2dr_tile_kernel -s 1 -c 1 -f -o gpurun_out/prof_iou_f64 python bench.py --op iou_f64 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_iou_f64.log 2>&1
 tail -2 gpurun_out/ncu_iou_f64.log
+ncu --set full --clock-control none --import-source on -k regex:iou2dr_tile_kernel -s 1 -c 1 -f -o gpurun_out/prof_iou_f32 python bench.py --op iou --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_iou_f32.log 2>&1
+tail -2 gpurun_out/ncu_iou_f32.log
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:nms -c 200 --csv --log-file gpurun_out/launches_c5.csv python bench.py --op c5 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/c5_under_ncu.log 2>&1
+tail -1 gpurun_out/launches_c5.csv | cut -c1-200
