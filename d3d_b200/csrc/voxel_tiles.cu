@@ -258,10 +258,11 @@ __global__ void __launch_bounds__(VT_THREADS, D3D_VT_SCTAS) vt_split_kernel(cons
 }
 
 // ------------------------------------------------------------------------------------------------ bucket
-// table slot: .x cell key, .y smallest point index, .z points, .w record of a crowded voxel
+// table slot s: tkey cell key, tmin smallest point index, tcnt points, trec record of a crowded voxel
 __global__ void __launch_bounds__(VT_BT, D3D_VT_BCTAS) vt_bucket_kernel(const VtArgs a)
 {
-    __shared__ uint4 tab[VT_SMAX];
+    // one array per field: the 32 lanes of an atomic on one field spread over all 32 banks (16-byte slots put a field on 8 of them)
+    __shared__ __align__(16) uint32_t tkey[VT_SMAX], tmin[VT_SMAX], tcnt[VT_SMAX], trec[VT_SMAX];
     __shared__ uint32_t pool[VT_POOL * VT_MAXK];   // records of VT_MAXK indices
     __shared__ uint32_t misc[4];                   // [1] records in use, [2] failure
     const VtGeom &g = a.g;
@@ -290,7 +291,11 @@ __global__ void __launch_bounds__(VT_BT, D3D_VT_BCTAS) vt_bucket_kernel(const Vt
     lgS = lgS < 6u ? 6u : lgS;
     if ((1u << lgS) > (uint32_t)VT_SMAX) lgS = 31u - (uint32_t)__clz(VT_SMAX);
     const uint32_t S = 1u << lgS, smask = S - 1, hshift = 32u - lgS;
-    for (uint32_t s = tid; s < S; s += VT_BT) tab[s] = make_uint4(VT_NONE, VT_NONE, 0u, 0u);
+    for (uint32_t s = tid; s < S / 4; s += VT_BT) {
+        reinterpret_cast<uint4 *>(tkey)[s] = make_uint4(VT_NONE, VT_NONE, VT_NONE, VT_NONE);
+        reinterpret_cast<uint4 *>(tmin)[s] = make_uint4(VT_NONE, VT_NONE, VT_NONE, VT_NONE);
+        reinterpret_cast<uint4 *>(tcnt)[s] = make_uint4(0u, 0u, 0u, 0u);
+    }
     if (tid == 0) { misc[1] = 0; misc[2] = 0; }
     __syncthreads();
     if (tid == 0) qcount[bk] = 0;   // everybody has read it: the counter is ready for the next chunk
@@ -298,43 +303,45 @@ __global__ void __launch_bounds__(VT_BT, D3D_VT_BCTAS) vt_bucket_kernel(const Vt
 
     // per-entry steps; the first VT_EPT entries of a thread live in registers with their slot, the rest of a long queue (rare) is read
     // again from the queue and finds its slot by probing
-    auto insert = [&](const uint2 x) -> uint32_t {
-        uint32_t s = vt_home(x.x, hshift);
-        for (uint32_t it = 0; it <= S; it++) {
-            const uint32_t old = atomicCAS(&tab[s].x, VT_NONE, x.x);
-            if (old == VT_NONE || old == x.x) break;
-            s = (s + 1) & smask;
-        }
-        atomicMin(&tab[s].y, x.y);
-        atomicAdd(&tab[s].z, 1u);
-        return s;
-    };
-    auto find = [&](const uint32_t key) -> uint32_t {
-        uint32_t s = vt_home(key, hshift);
-        while (tab[s].x != key) s = (s + 1) & smask;
-        return s;
-    };
     bool anyc = false;
-    auto open_rec = [&](const uint2 x, const uint32_t s) {
-        const uint4 t = tab[s];
-        if (t.z > cthr) {
+    // counts the point; the (K+1)-th arrival of a voxel opens the record of its K smallest indices (exactly one thread sees the count step
+    // from K to K+1, and the records are only read after the next barrier)
+    auto count_and_open = [&](const uint32_t s) {
+        const uint32_t c = atomicAdd(&tcnt[s], 1u);
+        if (c >= cthr) {
             anyc = true;
-            if (t.y == x.y) {   // the voxel's first point opens the record
+            if (c == cthr) {
                 const uint32_t r = atomicAdd(&misc[1], 1u);
                 if (r >= (uint32_t)VT_POOL) misc[2] = 1u;
                 else {
-                    tab[s].w = r;
+                    trec[s] = r;
                     for (uint32_t j = 0; j < K; j++) pool[r * VT_MAXK + j] = VT_NONE;
                 }
             }
         }
     };
+    auto insert = [&](const uint2 x) -> uint32_t {
+        uint32_t s = vt_home(x.x, hshift);
+        for (uint32_t it = 0; it <= S; it++) {
+            const uint32_t old = atomicCAS(&tkey[s], VT_NONE, x.x);
+            if (old == VT_NONE || old == x.x) break;
+            s = (s + 1) & smask;
+        }
+        atomicMin(&tmin[s], x.y);
+        count_and_open(s);
+        return s;
+    };
+    auto find = [&](const uint32_t key) -> uint32_t {
+        uint32_t s = vt_home(key, hshift);
+        while (tkey[s] != key) s = (s + 1) & smask;
+        return s;
+    };
     auto cascade = [&](const uint2 x, const uint32_t s) {
-        const uint4 t = tab[s];
-        if (t.z > cthr) {
+        const uint4 t = make_uint4(tkey[s], tmin[s], tcnt[s], trec[s]);
+        if (t.z > cthr && x.y != t.y) {   // the smallest index is already known (tmin): the record keeps the next K - 1
             uint32_t *rec = pool + t.w * VT_MAXK;
             uint32_t v = x.y;
-            for (uint32_t j = 0; j < K; j++) {
+            for (uint32_t j = 0; j + 1 < K; j++) {
                 const uint32_t old = atomicMin(&rec[j], v);
                 v = max(old, v);              // the larger value moves on to the next level
                 if (v == VT_NONE) break;
@@ -342,13 +349,13 @@ __global__ void __launch_bounds__(VT_BT, D3D_VT_BCTAS) vt_bucket_kernel(const Vt
         }
     };
     auto reply = [&](const uint2 x, const uint32_t s) {
-        const uint4 t = tab[s];
+        const uint4 t = make_uint4(tkey[s], tmin[s], tcnt[s], trec[s]);
         if (t.z != 1u) {
             uint32_t r;
             if ((long long)t.z < (long long)a.min_points) r = VT_W_NONE;
             else if (x.y == t.y) { r = VT_W_HEAD | min(t.z, VT_VAL); vt_st32(hkey + x.y, x.x, keep); }
             else {
-                const bool kept = !(t.z > cthr) || x.y <= pool[t.w * VT_MAXK + K - 1];
+                const bool kept = !(t.z > cthr) || (K >= 2u && x.y <= pool[t.w * VT_MAXK + K - 2]);
                 r = kept ? (VT_W_JOIN | t.y) : VT_W_NONE;
             }
             vt_st32(word + x.y, r, keep);
@@ -363,7 +370,7 @@ __global__ void __launch_bounds__(VT_BT, D3D_VT_BCTAS) vt_bucket_kernel(const Vt
     for (int k = 0; k < VT_EPT; k++) {
         sl[k] = 0; first[k] = VT_NONE;
         if (k * VT_BT >= n) break;
-        if (tid + k * VT_BT < n) { sl[k] = vt_home(en[k].x, hshift); first[k] = atomicCAS(&tab[sl[k]].x, VT_NONE, en[k].x); }
+        if (tid + k * VT_BT < n) { sl[k] = vt_home(en[k].x, hshift); first[k] = atomicCAS(&tkey[sl[k]], VT_NONE, en[k].x); }
     }
 #pragma unroll
     for (int k = 0; k < VT_EPT; k++) {
@@ -372,34 +379,24 @@ __global__ void __launch_bounds__(VT_BT, D3D_VT_BCTAS) vt_bucket_kernel(const Vt
             uint32_t s = sl[k], old = first[k];
             for (uint32_t it = 0; it <= S && !(old == VT_NONE || old == en[k].x); it++) {
                 s = (s + 1) & smask;
-                old = atomicCAS(&tab[s].x, VT_NONE, en[k].x);
+                old = atomicCAS(&tkey[s], VT_NONE, en[k].x);
             }
-            atomicMin(&tab[s].y, en[k].y);
-            atomicAdd(&tab[s].z, 1u);
+            atomicMin(&tmin[s], en[k].y);
+            count_and_open(s);
             sl[k] = s;
         }
     }
     for (uint32_t e = rest; e < n; e += VT_BT) insert(vt_ld64(q + e, keep));
-    __syncthreads();
-
     // voxels with more than K points: their K smallest indices
-    if (cthr != VT_NONE) {
+    if (__syncthreads_or((int)anyc)) {
+        if (misc[2]) { if (tid == 0) *a.bail = 1u; return; }
 #pragma unroll
         for (int k = 0; k < VT_EPT; k++) {
             if (k * VT_BT >= n) break;
-            if (tid + k * VT_BT < n) open_rec(en[k], sl[k]);
+            if (tid + k * VT_BT < n) cascade(en[k], sl[k]);
         }
-        for (uint32_t e = rest; e < n; e += VT_BT) { const uint2 x = vt_ld64(q + e, keep); open_rec(x, find(x.x)); }
-        if (__syncthreads_or((int)anyc)) {
-            if (misc[2]) { if (tid == 0) *a.bail = 1u; return; }
-#pragma unroll
-            for (int k = 0; k < VT_EPT; k++) {
-                if (k * VT_BT >= n) break;
-                if (tid + k * VT_BT < n) cascade(en[k], sl[k]);
-            }
-            for (uint32_t e = rest; e < n; e += VT_BT) { const uint2 x = vt_ld64(q + e, keep); cascade(x, find(x.x)); }
-            __syncthreads();
-        }
+        for (uint32_t e = rest; e < n; e += VT_BT) { const uint2 x = vt_ld64(q + e, keep); cascade(x, find(x.x)); }
+        __syncthreads();
     }
 
     // a new word for every point that shares its voxel (a point that hears nothing is the only point of its voxel)

@@ -673,7 +673,8 @@ def test_voxel_descending_and_crowded(dev, oracle):
     from d3d_b200.voxel import VoxelGenerator
     pts = lidar(np.random.default_rng(8), 30000)
     b, s = [0, 70.4, -40, 40, -3, 1], [44, 50, 4]
-    for kw in (dict(max_points=5, max_points_filter="trim"), dict(max_points=7, max_points_filter="trim", max_voxels=60, max_voxels_filter="trim"),
+    for kw in (dict(max_points=5, max_points_filter="trim"), dict(max_points=1, max_points_filter="trim"), dict(max_points=2, max_points_filter="trim"),
+               dict(max_points=8, max_points_filter="trim"), dict(max_points=7, max_points_filter="trim", max_voxels=60, max_voxels_filter="trim"),
                dict(max_voxels=50, max_voxels_filter="descending", min_points=3),
                dict(max_voxels=5000, max_voxels_filter="descending", max_points=4, max_points_filter="trim"),
                dict(dense=True, max_points=4, max_voxels=300, reduction="mean"), dict(dense=True, max_points=9, max_voxels=9000, reduction="min")):
