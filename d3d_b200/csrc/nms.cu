@@ -823,7 +823,7 @@ __global__ void __launch_bounds__(NMSB_SORT_THREADS) nmsb_sort_kernel(const T *_
     for (uint32_t k = 2; k <= npow; k <<= 1)
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
             for (uint32_t t = threadIdx.x; t < npow / 2; t += NMSB_SORT_THREADS) {
-                const uint32_t lo = ((t / j) * 2 * j) + (t % j), hi = lo + j;
+                const uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo + j;   // j is a power of two
                 const bool up = (lo & k) == 0;
                 const unsigned long long ka = sk[lo], kb = sk[hi];
                 const uint32_t ia = si[lo], ib = si[hi];
@@ -997,18 +997,69 @@ __global__ void __launch_bounds__(NMSB_SORT_THREADS) nmsb_morton_kernel(const T 
         si[p] = p < n ? p : 0xffffffffu;
     }
     __syncthreads();
-    for (uint32_t k = 2; k <= npow; k <<= 1)
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t t = threadIdx.x; t < npow / 2; t += NMSB_SORT_THREADS) {
-                const uint32_t lo = ((t / j) * 2 * j) + (t % j), hi = lo + j;
-                const bool up = (lo & k) == 0;
-                const unsigned long long ka = sk[lo], kb = sk[hi];
-                const uint32_t ia = si[lo], ib = si[hi];
-                const bool gt = ka > kb || (ka == kb && ia > ib);
-                if (gt == up) { sk[lo] = kb; sk[hi] = ka; si[lo] = ib; si[hi] = ia; }
-            }
-            __syncthreads();
+    if (npow >= 1024u && npow <= 4096u) {
+        // 1024 < n <= 4096 (the C5 shape): 32-bit keys (cell << 12 | index: unique, so the network needs no tie rule), npow / 1024 per
+        // thread, element e = r * 1024 + tid.  Steps between the elements of one thread run in registers, steps inside a warp as
+        // shuffles, the others through shared memory (two buffers in turn: one barrier per step) -- 25 of the 78 steps of a
+        // 4096-key network touch shared memory
+        const uint32_t R = npow >> 10, tid = threadIdx.x;
+        uint32_t *const buf0 = reinterpret_cast<uint32_t *>(sk), *const buf1 = buf0 + npow;
+        uint32_t v[4];
+#pragma unroll
+        for (uint32_t r = 0; r < 4; r++) {
+            const uint32_t e = r * 1024u + tid;
+            v[r] = e < n ? (((uint32_t)sk[e] << 12) | e) : 0xffffffffu;
         }
+        __syncthreads();   // the 64-bit keys have been read: their memory becomes the exchange buffers
+        auto cx = [](uint32_t &a, uint32_t &c, const bool up) {
+            const uint32_t lo = min(a, c), hi = max(a, c);
+            a = up ? lo : hi; c = up ? hi : lo;
+        };
+        int pb = 0;
+        for (uint32_t k = 2; k <= npow; k <<= 1)
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                if (j >= 1024u) {   // partner in the same thread (k > j >= 1024: the direction bit of e is a bit of r or above)
+                    if (j == 1024u) { cx(v[0], v[1], true); if (R > 2) cx(v[2], v[3], k != 2048u); }   // elements 2, 3 have bit 11 set: descending while k = 2048
+                    else { cx(v[0], v[2], true); cx(v[1], v[3], true); }                               // j = 2048, k = 4096
+                } else if (j < 32u) {
+#pragma unroll
+                    for (uint32_t r = 0; r < 4; r++)
+                        if (r < R) {
+                            const uint32_t e = r * 1024u + tid, o = __shfl_xor_sync(0xffffffffu, v[r], j);
+                            const bool takemin = ((e & j) == 0) == ((e & k) == 0);
+                            v[r] = takemin ? min(v[r], o) : max(v[r], o);
+                        }
+                } else {
+                    uint32_t *bf = pb ? buf1 : buf0; pb ^= 1;
+#pragma unroll
+                    for (uint32_t r = 0; r < 4; r++) if (r < R) bf[r * 1024u + tid] = v[r];
+                    __syncthreads();
+#pragma unroll
+                    for (uint32_t r = 0; r < 4; r++)
+                        if (r < R) {
+                            const uint32_t e = r * 1024u + tid, o = bf[e ^ j];
+                            const bool takemin = ((e & j) == 0) == ((e & k) == 0);
+                            v[r] = takemin ? min(v[r], o) : max(v[r], o);
+                        }
+                }
+            }
+#pragma unroll
+        for (uint32_t r = 0; r < 4; r++) if (r < R) si[r * 1024u + tid] = v[r] & 0xfffu;   // (entries past n are never read)
+        __syncthreads();
+    } else {
+        for (uint32_t k = 2; k <= npow; k <<= 1)
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t t = threadIdx.x; t < npow / 2; t += NMSB_SORT_THREADS) {
+                    const uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo + j;   // j is a power of two
+                    const bool up = (lo & k) == 0;
+                    const unsigned long long ka = sk[lo], kb = sk[hi];
+                    const uint32_t ia = si[lo], ib = si[hi];
+                    const bool gt = ka > kb || (ka == kb && ia > ib);
+                    if (gt == up) { sk[lo] = kb; sk[hi] = ka; si[lo] = ib; si[hi] = ia; }
+                }
+                __syncthreads();
+            }
+    }
     const int64_t base = f * stride;
     for (int64_t p = threadIdx.x; p < stride; p += NMSB_SORT_THREADS) {
         if (p < n) {
