@@ -648,6 +648,78 @@ nms_fixpoint_kernel(int64_t n, int64_t nwords, const uint8_t *__restrict__ valid
     if (gtid == 0) { ctl[2] = 1u; ctl[3] = round; }
 }
 
+// ------------------------------------------------------------------------------------------------ parallel resolve without rounds
+// The rounds above cost two grid barriers each (~20 rounds on C3: most of the kernel's 0.19 ms is barrier latency).  The same fixpoint
+// can be PULLED: box j is suppressed as soon as one of its higher-scored overlapping boxes is kept, and kept as soon as all of them are
+// suppressed.  Decisions are final and only depend on decided boxes of higher score, so every thread may simply re-read the states of its
+// box's predecessors until it can decide -- no barrier, no round counter; the box of highest score among the undecided ones can always be
+// decided, and the time is the depth of the longest chain of alternating decisions times one L2 round trip.  The predecessors of a box are
+// the transposed hit lists (nms_inlist_kernel: one list of at most NMS_IN_CAP entries per box; boxes at or below the score threshold never
+// suppress anything and are left out).  An overflow of a hit list or of an in-list leaves `done` at 0 and the list walk runs.
+constexpr uint32_t NMS_IN_CAP = 128;
+
+__global__ void __launch_bounds__(256)
+nms_inlist_kernel(int64_t n, int64_t nwords, const uint8_t *__restrict__ valid, const NmsLists lists, uint8_t *__restrict__ state, uint32_t *__restrict__ incnt,
+                  uint32_t *__restrict__ inlist, uint32_t *__restrict__ ctl /* [4]: an in-list overflowed */)
+{
+    if (lists.blkcnt[nwords] != 0u) return;   // a hit list overflowed (grid-uniform): the dense walk decides
+    const int64_t b = blockIdx.x;
+    const unsigned tid = threadIdx.x;
+    if (tid < 64u) { const int64_t j = b * 64 + tid; state[j] = (j < n && valid[j]) ? NMS_UNDECIDED : NMS_SUPPRESSED; }
+    const uint32_t c = min(lists.blkcnt[b], NMS_LIST_CAP);
+    const uint32_t *gw = lists.ent_w + b * NMS_LIST_CAP;
+    const uint64_t *gb = lists.ent_bits + b * NMS_LIST_CAP;
+    for (uint32_t e = tid; e < c; e += 256u) {
+        const uint32_t we = gw[e];
+        const int64_t i = b * 64 + (we >> 16);
+        if (!valid[i]) continue;
+        unsigned long long bits = gb[e];
+        const int64_t col0 = (int64_t)(we & 0xffffu) * 64;
+        while (bits) {
+            const int t = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            const int64_t j = col0 + t;
+            const uint32_t slot = atomicAdd(incnt + j, 1u);
+            if (slot < NMS_IN_CAP) inlist[j * NMS_IN_CAP + slot] = (uint32_t)i;
+            else ctl[4] = 1u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NMS_FIX_THREADS, 1)
+nms_pull_kernel(int64_t n, int64_t nwords, const uint32_t *__restrict__ order, uint8_t *__restrict__ suppressed, const NmsLists lists, uint8_t *state,
+                const uint32_t *__restrict__ incnt, const uint32_t *__restrict__ inlist, uint32_t *ctl /* [2] done, [4] in-list overflow */)
+{
+    if (lists.blkcnt[nwords] != 0u || ctl[4] != 0u) return;   // (both written by earlier kernels: grid-uniform)
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsize = (int64_t)gridDim.x * blockDim.x;
+    // a thread takes its boxes in ascending order, so whatever a box waits for is held by a thread that is running or done
+    for (int64_t j = gtid; j < n; j += gsize) {
+        uint32_t s = __ldcg(state + j);
+        if (s == NMS_UNDECIDED) {
+            const uint32_t c = incnt[j];
+            const uint32_t *L = inlist + j * NMS_IN_CAP;
+            bool done = false;
+            while (!done) {
+                bool kept = false, open = false;
+                for (uint32_t k = 0; k < c; k++) {
+                    const uint32_t si = __ldcg(state + __ldg(L + k));
+                    kept |= si == NMS_KEPT;
+                    open |= si == NMS_UNDECIDED;
+                }
+                if (kept || !open) {
+                    s = kept ? NMS_SUPPRESSED : NMS_KEPT;
+                    // published INSIDE the loop: lanes of this warp may be waiting for this box, and a lane parked behind the loop would
+                    // never let them see it
+                    asm volatile("st.global.cg.u8 [%0], %1;" ::"l"(state + j), "r"(s) : "memory");
+                    done = true;
+                }
+            }
+        }
+        suppressed[order[j]] = s == NMS_KEPT ? 0 : 1;
+    }
+    if (gtid == 0) ctl[2] = 1u;
+}
+
 // ------------------------------------------------------------------------------------------------ soft-NMS
 // LINEAR / GAUSSIAN suppression (reference d3d/box/nms.cpp:33-94; its CUDA version, nms_cuda.cu:108-153, needs a dense N x N
 // coefficient matrix and indexes it with tile-local positions).  The rule is sequential in the boxes AND in the scores: after
@@ -1372,7 +1444,8 @@ template <typename T> static size_t nms_ws_bytes(int64_t n)
            align_up((size_t)(nwords + 1) * 4) + align_up((size_t)nwords * NMS_LIST_CAP * 4) + align_up((size_t)nwords * NMS_LIST_CAP * 8) +
            align_up(sizeof(NmsGrid)) + 2 * align_up((size_t)2 * (NMS_GRID_CELLS + 1) * 4) + align_up((size_t)npad * sizeof(NmsCand<T>)) + scan_workspace_bytes(NMS_GRID_CELLS + 1) + 4096 +
            align_up((size_t)npad * sizeof(T)) + 3 * align_up((size_t)npad * 4) + 2 * align_up((size_t)npad) +   // soft-NMS state
-           align_up((size_t)npad) + align_up((size_t)npad * 4) + align_up(64);   // parallel resolve: state, blocked, control words
+           align_up((size_t)npad) + align_up((size_t)npad * 4) + align_up(64) +   // parallel resolve: state, blocked, control words
+           align_up((size_t)npad * 4) + align_up((size_t)npad * NMS_IN_CAP * 4);    // parallel resolve: in-list counts and in-lists
 }
 
 template <typename T>
@@ -1413,6 +1486,7 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
     soft.sup = a.take<uint8_t>(npad); soft.mk = a.take<uint8_t>(npad);
     uint8_t *fix_state = a.take<uint8_t>(npad);
     uint32_t *fix_blocked = a.take<uint32_t>(npad), *fix_ctl = a.take<uint32_t>(16);
+    uint32_t *fix_incnt = a.take<uint32_t>(npad), *fix_inlist = a.take<uint32_t>((size_t)npad * NMS_IN_CAP);
     if (!a.ok()) return D3D_ERR_WORKSPACE;
     // tuning / test override: D3D_B200_NMS_PATH=dense (dense matrix, dense resolve) | tiles (dense tiles + list resolve); default: spatial
     const int path_knob = tuning(D3D_TUNE_NMS_PATH, 0);
@@ -1474,18 +1548,29 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
     { const int v = tuning(D3D_TUNE_NMS_NT, 0); if (v >= 128 && v <= 1024 && v % 32 == 0) resolve_nt = v; }   // tuning override
     // parallel resolve for frames where the block-by-block walk is long; it leaves fix_ctl[2] = 1 when it produced the mask
     const uint32_t *skip_if = nullptr;
-    const int fix_knob = tuning(D3D_TUNE_NMS_FIX, -1);   // 0: never, 1: always (where lists exist); default: from 128 blocks (8192 boxes) on
-    if (lists.blkcnt && (fix_knob == 1 || (fix_knob < 0 && nwords >= 128))) {
+    const int fix_knob = tuning(D3D_TUNE_NMS_FIX, -1);   // 0: never, 1: always (where lists exist), 2: always, by rounds (nms_fixpoint_kernel); default: from 128 blocks (8192 boxes) on
+    if (lists.blkcnt && (fix_knob >= 1 || (fix_knob < 0 && nwords >= 128))) {
         int dev = 0, nsm = 0, per_sm = 0;
         D3D_CUDA_TRY(cudaGetDevice(&dev));
         D3D_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-        D3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nms_fixpoint_kernel, NMS_FIX_THREADS, 0));
+        const bool rounds = fix_knob == 2;
+        if (rounds) D3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nms_fixpoint_kernel, NMS_FIX_THREADS, 0));
+        else D3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nms_pull_kernel, NMS_FIX_THREADS, 0));
         if (nsm > 0 && per_sm > 0) {
             D3D_CUDA_TRY(cudaMemsetAsync(fix_ctl, 0, 64, st));
             int64_t n_ = n, nwords_ = nwords;
             const uint8_t *valid_ = valid; const uint32_t *order_ = order; uint8_t *sup_ = suppressed;
-            void *args[] = {&n_, &nwords_, &valid_, &order_, &sup_, &lists, &fix_state, &fix_blocked, &fix_ctl};
-            D3D_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)nms_fixpoint_kernel, dim3((unsigned)nsm), dim3(NMS_FIX_THREADS), args, 0, st)); D3D_LAUNCHED();
+            if (rounds) {
+                void *args[] = {&n_, &nwords_, &valid_, &order_, &sup_, &lists, &fix_state, &fix_blocked, &fix_ctl};
+                D3D_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)nms_fixpoint_kernel, dim3((unsigned)nsm), dim3(NMS_FIX_THREADS), args, 0, st)); D3D_LAUNCHED();
+            } else {
+                // every CTA of the pull kernel must be running while others wait for its boxes: a cooperative launch (one CTA per SM) guarantees it
+                D3D_CUDA_TRY(cudaMemsetAsync(fix_incnt, 0, (size_t)npad * 4, st));
+                nms_inlist_kernel<<<(unsigned)nwords, 256, 0, st>>>(n, nwords, valid, lists, fix_state, fix_incnt, fix_inlist, fix_ctl); D3D_LAUNCHED();
+                const uint32_t *incnt_ = fix_incnt, *inlist_ = fix_inlist;
+                void *args[] = {&n_, &nwords_, &order_, &sup_, &lists, &fix_state, &incnt_, &inlist_, &fix_ctl};
+                D3D_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)nms_pull_kernel, dim3((unsigned)nsm), dim3(NMS_FIX_THREADS), args, 0, st)); D3D_LAUNCHED();
+            }
             skip_if = fix_ctl + 2;
         }
     }

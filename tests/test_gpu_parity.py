@@ -448,10 +448,10 @@ def test_nms_batch_equals_per_frame(dev, oracle):
 
 
 def test_nms_parallel_resolve_equals_list_walk(dev, oracle):
-    """the resolve phase has two forms -- the block-by-block walk in score order on one SM and the parallel fixpoint (rounds of
-    keep / suppress decisions over the whole frame, default from 8192 boxes on) -- with the same keep mask: sizes on both sides of the
-    switch, both candidate back ends, score thresholds, and a chain of pairwise overlapping boxes whose depth exceeds the round limit
-    (the fixpoint gives up and the walk decides)"""
+    """the resolve phase has three forms -- the block-by-block walk in score order on one SM, the parallel fixpoint pulled over transposed
+    hit lists (default from 8192 boxes on) and the same fixpoint by rounds of keep / suppress decisions -- with the same keep mask: sizes on
+    both sides of the switch, both candidate back ends, score thresholds, and a chain of pairwise overlapping boxes whose depth exceeds the
+    round limit (the round form gives up and the walk decides; the pulled form follows the chain)"""
     from d3d_b200.box import box2d_nms
     rng = np.random.default_rng(11)
     cases = [proposals(rng, n, nobj, extent=ext) for n, nobj, ext in ((64, 4, 10.0), (1000, 30, 30.0), (4097, 150, 60.0), (12000, 500, 75.0))]
@@ -463,7 +463,7 @@ def test_nms_parallel_resolve_equals_list_walk(dev, oracle):
         for thr, sthr in ((0.5, 0.0), (0.3, 0.4)):
             exp = oracle.box2d_nms(P, sc, "rbox", iou_threshold=thr, score_threshold=sthr, cuda_score_rule=True)
             for path in (None, 1):          # spatial candidates | dense tiles
-                for fix in (0, 1):          # list walk | parallel fixpoint
+                for fix in (0, 1, 2):       # list walk | parallel fixpoint, pulled (no rounds) | parallel fixpoint by rounds
                     _cabi.tuning_set("D3D_B200_NMS_PATH", path)
                     _cabi.tuning_set("D3D_B200_NMS_FIX", fix)
                     got = box2d_nms(_t(P, dev), _t(sc, dev), "rbox", iou_threshold=thr, score_threshold=sthr).cpu().numpy()
