@@ -1309,43 +1309,130 @@ nmsb_clip_kernel(const BoxRec<T> *__restrict__ recs_all, const T *__restrict__ r
     }
 }
 
-// one CTA per frame: rounds of keep / suppress decisions over the frame's edge list (see nms_fixpoint_kernel), states in shared memory
+// one CTA per frame: the keep mask as the fixpoint over the frame's edge list, everything in shared memory.
+// Pushed form: the edges are gathered into one list of successors per box (count, prefix sum, fill: two passes over the edge list)
+// and every box counts its predecessors.  A thread owns the boxes tid, tid + 1024, ...: a box whose predecessors have all reported
+// "suppressed" is kept; a decided box reports to its successors once -- a kept box marks them suppressed, a suppressed box takes itself
+// off their counts -- so the work is one visit per edge and the time is the depth of the longest chain of alternating decisions times a
+// shared-memory round trip.  (Polling the predecessors instead, as nms_pull_kernel does with a thread per box, costs depth x in-degree
+// here: 38 us per frame against 8.)  The boxes of a frame are in Morton order, not score order, so a thread never WAITS for one box
+// (two threads could wait for each other's second box): it sweeps over its boxes and takes what can be decided.  Boxes at or below the
+// score threshold never suppress anything and are left out of lists and counts.
+// Frames whose edges do not fit the shared-memory lists run the rounds of nms_fixpoint_kernel over the edge list in global memory.
 __global__ void __launch_bounds__(1024)
 nmsb_fix_kernel(const uint32_t *__restrict__ edges_all, const uint32_t *__restrict__ ecount, uint32_t ecap, const int64_t *__restrict__ offs, int64_t stride,
-                const uint8_t *__restrict__ valid_all, const uint32_t *__restrict__ order_all, uint8_t *__restrict__ suppressed, const uint32_t *__restrict__ fail)
+                const uint8_t *__restrict__ valid_all, const uint32_t *__restrict__ order_all, uint8_t *__restrict__ suppressed, const uint32_t *__restrict__ fail,
+                uint32_t lcap /* predecessor entries that fit the dynamic shared memory */)
 {
-    __shared__ uint8_t state[NMSB_MAX];
-    __shared__ uint16_t blocked[NMSB_MAX];
+    extern __shared__ __align__(16) unsigned char fx_dyn[];
     if (fail[1]) return;   // an edge list overflowed: the dense kernels behind this one redo the batch (CTA-uniform)
     const int64_t f = blockIdx.x, b = offs[f];
     const uint32_t n = (uint32_t)min(offs[f + 1] - b, stride);
     if (n == 0) return;
+    const uint32_t npad = ((uint32_t)stride + 3u) & ~3u;
+    // layout: off[npad + 4] u32 | cnt[npad] u32 (the rounds form keeps its u16 stamps there) | pend[npad] u32 | state[npad] u8 | lst[lcap] u16
+    uint32_t *off = reinterpret_cast<uint32_t *>(fx_dyn), *cnt = off + npad + 4, *pend = cnt + npad;
+    uint8_t *state = reinterpret_cast<uint8_t *>(pend + npad);
+    uint16_t *lst = reinterpret_cast<uint16_t *>(state + npad);
+    __shared__ uint32_t s_warp[32], s_total;
     const uint32_t ne = min(ecount[f], ecap);
     const uint32_t *edges = edges_all + (size_t)f * ecap;
     const uint8_t *valid = valid_all + f * stride;
-    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) { state[j] = valid[j] ? NMS_UNDECIDED : NMS_SUPPRESSED; blocked[j] = 0; }
+    const uint32_t *order = order_all + f * stride;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+    for (uint32_t j = tid; j < n; j += 1024u) { state[j] = valid[j] ? NMS_UNDECIDED : NMS_SUPPRESSED; cnt[j] = 0; pend[j] = 0; }
     __syncthreads();
-    for (uint32_t round = 1;; round++) {
-        const uint16_t stamp = (uint16_t)(1u + (round - 1u) % 65535u);   // never 0; a stamp is only compared within its own round
-        if (stamp == 1u && round > 1u) { for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) blocked[j] = 0; __syncthreads(); }
-        for (uint32_t e = threadIdx.x; e < ne; e += blockDim.x) {
-            const uint32_t ed = edges[e], src = ed & 0xffffu, dst = ed >> 16;
-            const uint8_t ss = state[src];
-            if (ss == NMS_KEPT) state[dst] = NMS_SUPPRESSED;
-            else if (ss == NMS_UNDECIDED) blocked[dst] = stamp;   // a box that comes first and overlaps is still undecided
+    // successors per box and predecessors still open per box
+    const uint4 *edges4 = reinterpret_cast<const uint4 *>(edges);   // four edges per load: a frame's list starts on a 16-byte boundary
+    const uint32_t ne4 = (ne + 3u) / 4u;
+    for (uint32_t e = tid; e < ne4; e += 1024u) {
+        const uint4 q = edges4[e];
+        const uint32_t ed[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t src = ed[u] & 0xffffu, dst = ed[u] >> 16;
+            if (e * 4u + u < ne && state[src] != NMS_SUPPRESSED) { atomicAdd(&cnt[src], 1u); atomicAdd(&pend[dst], 1u); }
         }
-        __syncthreads();
-        int left = 0;
-        for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
-            if (state[j] == NMS_UNDECIDED) {
-                if (blocked[j] != stamp) state[j] = NMS_KEPT;
-                else left = 1;
+    }
+    __syncthreads();
+    // exclusive prefix of cnt over the frame's boxes: a thread owns the boxes [tid * per, tid * per + per)
+    const uint32_t per = (n + 1023u) / 1024u;
+    uint32_t mine = 0;
+    for (uint32_t k = 0; k < per; k++) { const uint32_t j = tid * per + k; if (j < n) mine += cnt[j]; }
+    uint32_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (unsigned)d) inc += x; }
+    if (lane == 31u) s_warp[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t x = s_warp[lane], y = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t z = __shfl_up_sync(0xffffffffu, y, d); if (lane >= (unsigned)d) y += z; }
+        s_warp[lane] = y - x;
+        if (lane == 31u) s_total = y;
+    }
+    __syncthreads();
+    uint32_t run = s_warp[w] + inc - mine;
+    for (uint32_t k = 0; k < per; k++) { const uint32_t j = tid * per + k; if (j < n) { off[j] = run; run += cnt[j]; } }
+    if (tid == 0) off[n] = s_total;
+    __syncthreads();
+    if (s_total <= lcap) {
+        for (uint32_t e = tid; e < ne4; e += 1024u) {
+            const uint4 q = edges4[e];
+            const uint32_t ed[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t src = ed[u] & 0xffffu, dst = ed[u] >> 16;
+                if (e * 4u + u < ne && state[src] != NMS_SUPPRESSED) lst[off[src] + atomicSub(&cnt[src], 1u) - 1u] = (uint16_t)dst;
             }
         }
-        if (!__syncthreads_or(left)) break;
+        __syncthreads();
+        volatile uint8_t *vstate = state;
+        volatile uint32_t *vpend = pend;
+        uint32_t todo = 0;   // bit u: box tid + 1024 u has not reported to its successors yet
+        for (uint32_t j = tid, u = 0; j < n; j += 1024u, u++) if (state[j] == NMS_UNDECIDED) todo |= 1u << u;
+        while (todo) {
+            for (uint32_t m = todo; m; m &= m - 1u) {
+                const uint32_t u = (uint32_t)__ffs((int)m) - 1u, j = tid + 1024u * u;
+                uint8_t st = vstate[j];
+                if (st == NMS_UNDECIDED && vpend[j] == 0u) { st = NMS_KEPT; vstate[j] = NMS_KEPT; }
+                if (st != NMS_UNDECIDED) {   // (all of this inside the loop: lanes of this warp may be waiting for these reports)
+                    for (uint32_t k = off[j], k1 = off[j + 1]; k < k1; k++) {
+                        const uint32_t d = lst[k];
+                        if (st == NMS_KEPT) vstate[d] = NMS_SUPPRESSED;   // d still counts this box: it cannot have been kept
+                        else atomicSub(&pend[d], 1u);
+                    }
+                    todo &= ~(1u << u);
+                }
+            }
+        }
+        __syncthreads();
+    } else {
+        uint16_t *blocked = reinterpret_cast<uint16_t *>(cnt);
+        __syncthreads();
+        for (uint32_t j = tid; j < n; j += 1024u) blocked[j] = 0;
+        __syncthreads();
+        for (uint32_t round = 1;; round++) {
+            const uint16_t stamp = (uint16_t)(1u + (round - 1u) % 65535u);   // never 0; a stamp is only compared within its own round
+            if (stamp == 1u && round > 1u) { for (uint32_t j = tid; j < n; j += 1024u) blocked[j] = 0; __syncthreads(); }
+            for (uint32_t e = tid; e < ne; e += 1024u) {
+                const uint32_t ed = edges[e], src = ed & 0xffffu, dst = ed >> 16;
+                const uint8_t ss = state[src];
+                if (ss == NMS_KEPT) state[dst] = NMS_SUPPRESSED;
+                else if (ss == NMS_UNDECIDED) blocked[dst] = stamp;   // a box that comes first and overlaps is still undecided
+            }
+            __syncthreads();
+            int left = 0;
+            for (uint32_t j = tid; j < n; j += 1024u) {
+                if (state[j] == NMS_UNDECIDED) {
+                    if (blocked[j] != stamp) state[j] = NMS_KEPT;
+                    else left = 1;
+                }
+            }
+            if (!__syncthreads_or(left)) break;
+        }
     }
-    const uint32_t *order = order_all + f * stride;
-    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) suppressed[b + order[j]] = state[j] == NMS_KEPT ? 0 : 1;
+    for (uint32_t j = tid; j < n; j += 1024u) suppressed[b + order[j]] = state[j] == NMS_KEPT ? 0 : 1;
 }
 
 template <typename T> static size_t nmsb_ws_bytes(int64_t nframes, int64_t max_frame_boxes)
@@ -1413,7 +1500,15 @@ static int nmsb_impl(const T *boxes, const T *scores, int64_t total, const int64
         nmsb_clip_kernel<T><<<dim3(32, (unsigned)nframes), NMS_THREADS, 0, st>>>((const BoxRec<T> *)recs, recheck ? raw : nullptr, stride, thr, reinterpret_cast<const uint32_t *>(mask),
                                                                               ccount, ccap, cand_stride, edges, ecount, ecap, fail);
         D3D_LAUNCHED();
-        nmsb_fix_kernel<<<(unsigned)nframes, 1024, 0, st>>>(edges, ecount, ecap, offs, stride, valid, order, suppressed, fail); D3D_LAUNCHED();
+        {
+            // shared memory of the per-frame resolve: offsets, counters, states + as many predecessor entries as fit (D3D_B200_NMS_FIX=2: none, rounds only)
+            const size_t spad = ((size_t)stride + 3) & ~(size_t)3, fixed = (spad + 4) * 4 + spad * 8 + spad;
+            const size_t room = 200 * 1024 > fixed ? 200 * 1024 - fixed : 0;
+            const uint32_t lcap = tuning(D3D_TUNE_NMS_FIX, -1) == 2 ? 0u : (uint32_t)(room / 2);
+            const size_t fx_smem = fixed + (size_t)lcap * 2;
+            if (fx_smem > 40 * 1024) D3D_CUDA_TRY(cudaFuncSetAttribute(nmsb_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fx_smem));
+            nmsb_fix_kernel<<<(unsigned)nframes, 1024, fx_smem, st>>>(edges, ecount, ecap, offs, stride, valid, order, suppressed, fail, lcap); D3D_LAUNCHED();
+        }
         run_if = fail + 1;   // the dense kernels below leave at once unless an edge list overflowed
     }
     if (aabb) {

@@ -445,6 +445,20 @@ def test_nms_batch_equals_per_frame(dev, oracle):
         for (b, s), k0, k1 in zip(mixed, out[None], out[1]):
             assert torch.equal(k0, k1), (thr, len(b))
             assert torch.equal(k0, box2d_nms(_t(b, dev), _t(s, dev), "rbox", iou_threshold=thr)), (thr, len(b))
+    # the per-frame resolve of the edge path has two forms (pulled over predecessor lists in shared memory | rounds over the edge list,
+    # the fallback of frames with too many edges): same masks; a 300-deep chain of alternating decisions in one frame
+    m = 600
+    chain = (np.stack([0.2 * np.arange(m), np.zeros(m), np.ones(m), np.ones(m), 0.37 * np.arange(m)], 1), rng.random(m))
+    deep = [frames[4], chain, frames[6], frames[0]]
+    got = {}
+    for fix in (None, 2):
+        _cabi.tuning_set("D3D_B200_NMS_FIX", fix)
+        got[fix] = box2d_nms_batch([_t(b, dev) for b, _ in deep], [_t(s, dev) for _, s in deep], iou_method="rbox", iou_threshold=0.5)
+    _cabi.tuning_set("D3D_B200_NMS_FIX", None)
+    for (b, s), k0, k2 in zip(deep, got[None], got[2]):
+        assert torch.equal(k0, k2), len(b)
+        assert torch.equal(k0, box2d_nms(_t(b, dev), _t(s, dev), "rbox", iou_threshold=0.5)), len(b)
+    assert np.array_equal(got[None][1].cpu().numpy(), oracle.box2d_nms(chain[0], chain[1], "rbox", iou_threshold=0.5, cuda_score_rule=True))
 
 
 def test_nms_parallel_resolve_equals_list_walk(dev, oracle):
