@@ -60,28 +60,69 @@ __global__ void __launch_bounds__(256) nms_keys_kernel(const T *__restrict__ sco
 
 constexpr int NMS_TILE = 64;
 
+// extent of the box centres and the largest bounding radius, reduced by the gather kernel for the candidate grid: five minima of
+// order-preserving encodings of x, y, -x, -y, -rho (one memset to 0xff initialises all of them) and a word that is cleared when a box
+// is not finite
+struct NmsExt { unsigned long long v[5]; uint32_t good, pad; };
+__device__ __forceinline__ unsigned long long ext_enc(double x)
+{
+    const unsigned long long u = (unsigned long long)__double_as_longlong(x);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ext_dec(unsigned long long e)
+{
+    return __longlong_as_double((long long)((e >> 63) ? (e & 0x7fffffffffffffffull) : ~e));
+}
+
 // sorted position p -> record of box order[p]; padded to a multiple of 64 with NaN-rho records
 template <typename T, bool AABB>
 __global__ void __launch_bounds__(256) nms_gather_kernel(const T *__restrict__ boxes, const T *__restrict__ scores, const uint32_t *__restrict__ order,
                                                          int64_t n, int64_t npad, float score_thr, BoxRec<T> *__restrict__ recs,
-                                                         AABBRec<T> *__restrict__ arecs, T *__restrict__ raw, uint8_t *__restrict__ valid)
+                                                         AABBRec<T> *__restrict__ arecs, T *__restrict__ raw, uint8_t *__restrict__ valid, NmsExt *__restrict__ ext)
 {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npad) return;
+    double e[5] = {1e300, 1e300, 1e300, 1e300, 0.0};   // x, y, -x, -y, -rho
+    int bad = 0;
     if (p < n) {
         const uint32_t i = order[p];
         const T *b = boxes + 5 * (int64_t)i;
         if (AABB) arecs[p] = make_aabb_rec<T>(b[0], b[1], b[2], b[3], b[4]);
         else {
-            recs[p] = make_box_rec<T>(b[0], b[1], b[2], b[3], b[4]);
+            const BoxRec<T> r = make_box_rec<T>(b[0], b[1], b[2], b[3], b[4]);
+            recs[p] = r;
             if (raw) { for (int k = 0; k < 5; k++) raw[5 * p + k] = b[k]; }
+            const double x = (double)r.cx, y = (double)r.cy, rho = (double)r.rho;
+            if (!(fabs(x) < 1e150) || !(fabs(y) < 1e150) || !(rho < 1e150) || !(rho >= 0)) bad = 1;
+            else { e[0] = x; e[1] = y; e[2] = -x; e[3] = -y; e[4] = -rho; }
         }
         valid[p] = scores[i] > score_thr ? 1 : 0;   // T vs float, promoted to T (nms.cpp:26, nms_cuda.cu:223)
-    } else {
+    } else if (p < npad) {
         if (AABB) { AABBRec<T> a; a.minx = a.maxx = a.miny = a.maxy = T(NAN); arecs[p] = a; }
         else { BoxRec<T> r; r.cx = r.cy = r.c = r.s = r.hw = r.hh = r.area = T(0); r.rho = T(NAN); recs[p] = r; }
         valid[p] = 0;
     }
+    if (AABB || !ext) return;   // (uniform)
+    __shared__ double sred[5][8];
+    __shared__ int sbad;
+    if (threadIdx.x == 0) sbad = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++)
+#pragma unroll
+        for (int d = 16; d; d >>= 1) e[k] = fmin(e[k], __shfl_xor_sync(0xffffffffu, e[k], d));
+    bad = __any_sync(0xffffffffu, bad);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) sred[k][threadIdx.x >> 5] = e[k];
+        if (bad) sbad = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double m = sred[threadIdx.x][0];
+        for (int w = 1; w < 8; w++) m = fmin(m, sred[threadIdx.x][w]);
+        atomicMin(&ext->v[threadIdx.x], ext_enc(m));
+    }
+    if (threadIdx.x == 5 && sbad) atomicAnd(&ext->good, 0u);
 }
 
 constexpr int NMS_THREADS = 128;
@@ -154,45 +195,27 @@ constexpr int NMS_GRID_MAX = 256;                                   // cells per
 constexpr int NMS_GRID_CELLS = NMS_GRID_MAX * NMS_GRID_MAX;
 struct NmsGrid { double minx, miny, inv_cell; int nx, ny; uint32_t ok; uint32_t pad; };
 // what the candidate scan needs of a box, stored in cell order so that a warp reads consecutive records
-template <typename T> struct __align__(16) NmsCand { T cx, cy, rho; uint32_t idx, pad; };
+// (single precision whatever the box type: 16 bytes per entry.  The circle test on these numbers is widened by the conversion error of
+// the centres, so it passes a superset of the pairs whose circles meet -- the clip decides, the keep mask does not depend on it)
+struct __align__(16) NmsCandF { float cx, cy, rho; uint32_t idx; };
+template <typename T> using NmsCand = NmsCandF;
 
-template <typename T>
-__global__ void __launch_bounds__(1024) nms_grid_kernel(const BoxRec<T> *__restrict__ recs, int64_t n, NmsGrid *__restrict__ g)
+// grid geometry from the extents the gather kernel reduced (one thread)
+__global__ void nms_grid_kernel(const NmsExt *__restrict__ ext, int64_t n, NmsGrid *__restrict__ g)
 {
-    __shared__ double smin[2][32], smax[2][32], srho[32];
-    __shared__ int sbad[32];
-    double mnx = 1e300, mny = 1e300, mxx = -1e300, mxy = -1e300, mr = 0;
-    int bad = 0;
-    for (int64_t p = threadIdx.x; p < n; p += blockDim.x) {
-        const double x = (double)recs[p].cx, y = (double)recs[p].cy, r = (double)recs[p].rho;
-        if (!(fabs(x) < 1e150) || !(fabs(y) < 1e150) || !(r < 1e150) || !(r >= 0)) bad = 1;
-        mnx = fmin(mnx, x); mny = fmin(mny, y); mxx = fmax(mxx, x); mxy = fmax(mxy, y); mr = fmax(mr, r);
+    if (threadIdx.x != 0) return;
+    const double mnx = ext_dec(ext->v[0]), mny = ext_dec(ext->v[1]), mxx = -ext_dec(ext->v[2]), mxy = -ext_dec(ext->v[3]), mr = -ext_dec(ext->v[4]);
+    const bool bad = ext->good == 0u || !(mnx <= mxx) || !(mny <= mxy);
+    NmsGrid o;
+    o.minx = mnx; o.miny = mny; o.inv_cell = 0; o.nx = o.ny = 1; o.ok = 0; o.pad = 0;
+    const double ex = mxx - mnx, ey = mxy - mny;
+    double cell = 2.0 * mr * (1.0 + 1e-6);     // the margin absorbs the rounding of the cell index
+    cell = fmax(cell, fmax(ex, ey) / NMS_GRID_MAX * (1.0 + 1e-6));
+    if (!bad && n > 0 && cell > 0 && cell < 1e150) {
+        const int nx = (int)fmin((double)NMS_GRID_MAX, floor(ex / cell) + 1), ny = (int)fmin((double)NMS_GRID_MAX, floor(ey / cell) + 1);
+        if ((int64_t)nx * ny >= 16) { o.inv_cell = 1.0 / cell; o.nx = nx; o.ny = ny; o.ok = 1; }
     }
-#pragma unroll
-    for (int d = 16; d; d >>= 1) {
-        mnx = fmin(mnx, __shfl_xor_sync(0xffffffffu, mnx, d)); mny = fmin(mny, __shfl_xor_sync(0xffffffffu, mny, d));
-        mxx = fmax(mxx, __shfl_xor_sync(0xffffffffu, mxx, d)); mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
-        mr = fmax(mr, __shfl_xor_sync(0xffffffffu, mr, d)); bad |= __shfl_xor_sync(0xffffffffu, bad, d);
-    }
-    const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) { smin[0][w] = mnx; smin[1][w] = mny; smax[0][w] = mxx; smax[1][w] = mxy; srho[w] = mr; sbad[w] = bad; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (unsigned k = 1; k < blockDim.x / 32; k++) {
-            mnx = fmin(mnx, smin[0][k]); mny = fmin(mny, smin[1][k]); mxx = fmax(mxx, smax[0][k]); mxy = fmax(mxy, smax[1][k]);
-            mr = fmax(mr, srho[k]); bad |= sbad[k];
-        }
-        NmsGrid o;
-        o.minx = mnx; o.miny = mny; o.inv_cell = 0; o.nx = o.ny = 1; o.ok = 0; o.pad = 0;
-        const double ex = mxx - mnx, ey = mxy - mny;
-        double cell = 2.0 * mr * (1.0 + 1e-6);     // the margin absorbs the rounding of the cell index
-        cell = fmax(cell, fmax(ex, ey) / NMS_GRID_MAX * (1.0 + 1e-6));
-        if (!bad && n > 0 && cell > 0 && cell < 1e150) {
-            const int nx = (int)fmin((double)NMS_GRID_MAX, floor(ex / cell) + 1), ny = (int)fmin((double)NMS_GRID_MAX, floor(ey / cell) + 1);
-            if ((int64_t)nx * ny >= 16) { o.inv_cell = 1.0 / cell; o.nx = nx; o.ny = ny; o.ok = 1; }
-        }
-        *g = o;
-    }
+    *g = o;
 }
 
 template <typename T>
@@ -216,7 +239,7 @@ __global__ void __launch_bounds__(256) nms_bin_kernel(const BoxRec<T> *__restric
     nms_cell_of<T>(*g, r, &ix, &iy);
     const uint32_t c = (uint32_t)(iy * g->nx + ix);
     const uint32_t at = atomicAdd(cellcnt + c, 1u);
-    if (PASS == 1) { NmsCand<T> e; e.cx = r.cx; e.cy = r.cy; e.rho = r.rho; e.idx = (uint32_t)p; e.pad = 0; celllist[cellptr[c] + at] = e; }
+    if (PASS == 1) { NmsCand<T> e; e.cx = (float)r.cx; e.cy = (float)r.cy; e.rho = __double2float_ru((double)r.rho); e.idx = (uint32_t)p; celllist[cellptr[c] + at] = e; }
 }
 
 constexpr int NMS_PAIR_THREADS = 256;
@@ -231,8 +254,11 @@ __global__ void __launch_bounds__(NMS_PAIR_THREADS, D3D_NMS_PAIR_CTAS) nms_pairs
     if (!g->ok) return;
     __shared__ uint32_t queue[NMS_PAIR_THREADS / 32][64];
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
-    const int64_t i = (int64_t)blockIdx.x * (NMS_PAIR_THREADS / 32) + w;   // one warp per row of the sorted matrix
-    if (i >= n) return;
+    // one warp per row of the sorted matrix, rows taken in CELL order: the warps of a CTA scan the same three grid rows and clip
+    // against the same records, out of L1
+    const int64_t slot = (int64_t)blockIdx.x * (NMS_PAIR_THREADS / 32) + w;
+    if (slot >= n) return;
+    const int64_t i = celllist[slot].idx;
     const BoxRec<T> A = recs[i];
     const NmsGrid G = *g;
     int ix, iy;
@@ -240,6 +266,7 @@ __global__ void __launch_bounds__(NMS_PAIR_THREADS, D3D_NMS_PAIR_CTAS) nms_pairs
     uint32_t *q = queue[w];
     unsigned head = 0, tail = 0;
     const uint32_t rb = (uint32_t)(i >> 6), trow = (uint32_t)(i & 63);
+    const float fax = (float)A.cx, fay = (float)A.cy, far = __double2float_ru((double)A.rho), faerr = fabsf(fax) + fabsf(fay);
     auto drain = [&](bool all) {
         while (tail - head >= 32u || (all && tail != head)) {
             __syncwarp();
@@ -277,8 +304,9 @@ __global__ void __launch_bounds__(NMS_PAIR_THREADS, D3D_NMS_PAIR_CTAS) nms_pairs
                 const NmsCand<T> e = celllist[k];   // coalesced: the cell lists hold the three numbers the circle test needs
                 j = e.idx;
                 if ((int64_t)j > i) {
-                    const T dx = A.cx - e.cx, dyy = A.cy - e.cy, rs = A.rho + e.rho;
-                    cand = dx * dx + dyy * dyy <= rs * rs;
+                    const float dx = fax - e.cx, dyy = fay - e.cy;
+                    const float rs = far + e.rho + (faerr + fabsf(e.cx) + fabsf(e.cy)) * 2.4e-7f;   // + 2^-22 of the coordinates: what the float centres may be off by
+                    cand = dx * dx + dyy * dyy <= rs * rs * 1.00001f;
                 }
             }
             const unsigned bal = __ballot_sync(0xffffffffu, cand);
@@ -1537,7 +1565,7 @@ template <typename T> static size_t nms_ws_bytes(int64_t n)
     return align_up((size_t)n * 8) + align_up((size_t)n * 4) + radix_sort_workspace_bytes(n) + align_up((size_t)npad * recs) +
            align_up((size_t)npad * 5 * sizeof(T)) + align_up((size_t)npad) + align_up((size_t)npad * nwords * 8) +
            align_up((size_t)(nwords + 1) * 4) + align_up((size_t)nwords * NMS_LIST_CAP * 4) + align_up((size_t)nwords * NMS_LIST_CAP * 8) +
-           align_up(sizeof(NmsGrid)) + 2 * align_up((size_t)2 * (NMS_GRID_CELLS + 1) * 4) + align_up((size_t)npad * sizeof(NmsCand<T>)) + scan_workspace_bytes(NMS_GRID_CELLS + 1) + 4096 +
+           align_up(sizeof(NmsGrid)) + align_up(sizeof(NmsExt)) + 2 * align_up((size_t)2 * (NMS_GRID_CELLS + 1) * 4) + align_up((size_t)npad * sizeof(NmsCand<T>)) + scan_workspace_bytes(NMS_GRID_CELLS + 1) + 4096 +
            align_up((size_t)npad * sizeof(T)) + 3 * align_up((size_t)npad * 4) + 2 * align_up((size_t)npad) +   // soft-NMS state
            align_up((size_t)npad) + align_up((size_t)npad * 4) + align_up(64) +   // parallel resolve: state, blocked, control words
            align_up((size_t)npad * 4) + align_up((size_t)npad * NMS_IN_CAP * 4);    // parallel resolve: in-list counts and in-lists
@@ -1571,6 +1599,7 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
     uint32_t *ent_w = a.take<uint32_t>((size_t)nwords * NMS_LIST_CAP);
     uint64_t *ent_bits = a.take<uint64_t>((size_t)nwords * NMS_LIST_CAP);
     NmsGrid *grid = a.take<NmsGrid>(1);
+    NmsExt *ext = a.take<NmsExt>(1);
     uint32_t *cellcnt = a.take<uint32_t>((size_t)2 * (NMS_GRID_CELLS + 1));   // [0] counts (pass 0), [1] fill cursors (pass 1)
     uint32_t *cellptr = a.take<uint32_t>((size_t)2 * (NMS_GRID_CELLS + 1));
     NmsCand<T> *celllist = a.take<NmsCand<T>>((size_t)npad);
@@ -1596,9 +1625,11 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
     if (rc) return rc;
     const bool recheck = sizeof(T) == 4 && !aabb;
     if (aabb)
-        nms_gather_kernel<T, true><<<(unsigned)cdiv(npad, 256), 256, 0, st>>>(boxes, scores, order, n, npad, score_thr, nullptr, (AABBRec<T> *)recs, nullptr, valid);
-    else
-        nms_gather_kernel<T, false><<<(unsigned)cdiv(npad, 256), 256, 0, st>>>(boxes, scores, order, n, npad, score_thr, (BoxRec<T> *)recs, nullptr, recheck ? raw : nullptr, valid);
+        nms_gather_kernel<T, true><<<(unsigned)cdiv(npad, 256), 256, 0, st>>>(boxes, scores, order, n, npad, score_thr, nullptr, (AABBRec<T> *)recs, nullptr, valid, nullptr);
+    else {
+        D3D_CUDA_TRY(cudaMemsetAsync(ext, 0xff, sizeof(NmsExt), st));
+        nms_gather_kernel<T, false><<<(unsigned)cdiv(npad, 256), 256, 0, st>>>(boxes, scores, order, n, npad, score_thr, (BoxRec<T> *)recs, nullptr, recheck ? raw : nullptr, valid, ext);
+    }
     D3D_LAUNCHED();
     const T thr = (T)iou_thr;   // (T)(float): SURVEY.md 8(c) T2
     const int stop = tuning(D3D_TUNE_NMS_STOP, 0);   // measurement only (bench.py phase times): 1 = stop after sort + gather, 2 = after the candidate phase
@@ -1616,7 +1647,7 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
         const BoxRec<T> *br = (const BoxRec<T> *)recs;
         const unsigned gb = (unsigned)cdiv(n, 256);
         D3D_CUDA_TRY(cudaMemsetAsync(cellcnt, 0, (size_t)2 * (NMS_GRID_CELLS + 1) * 4, st));
-        nms_grid_kernel<T><<<1, 1024, 0, st>>>(br, n, grid); D3D_LAUNCHED();
+        nms_grid_kernel<<<1, 32, 0, st>>>(ext, n, grid); D3D_LAUNCHED();
         nms_bin_kernel<T, 0><<<gb, 256, 0, st>>>(br, n, grid, cellcnt, nullptr, nullptr); D3D_LAUNCHED();
         if ((rc = exclusive_scan_u32(cellcnt, cellptr, NMS_GRID_CELLS + 1, nullptr, cell_scan_ws, st))) return rc;
         nms_bin_kernel<T, 1><<<gb, 256, 0, st>>>(br, n, grid, cellcnt + NMS_GRID_CELLS + 1, cellptr, celllist); D3D_LAUNCHED();
