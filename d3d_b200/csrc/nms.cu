@@ -243,6 +243,7 @@ __global__ void __launch_bounds__(256) nms_bin_kernel(const BoxRec<T> *__restric
 }
 
 constexpr int NMS_PAIR_THREADS = 256;
+constexpr int NMS_PAIR_HITS = 96;   // hits of a row kept in shared memory before they are appended to the block's list
 #ifndef D3D_NMS_PAIR_CTAS
 #define D3D_NMS_PAIR_CTAS 3   // 85 registers: 1.54 ms on C3 against 1.62 ms with 2 CTAs (92 registers) and 1.55 ms with 4 (tools/nms_occ_probe.sh)
 #endif
@@ -253,6 +254,7 @@ __global__ void __launch_bounds__(NMS_PAIR_THREADS, D3D_NMS_PAIR_CTAS) nms_pairs
 {
     if (!g->ok) return;
     __shared__ uint32_t queue[NMS_PAIR_THREADS / 32][64];
+    __shared__ uint32_t hits[NMS_PAIR_THREADS / 32][NMS_PAIR_HITS];
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
     // one warp per row of the sorted matrix, rows taken in CELL order: the warps of a CTA scan the same three grid rows and clip
     // against the same records, out of L1
@@ -267,6 +269,23 @@ __global__ void __launch_bounds__(NMS_PAIR_THREADS, D3D_NMS_PAIR_CTAS) nms_pairs
     unsigned head = 0, tail = 0;
     const uint32_t rb = (uint32_t)(i >> 6), trow = (uint32_t)(i & 63);
     const float fax = (float)A.cx, fay = (float)A.cy, far = __double2float_ru((double)A.rho), faerr = fabsf(fax) + fabsf(fay);
+    uint32_t *hb = hits[w];
+    unsigned nhits = 0;
+    auto flush = [&]() {   // every hit of this row goes to the list of its 64-row block
+        __syncwarp();
+        uint32_t at = 0;
+        if (lane == 0) at = atomicAdd(lists.blkcnt + rb, nhits);
+        at = __shfl_sync(0xffffffffu, at, 0);
+        for (unsigned h = lane; h < nhits; h += 32) {
+            const uint32_t j = hb[h];
+            if (at + h < NMS_LIST_CAP) {
+                lists.ent_w[(size_t)rb * NMS_LIST_CAP + at + h] = (j >> 6) | (trow << 16);
+                lists.ent_bits[(size_t)rb * NMS_LIST_CAP + at + h] = 1ull << (j & 63u);
+            } else lists.blkcnt[nwords] = 1u;
+        }
+        nhits = 0;
+        __syncwarp();
+    };
     auto drain = [&](bool all) {
         while (tail - head >= 32u || (all && tail != head)) {
             __syncwarp();
@@ -276,16 +295,10 @@ __global__ void __launch_bounds__(NMS_PAIR_THREADS, D3D_NMS_PAIR_CTAS) nms_pairs
             const T v = rbox_iou<T>(A, B);   // iou(higher score box, lower score box), nms.cpp:50
             const bool hit = lane < cnt && over_threshold<T>(v, thr, raw, (unsigned)i, j);
             const unsigned bal = __ballot_sync(0xffffffffu, hit);
-            if (bal) {   // one reservation per warp: every hit of this row goes to the list of its 64-row block
-                uint32_t at = 0;
-                if (lane == 0) at = atomicAdd(lists.blkcnt + rb, (uint32_t)__popc(bal));
-                at = __shfl_sync(0xffffffffu, at, 0) + __popc(bal & lanemask_lt());
-                if (hit) {
-                    if (at < NMS_LIST_CAP) {
-                        lists.ent_w[(size_t)rb * NMS_LIST_CAP + at] = (j >> 6) | (trow << 16);
-                        lists.ent_bits[(size_t)rb * NMS_LIST_CAP + at] = 1ull << (j & 63u);
-                    } else lists.blkcnt[nwords] = 1u;
-                }
+            if (bal) {   // the hits of this row wait in shared memory: one reservation in the block's list per row, not per step (the warp would sit on the atomic's round trip)
+                if (nhits + 32u > (unsigned)NMS_PAIR_HITS) flush();
+                if (hit) hb[nhits + __popc(bal & lanemask_lt())] = j;
+                nhits += __popc(bal);
             }
             head += cnt;
             __syncwarp();
@@ -316,6 +329,7 @@ __global__ void __launch_bounds__(NMS_PAIR_THREADS, D3D_NMS_PAIR_CTAS) nms_pairs
         }
     }
     drain(true);
+    if (nhits) flush();
 }
 
 template <typename T>
