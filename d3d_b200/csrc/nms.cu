@@ -1067,6 +1067,8 @@ nmsb_resolve_kernel(const uint64_t *__restrict__ mask_all, const int64_t *__rest
 // CTA per frame, box states in shared memory.  An edge list that overflows its capacity (frames of near-identical boxes) raises a
 // device flag and the dense kernels, launched behind it, redo the batch.
 constexpr int NMSB_ECAP_PER_BOX = 32;   // edge capacity per frame = 32 x max_frame_boxes
+constexpr int NMSB_HQ = 256;            // hits a warp of the clip kernel collects before it reserves room in the frame's edge list
+constexpr int NMSB_CQ = 512;            // candidates a warp of the candidate kernel collects before it reserves room in the frame's list
 
 __device__ __forceinline__ uint32_t morton_part(uint32_t x) { x &= 0x3ffu; x = (x | (x << 8)) & 0x00ff00ffu; x = (x | (x << 4)) & 0x0f0f0f0fu; x = (x | (x << 2)) & 0x33333333u; return (x | (x << 1)) & 0x55555555u; }
 
@@ -1233,14 +1235,17 @@ nmsb_cand_kernel(const BoxRec<T> *__restrict__ recs_all, const uint64_t *__restr
     const uint32_t *order = order_all + f * stride;
     const float4 *bounds = bounds_all + f * nwords;
     uint32_t *cands = cands_all + (size_t)f * cand_stride;
-    __shared__ T ax_[NMS_TILE], ay_[NMS_TILE], ar_[NMS_TILE];
+    // the circle test runs in single precision, widened by what the converted centres may be off by: it passes a superset of the pairs
+    // whose circles meet, the clip decides
+    __shared__ float ax_[NMS_TILE], ay_[NMS_TILE], ar_[NMS_TILE];
     __shared__ unsigned long long kA[NMS_TILE], kB[NMS_TILE];
     __shared__ uint32_t oA[NMS_TILE], oB[NMS_TILE];
-    __shared__ uint32_t queue[NMS_WARPS][64];
+    __shared__ uint32_t queue[NMS_WARPS][NMSB_CQ];
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
     if (threadIdx.x < NMS_TILE) {
         const BoxRec<T> a = recs[rb * NMS_TILE + threadIdx.x];
-        ax_[threadIdx.x] = a.cx; ay_[threadIdx.x] = a.cy; ar_[threadIdx.x] = a.rho;
+        const float fx = (float)a.cx, fy = (float)a.cy;
+        ax_[threadIdx.x] = fx; ay_[threadIdx.x] = fy; ar_[threadIdx.x] = __double2float_ru((double)a.rho) + (fabsf(fx) + fabsf(fy)) * 2.4e-7f;   // + 2^-22 of the coordinates
         kA[threadIdx.x] = skey[rb * NMS_TILE + threadIdx.x]; oA[threadIdx.x] = order[rb * NMS_TILE + threadIdx.x];
     }
     // the column blocks whose rectangle meets this row block's, compacted in ascending order (one global round trip for all of them).
@@ -1269,45 +1274,47 @@ nmsb_cand_kernel(const BoxRec<T> *__restrict__ recs_all, const uint64_t *__restr
     __syncthreads();
     const uint32_t ntiles = ncbs;
     uint32_t *q = queue[w];
-    unsigned head = 0, tail = 0;
-    auto flush = [&](bool all) {   // full groups of 32 candidates (at the end: the rest) leave for the frame's list with one reservation
-        while (tail - head >= 32u || (all && tail != head)) {
+    unsigned tail = 0;
+    auto flush = [&](bool all) {   // a nearly full queue (at the end: the rest) leaves for the frame's list with ONE reservation: the warp waits for the atomic's round trip
+        if (tail > (unsigned)NMSB_CQ - 32u || (all && tail != 0u)) {
             __syncwarp();
-            const unsigned cnt = min(tail - head, 32u);
             uint32_t at = 0;
-            if (lane == 0) at = atomicAdd(ccount + f, cnt);
+            if (lane == 0) at = atomicAdd(ccount + f, tail);
             at = __shfl_sync(0xffffffffu, at, 0);
-            if (lane < cnt) {
-                if (at + lane < ccap) cands[at + lane] = q[(head + lane) & 63];
+            for (unsigned h = lane; h < tail; h += 32) {
+                if (at + h < ccap) cands[at + h] = q[h];
                 else fail[1] = 1u;
             }
-            head += cnt;
+            tail = 0;
             __syncwarp();
         }
     };
     for (uint32_t ti = blockIdx.z; ti < ntiles; ti += gridDim.z) {   // the row block's tiles are dealt to gridDim.z CTAs
         const int64_t cb = cbs[ti];
         __syncthreads();   // the previous tile's readers are done with the column arrays
-        T bx[KC], by[KC], br[KC];
+        float bx[KC], by[KC], br[KC];
 #pragma unroll
-        for (int k = 0; k < KC; k++) { const BoxRec<T> bb = recs[cb * NMS_TILE + k * 32 + lane]; bx[k] = bb.cx; by[k] = bb.cy; br[k] = bb.rho; }
+        for (int k = 0; k < KC; k++) {
+            const BoxRec<T> bb = recs[cb * NMS_TILE + k * 32 + lane];
+            bx[k] = (float)bb.cx; by[k] = (float)bb.cy; br[k] = __double2float_ru((double)bb.rho) + (fabsf(bx[k]) + fabsf(by[k])) * 2.4e-7f;
+        }
         if (threadIdx.x < NMS_TILE) { kB[threadIdx.x] = skey[cb * NMS_TILE + threadIdx.x]; oB[threadIdx.x] = order[cb * NMS_TILE + threadIdx.x]; }
         __syncthreads();
         const bool diag = (rb == cb);
 #pragma unroll 1
         for (int r = 0; r < RW; r++) {
             const unsigned rl = w * RW + r;
-            const T ax = ax_[rl], ay = ay_[rl], ar = ar_[rl];
+            const float ax = ax_[rl], ay = ay_[rl], ar = ar_[rl];
 #pragma unroll
             for (int k = 0; k < KC; k++) {
                 const unsigned cl = k * 32 + lane;
-                T dx = ax - bx[k], dy = ay - by[k], rs = ar + br[k];
-                const bool cand = (dx * dx + dy * dy <= rs * rs) && (!diag || cl > rl);   // every unordered pair once
+                const float dx = ax - bx[k], dy = ay - by[k], rs = ar + br[k];
+                const bool cand = (dx * dx + dy * dy <= rs * rs * 1.00001f) && (!diag || cl > rl);   // every unordered pair once
                 const unsigned bal = __ballot_sync(0xffffffffu, cand);
                 if (cand) {
                     const bool a_first = kA[rl] < kB[cl] || (kA[rl] == kB[cl] && oA[rl] < oB[cl]);
                     const uint32_t pa = (uint32_t)(rb * NMS_TILE + rl), pb = (uint32_t)(cb * NMS_TILE + cl);
-                    q[(tail + __popc(bal & lanemask_lt())) & 63] = a_first ? (pa | (pb << 16)) : (pb | (pa << 16));
+                    q[tail + __popc(bal & lanemask_lt())] = a_first ? (pa | (pb << 16)) : (pb | (pa << 16));
                 }
                 tail += __popc(bal);
                 flush(false);
@@ -1331,6 +1338,21 @@ nmsb_clip_kernel(const BoxRec<T> *__restrict__ recs_all, const T *__restrict__ r
     const uint32_t *cands = cands_all + (size_t)f * cand_stride;
     uint32_t *edges = edges_all + (size_t)f * ecap;
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
+    __shared__ uint32_t hits[NMS_WARPS][NMSB_HQ];
+    uint32_t *hb = hits[w];
+    unsigned nh = 0;
+    auto flush = [&]() {   // the warp's hits leave with one reservation in the frame's edge list
+        __syncwarp();
+        uint32_t at = 0;
+        if (lane == 0) at = atomicAdd(ecount + f, nh);
+        at = __shfl_sync(0xffffffffu, at, 0);
+        for (unsigned h = lane; h < nh; h += 32) {
+            if (at + h < ecap) edges[at + h] = hb[h];   // source | destination << 16
+            else fail[1] = 1u;
+        }
+        nh = 0;
+        __syncwarp();
+    };
     for (uint32_t base = (blockIdx.x * NMS_WARPS + w) * 32u; base < nc; base += gridDim.x * NMS_WARPS * 32u) {
         const bool live = base + lane < nc;
         const uint32_t c = cands[live ? base + lane : nc - 1];
@@ -1340,15 +1362,12 @@ nmsb_clip_kernel(const BoxRec<T> *__restrict__ recs_all, const T *__restrict__ r
         const bool hit = live && over_threshold<T>(v, thr, raw, pa, pb);
         const unsigned bal = __ballot_sync(0xffffffffu, hit);
         if (bal) {
-            uint32_t at = 0;
-            if (lane == 0) at = atomicAdd(ecount + f, (uint32_t)__popc(bal));
-            at = __shfl_sync(0xffffffffu, at, 0) + __popc(bal & lanemask_lt());
-            if (hit) {
-                if (at < ecap) edges[at] = c;   // source | destination << 16
-                else fail[1] = 1u;
-            }
+            if (nh + 32u > (unsigned)NMSB_HQ) flush();
+            if (hit) hb[nh + __popc(bal & lanemask_lt())] = c;
+            nh += __popc(bal);
         }
     }
+    if (nh) flush();
 }
 
 // one CTA per frame: the keep mask as the fixpoint over the frame's edge list, everything in shared memory.
