@@ -870,8 +870,8 @@ def bench_nms(args, rank, world, barrier):
     roof = alu_roofline(1, clips * W_CAND / (ms_pairs * 1e-3) / 1e12, clk)
     roof.update(phase="candidate phase (nms_pairs_kernel): clips x 230 flop over its own time", clips=clips, ms_sort_gather=ms_sort, ms_candidates=ms_pairs,
                 ms_resolve=ms_resolve, resolve_us_per_64_box_block=ms_resolve * 1e3 / ((n + 63) // 64),
-                note="the resolve is a fixpoint of keep / suppress decisions reached in parallel rounds on a cooperative grid (two grid barriers per round, latency: "
-                     "no roofline; D3D_B200_NMS_FIX=0: the block-by-block walk in score order on one SM, 0.97 ms); frame-batched NMS (ops.c5) runs one walk per frame")
+                note="the resolve is the fixpoint of keep / suppress decisions, pulled by a thread per box over the transposed hit lists (latency of the longest chain "
+                     "of decisions: no roofline; D3D_B200_NMS_FIX=2: the same fixpoint by rounds with grid barriers, 0.23 ms; =0: the block-by-block walk in score order on one SM, 0.97 ms)")
     return dict(metric="NMS boxes/sec", unit="boxes/s", value=n * world / (ms * 1e-3), ms_per_step=ms, dtype="f64", scaling="weak",
                 gpu_launches=int(launches),
                 config=dict(workload=f"C3 BEV rotated NMS: {n} clustered proposals/frame (2000 objects), rbox thr 0.5, precise=True (fp64), "
@@ -941,7 +941,24 @@ def bench_c5(args, rank, world, barrier):
             gen.batch(hclouds)
             box2d_nms_batch(hb, hs, iou_method="rbox", iou_threshold=0.5)
     ms_e2e = max_over_ranks(timed(e2e_step, 2, 1, barrier), world)
-    return dict(metric="voxelize->NMS pipeline frames/sec", unit="frames/s", value=F / (ms * 1e-3), ms_per_step=ms, dtype="f32 voxels, f64 NMS", scaling="strong",
+    weak = None
+    if world > 1:
+        # the same pipeline with the whole 64-frame batch on EVERY rank (weak scaling): what the box delivers when every GPU has a full batch,
+        # beside the strong-scaling line above, whose per-rank share (F / world frames) is bound by the latency of the kernel chain
+        wc = [lidar(500 + rank * F + f) for f in range(F)]
+        wp = [proposals(900 + rank * F + f, NP, 160) for f in range(F)]
+        w_pts = torch.cat([torch.from_numpy(x) for x in wc], 0).cuda()
+        w_offs = torch.zeros(F + 1, dtype=torch.int64); w_offs[1:] = torch.tensor([len(x) for x in wc], dtype=torch.int64).cumsum(0)
+        w_offs_dev = w_offs.cuda()
+        w_pb = torch.cat([torch.from_numpy(b) for b, _ in wp], 0).cuda(); w_ps = torch.cat([torch.from_numpy(s_) for _, s_ in wp], 0).cuda()
+        w_poffs = torch.arange(F + 1, dtype=torch.int64) * NP; w_poffs_dev = w_poffs.cuda()
+
+        def wstep():
+            gen.batch_packed(w_pts, w_offs, w_offs_dev)
+            box2d_nms_batch(w_pb, w_ps, w_poffs, iou_method="rbox", iou_threshold=0.5, offsets_dev=w_poffs_dev)
+        wms = max_over_ranks(timed(wstep, args.steps, args.warmup, barrier), world)
+        weak = dict(frames_per_gpu=F, ms_per_step=wms, value=F * world / (wms * 1e-3), unit="frames/s", scaling="weak")
+    return dict(metric="voxelize->NMS pipeline frames/sec", unit="frames/s", value=F / (ms * 1e-3), ms_per_step=ms, dtype="f32 voxels, f64 NMS", scaling="strong", weak=weak,
                 gpu_launches=int(launches),
                 config=dict(workload=f"C5: batch of {F} frames x (C2 cloud of {C2_POINTS} points + {NP} BEV proposals), voxelize -> rotated NMS thr 0.5, "
                                      f"frames sharded over {world} GPU(s)", frames=F, frames_this_rank=nf, kept_boxes=kept, voxels=voxels,
