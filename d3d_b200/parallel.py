@@ -40,24 +40,40 @@ def iou_row_block(boxes1, boxes2, method="rbox", precise=False, rank=None, world
     return box2d_iou(boxes1[lo:hi], boxes2, method=method, precise=precise), (lo, hi)
 
 
+def _all_gather_flat(x):
+    """all_gather of equally sized 1-D tensors into one [world * len] tensor (one collective, no per-rank Python objects)."""
+    _, w = world()
+    out = torch.empty(w * x.numel(), dtype=x.dtype, device=x.device)
+    try:
+        dist.all_gather_into_tensor(out, x.contiguous())
+    except (RuntimeError, NotImplementedError, AttributeError):   # a backend without the flat form
+        parts = [torch.empty_like(x) for _ in range(w)]
+        dist.all_gather(parts, x.contiguous())
+        out = torch.cat(parts)
+    return out
+
+
+def _gather_padded(t, sizes):
+    """payload of every rank, given everybody's sizes (host ints): one padded all_gather, sliced per rank"""
+    _, w = world()
+    mx = max(max(sizes), 1)
+    pad = torch.zeros(mx, dtype=t.dtype, device=t.device)
+    pad[:t.numel()] = t.reshape(-1)
+    buf = _all_gather_flat(pad)
+    return [buf[r * mx:r * mx + sizes[r]] for r in range(w)]
+
+
 def gather_ragged(t, dst=None):
     """Gather 1-D tensors of different lengths from every rank (all ranks get the list, or only `dst`).
 
-    Sizes travel first (all_gather of one int64), then the payload padded to the longest -- the only
-    collective the pipeline needs, run after the timed compute."""
+    Sizes travel first (one all_gather of an int64 per rank, read back with a single device-to-host copy), then the payload padded to
+    the longest -- the only collective the pipeline needs, run after the timed compute."""
     rank, w = world()
     if w == 1:
         return [t]
     n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
-    sizes = [torch.zeros_like(n) for _ in range(w)]
-    dist.all_gather(sizes, n)
-    sizes = [int(s.item()) for s in sizes]
-    mx = max(max(sizes), 1)
-    pad = torch.zeros(mx, dtype=t.dtype, device=t.device)
-    pad[:t.numel()] = t.reshape(-1)
-    bufs = [torch.empty_like(pad) for _ in range(w)]
-    dist.all_gather(bufs, pad)
-    out = [b[:s] for b, s in zip(bufs, sizes)]
+    sizes = _all_gather_flat(n).tolist()
+    out = _gather_padded(t, sizes)
     if dst is not None and rank != dst:
         return None
     return out
@@ -68,7 +84,10 @@ def gather_frames(per_frame, nframes, dtype=None, device=None):
 
     `dtype` / `device` of the payload must be the same on every rank; a rank whose shard is empty (more ranks than frames) cannot read
     them off its tensors, so pass them whenever that can happen (default: those of the rank's first tensor, else float32 on the
-    current CUDA device under NCCL / the CPU under gloo)."""
+    current CUDA device under NCCL / the CPU under gloo).
+
+    Two collectives and one device-to-host copy whatever the number of frames: the frame lengths (every rank owns at most
+    ceil(nframes / world) frames, so the length vectors have one known size) and the concatenated payload."""
     rank, w = world()
     if w == 1:
         return list(per_frame)
@@ -76,15 +95,17 @@ def gather_frames(per_frame, nframes, dtype=None, device=None):
         device = per_frame[0].device if per_frame else (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu"))
     if dtype is None:
         dtype = per_frame[0].dtype if per_frame else torch.float32
-    lens = torch.tensor([x.numel() for x in per_frame], dtype=torch.int64, device=device)
+    maxf = (nframes + w - 1) // w
+    mine = [int(x.numel()) for x in per_frame]
+    lens = torch.tensor(mine + [0] * (maxf - len(mine)), dtype=torch.int64).to(device)
+    all_lens = _all_gather_flat(lens).reshape(w, maxf).tolist() if maxf else [[] for _ in range(w)]
     flat = torch.cat([x.reshape(-1) for x in per_frame]).to(device=device, dtype=dtype) if per_frame else torch.zeros(0, dtype=dtype, device=device)
-    all_lens = gather_ragged(lens)
-    all_flat = gather_ragged(flat)
+    all_flat = _gather_padded(flat, [sum(row) for row in all_lens])
     out = [None] * nframes
     for r in range(w):
         off = 0
         for k, f in enumerate(frame_shard(nframes, r, w)):
-            ln = int(all_lens[r][k])
+            ln = all_lens[r][k]
             out[f] = all_flat[r][off:off + ln]
             off += ln
     return out
