@@ -1654,7 +1654,8 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
     }
 
     nms_keys_kernel<T><<<(unsigned)cdiv(n, 256), 256, 0, st>>>(scores, n, keys, order); D3D_LAUNCHED();
-    int rc = radix_sort_pairs_u64(keys, order, n, KeyBits<T>::bits, sort_ws, sort_bytes, st);
+    int rc = KeyBits<T>::bits == 64 ? radix_sort_pairs_u64_hi32(keys, order, n, sort_ws, sort_bytes, fix_ctl + 8, st)
+                                    : radix_sort_pairs_u64(keys, order, n, KeyBits<T>::bits, sort_ws, sort_bytes, st);
     if (rc) return rc;
     const bool recheck = sizeof(T) == 4 && !aabb;
     if (aabb)

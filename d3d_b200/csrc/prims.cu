@@ -195,9 +195,13 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t *
 constexpr int RS_COOP_TILES = 64;
 
 __global__ void __launch_bounds__(RS_THREADS) rs_coop_kernel(uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, int64_t n, int passes, int ntiles,
-                                                             uint32_t *__restrict__ hist /*[256][ntiles]*/)
+                                                             uint32_t *__restrict__ hist /*[256][ntiles]*/, int shift0, const uint32_t *__restrict__ run_if)
 {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    if (run_if && *run_if == 0u) {   // (grid-uniform) nothing to sort: the sequence the previous step left in k1 / v1 is the result
+        for (int64_t i = (int64_t)blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RS_THREADS) { k0[i] = k1[i]; v0[i] = v1[i]; }
+        return;
+    }
     __shared__ uint32_t cnt[RS_WARPS][RS_BINS];
     __shared__ uint32_t binbase[RS_BINS];
     const unsigned w = threadIdx.x >> 5, lane = lane_id();
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_coop_kernel(uint64_t *k0, uint3
     uint64_t *ki = k0, *ko = k1;
     uint32_t *vi = v0, *vo = v1;
     for (int p = 0; p < passes; p++) {
-        const int shift = p * 8;
+        const int shift = shift0 + p * 8;
         for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&cnt[0][0])[i] = 0;
         __syncthreads();
         // ranks inside the tile (warp match + per-warp digit counters), as in rs_scatter_kernel
@@ -293,8 +297,9 @@ int radix_sort_pairs_u64(uint64_t *keys, uint32_t *vals, int64_t n, int key_bits
     int passes = (key_bits + 7) / 8;
     if (passes < 1) passes = 1;
     if (ntiles <= RS_COOP_TILES && tuning(D3D_TUNE_SORT_COOP, 1)) {   // one CTA per tile: always co-resident (<= 64 CTAs of 256 threads)
-        int nt = (int)ntiles;
-        void *args[] = {&keys, &vals, &k2, &v2, &n, &passes, &nt, &hist};
+        int nt = (int)ntiles, shift0 = 0;
+        const uint32_t *run_if = nullptr;
+        void *args[] = {&keys, &vals, &k2, &v2, &n, &passes, &nt, &hist, &shift0, &run_if};
         D3D_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)rs_coop_kernel, dim3((unsigned)ntiles), dim3(RS_THREADS), args, 0, st)); D3D_LAUNCHED();
         return D3D_OK;
     }
@@ -311,6 +316,64 @@ int radix_sort_pairs_u64(uint64_t *keys, uint32_t *vals, int64_t n, int key_bits
     if (ki != keys) {
         D3D_CUDA_TRY(cudaMemcpyAsync(keys, ki, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
         D3D_CUDA_TRY(cudaMemcpyAsync(vals, vi, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    }
+    return D3D_OK;
+}
+
+// ---- 64-bit keys whose low half rarely decides the order (scores in double precision: the high half holds sign, exponent and 20
+// mantissa bits).  Four passes over the high half, then every element looks at the run of equal high halves around it -- one or two
+// elements almost always -- and takes its place inside the run by counting (low half, then position: the stable order of the full key).
+// A run longer than RS_RUN_MAX on either side raises a device flag and the eight passes of the full sort run on the sequence as it
+// stands (a stable sort of any arrangement that kept equal keys in index order gives the same result); otherwise that launch only
+// copies the fixed-up sequence back to the caller's arrays.  Same result as radix_sort_pairs_u64(..., 64, ...).
+constexpr int RS_RUN_MAX = 16;
+
+__global__ void __launch_bounds__(256) rs_runfix_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, int64_t n,
+                                                        uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t *__restrict__ flag)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint64_t k = keys[p];
+    const uint32_t hi = (uint32_t)(k >> 32), lo = (uint32_t)k;
+    int64_t s = p, e = p + 1;
+    while (s > 0 && p - s < RS_RUN_MAX && (uint32_t)(keys[s - 1] >> 32) == hi) s--;
+    while (e < n && e - p <= RS_RUN_MAX && (uint32_t)(keys[e] >> 32) == hi) e++;
+    if ((s > 0 && (uint32_t)(keys[s - 1] >> 32) == hi) || (e < n && (uint32_t)(keys[e] >> 32) == hi)) *flag = 1u;   // the run goes on: the full sort decides
+    int64_t at = s;
+    for (int64_t q = s; q < e; q++) {
+        const uint32_t lq = (uint32_t)keys[q];
+        at += (lq < lo || (lq == lo && q < p)) ? 1 : 0;
+    }
+    keys_out[at] = k;
+    vals_out[at] = vals[p];
+}
+
+int radix_sort_pairs_u64_hi32(uint64_t *keys, uint32_t *vals, int64_t n, void *ws, size_t ws_bytes, uint32_t *flag, cudaStream_t st)
+{
+    if (n <= 1) return D3D_OK;
+    const int64_t ntiles = cdiv(n, RS_TILE);
+    if (ntiles > RS_COOP_TILES || !tuning(D3D_TUNE_SORT_COOP, 1) || tuning(D3D_TUNE_SORT_COOP, 1) == 2)   // D3D_B200_SORT_COOP=2: all eight passes (A/B, tests)
+        return radix_sort_pairs_u64(keys, vals, n, 64, ws, ws_bytes, st);
+    if (ws_bytes < radix_sort_workspace_bytes(n)) return D3D_ERR_WORKSPACE;
+    Arena a(ws, ws_bytes);
+    uint64_t *k2 = a.take<uint64_t>(n);
+    uint32_t *v2 = a.take<uint32_t>(n);
+    uint32_t *hist = a.take<uint32_t>((size_t)RS_BINS * ntiles);
+    D3D_CUDA_TRY(cudaMemsetAsync(flag, 0, 4, st));
+    int64_t n_ = n;
+    int nt = (int)ntiles;
+    {
+        int passes = 4, shift0 = 32;
+        const uint32_t *run_if = nullptr;
+        void *args[] = {&keys, &vals, &k2, &v2, &n_, &passes, &nt, &hist, &shift0, &run_if};
+        D3D_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)rs_coop_kernel, dim3((unsigned)ntiles), dim3(RS_THREADS), args, 0, st)); D3D_LAUNCHED();
+    }
+    rs_runfix_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(keys, vals, n, k2, v2, flag); D3D_LAUNCHED();
+    {
+        int passes = 8, shift0 = 0;
+        const uint32_t *run_if = flag;
+        void *args[] = {&keys, &vals, &k2, &v2, &n_, &passes, &nt, &hist, &shift0, &run_if};
+        D3D_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)rs_coop_kernel, dim3((unsigned)ntiles), dim3(RS_THREADS), args, 0, st)); D3D_LAUNCHED();
     }
     return D3D_OK;
 }

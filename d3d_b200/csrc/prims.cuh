@@ -9,4 +9,7 @@ int exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, uint32_t *t
 size_t radix_sort_workspace_bytes(int64_t n);
 // stable ascending sort of (key, val) on the low key_bits bits of key
 int radix_sort_pairs_u64(uint64_t *keys, uint32_t *vals, int64_t n, int key_bits, void *ws, size_t ws_bytes, cudaStream_t st);
+// the same order for full 64-bit keys whose low half rarely decides (double-precision scores): four passes on the high half + a fix-up of
+// the runs of equal high halves; `flag` is one device word of scratch
+int radix_sort_pairs_u64_hi32(uint64_t *keys, uint32_t *vals, int64_t n, void *ws, size_t ws_bytes, uint32_t *flag, cudaStream_t st);
 }  // namespace d3d
