@@ -20,7 +20,7 @@ static std::atomic<int> g_tune_val[D3D_TUNE_COUNT];
 static std::atomic<int> g_tune_state[D3D_TUNE_COUNT];   // 0 unread, 1 unset, 2 set
 static int tune_parse(int knob, const char *e)
 {
-    if (knob == D3D_TUNE_NMS_PATH) return e[0] == 'd' ? 2 : (e[0] == 't' ? 1 : atoi(e));     // dense | tiles | (spatial)
+    if (knob == D3D_TUNE_NMS_PATH) return e[0] == 'd' ? 2 : (e[0] == 't' ? 1 : (e[0] == 'w' ? 3 : atoi(e)));     // dense | tiles | warp (spatial, a warp per box) | (spatial, a CTA per cell)
     if (knob == D3D_TUNE_CROP_PATH) return e[0] == 'b' ? 1 : (e[0] == 'g' ? 2 : atoi(e));    // brute | grid | (auto)
     if (knob == D3D_TUNE_NMS_BATCH_PATH) return e[0] == 'd' ? 1 : atoi(e);                  // dense | (edges)
     if (knob == D3D_TUNE_SCATTER_PATH) return e[0] == 'g' ? 1 : (e[0] == 't' ? 2 : atoi(e)); // gather | tiles | (auto)

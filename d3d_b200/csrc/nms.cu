@@ -332,6 +332,131 @@ __global__ void __launch_bounds__(NMS_PAIR_THREADS, D3D_NMS_PAIR_CTAS) nms_pairs
     if (nhits) flush();
 }
 
+// ---- the same candidate search, a CTA per grid cell (default).  The kernel above gives every box a warp: its clips read their records
+// from global memory, and the last clip step of every box runs with the lanes that are left (ncu: half the clip rate of the IoU tile
+// kernel).  Here the boxes of one cell are the rows of a tile and the boxes of its 3x3 neighbourhood the columns, both staged in shared
+// memory; every thread tests its column against the rows (single precision, widened as above), the survivors of a 64 x 128 tile go to
+// one queue of the CTA, and the warps clip them 32 at a time -- full warps except for the tile's last step.  The hits of a row chunk wait in
+// shared memory and are appended to their rows' block lists together (the atomics' round trips overlap).  NC_SPLIT work items share a cell,
+// each taking every NC_SPLIT-th column chunk.
+#ifndef D3D_NC_SPLIT
+#define D3D_NC_SPLIT 4
+#endif
+#ifndef D3D_NC_CTAS
+#define D3D_NC_CTAS 3
+#endif
+constexpr int NC_ROWS = 64, NC_COLS = 128, NC_THREADS = 256, NC_SPLIT = D3D_NC_SPLIT, NC_HB = 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(NC_THREADS, D3D_NC_CTAS) nms_cells_kernel(const BoxRec<T> *__restrict__ recs, const T *__restrict__ raw, int64_t n, int64_t nwords, T thr,
+                                                                  const NmsGrid *__restrict__ g, const uint32_t *__restrict__ cellptr,
+                                                                  const NmsCand<T> *__restrict__ celllist, const NmsLists lists, uint32_t *__restrict__ ticket)
+{
+    if (!g->ok) return;
+    const NmsGrid G = *g;
+    __shared__ BoxRec<T> sR[NC_ROWS], sC[NC_COLS];
+    __shared__ float4 fR[NC_ROWS];                    // centre, widened radius, index (bits) of the rows
+    __shared__ uint32_t cidx[NC_COLS];
+    __shared__ uint16_t queue[NC_ROWS * NC_COLS];     // row << 8 | column of the pairs that passed the circle test
+    __shared__ uint2 hbuf[NC_HB];                     // hits (row box, column box) of the row chunk
+    __shared__ uint32_t seg_beg[3], seg_off[4], qn, hn, s_item;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+    auto append = [&](const uint32_t i, const uint32_t j) {   // one entry of row i's 64-row block
+        const uint32_t rb = i >> 6, at = atomicAdd(lists.blkcnt + rb, 1u);
+        if (at < NMS_LIST_CAP) {
+            lists.ent_w[(size_t)rb * NMS_LIST_CAP + at] = (j >> 6) | ((i & 63u) << 16);
+            lists.ent_bits[(size_t)rb * NMS_LIST_CAP + at] = 1ull << (j & 63u);
+        } else lists.blkcnt[nwords] = 1u;
+    };
+    // work items (cell, share of the column chunks) are handed out by a ticket counter (the grid does not know how many cells the frame has;
+    // the counter starts at 0xffffffff: it shares the memset of the extents)
+    const uint32_t items = (uint32_t)(G.nx * G.ny) * NC_SPLIT;
+  for (;;) {
+    __syncthreads();   // the previous item is done with the shared words
+    if (tid == 0) s_item = atomicAdd(ticket, 1u) + 1u;
+    __syncthreads();
+    const uint32_t item = s_item;
+    if (item >= items) break;
+    const int cell = (int)(item / NC_SPLIT);
+    const uint32_t split = item % NC_SPLIT;
+    const uint32_t r_beg = cellptr[cell], r_end = cellptr[cell + 1];
+    if (r_beg == r_end) continue;   // (CTA-uniform)
+    if (tid == 0) {   // the three cells of a grid row are contiguous in the cell-sorted list
+        const int ix = cell % G.nx, iy = cell / G.nx;
+        uint32_t off = 0;
+        for (int k = 0; k < 3; k++) {
+            const int cy = iy + k - 1;
+            uint32_t beg = 0, len = 0;
+            if (cy >= 0 && cy < G.ny) {
+                const int x0 = max(ix - 1, 0), x1 = min(ix + 1, G.nx - 1);
+                beg = cellptr[cy * G.nx + x0];
+                len = cellptr[cy * G.nx + x1 + 1] - beg;
+            }
+            seg_beg[k] = beg; seg_off[k] = off; off += len;
+        }
+        seg_off[3] = off;
+        hn = 0;
+    }
+    __syncthreads();
+    const uint32_t ncols = seg_off[3];
+    for (uint32_t rc = r_beg; rc < r_end; rc += NC_ROWS) {
+        const uint32_t nr = min((uint32_t)NC_ROWS, r_end - rc);
+        __syncthreads();   // the previous row chunk is done with the row arrays
+        if (tid < nr) {
+            const NmsCand<T> e = celllist[rc + tid];
+            sR[tid] = recs[e.idx];
+            fR[tid] = make_float4(e.cx, e.cy, e.rho + (fabsf(e.cx) + fabsf(e.cy)) * 2.4e-7f, __uint_as_float(e.idx));
+        }
+        for (uint32_t cc = split * NC_COLS; cc < ncols; cc += NC_SPLIT * NC_COLS) {
+            __syncthreads();   // rows staged; the previous tile is done with the columns and the queue
+            if (tid == 0) qn = 0;
+            const uint32_t c = tid & (NC_COLS - 1), v = cc + c;
+            const bool have = v < ncols;
+            NmsCand<T> ce;
+            ce.cx = ce.cy = ce.rho = 0.f; ce.idx = 0;
+            if (have) {
+                const int sg = v >= seg_off[2] ? 2 : (v >= seg_off[1] ? 1 : 0);
+                ce = celllist[seg_beg[sg] + (v - seg_off[sg])];
+                if (tid < NC_COLS) { sC[c] = recs[ce.idx]; cidx[c] = ce.idx; }
+            }
+            __syncthreads();
+            const float cr = ce.rho + (fabsf(ce.cx) + fabsf(ce.cy)) * 2.4e-7f;
+            for (uint32_t r = tid / NC_COLS; r < nr; r += NC_THREADS / NC_COLS) {   // (warp-uniform r)
+                const float4 f = fR[r];
+                const float dx = f.x - ce.cx, dy = f.y - ce.cy, rs = f.z + cr;
+                const bool cand = have && ce.idx > __float_as_uint(f.w) && dx * dx + dy * dy <= rs * rs * 1.00001f;   // every unordered pair once: from its higher-scored box
+                const unsigned bal = __ballot_sync(0xffffffffu, cand);
+                if (bal) {
+                    uint32_t at = 0;
+                    if (lane == 0) at = atomicAdd(&qn, (uint32_t)__popc(bal));
+                    at = __shfl_sync(0xffffffffu, at, 0);
+                    if (cand) queue[at + __popc(bal & lanemask_lt())] = (uint16_t)((r << 8) | c);
+                }
+            }
+            __syncthreads();
+            const uint32_t nq = qn;
+            for (uint32_t e0 = w * 32u; e0 < nq; e0 += (NC_THREADS / 32) * 32u) {
+                const bool live = e0 + lane < nq;
+                const uint32_t ent = queue[live ? e0 + lane : nq - 1];
+                const uint32_t r = ent >> 8, cq = ent & 255u;
+                const uint32_t i = __float_as_uint(fR[r].w), j = cidx[cq];
+                const T iou = rbox_iou<T>(sR[r], sC[cq]);   // iou(higher score box, lower score box), nms.cpp:50
+                if (live && over_threshold<T>(iou, thr, raw, i, j)) {
+                    const uint32_t h = atomicAdd(&hn, 1u);
+                    if (h < (uint32_t)NC_HB) hbuf[h] = make_uint2(i, j);
+                    else append(i, j);
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t nh = min(hn, (uint32_t)NC_HB);
+        for (uint32_t h = tid; h < nh; h += NC_THREADS) append(hbuf[h].x, hbuf[h].y);
+        __syncthreads();
+        if (tid == 0) hn = 0;
+    }
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ void nms_mask_rbox_body(const BoxRec<T> *__restrict__ recs, const T *__restrict__ raw, int64_t n, int64_t nwords, T thr, uint64_t *__restrict__ mask,
                                                    const NmsLists lists, const int64_t cb, const int64_t rb_first, const int64_t rb_stride)
@@ -1680,12 +1805,19 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
     if (spatial) {
         const BoxRec<T> *br = (const BoxRec<T> *)recs;
         const unsigned gb = (unsigned)cdiv(n, 256);
+        int dev_c = 0, nsm_cells = 0;
+        D3D_CUDA_TRY(cudaGetDevice(&dev_c));
+        D3D_CUDA_TRY(cudaDeviceGetAttribute(&nsm_cells, cudaDevAttrMultiProcessorCount, dev_c));
+        if (nsm_cells < 1) nsm_cells = 1;
         D3D_CUDA_TRY(cudaMemsetAsync(cellcnt, 0, (size_t)2 * (NMS_GRID_CELLS + 1) * 4, st));
         nms_grid_kernel<<<1, 32, 0, st>>>(ext, n, grid); D3D_LAUNCHED();
         nms_bin_kernel<T, 0><<<gb, 256, 0, st>>>(br, n, grid, cellcnt, nullptr, nullptr); D3D_LAUNCHED();
         if ((rc = exclusive_scan_u32(cellcnt, cellptr, NMS_GRID_CELLS + 1, nullptr, cell_scan_ws, st))) return rc;
         nms_bin_kernel<T, 1><<<gb, 256, 0, st>>>(br, n, grid, cellcnt + NMS_GRID_CELLS + 1, cellptr, celllist); D3D_LAUNCHED();
-        nms_pairs_kernel<T><<<(unsigned)cdiv(n, NMS_PAIR_THREADS / 32), NMS_PAIR_THREADS, 0, st>>>(br, recheck ? raw : nullptr, n, nwords, thr, grid, cellptr, celllist, lists);
+        if (tuning(D3D_TUNE_NMS_PATH, 0) == 3)   // D3D_B200_NMS_PATH=warp: a warp per box (the round's earlier candidate kernel)
+            nms_pairs_kernel<T><<<(unsigned)cdiv(n, NMS_PAIR_THREADS / 32), NMS_PAIR_THREADS, 0, st>>>(br, recheck ? raw : nullptr, n, nwords, thr, grid, cellptr, celllist, lists);
+        else   // a CTA per grid cell (cells that do not exist or hold no box leave at once)
+            nms_cells_kernel<T><<<(unsigned)(nsm_cells * D3D_NC_CTAS), NC_THREADS, 0, st>>>(br, recheck ? raw : nullptr, n, nwords, thr, grid, cellptr, celllist, lists, &ext->pad);
         D3D_LAUNCHED();
     }
     dim3 tiles((unsigned)nwords, (unsigned)nwords);
