@@ -535,19 +535,19 @@ def test_sort_forms_agree(dev):
 
 
 def test_nms_back_ends_agree(dev):
-    """the three NMS back ends (spatial candidate grid, dense tiles + list resolve, dense matrix + dense resolve) give the
-    same keep mask (the knob is set through d3d_tuning_set: the environment is read once)"""
+    """the NMS back ends (spatial candidate grid with a CTA per cell or a warp per box, dense tiles + list resolve, dense matrix + dense
+    resolve) give the same keep mask (the knob is set through d3d_tuning_set: the environment is read once)"""
     from d3d_b200.box import box2d_nms
     rng = np.random.default_rng(5)
     for n, nobj, extent in ((20000, 800, 75.0), (3000, 40, 30.0), (700, 700, 400.0)):
         P, s = proposals(rng, n, nobj, extent=extent)
         for dt in (np.float64, np.float32):
             out = {}
-            for path in ("", "tiles", "dense"):
-                _cabi.tuning_set("D3D_B200_NMS_PATH", {"": None, "dense": 2, "tiles": 1}[path])
+            for path in ("", "warp", "tiles", "dense"):   # "": spatial grid, a CTA per cell (default); "warp": spatial grid, a warp per box
+                _cabi.tuning_set("D3D_B200_NMS_PATH", {"": None, "dense": 2, "tiles": 1, "warp": 3}[path])
                 out[path] = box2d_nms(_t(P.astype(dt), dev), _t(s.astype(dt), dev), "rbox", iou_threshold=0.45, precise=dt == np.float64).cpu().numpy()
             _cabi.tuning_set("D3D_B200_NMS_PATH", None)
-            assert np.array_equal(out[""], out["dense"]) and np.array_equal(out["tiles"], out["dense"]), (n, dt)
+            assert np.array_equal(out[""], out["dense"]) and np.array_equal(out["tiles"], out["dense"]) and np.array_equal(out["warp"], out["dense"]), (n, dt)
             assert 0 < out[""].sum() < n
     # a negative threshold suppresses disjoint pairs too (IoU 0 > thr), like the reference: only the best box survives
     P, s = proposals(rng, 500, 50, extent=100.0)
