@@ -69,9 +69,34 @@ template <> struct Num<float> {
     static D3D_HD float fmax_(float a, float b) { return fmaxf(a, b); }
     static D3D_HD float abs_(float a) { return fabsf(a); }
 };
+// Double precision on the device: fmin / fmax cost 7 instructions each on sm_100a (DSETP.MIN + selects + NaN canonicalisation, there
+// is no DMNMX) and 1.0 / x is MUFU.RCP64H + five DFMA behind a range check with a call for zero, infinite and subnormal arguments --
+// a horizontal edge (d = 0) of an axis-aligned box takes that call.  The clip only needs: min / max of finite numbers, sat with
+// NaN -> 0, and a reciprocal that is +-inf for 0 and good to an ulp elsewhere; written as compare + select (3 instructions) and as
+// RCP64H + two Newton steps without a branch they take a fifth off the clip's instruction count.
 template <> struct Num<double> {
-    static D3D_HD double rcp(double x) { return 1.0 / x; }
-    static D3D_HD double sat(double x) { return fmin(fmax(x, 0.0), 1.0); }  // NaN -> 0
+    static D3D_HD double rcp(double x)
+    {
+#ifdef __CUDA_ARCH__
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));   // ~20 bits; 0 (and subnormals) -> inf, inf -> 0
+        const double e0 = fma(-x, r, 1.0), q0 = fma(r, e0, r);
+        const double e1 = fma(-x, q0, 1.0), q1 = fma(q0, e1, q0);
+        const double ar = fabs(r);
+        return (ar > 0.0 && ar < 1.7976931348623157e308) ? q1 : r;   // the Newton steps turn 0 and inf into NaN: keep the seed there
+#else
+        return 1.0 / x;
+#endif
+    }
+    static D3D_HD double sat(double x)   // NaN -> 0
+    {
+#ifdef __CUDA_ARCH__
+        const double lo = x > 0.0 ? x : 0.0;
+        return lo < 1.0 ? lo : 1.0;
+#else
+        return fmin(fmax(x, 0.0), 1.0);
+#endif
+    }
     static D3D_HD double mul_rn(double a, double b)
     {
 #ifdef __CUDA_ARCH__
@@ -82,8 +107,13 @@ template <> struct Num<double> {
     }
     static D3D_HD double tiny() { return 1e-280; }
     static D3D_HD double snap() { return 1e-12; }
+#ifdef __CUDA_ARCH__
+    static D3D_HD double fmin_(double a, double b) { return a < b ? a : b; }   // (finite arguments)
+    static D3D_HD double fmax_(double a, double b) { return a > b ? a : b; }
+#else
     static D3D_HD double fmin_(double a, double b) { return fmin(a, b); }
     static D3D_HD double fmax_(double a, double b) { return fmax(a, b); }
+#endif
     static D3D_HD double abs_(double a) { return fabs(a); }
 };
 
