@@ -1822,7 +1822,8 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
     }
     dim3 tiles((unsigned)nwords, (unsigned)nwords);
     if (aabb) nms_mask_aabb_kernel<T><<<tiles, NMS_TILE, 0, st>>>((const AABBRec<T> *)recs, n, nwords, thr, mask, lists);
-    else nms_mask_rbox_kernel<T><<<dim3((unsigned)nwords, (unsigned)(nwords < 24 ? nwords : 24)), NMS_THREADS, 0, st>>>((const BoxRec<T> *)recs, recheck ? raw : nullptr, n, nwords, thr, mask, lists, spatial ? grid : nullptr);
+    // (behind the spatial path of a large frame its CTAs only read the grid's flag and leave: fewer of them, each striding over more row tiles)
+    else nms_mask_rbox_kernel<T><<<dim3((unsigned)nwords, (unsigned)(spatial && nwords >= 128 ? 4 : (nwords < 24 ? nwords : 24))), NMS_THREADS, 0, st>>>((const BoxRec<T> *)recs, recheck ? raw : nullptr, n, nwords, thr, mask, lists, spatial ? grid : nullptr);
     D3D_LAUNCHED();
     if (stop == 2) return D3D_OK;
     size_t smem = (size_t)nwords * 8;
