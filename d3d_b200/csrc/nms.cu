@@ -332,6 +332,23 @@ __global__ void __launch_bounds__(NMS_PAIR_THREADS, D3D_NMS_PAIR_CTAS) nms_pairs
     if (nhits) flush();
 }
 
+// A pair can only pass an IoU threshold t if its intersection exceeds t / (1 + t) of the two areas together (IoU = I / (S - I)), and the
+// intersection lies inside box B and inside the bounding rectangle of box A in B's frame, so I <= ox * oy, the overlaps of those two
+// rectangles along B's axes.  For the near-parallel proposals around one object this bound is almost the intersection itself, and most
+// pairs whose circles meet but whose IoU stays below the threshold never reach the clip.  Single precision: the overlaps are grown by
+// what the converted centres may be off by (err) and the comparison keeps a 1e-3 margin, so the test only drops pairs whose true IoU is
+// below the threshold -- the keep mask cannot change.  (px, py): A's centre in B's frame needs B's axes (bc, bs).
+struct NmsShape { float c, s, hw, hh; };
+__device__ __forceinline__ bool nms_area_bound(const float dx, const float dy, const NmsShape A, const float areaA, const NmsShape B, const float areaB,
+                                               const float err, const float tau)
+{
+    const float px = B.c * dx + B.s * dy, py = B.c * dy - B.s * dx;
+    const float cr = fabsf(A.c * B.c + A.s * B.s), sr = fabsf(A.s * B.c - A.c * B.s);
+    const float ex = cr * A.hw + sr * A.hh + err, ey = sr * A.hw + cr * A.hh + err;
+    const float ox = fminf(B.hw, px + ex) - fmaxf(-B.hw, px - ex), oy = fminf(B.hh, py + ey) - fmaxf(-B.hh, py - ey);
+    return fmaxf(ox, 0.f) * fmaxf(oy, 0.f) * 1.001f >= tau * (areaA + areaB);
+}
+
 // ---- the same candidate search, a CTA per grid cell (default).  The kernel above gives every box a warp: its clips read their records
 // from global memory, and the last clip step of every box runs with the lanes that are left (ncu: half the clip rate of the IoU tile
 // kernel).  Here the boxes of one cell are the rows of a tile and the boxes of its 3x3 neighbourhood the columns, both staged in shared
@@ -356,6 +373,8 @@ __global__ void __launch_bounds__(NC_THREADS, D3D_NC_CTAS) nms_cells_kernel(cons
     const NmsGrid G = *g;
     __shared__ BoxRec<T> sR[NC_ROWS], sC[NC_COLS];
     __shared__ float4 fR[NC_ROWS];                    // centre, widened radius, index (bits) of the rows
+    __shared__ NmsShape gR[NC_ROWS];                  // axes and half extents of the rows (area bound)
+    __shared__ float aR[NC_ROWS], eR[NC_ROWS];        // area, coordinate error of the rows
     __shared__ uint32_t cidx[NC_COLS];
     __shared__ uint16_t queue[NC_ROWS * NC_COLS];     // row << 8 | column of the pairs that passed the circle test
     __shared__ uint2 hbuf[NC_HB];                     // hits (row box, column box) of the row chunk
@@ -371,6 +390,7 @@ __global__ void __launch_bounds__(NC_THREADS, D3D_NC_CTAS) nms_cells_kernel(cons
     // work items (cell, share of the column chunks) are handed out by a ticket counter (the grid does not know how many cells the frame has;
     // the counter starts at 0xffffffff: it shares the memset of the extents)
     const uint32_t items = (uint32_t)(G.nx * G.ny) * NC_SPLIT;
+    const float tau = (float)thr / (1.f + (float)thr) * 0.999999f;
   for (;;) {
     __syncthreads();   // the previous item is done with the shared words
     if (tid == 0) s_item = atomicAdd(ticket, 1u) + 1u;
@@ -404,8 +424,12 @@ __global__ void __launch_bounds__(NC_THREADS, D3D_NC_CTAS) nms_cells_kernel(cons
         __syncthreads();   // the previous row chunk is done with the row arrays
         if (tid < nr) {
             const NmsCand<T> e = celllist[rc + tid];
-            sR[tid] = recs[e.idx];
-            fR[tid] = make_float4(e.cx, e.cy, e.rho + (fabsf(e.cx) + fabsf(e.cy)) * 2.4e-7f, __uint_as_float(e.idx));
+            const BoxRec<T> rr = recs[e.idx];
+            sR[tid] = rr;
+            const float er = (fabsf(e.cx) + fabsf(e.cy)) * 2.4e-7f;   // 2^-22 of the coordinates: what the float centres may be off by
+            fR[tid] = make_float4(e.cx, e.cy, e.rho + er, __uint_as_float(e.idx));
+            NmsShape sh; sh.c = (float)rr.c; sh.s = (float)rr.s; sh.hw = (float)rr.hw * 1.000001f; sh.hh = (float)rr.hh * 1.000001f;
+            gR[tid] = sh; aR[tid] = (float)rr.area; eR[tid] = er;
         }
         for (uint32_t cc = split * NC_COLS; cc < ncols; cc += NC_SPLIT * NC_COLS) {
             __syncthreads();   // rows staged; the previous tile is done with the columns and the queue
@@ -420,11 +444,14 @@ __global__ void __launch_bounds__(NC_THREADS, D3D_NC_CTAS) nms_cells_kernel(cons
                 if (tid < NC_COLS) { sC[c] = recs[ce.idx]; cidx[c] = ce.idx; }
             }
             __syncthreads();
-            const float cr = ce.rho + (fabsf(ce.cx) + fabsf(ce.cy)) * 2.4e-7f;
+            const float cerr = (fabsf(ce.cx) + fabsf(ce.cy)) * 2.4e-7f, cr = ce.rho + cerr;
+            NmsShape csh; csh.c = (float)sC[c].c; csh.s = (float)sC[c].s; csh.hw = (float)sC[c].hw * 1.000001f; csh.hh = (float)sC[c].hh * 1.000001f;
+            const float carea = (float)sC[c].area;
             for (uint32_t r = tid / NC_COLS; r < nr; r += NC_THREADS / NC_COLS) {   // (warp-uniform r)
                 const float4 f = fR[r];
                 const float dx = f.x - ce.cx, dy = f.y - ce.cy, rs = f.z + cr;
-                const bool cand = have && ce.idx > __float_as_uint(f.w) && dx * dx + dy * dy <= rs * rs * 1.00001f;   // every unordered pair once: from its higher-scored box
+                bool cand = have && ce.idx > __float_as_uint(f.w) && dx * dx + dy * dy <= rs * rs * 1.00001f;   // every unordered pair once: from its higher-scored box
+                if (cand) cand = nms_area_bound(dx, dy, gR[r], aR[r], csh, carea, 2.f * (eR[r] + cerr), tau);
                 const unsigned bal = __ballot_sync(0xffffffffu, cand);
                 if (bal) {
                     uint32_t at = 0;
