@@ -1374,7 +1374,7 @@ template <typename T>
 __global__ void __launch_bounds__(NMS_THREADS)
 nmsb_cand_kernel(const BoxRec<T> *__restrict__ recs_all, const uint64_t *__restrict__ skey_all, const uint32_t *__restrict__ order_all,
                  const float4 *__restrict__ bounds_all, const int64_t *__restrict__ offs, int64_t stride, int64_t nwords, uint32_t *__restrict__ cands_all,
-                 uint32_t *__restrict__ ccount, uint32_t ccap, size_t cand_stride, uint32_t *__restrict__ fail)
+                 uint32_t *__restrict__ ccount, uint32_t ccap, size_t cand_stride, uint32_t *__restrict__ fail, float tau /* thr / (1 + thr): area bound */)
 {
     constexpr int RW = NMS_TILE / NMS_WARPS;  // 16 rows per warp
     constexpr int KC = NMS_TILE / 32;         // 2 column chunks
@@ -1389,15 +1389,22 @@ nmsb_cand_kernel(const BoxRec<T> *__restrict__ recs_all, const uint64_t *__restr
     uint32_t *cands = cands_all + (size_t)f * cand_stride;
     // the circle test runs in single precision, widened by what the converted centres may be off by: it passes a superset of the pairs
     // whose circles meet, the clip decides
-    __shared__ float ax_[NMS_TILE], ay_[NMS_TILE], ar_[NMS_TILE];
+    __shared__ float ax_[NMS_TILE], ay_[NMS_TILE], ar_[NMS_TILE], aa_[NMS_TILE], ae_[NMS_TILE];   // + area, coordinate error
+    __shared__ NmsShape as_[NMS_TILE];                                                              // axes and half extents (area bound)
     __shared__ unsigned long long kA[NMS_TILE], kB[NMS_TILE];
     __shared__ uint32_t oA[NMS_TILE], oB[NMS_TILE];
     __shared__ uint32_t queue[NMS_WARPS][NMSB_CQ];
+    __shared__ uint16_t stage[NMS_WARPS][(NMS_TILE / NMS_WARPS) * NMS_TILE];   // a warp's circle-test survivors of the current tile
+    __shared__ float bx_[NMS_TILE], by_[NMS_TILE], ba_[NMS_TILE], be_[NMS_TILE];
+    __shared__ NmsShape bs_[NMS_TILE];
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
+    uint16_t *sq = stage[w];
     if (threadIdx.x < NMS_TILE) {
         const BoxRec<T> a = recs[rb * NMS_TILE + threadIdx.x];
-        const float fx = (float)a.cx, fy = (float)a.cy;
-        ax_[threadIdx.x] = fx; ay_[threadIdx.x] = fy; ar_[threadIdx.x] = __double2float_ru((double)a.rho) + (fabsf(fx) + fabsf(fy)) * 2.4e-7f;   // + 2^-22 of the coordinates
+        const float fx = (float)a.cx, fy = (float)a.cy, fe = (fabsf(fx) + fabsf(fy)) * 2.4e-7f;   // 2^-22 of the coordinates
+        ax_[threadIdx.x] = fx; ay_[threadIdx.x] = fy; ar_[threadIdx.x] = __double2float_ru((double)a.rho) + fe;
+        NmsShape sh; sh.c = (float)a.c; sh.s = (float)a.s; sh.hw = (float)a.hw * 1.000001f; sh.hh = (float)a.hh * 1.000001f;
+        as_[threadIdx.x] = sh; aa_[threadIdx.x] = (float)a.area; ae_[threadIdx.x] = fe;
         kA[threadIdx.x] = skey[rb * NMS_TILE + threadIdx.x]; oA[threadIdx.x] = order[rb * NMS_TILE + threadIdx.x];
     }
     // the column blocks whose rectangle meets this row block's, compacted in ascending order (one global round trip for all of them).
@@ -1448,11 +1455,21 @@ nmsb_cand_kernel(const BoxRec<T> *__restrict__ recs_all, const uint64_t *__restr
 #pragma unroll
         for (int k = 0; k < KC; k++) {
             const BoxRec<T> bb = recs[cb * NMS_TILE + k * 32 + lane];
-            bx[k] = (float)bb.cx; by[k] = (float)bb.cy; br[k] = __double2float_ru((double)bb.rho) + (fabsf(bx[k]) + fabsf(by[k])) * 2.4e-7f;
+            bx[k] = (float)bb.cx; by[k] = (float)bb.cy;
+            const float fe = (fabsf(bx[k]) + fabsf(by[k])) * 2.4e-7f;
+            br[k] = __double2float_ru((double)bb.rho) + fe;
+            if (w == 0) {   // the first warp also leaves the columns' numbers for the area bound in shared memory
+                const unsigned cl = k * 32 + lane;
+                NmsShape sh; sh.c = (float)bb.c; sh.s = (float)bb.s; sh.hw = (float)bb.hw * 1.000001f; sh.hh = (float)bb.hh * 1.000001f;
+                bs_[cl] = sh; bx_[cl] = bx[k]; by_[cl] = by[k]; ba_[cl] = (float)bb.area; be_[cl] = fe;
+            }
         }
         if (threadIdx.x < NMS_TILE) { kB[threadIdx.x] = skey[cb * NMS_TILE + threadIdx.x]; oB[threadIdx.x] = order[cb * NMS_TILE + threadIdx.x]; }
         __syncthreads();
         const bool diag = (rb == cb);
+        // first the circle test of the warp's 16 x 64 pairs (the survivors wait as row << 8 | column), then the area bound and the
+        // orientation of the survivors with all lanes busy
+        unsigned ns = 0;
 #pragma unroll 1
         for (int r = 0; r < RW; r++) {
             const unsigned rl = w * RW + r;
@@ -1461,16 +1478,25 @@ nmsb_cand_kernel(const BoxRec<T> *__restrict__ recs_all, const uint64_t *__restr
             for (int k = 0; k < KC; k++) {
                 const unsigned cl = k * 32 + lane;
                 const float dx = ax - bx[k], dy = ay - by[k], rs = ar + br[k];
-                const bool cand = (dx * dx + dy * dy <= rs * rs * 1.00001f) && (!diag || cl > rl);   // every unordered pair once
+                const bool cand = (dx * dx + dy * dy <= rs * rs * 1.00001f) && (!diag || cl > rl);   // every unordered pair once (NaN padding fails)
                 const unsigned bal = __ballot_sync(0xffffffffu, cand);
-                if (cand) {
-                    const bool a_first = kA[rl] < kB[cl] || (kA[rl] == kB[cl] && oA[rl] < oB[cl]);
-                    const uint32_t pa = (uint32_t)(rb * NMS_TILE + rl), pb = (uint32_t)(cb * NMS_TILE + cl);
-                    q[tail + __popc(bal & lanemask_lt())] = a_first ? (pa | (pb << 16)) : (pb | (pa << 16));
-                }
-                tail += __popc(bal);
-                flush(false);
+                if (cand) sq[ns + __popc(bal & lanemask_lt())] = (uint16_t)((rl << 8) | cl);
+                ns += __popc(bal);
             }
+        }
+        __syncwarp();
+        for (unsigned e0 = 0; e0 < ns; e0 += 32) {
+            const bool live = e0 + lane < ns;
+            const unsigned ent = sq[live ? e0 + lane : ns - 1], rl = ent >> 8, cl = ent & 255u;
+            const bool cand = live && nms_area_bound(ax_[rl] - bx_[cl], ay_[rl] - by_[cl], as_[rl], aa_[rl], bs_[cl], ba_[cl], 2.f * (ae_[rl] + be_[cl]), tau);
+            const unsigned bal = __ballot_sync(0xffffffffu, cand);
+            if (cand) {
+                const bool a_first = kA[rl] < kB[cl] || (kA[rl] == kB[cl] && oA[rl] < oB[cl]);
+                const uint32_t pa = (uint32_t)(rb * NMS_TILE + rl), pb = (uint32_t)(cb * NMS_TILE + cl);
+                q[tail + __popc(bal & lanemask_lt())] = a_first ? (pa | (pb << 16)) : (pb | (pa << 16));
+            }
+            tail += __popc(bal);
+            flush(false);
         }
     }
     flush(true);
@@ -1708,7 +1734,8 @@ static int nmsb_impl(const T *boxes, const T *scores, int64_t total, const int64
         const size_t cand_stride = (size_t)stride * nwords * 2;
         const uint32_t ccap = (uint32_t)(cand_stride < 0xffffffffull ? cand_stride : 0xffffffffull);
         nmsb_cand_kernel<T><<<dim3((unsigned)nwords, (unsigned)nframes, 4), NMS_THREADS, 0, st>>>((const BoxRec<T> *)recs, skey, order, bounds, offs, stride, nwords,
-                                                                                           reinterpret_cast<uint32_t *>(mask), ccount, ccap, cand_stride, fail);
+                                                                                           reinterpret_cast<uint32_t *>(mask), ccount, ccap, cand_stride, fail,
+                                                                                           (float)thr / (1.f + (float)thr) * 0.999999f);
         D3D_LAUNCHED();
         nmsb_clip_kernel<T><<<dim3(32, (unsigned)nframes), NMS_THREADS, 0, st>>>((const BoxRec<T> *)recs, recheck ? raw : nullptr, stride, thr, reinterpret_cast<const uint32_t *>(mask),
                                                                               ccount, ccap, cand_stride, edges, ecount, ecap, fail);
