@@ -376,9 +376,12 @@ __global__ void __launch_bounds__(NC_THREADS, D3D_NC_CTAS) nms_cells_kernel(cons
     __shared__ NmsShape gR[NC_ROWS];                  // axes and half extents of the rows (area bound)
     __shared__ float aR[NC_ROWS], eR[NC_ROWS];        // area, coordinate error of the rows
     __shared__ uint32_t cidx[NC_COLS];
-    __shared__ uint16_t queue[NC_ROWS * NC_COLS];     // row << 8 | column of the pairs that passed the circle test
+    extern __shared__ __align__(16) uint16_t queue0[];   // [NC_ROWS * NC_COLS] row << 8 | column of the pairs that passed the circle test (dynamic: 56 KB in all)
+    __shared__ uint16_t queue[NC_ROWS * NC_COLS];     // ... and the area bound: the clip queue
+    __shared__ NmsShape gC[NC_COLS];                  // axes and half extents of the columns
+    __shared__ float4 cC[NC_COLS];                    // centre, area, coordinate error of the columns
     __shared__ uint2 hbuf[NC_HB];                     // hits (row box, column box) of the row chunk
-    __shared__ uint32_t seg_beg[3], seg_off[4], qn, hn, s_item;
+    __shared__ uint32_t seg_beg[3], seg_off[4], qn, qn0, hn, s_item;
     const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
     auto append = [&](const uint32_t i, const uint32_t j) {   // one entry of row i's 64-row block
         const uint32_t rb = i >> 6, at = atomicAdd(lists.blkcnt + rb, 1u);
@@ -433,7 +436,7 @@ __global__ void __launch_bounds__(NC_THREADS, D3D_NC_CTAS) nms_cells_kernel(cons
         }
         for (uint32_t cc = split * NC_COLS; cc < ncols; cc += NC_SPLIT * NC_COLS) {
             __syncthreads();   // rows staged; the previous tile is done with the columns and the queue
-            if (tid == 0) qn = 0;
+            if (tid == 0) { qn = 0; qn0 = 0; }
             const uint32_t c = tid & (NC_COLS - 1), v = cc + c;
             const bool have = v < ncols;
             NmsCand<T> ce;
@@ -441,23 +444,41 @@ __global__ void __launch_bounds__(NC_THREADS, D3D_NC_CTAS) nms_cells_kernel(cons
             if (have) {
                 const int sg = v >= seg_off[2] ? 2 : (v >= seg_off[1] ? 1 : 0);
                 ce = celllist[seg_beg[sg] + (v - seg_off[sg])];
-                if (tid < NC_COLS) { sC[c] = recs[ce.idx]; cidx[c] = ce.idx; }
+                if (tid < NC_COLS) {
+                    const BoxRec<T> cr_ = recs[ce.idx];
+                    sC[c] = cr_; cidx[c] = ce.idx;
+                    NmsShape sh; sh.c = (float)cr_.c; sh.s = (float)cr_.s; sh.hw = (float)cr_.hw * 1.000001f; sh.hh = (float)cr_.hh * 1.000001f;
+                    gC[c] = sh; cC[c] = make_float4(ce.cx, ce.cy, (float)cr_.area, (fabsf(ce.cx) + fabsf(ce.cy)) * 2.4e-7f);
+                }
             }
             __syncthreads();
             const float cerr = (fabsf(ce.cx) + fabsf(ce.cy)) * 2.4e-7f, cr = ce.rho + cerr;
-            NmsShape csh; csh.c = (float)sC[c].c; csh.s = (float)sC[c].s; csh.hw = (float)sC[c].hw * 1.000001f; csh.hh = (float)sC[c].hh * 1.000001f;
-            const float carea = (float)sC[c].area;
             for (uint32_t r = tid / NC_COLS; r < nr; r += NC_THREADS / NC_COLS) {   // (warp-uniform r)
                 const float4 f = fR[r];
                 const float dx = f.x - ce.cx, dy = f.y - ce.cy, rs = f.z + cr;
-                bool cand = have && ce.idx > __float_as_uint(f.w) && dx * dx + dy * dy <= rs * rs * 1.00001f;   // every unordered pair once: from its higher-scored box
-                if (cand) cand = nms_area_bound(dx, dy, gR[r], aR[r], csh, carea, 2.f * (eR[r] + cerr), tau);
+                const bool cand = have && ce.idx > __float_as_uint(f.w) && dx * dx + dy * dy <= rs * rs * 1.00001f;   // every unordered pair once: from its higher-scored box
+                const unsigned bal = __ballot_sync(0xffffffffu, cand);
+                if (bal) {
+                    uint32_t at = 0;
+                    if (lane == 0) at = atomicAdd(&qn0, (uint32_t)__popc(bal));
+                    at = __shfl_sync(0xffffffffu, at, 0);
+                    if (cand) queue0[at + __popc(bal & lanemask_lt())] = (uint16_t)((r << 8) | c);
+                }
+            }
+            __syncthreads();
+            // the area bound on the survivors of the circle test, all lanes busy; what passes goes to the clip queue
+            const uint32_t n0 = qn0;
+            for (uint32_t e0 = w * 32u; e0 < n0; e0 += (NC_THREADS / 32) * 32u) {
+                const bool live = e0 + lane < n0;
+                const uint32_t ent = queue0[live ? e0 + lane : n0 - 1], r = ent >> 8, cq = ent & 255u;
+                const float4 f = fR[r];
+                const bool cand = live && nms_area_bound(f.x - cC[cq].x, f.y - cC[cq].y, gR[r], aR[r], gC[cq], cC[cq].z, 2.f * (eR[r] + cC[cq].w), tau);
                 const unsigned bal = __ballot_sync(0xffffffffu, cand);
                 if (bal) {
                     uint32_t at = 0;
                     if (lane == 0) at = atomicAdd(&qn, (uint32_t)__popc(bal));
                     at = __shfl_sync(0xffffffffu, at, 0);
-                    if (cand) queue[at + __popc(bal & lanemask_lt())] = (uint16_t)((r << 8) | c);
+                    if (cand) queue[at + __popc(bal & lanemask_lt())] = (uint16_t)ent;
                 }
             }
             __syncthreads();
@@ -1868,10 +1889,11 @@ static int nms_impl(const T *boxes, const T *scores, int64_t n, int iou_type, in
         nms_bin_kernel<T, 0><<<gb, 256, 0, st>>>(br, n, grid, cellcnt, nullptr, nullptr); D3D_LAUNCHED();
         if ((rc = exclusive_scan_u32(cellcnt, cellptr, NMS_GRID_CELLS + 1, nullptr, cell_scan_ws, st))) return rc;
         nms_bin_kernel<T, 1><<<gb, 256, 0, st>>>(br, n, grid, cellcnt + NMS_GRID_CELLS + 1, cellptr, celllist); D3D_LAUNCHED();
+        D3D_CUDA_TRY(cudaFuncSetAttribute(nms_cells_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, NC_ROWS * NC_COLS * 2));   // static + dynamic > 48 KB
         if (tuning(D3D_TUNE_NMS_PATH, 0) == 3)   // D3D_B200_NMS_PATH=warp: a warp per box (the round's earlier candidate kernel)
             nms_pairs_kernel<T><<<(unsigned)cdiv(n, NMS_PAIR_THREADS / 32), NMS_PAIR_THREADS, 0, st>>>(br, recheck ? raw : nullptr, n, nwords, thr, grid, cellptr, celllist, lists);
         else   // a CTA per grid cell (cells that do not exist or hold no box leave at once)
-            nms_cells_kernel<T><<<(unsigned)(nsm_cells * D3D_NC_CTAS), NC_THREADS, 0, st>>>(br, recheck ? raw : nullptr, n, nwords, thr, grid, cellptr, celllist, lists, &ext->pad);
+            nms_cells_kernel<T><<<(unsigned)(nsm_cells * D3D_NC_CTAS), NC_THREADS, NC_ROWS * NC_COLS * 2, st>>>(br, recheck ? raw : nullptr, n, nwords, thr, grid, cellptr, celllist, lists, &ext->pad);
         D3D_LAUNCHED();
     }
     dim3 tiles((unsigned)nwords, (unsigned)nwords);
