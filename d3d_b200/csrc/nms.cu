@@ -197,7 +197,9 @@ struct NmsGrid { double minx, miny, inv_cell; int nx, ny; uint32_t ok; uint32_t 
 // what the candidate scan needs of a box, stored in cell order so that a warp reads consecutive records
 // (single precision whatever the box type: 16 bytes per entry.  The circle test on these numbers is widened by the conversion error of
 // the centres, so it passes a superset of the pairs whose circles meet -- the clip decides, the keep mask does not depend on it)
-struct __align__(16) NmsCandF { float cx, cy, rho; uint32_t idx; };
+// The entry also carries the numbers of the area bound (axes, half extents grown by 1e-6, area): a tile of the cell kernel stages its
+// columns with one coalesced pass over the list, no gather of records.
+struct __align__(16) NmsCandF { float cx, cy, rho; uint32_t idx; float c, s, hw, hh; float area, pad0, pad1, pad2; };
 template <typename T> using NmsCand = NmsCandF;
 
 // grid geometry from the extents the gather kernel reduced (one thread)
@@ -239,7 +241,13 @@ __global__ void __launch_bounds__(256) nms_bin_kernel(const BoxRec<T> *__restric
     nms_cell_of<T>(*g, r, &ix, &iy);
     const uint32_t c = (uint32_t)(iy * g->nx + ix);
     const uint32_t at = atomicAdd(cellcnt + c, 1u);
-    if (PASS == 1) { NmsCand<T> e; e.cx = (float)r.cx; e.cy = (float)r.cy; e.rho = __double2float_ru((double)r.rho); e.idx = (uint32_t)p; celllist[cellptr[c] + at] = e; }
+    if (PASS == 1) {
+        NmsCand<T> e;
+        e.cx = (float)r.cx; e.cy = (float)r.cy; e.rho = __double2float_ru((double)r.rho); e.idx = (uint32_t)p;
+        e.c = (float)r.c; e.s = (float)r.s; e.hw = (float)r.hw * 1.000001f; e.hh = (float)r.hh * 1.000001f;
+        e.area = (float)r.area; e.pad0 = e.pad1 = e.pad2 = 0.f;
+        celllist[cellptr[c] + at] = e;
+    }
 }
 
 constexpr int NMS_PAIR_THREADS = 256;
@@ -314,7 +322,8 @@ __global__ void __launch_bounds__(NMS_PAIR_THREADS, D3D_NMS_PAIR_CTAS) nms_pairs
             bool cand = false;
             uint32_t j = 0;
             if (k < end) {
-                const NmsCand<T> e = celllist[k];   // coalesced: the cell lists hold the three numbers the circle test needs
+                const float4 e4 = *reinterpret_cast<const float4 *>(celllist + k);   // the first 16 bytes of the entry: the three numbers the circle test needs + index
+                NmsCand<T> e; e.cx = e4.x; e.cy = e4.y; e.rho = e4.z; e.idx = __float_as_uint(e4.w);
                 j = e.idx;
                 if ((int64_t)j > i) {
                     const float dx = fax - e.cx, dyy = fay - e.cy;
@@ -371,7 +380,7 @@ __global__ void __launch_bounds__(NC_THREADS, D3D_NC_CTAS) nms_cells_kernel(cons
 {
     if (!g->ok) return;
     const NmsGrid G = *g;
-    __shared__ BoxRec<T> sR[NC_ROWS], sC[NC_COLS];
+    __shared__ BoxRec<T> sR[NC_ROWS];
     __shared__ float4 fR[NC_ROWS];                    // centre, widened radius, index (bits) of the rows
     __shared__ NmsShape gR[NC_ROWS];                  // axes and half extents of the rows (area bound)
     __shared__ float aR[NC_ROWS], eR[NC_ROWS];        // area, coordinate error of the rows
@@ -431,8 +440,8 @@ __global__ void __launch_bounds__(NC_THREADS, D3D_NC_CTAS) nms_cells_kernel(cons
             sR[tid] = rr;
             const float er = (fabsf(e.cx) + fabsf(e.cy)) * 2.4e-7f;   // 2^-22 of the coordinates: what the float centres may be off by
             fR[tid] = make_float4(e.cx, e.cy, e.rho + er, __uint_as_float(e.idx));
-            NmsShape sh; sh.c = (float)rr.c; sh.s = (float)rr.s; sh.hw = (float)rr.hw * 1.000001f; sh.hh = (float)rr.hh * 1.000001f;
-            gR[tid] = sh; aR[tid] = (float)rr.area; eR[tid] = er;
+            NmsShape sh; sh.c = e.c; sh.s = e.s; sh.hw = e.hw; sh.hh = e.hh;
+            gR[tid] = sh; aR[tid] = e.area; eR[tid] = er;
         }
         for (uint32_t cc = split * NC_COLS; cc < ncols; cc += NC_SPLIT * NC_COLS) {
             __syncthreads();   // rows staged; the previous tile is done with the columns and the queue
@@ -445,10 +454,9 @@ __global__ void __launch_bounds__(NC_THREADS, D3D_NC_CTAS) nms_cells_kernel(cons
                 const int sg = v >= seg_off[2] ? 2 : (v >= seg_off[1] ? 1 : 0);
                 ce = celllist[seg_beg[sg] + (v - seg_off[sg])];
                 if (tid < NC_COLS) {
-                    const BoxRec<T> cr_ = recs[ce.idx];
-                    sC[c] = cr_; cidx[c] = ce.idx;
-                    NmsShape sh; sh.c = (float)cr_.c; sh.s = (float)cr_.s; sh.hw = (float)cr_.hw * 1.000001f; sh.hh = (float)cr_.hh * 1.000001f;
-                    gC[c] = sh; cC[c] = make_float4(ce.cx, ce.cy, (float)cr_.area, (fabsf(ce.cx) + fabsf(ce.cy)) * 2.4e-7f);
+                    cidx[c] = ce.idx;
+                    NmsShape sh; sh.c = ce.c; sh.s = ce.s; sh.hw = ce.hw; sh.hh = ce.hh;
+                    gC[c] = sh; cC[c] = make_float4(ce.cx, ce.cy, ce.area, (fabsf(ce.cx) + fabsf(ce.cy)) * 2.4e-7f);
                 }
             }
             __syncthreads();
@@ -488,7 +496,7 @@ __global__ void __launch_bounds__(NC_THREADS, D3D_NC_CTAS) nms_cells_kernel(cons
                 const uint32_t ent = queue[live ? e0 + lane : nq - 1];
                 const uint32_t r = ent >> 8, cq = ent & 255u;
                 const uint32_t i = __float_as_uint(fR[r].w), j = cidx[cq];
-                const T iou = rbox_iou<T>(sR[r], sC[cq]);   // iou(higher score box, lower score box), nms.cpp:50
+                const T iou = rbox_iou<T>(sR[r], recs[j]);   // iou(higher score box, lower score box), nms.cpp:50; few pairs get here: the column's record comes from L2
                 if (live && over_threshold<T>(iou, thr, raw, i, j)) {
                     const uint32_t h = atomicAdd(&hn, 1u);
                     if (h < (uint32_t)NC_HB) hbuf[h] = make_uint2(i, j);
