@@ -369,7 +369,7 @@ __device__ __forceinline__ bool nms_area_bound(const float dx, const float dy, c
 #define D3D_NC_SPLIT 4
 #endif
 #ifndef D3D_NC_CTAS
-#define D3D_NC_CTAS 3
+#define D3D_NC_CTAS 4
 #endif
 constexpr int NC_ROWS = 64, NC_COLS = 128, NC_THREADS = 256, NC_SPLIT = D3D_NC_SPLIT, NC_HB = 1024;
 
