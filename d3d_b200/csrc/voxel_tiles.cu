@@ -258,11 +258,13 @@ __global__ void __launch_bounds__(VT_THREADS, D3D_VT_SCTAS) vt_split_kernel(cons
 }
 
 // ------------------------------------------------------------------------------------------------ bucket
-// table slot s: tkey cell key, tmin smallest point index, tcnt points, trec record of a crowded voxel
+// table slot s: tkey cell key, tmc {smallest point index, points}, trec record of a crowded voxel
 __global__ void __launch_bounds__(VT_BT, D3D_VT_BCTAS) vt_bucket_kernel(const VtArgs a)
 {
-    // one array per field: the 32 lanes of an atomic on one field spread over all 32 banks (16-byte slots put a field on 8 of them)
-    __shared__ __align__(16) uint32_t tkey[VT_SMAX], tmin[VT_SMAX], tcnt[VT_SMAX], trec[VT_SMAX];
+    // keys apart from the {smallest index, count} pairs: the 32 lanes of a key claim spread over all 32 banks, those of the other two atomics over
+    // 16 (16-byte slots put every field on 8 of them), and a lookup reads its pair with one load
+    __shared__ __align__(16) uint32_t tkey[VT_SMAX], trec[VT_SMAX];
+    __shared__ __align__(16) uint2 tmc[VT_SMAX];   // the pair every lookup reads comes with one 64-bit load
     __shared__ uint32_t pool[VT_POOL * VT_MAXK];   // records of VT_MAXK indices
     __shared__ uint32_t misc[4];                   // [1] records in use, [2] failure
     const VtGeom &g = a.g;
@@ -293,8 +295,8 @@ __global__ void __launch_bounds__(VT_BT, D3D_VT_BCTAS) vt_bucket_kernel(const Vt
     const uint32_t S = 1u << lgS, smask = S - 1, hshift = 32u - lgS;
     for (uint32_t s = tid; s < S / 4; s += VT_BT) {
         reinterpret_cast<uint4 *>(tkey)[s] = make_uint4(VT_NONE, VT_NONE, VT_NONE, VT_NONE);
-        reinterpret_cast<uint4 *>(tmin)[s] = make_uint4(VT_NONE, VT_NONE, VT_NONE, VT_NONE);
-        reinterpret_cast<uint4 *>(tcnt)[s] = make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4 *>(tmc)[2 * s] = make_uint4(VT_NONE, 0u, VT_NONE, 0u);
+        reinterpret_cast<uint4 *>(tmc)[2 * s + 1] = make_uint4(VT_NONE, 0u, VT_NONE, 0u);
     }
     if (tid == 0) { misc[1] = 0; misc[2] = 0; }
     __syncthreads();
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(VT_BT, D3D_VT_BCTAS) vt_bucket_kernel(const Vt
     // counts the point; the (K+1)-th arrival of a voxel opens the record of its K smallest indices (exactly one thread sees the count step
     // from K to K+1, and the records are only read after the next barrier)
     auto count_and_open = [&](const uint32_t s) {
-        const uint32_t c = atomicAdd(&tcnt[s], 1u);
+        const uint32_t c = atomicAdd(&tmc[s].y, 1u);
         if (c >= cthr) {
             anyc = true;
             if (c == cthr) {
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(VT_BT, D3D_VT_BCTAS) vt_bucket_kernel(const Vt
             if (old == VT_NONE || old == x.x) break;
             s = (s + 1) & smask;
         }
-        atomicMin(&tmin[s], x.y);
+        atomicMin(&tmc[s].x, x.y);
         count_and_open(s);
         return s;
     };
@@ -337,9 +339,10 @@ __global__ void __launch_bounds__(VT_BT, D3D_VT_BCTAS) vt_bucket_kernel(const Vt
         return s;
     };
     auto cascade = [&](const uint2 x, const uint32_t s) {
-        const uint4 t = make_uint4(tkey[s], tmin[s], tcnt[s], trec[s]);
-        if (t.z > cthr && x.y != t.y) {   // the smallest index is already known (tmin): the record keeps the next K - 1
-            uint32_t *rec = pool + t.w * VT_MAXK;
+        const uint2 mc = tmc[s];
+        const uint4 t = make_uint4(0u, mc.x, mc.y, 0u);
+        if (t.z > cthr && x.y != t.y) {   // the smallest index is already known: the record keeps the next K - 1
+            uint32_t *rec = pool + trec[s] * VT_MAXK;
             uint32_t v = x.y;
             for (uint32_t j = 0; j + 1 < K; j++) {
                 const uint32_t old = atomicMin(&rec[j], v);
@@ -349,13 +352,14 @@ __global__ void __launch_bounds__(VT_BT, D3D_VT_BCTAS) vt_bucket_kernel(const Vt
         }
     };
     auto reply = [&](const uint2 x, const uint32_t s) {
-        const uint4 t = make_uint4(tkey[s], tmin[s], tcnt[s], trec[s]);
+        const uint2 mc = tmc[s];
+        const uint4 t = make_uint4(0u, mc.x, mc.y, 0u);
         if (t.z != 1u) {
             uint32_t r;
             if ((long long)t.z < (long long)a.min_points) r = VT_W_NONE;
             else if (x.y == t.y) { r = VT_W_HEAD | min(t.z, VT_VAL); vt_st32(hkey + x.y, x.x, keep); }
             else {
-                const bool kept = !(t.z > cthr) || (K >= 2u && x.y <= pool[t.w * VT_MAXK + K - 2]);
+                const bool kept = !(t.z > cthr) || (K >= 2u && x.y <= pool[trec[s] * VT_MAXK + K - 2]);
                 r = kept ? (VT_W_JOIN | t.y) : VT_W_NONE;
             }
             vt_st32(word + x.y, r, keep);
@@ -381,7 +385,7 @@ __global__ void __launch_bounds__(VT_BT, D3D_VT_BCTAS) vt_bucket_kernel(const Vt
                 s = (s + 1) & smask;
                 old = atomicCAS(&tkey[s], VT_NONE, en[k].x);
             }
-            atomicMin(&tmin[s], en[k].y);
+            atomicMin(&tmc[s].x, en[k].y);
             count_and_open(s);
             sl[k] = s;
         }
