@@ -1086,6 +1086,8 @@ def main():
                 line[keys[0]] = res[op]["value"]
                 if keys[1]:
                     line[keys[1]] = res[op]["roofline"].get("frac")
+        if "c5" in res and res["c5"].get("weak"):   # config 5 with a full batch on every rank, beside the strong-scaling number
+            line["c5_weak_frames_per_s"] = res["c5"]["weak"]["value"]
         if len(ops) > 1:
             line["ops"] = {op: res[op] for op in ops[1:]}
         print(json.dumps(line))
