@@ -868,7 +868,9 @@ def bench_nms(args, rank, world, barrier):
             f = lambda: box2d_nms(sP, ss, "rbox", "gaussian", iou_threshold=0.3, score_threshold=0.2, supression_param=0.5)  # noqa: E731
             soft[str(m)] = dict(ms=timed(f, 3, 1, lambda: None), kept=int(f().sum().item()))
     roof = alu_roofline(1, clips * W_CAND / (ms_pairs * 1e-3) / 1e12, clk)
-    roof.update(phase="candidate phase (nms_pairs_kernel): clips x 230 flop over its own time", clips=clips, ms_sort_gather=ms_sort, ms_candidates=ms_pairs,
+    roof.update(phase="candidate phase (nms_cells_kernel): pairs whose bounding circles meet x 230 flop (SURVEY.md 8(d): the work a clip-every-candidate kernel "
+                      "would do) over its own time; the kernel drops most of these pairs with an area bound before the clip, so its FP64 pipe is far less busy "
+                      "than this fraction suggests (ncu: 7 %) -- read it as candidates per second, not as pipe utilisation", clips=clips, ms_sort_gather=ms_sort, ms_candidates=ms_pairs,
                 ms_resolve=ms_resolve, resolve_us_per_64_box_block=ms_resolve * 1e3 / ((n + 63) // 64),
                 note="the resolve is the fixpoint of keep / suppress decisions, pulled by a thread per box over the transposed hit lists (latency of the longest chain "
                      "of decisions: no roofline; D3D_B200_NMS_FIX=2: the same fixpoint by rounds with grid barriers, 0.23 ms; =0: the block-by-block walk in score order on one SM, 0.97 ms)")
